@@ -1,0 +1,210 @@
+/* swapnet_b200 — C ABI of the B200-native SwapNet hot path (libswapnet_b200.so).
+ *
+ * The reference (andrewjong/SwapNet) has no FFI: its plugin boundary is the Python class
+ * protocol of models/__init__.py:5-44.  This header is the NEW lower boundary under that
+ * protocol: what a maintainer binds (ctypes) to replace the eager
+ * torch ops of
+ *     modules/layers.py:12-63,126-144        (UNetDown / UNetUp / DualUNetUp / ResidualBlock)
+ *     modules/swapnet_modules.py:85-90,92-151,209-260 (head conv, WarpModule, TextureModule)
+ *     modules/pix2pix_modules.py:180-262     (UnetSkipConnectionBlock)
+ *     modules/discriminators.py:91-136       (NLayerDiscriminator / PatchGAN)
+ *     modules/loss.py:110-130, models/warp_model.py:147-150, models/texture_model.py:168-170
+ *     torchvision.ops.roi_align as called at modules/swapnet_modules.py:166-168,234
+ *
+ * Conventions
+ *   - every pointer is a caller-owned DEVICE pointer (torch tensor.data_ptr()); the library
+ *     allocates nothing persistent except plan handles;
+ *   - every call takes the CUDA stream to run on (a cudaStream_t passed as void*), is
+ *     asynchronous, and returns 0 on success or a negative code (message: sn_last_error());
+ *   - activations are NHWC ("channels-last") fp32 with an explicit pixel pitch (elements per
+ *     pixel in memory >= channels) so that a tensor can live inside a channel slice of a
+ *     wider concat buffer;
+ *   - a GEMM operand is a "split plane pair": two bf16 NHWC tensors hi = bf16(v),
+ *     lo = bf16(v - hi) (fp32 carried as 2 x bf16; products are evaluated as
+ *     hi*hi + lo*hi + hi*lo on the tcgen05 tensor cores with fp32 accumulation).
+ */
+#ifndef SWAPNET_B200_H
+#define SWAPNET_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SN_MAX_TAPS 32
+#define SN_MAX_SRC 3
+
+enum { SN_ACT_NONE = 0, SN_ACT_TANH = 1, SN_ACT_LRELU = 2, SN_ACT_RELU = 3 };
+enum { SN_LAYOUT_NCHW = 0, SN_LAYOUT_NHWC = 1 };
+
+const char* sn_version(void);
+const char* sn_last_error(void);
+/* number of kernel launches issued by this library since process start (bench.py: gpu_launches) */
+long long sn_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------
+ * tensor-core contractions
+ * ---------------------------------------------------------------------------------------- */
+typedef struct sn_tap {
+  int c_off;  /* channel offset inside the A tensor view (parity view: pw * pitch) */
+  int kb_off; /* K offset of this tap in the packed weight matrix (tap GEMM only) */
+  int dw, dh; /* GEMM-row (h, w) -> source pixel (h + dh, w + dw); out of range = zero */
+  int hp;     /* parity view only: h parity plane (0/1); 0 otherwise */
+} sn_tap;
+
+/* D[(n,h,w), j] = sum_t sum_c A[n, h+dh_t, w+dw_t, c_off_t + c] * B[j, kb_off_t + c]  (+bias, act)
+ * Lowers Conv2d / ConvTranspose2d forward and their dgrad; see swapnet_b200/lowering.py. */
+typedef struct sn_tap_gemm_desc {
+  const void* a_hi; const void* a_lo;   /* split planes, logical [a_n, a_h, a_w, a_c], pitch a_pitch */
+  int a_n, a_h, a_w, a_c, a_pitch;
+  int a_parity;                          /* 1: address through the 2x2 parity view (stride-2) */
+  const void* b_hi; const void* b_lo;   /* packed weights [b_rows][b_k] bf16, K contiguous */
+  int b_rows; long long b_k;
+  int m_n, m_h, m_w;                     /* GEMM row grid */
+  int ntaps; int k_per_tap;              /* k_per_tap % 64 == 0 */
+  sn_tap taps[SN_MAX_TAPS];
+  float* out;                            /* fp32, element strides below, channel stride 1 */
+  long long out_sn, out_sh, out_sw;
+  int out_mul_h, out_off_h, out_mul_w, out_off_w; /* row (h,w) -> out pixel (h*mul+off, ...) */
+  int n_valid;                           /* output channels actually written */
+  int block_n;                           /* N tile: multiple of 16, <= 128 */
+  const float* bias;                     /* optional [n_valid] */
+  int act;                               /* SN_ACT_NONE | SN_ACT_TANH */
+  int nsplit;                            /* 3 = fp32-faithful split product, 1 = bf16 fast mode */
+} sn_tap_gemm_desc;
+
+/* G[i*s_row + j*s_col + tap_off[t]] += sum_{(n,h,w)} X[n, h+dh_t, w+dw_t, xc_t + i] * Y[n, h+dh'_t, w+dw'_t, yc_t + j]
+ * Lowers every weight gradient (atomic accumulation into a zeroed fp32 buffer, which can be the
+ * torch-layout .grad tensor itself). */
+typedef struct sn_wgrad_desc {
+  const void* x_hi; const void* x_lo; int x_n, x_h, x_w, x_c, x_pitch, x_parity;
+  const void* y_hi; const void* y_lo; int y_n, y_h, y_w, y_c, y_pitch, y_parity;
+  int m_n, m_h, m_w;                     /* pixel grid the reduction runs over */
+  int ntaps;
+  sn_tap xtaps[SN_MAX_TAPS];
+  sn_tap ytaps[SN_MAX_TAPS];
+  long long tap_off[SN_MAX_TAPS];
+  float* out; long long s_row, s_col;
+  int rows_valid, cols_valid;
+  int block_n;                           /* 64 or 128 */
+  int ksplit;                            /* 0 = auto */
+  int nsplit;
+} sn_wgrad_desc;
+
+typedef struct sn_plan sn_plan; /* opaque; owns the encoded TMA descriptors of one launch */
+
+int sn_tap_gemm_plan_create(const sn_tap_gemm_desc* desc, sn_plan** out);
+int sn_wgrad_plan_create(const sn_wgrad_desc* desc, sn_plan** out);
+int sn_plan_run(const sn_plan* plan, void* stream);
+void sn_plan_destroy(sn_plan* plan);
+
+/* ------------------------------------------------------------------------------------------
+ * operand packing
+ * ---------------------------------------------------------------------------------------- */
+/* fp32 image tensor (NCHW contiguous, or NHWC with src_pitch) -> split planes at channel
+ * offset dst_coff of an NHWC plane pair with pitch dst_pitch.  Replaces the torch.cat /
+ * .to(device) glue of warp_model.py:99-116 and swapnet_modules.py:258. */
+int sn_pack_planes(const float* src, int src_layout, int src_pitch, int n, int c, int h, int w,
+                   void* dst_hi, void* dst_lo, int dst_pitch, int dst_coff, void* stream);
+
+/* weights -> packed [rows][taps][k_pad] split planes.  Source element (row r, tap t, k) is read
+ * at src[r*s_row + k*s_k + t] (taps contiguous, as in torch OIHW / IOHW).  k >= k_real is zero. */
+int sn_pack_weights(const float* src, long long s_row, long long s_k, int rows, int taps, int k_real,
+                    int k_pad, void* dst_hi, void* dst_lo, void* stream);
+
+/* head conv (swapnet_modules.py:85-90): nearest x2 upsample + ZeroPad2d((1,0,1,0)) + Conv2d(k4,p1)
+ * folded into 4 output-parity phases with 2/3 effective taps per dim (25 taps in total).
+ *   fwd pack:  dst[phase][row=co (rows_pad)][teff][ci (k_pad)]   (rows >= cout are zero)
+ *   dgrad pack: dst[row=ci][ (phase,teff) ][co (k_pad)]
+ * src is torch OIHW [cout][cin][4][4]. */
+int sn_pack_head_weights(const float* src, int cout, int cin, int rows_pad, int k_pad, int dgrad,
+                         void* dst_hi, void* dst_lo, void* stream);
+/* fold the 25 effective-tap gradients [cout][25][cin] back onto dW [cout][cin][4][4] (+=) */
+int sn_fold_head_wgrad(const float* geff, int cout, int cin, float* dw, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * InstanceNorm / activation / dropout blocks (layers.py:17-20,32-36,133-138)
+ * ---------------------------------------------------------------------------------------- */
+/* per-(n,c) InstanceNorm statistics over the plane -> stats[n][c] = (mean, 1/sqrt(var_biased + eps))
+ * as doubles (accumulated in fp64). */
+int sn_plane_stats(const float* y, int pitch, int n, int hw, int c, float eps, double* stats,
+                   void* stream);
+
+typedef struct sn_norm_act_desc {
+  const float* y; int y_pitch;           /* conv output, [n, h, w, c] */
+  int n, h, w, c;
+  const double* stats;                   /* (mean, rstd) [n][c][2] or NULL (no InstanceNorm) */
+  int act; float slope;                  /* SN_ACT_NONE / LRELU / RELU */
+  float drop_p; unsigned long long drop_seed; /* drop_p == 0: no dropout */
+  const float* residual; int res_pitch;  /* optional: out = residual + xhat (ResidualBlock tail) */
+  void* out_hi; void* out_lo; int out_pitch, out_coff; /* optional split planes */
+  int out_reflect_pad;                   /* 1: planes are [n, h+2, w+2] with ReflectionPad2d(1) */
+  float* out_f32; int f32_pitch;         /* optional fp32 copy (residual stream) */
+} sn_norm_act_desc;
+int sn_norm_act_fwd(const sn_norm_act_desc* d, void* stream);
+
+typedef struct sn_grad_src {
+  const float* ptr; int pitch; int c_off;
+  int reflect_padded;                    /* 1: [n, h+2, w+2] gradient of a reflect-padded operand */
+} sn_grad_src;
+
+typedef struct sn_norm_act_bwd_desc {
+  sn_grad_src src[SN_MAX_SRC]; int nsrc; /* upstream gradients w.r.t. the block output (summed) */
+  const float* y; int y_pitch;
+  int n, h, w, c;
+  const double* stats;
+  int act; float slope;
+  float drop_p; unsigned long long drop_seed;
+  double* gstats;                        /* scratch [n][c][2] (needed when stats != NULL) */
+  void* dy_hi; void* dy_lo; int dy_pitch, dy_coff; /* split planes of dL/dy */
+} sn_norm_act_bwd_desc;
+int sn_norm_act_bwd(const sn_norm_act_bwd_desc* d, void* stream);
+
+/* dst[n,h,w,c] = sum_i src_i (fp32), e.g. the residual-stream gradient of a ResidualBlock */
+int sn_sum_grads(const sn_grad_src* src, int nsrc, int n, int h, int w, int c, float* dst,
+                 int dst_pitch, void* stream);
+
+/* dL/dy of a tanh output: (sum_i src_i) * (1 - out^2) -> split planes */
+int sn_tanh_bwd(const sn_grad_src* src, int nsrc, const float* out, int out_pitch, int n, int h,
+                int w, int c, void* dy_hi, void* dy_lo, int dy_pitch, int dy_coff, void* stream);
+
+/* deterministic dropout keep-mask shared by forward, backward and the test oracle:
+ * keep(seed, idx) with idx the linear NHWC element index; returns 0/1 bytes. */
+int sn_dropout_mask(unsigned long long seed, float p, long long count, uint8_t* out, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * losses (value + gradient in one pass)
+ * ---------------------------------------------------------------------------------------- */
+/* CrossEntropyLoss(logits, argmax(target,1)) * weight  (warp_model.py:147-150).
+ * logits NHWC [n,h,w,c] (pitch), target NCHW [n,c,h,w]; loss accumulated into *loss_acc
+ * (double, caller zeroes); grad NHWC fp32 (pitch c). */
+int sn_ce_loss_fwd_bwd(const float* logits, int pitch, const float* target_nchw, int n, int h, int w,
+                       int c, float weight, double* loss_acc, float* grad, int grad_pitch, void* stream);
+/* BCEWithLogitsLoss(pred, t) over two consecutive halves of `count` elements each with its own
+ * target (loss.py:58,110-122): loss_acc[half] += mean, dpred = gscale * (sigmoid(x) - t)/count. */
+int sn_bce_logits_fwd_bwd(const float* pred, long long count_per_half, int halves, float t0, float t1,
+                          float gscale, double* loss_acc, float* dpred, void* stream);
+/* L1Loss(a, b) * weight (texture_model.py:168-170); a NHWC (pitch), b NCHW; grad wrt a. */
+int sn_l1_loss_fwd_bwd(const float* a, int pitch, const float* b_nchw, int n, int h, int w, int c,
+                       float weight, double* loss_acc, float* grad, int grad_pitch, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * ROIAlign + channel repack (swapnet_modules.py:209-240, torchvision roi_align aligned=False,
+ * spatial_scale=1, sampling_ratio=1, output 128x128): tex NCHW [b,3,h,w], rois [b,nroi,4]
+ * (x1,y1,x2,y2) -> fp32 NHWC [b,pool,pool,3*nroi] and/or split planes.
+ * ---------------------------------------------------------------------------------------- */
+int sn_roi_align_pack_fwd(const float* tex_nchw, int b, int ch, int h, int w, const float* rois,
+                          int nroi, int pool, float* out_f32, int out_pitch, void* out_hi,
+                          void* out_lo, int plane_pitch, int plane_coff, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * reference-free fp32 CUDA-core contraction with the tap-GEMM semantics (no tensor cores).
+ * Used by the tests as an on-device cross-check of the tcgen05 path, never by the plugin.
+ * ---------------------------------------------------------------------------------------- */
+int sn_tap_gemm_simt(const sn_tap_gemm_desc* desc, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SWAPNET_B200_H */

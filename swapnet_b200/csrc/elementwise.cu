@@ -1,0 +1,872 @@
+// swapnet_b200 — HBM-bound kernels of the SwapNet hot path (sm_100a).
+//
+// Operand packing (fp32 -> split-bf16 NHWC planes), InstanceNorm statistics, the fused
+// InstanceNorm-apply + activation + dropout (+ residual, + reflect padding) forward and
+// backward blocks, gradient merges and the loss kernels.  Reference semantics:
+//   modules/layers.py:12-63,126-144 (UNetDown/UNetUp/ResidualBlock element ops),
+//   modules/__init__.py:67-69 (InstanceNorm2d: eps 1e-5, biased variance, no affine),
+//   models/warp_model.py:147-150 (CE on argmax targets), modules/loss.py:58,110-122 (BCE),
+//   models/texture_model.py:168-170 (L1).
+// All tensors are NHWC fp32 with an explicit pixel pitch; threads map to channels fastest
+// so that every warp touches contiguous 128-B lines.
+#include "common.cuh"
+#include "../../include/swapnet_b200.h"
+
+void sn_count_launch(int n);
+
+namespace {
+
+constexpr int kEwThreads = 256;
+
+// ---------------------------------------------------------------------------------
+// dropout: counter-based keep mask.  keep(seed, idx) must be reproducible on the host
+// (oracle/dropout.py restates it) so that parity tests can share masks.
+// ---------------------------------------------------------------------------------
+__host__ __device__ __forceinline__ uint32_t sn_hash32(unsigned long long seed, unsigned long long idx) {
+  unsigned long long z = idx + seed * 0x9E3779B97F4A7C15ull + 0x632BE59BD9B4E019ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  z = z ^ (z >> 31);
+  return (uint32_t)(z >> 32);
+}
+__host__ __device__ __forceinline__ bool sn_keep(unsigned long long seed, unsigned long long idx,
+                                                 uint32_t thresh) {
+  return sn_hash32(seed, idx) >= thresh;  // P(drop) = thresh / 2^32
+}
+__host__ __device__ __forceinline__ uint32_t drop_thresh(float p) {
+  double t = (double)p * 4294967296.0;
+  if (t < 0) t = 0;
+  if (t > 4294967295.0) t = 4294967295.0;
+  return (uint32_t)t;
+}
+
+__device__ __forceinline__ void store_split(__nv_bfloat16* hi, __nv_bfloat16* lo, long long off, float v) {
+  __nv_bfloat16 h, l;
+  split_bf16(v, h, l);
+  hi[off] = h;
+  if (lo) lo[off] = l;
+}
+
+// ---------------------------------------------------------------------------------
+// pack_planes
+// ---------------------------------------------------------------------------------
+// NCHW source: one block per (n, h, 32-pixel run); smem transposes [c][w] -> [w][c].
+__global__ void pack_planes_nchw_kernel(const float* __restrict__ src, int N, int C, int H, int W,
+                                        __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo,
+                                        int pitch, int coff) {
+  extern __shared__ float tile[];  // [C][33]
+  const int w0 = blockIdx.x * 32;
+  const int h = blockIdx.y;
+  const int n = blockIdx.z;
+  for (int i = threadIdx.x; i < C * 32; i += blockDim.x) {
+    const int c = i / 32, w = i % 32;
+    float v = 0.f;
+    if (w0 + w < W) v = src[(((long long)n * C + c) * H + h) * W + w0 + w];
+    tile[c * 33 + w] = v;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < C * 32; i += blockDim.x) {
+    const int w = i / C, c = i % C;
+    if (w0 + w < W) {
+      const long long off = (((long long)n * H + h) * W + w0 + w) * pitch + coff + c;
+      store_split(hi, lo, off, tile[c * 33 + w]);
+    }
+  }
+}
+__global__ void pack_planes_nhwc_kernel(const float* __restrict__ src, int src_pitch, long long npix,
+                                        int C, __nv_bfloat16* __restrict__ hi,
+                                        __nv_bfloat16* __restrict__ lo, int pitch, int coff) {
+  const long long total = npix * C;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long pix = i / C;
+    const int c = (int)(i - pix * C);
+    store_split(hi, lo, pix * pitch + coff + c, src[pix * src_pitch + c]);
+  }
+}
+
+// ---------------------------------------------------------------------------------
+// pack_weights: dst[r][t][k] <- src[r*s_row + k*s_k + t]
+// ---------------------------------------------------------------------------------
+__global__ void pack_weights_kernel(const float* __restrict__ src, long long s_row, long long s_k,
+                                    int taps, int k_real, int k_pad, __nv_bfloat16* __restrict__ hi,
+                                    __nv_bfloat16* __restrict__ lo) {
+  extern __shared__ float tile[];  // [32][taps + 1]
+  const int r = blockIdx.y;
+  const int k0 = blockIdx.x * 32;
+  const int T1 = taps + 1;
+  for (int i = threadIdx.x; i < 32 * taps; i += blockDim.x) {
+    const int kk = i / taps, t = i % taps;
+    float v = 0.f;
+    if (k0 + kk < k_real) v = src[r * s_row + (long long)(k0 + kk) * s_k + t];
+    tile[kk * T1 + t] = v;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 32 * taps; i += blockDim.x) {
+    const int t = i / 32, kk = i % 32;
+    if (k0 + kk < k_pad) {
+      const long long off = ((long long)r * taps + t) * k_pad + k0 + kk;
+      store_split(hi, lo, off, tile[kk * T1 + t]);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------
+// head weights: nearest-x2 upsample + ZeroPad2d((1,0,1,0)) + Conv2d(k=4, p=1) seen from an
+// output pixel o = 2m + par reads up-sampled u = o + k - 2, k = 0..3, i.e. source s = u >> 1:
+//   par 0: k=0,1 -> m-1 ; k=2,3 -> m          (2 effective taps: d = -1, 0)
+//   par 1: k=0 -> m-1 ; k=1,2 -> m ; k=3 -> m+1 (3 effective taps: d = -1, 0, +1)
+// effective tap index e = d + 1.  Phase p = 2*py + px owns neff(py) x neff(px) taps, laid out
+// contiguously: phase offsets {0, 4, 10, 16}, 25 taps in total, order (ey, ex) row-major.
+// ---------------------------------------------------------------------------------
+__host__ __device__ __forceinline__ int head_neff(int par) { return par ? 3 : 2; }
+__host__ __device__ __forceinline__ int head_phase_off(int p) {
+  const int o[4] = {0, 4, 10, 16};
+  return o[p];
+}
+// which original taps k map onto effective tap e for parity par: returns count, fills ks[]
+__host__ __device__ __forceinline__ int head_taps_of(int par, int e, int ks[2]) {
+  if (par == 0) {
+    ks[0] = 2 * e; ks[1] = 2 * e + 1;
+    return 2;
+  }
+  if (e == 0) { ks[0] = 0; return 1; }
+  if (e == 1) { ks[0] = 1; ks[1] = 2; return 2; }
+  ks[0] = 3;
+  return 1;
+}
+__global__ void pack_head_weights_kernel(const float* __restrict__ w, int cout, int cin, int rows_pad,
+                                         int k_pad, int dgrad, __nv_bfloat16* __restrict__ hi,
+                                         __nv_bfloat16* __restrict__ lo) {
+  // one thread per (co, te, ci) with te the global effective tap 0..24
+  const long long total = (long long)cout * 25 * cin;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int ci = (int)(i % cin);
+    const int te = (int)((i / cin) % 25);
+    const int co = (int)(i / ((long long)cin * 25));
+    int p = 3;
+    while (te < head_phase_off(p)) --p;
+    const int py = p >> 1, px = p & 1;
+    const int local = te - head_phase_off(p);
+    const int ey = local / head_neff(px), ex = local % head_neff(px);
+    int kys[2], kxs[2];
+    const int ny = head_taps_of(py, ey, kys), nx = head_taps_of(px, ex, kxs);
+    float acc = 0.f;
+    for (int a = 0; a < ny; ++a)
+      for (int b = 0; b < nx; ++b) acc += w[(((long long)co * cin + ci) * 4 + kys[a]) * 4 + kxs[b]];
+    long long off;
+    if (!dgrad) {
+      // [phase][rows_pad][neff taps][k_pad] with per-phase base = rows_pad * k_pad * phase_off
+      off = (long long)rows_pad * k_pad * head_phase_off(p) +
+            ((long long)co * (head_neff(py) * head_neff(px)) + local) * k_pad + ci;
+    } else {
+      off = ((long long)ci * 25 + te) * k_pad + co;  // [ci][25][k_pad]
+    }
+    store_split(hi, lo, off, acc);
+  }
+}
+__global__ void fold_head_wgrad_kernel(const float* __restrict__ geff, int cout, int cin,
+                                       float* __restrict__ dw) {
+  const long long total = (long long)cout * cin * 16;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int kx = (int)(i & 3), ky = (int)((i >> 2) & 3);
+    const int ci = (int)((i >> 4) % cin);
+    const int co = (int)((i >> 4) / cin);
+    float acc = 0.f;
+    for (int p = 0; p < 4; ++p) {
+      const int py = p >> 1, px = p & 1;
+      const int ey = py == 0 ? (ky >> 1) : (ky == 0 ? 0 : (ky == 3 ? 2 : 1));
+      const int ex = px == 0 ? (kx >> 1) : (kx == 0 ? 0 : (kx == 3 ? 2 : 1));
+      const int te = head_phase_off(p) + ey * head_neff(px) + ex;
+      acc += geff[((long long)co * 25 + te) * cin + ci];
+    }
+    dw[i] += acc;
+  }
+}
+
+// ---------------------------------------------------------------------------------
+// plane statistics
+// ---------------------------------------------------------------------------------
+__device__ __forceinline__ double atomic_add_f64(double* a, double v) { return atomicAdd(a, v); }
+
+// grid (ceil(C/32), slabs, N), block (32, 8)
+__global__ void plane_stats_kernel(const float* __restrict__ y, int pitch, int hw, int C,
+                                   double* __restrict__ stats) {
+  __shared__ float s1s[8][33], s2s[8][33];
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  const int n = blockIdx.z;
+  const int per = (hw + gridDim.y - 1) / gridDim.y;
+  const int p0 = blockIdx.y * per;
+  const int p1 = min(hw, p0 + per);
+  float s1 = 0.f, s2 = 0.f;
+  if (c < C) {
+    const float* base = y + (long long)n * hw * pitch + c;
+    for (int p = p0 + threadIdx.y; p < p1; p += 8) {
+      const float v = base[(long long)p * pitch];
+      s1 += v;
+      s2 += v * v;
+    }
+  }
+  s1s[threadIdx.y][threadIdx.x] = s1;
+  s2s[threadIdx.y][threadIdx.x] = s2;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < C) {
+    double a = 0.0, b = 0.0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      a += (double)s1s[j][threadIdx.x];
+      b += (double)s2s[j][threadIdx.x];
+    }
+    atomic_add_f64(&stats[((long long)n * C + c) * 2 + 0], a);
+    atomic_add_f64(&stats[((long long)n * C + c) * 2 + 1], b);
+  }
+}
+// (sum, sumsq) -> (mean, rstd), biased variance (torch instance_norm)
+__global__ void stats_finalize_kernel(double* stats, int count, int hw, double eps) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < count) {
+    const double mean = stats[2 * i] / hw;
+    double var = stats[2 * i + 1] / hw - mean * mean;
+    if (var < 0) var = 0;
+    stats[2 * i] = mean;
+    stats[2 * i + 1] = rsqrt(var + eps);
+  }
+}
+// (sum g, sum g*xhat) -> means
+__global__ void gstats_finalize_kernel(double* g, int count, int hw) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < count) {
+    g[2 * i] /= hw;
+    g[2 * i + 1] /= hw;
+  }
+}
+
+// ---------------------------------------------------------------------------------
+// InstanceNorm-apply + activation + dropout (+ residual) forward
+// grid (slabs, N); block (cx, py): cx threads over channels, py over pixels
+// ---------------------------------------------------------------------------------
+struct NormActFwdArgs {
+  const float* y; int y_pitch;
+  int H, W, C;
+  const double* stats;
+  int act; float slope;
+  uint32_t drop_thresh; float drop_scale; unsigned long long seed;
+  const float* residual; int res_pitch;
+  __nv_bfloat16* hi; __nv_bfloat16* lo; int out_pitch, out_coff, reflect;
+  float* f32; int f32_pitch;
+};
+
+__device__ __forceinline__ float act_fwd(float v, int act, float slope) {
+  if (act == SN_ACT_LRELU) return v > 0.f ? v : v * slope;
+  if (act == SN_ACT_RELU) return v > 0.f ? v : 0.f;
+  return v;
+}
+__device__ __forceinline__ float act_grad(float xhat, int act, float slope) {
+  if (act == SN_ACT_LRELU) return xhat > 0.f ? 1.f : slope;
+  if (act == SN_ACT_RELU) return xhat > 0.f ? 1.f : 0.f;
+  return 1.f;
+}
+
+__global__ void norm_act_fwd_kernel(const NormActFwdArgs a) {
+  const int n = blockIdx.y;
+  const int HW = a.H * a.W;
+  const int per = (HW + gridDim.x - 1) / gridDim.x;
+  const int p0 = blockIdx.x * per, p1 = min(HW, p0 + per);
+  for (int c = threadIdx.x; c < a.C; c += blockDim.x) {
+    float mean = 0.f, rstd = 1.f;
+    if (a.stats) {
+      mean = (float)a.stats[((long long)n * a.C + c) * 2];
+      rstd = (float)a.stats[((long long)n * a.C + c) * 2 + 1];
+    }
+    for (int p = p0 + threadIdx.y; p < p1; p += blockDim.y) {
+      const long long pix = (long long)n * HW + p;
+      float v = a.y[pix * a.y_pitch + c];
+      v = (v - mean) * rstd;
+      v = act_fwd(v, a.act, a.slope);
+      if (a.drop_thresh) {
+        const bool keep = sn_keep(a.seed, (unsigned long long)pix * a.C + c, a.drop_thresh);
+        v = keep ? v * a.drop_scale : 0.f;
+      }
+      if (a.residual) v += a.residual[pix * a.res_pitch + c];
+      if (a.f32) a.f32[pix * a.f32_pitch + c] = v;
+      if (a.hi) {
+        __nv_bfloat16 h, l;
+        split_bf16(v, h, l);
+        if (!a.reflect) {
+          const long long off = pix * a.out_pitch + a.out_coff + c;
+          a.hi[off] = h;
+          if (a.lo) a.lo[off] = l;
+        } else {
+          const int hh = p / a.W, ww = p - hh * a.W;
+          const int Hp = a.H + 2, Wp = a.W + 2;
+          int rows[2], cols[2], nr = 1, nc = 1;
+          rows[0] = hh + 1;
+          cols[0] = ww + 1;
+          if (hh == 1) rows[nr++] = 0;
+          if (hh == a.H - 2) rows[nr++] = a.H + 1;
+          if (ww == 1) cols[nc++] = 0;
+          if (ww == a.W - 2) cols[nc++] = a.W + 1;
+          for (int i = 0; i < nr; ++i)
+            for (int j = 0; j < nc; ++j) {
+              const long long off =
+                  (((long long)n * Hp + rows[i]) * Wp + cols[j]) * a.out_pitch + a.out_coff + c;
+              a.hi[off] = h;
+              if (a.lo) a.lo[off] = l;
+            }
+        }
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------
+// backward of the same block
+// ---------------------------------------------------------------------------------
+struct GradSrcs {
+  sn_grad_src s[SN_MAX_SRC];
+  int n;
+};
+// upstream gradient at (n, h, w, c): sum of sources; a reflect-padded source folds its
+// mirrored border rows/cols back onto the interior pixel (adjoint of ReflectionPad2d(1)).
+__device__ __forceinline__ float gather_grad(const GradSrcs& g, int n, int h, int w, int H, int W, int c) {
+  float acc = 0.f;
+  for (int i = 0; i < g.n; ++i) {
+    const sn_grad_src& s = g.s[i];
+    if (!s.reflect_padded) {
+      acc += s.ptr[(((long long)n * H + h) * W + w) * s.pitch + s.c_off + c];
+    } else {
+      const int Hp = H + 2, Wp = W + 2;
+      int rows[2], cols[2], nr = 1, nc = 1;
+      rows[0] = h + 1;
+      cols[0] = w + 1;
+      if (h == 1) rows[nr++] = 0;
+      if (h == H - 2) rows[nr++] = H + 1;
+      if (w == 1) cols[nc++] = 0;
+      if (w == W - 2) cols[nc++] = W + 1;
+      for (int a = 0; a < nr; ++a)
+        for (int b = 0; b < nc; ++b)
+          acc += s.ptr[(((long long)n * Hp + rows[a]) * Wp + cols[b]) * s.pitch + s.c_off + c];
+    }
+  }
+  return acc;
+}
+
+struct NormActBwdArgs {
+  GradSrcs g;
+  const float* y; int y_pitch;
+  int H, W, C;
+  const double* stats;
+  int act; float slope;
+  uint32_t drop_thresh; float drop_scale; unsigned long long seed;
+  double* gstats;
+  __nv_bfloat16* hi; __nv_bfloat16* lo; int dy_pitch, dy_coff;
+};
+
+// gradient w.r.t. xhat (before the InstanceNorm backward), and xhat itself
+__device__ __forceinline__ float grad_xhat(const NormActBwdArgs& a, int n, int p, int c, float mean,
+                                           float rstd, float* xhat_out) {
+  const int HW = a.H * a.W;
+  const long long pix = (long long)n * HW + p;
+  const int h = p / a.W, w = p - h * a.W;
+  float g = gather_grad(a.g, n, h, w, a.H, a.W, c);
+  const float xhat = (a.y[pix * a.y_pitch + c] - mean) * rstd;
+  if (a.drop_thresh) {
+    const bool keep = sn_keep(a.seed, (unsigned long long)pix * a.C + c, a.drop_thresh);
+    g = keep ? g * a.drop_scale : 0.f;
+  }
+  g *= act_grad(xhat, a.act, a.slope);
+  *xhat_out = xhat;
+  return g;
+}
+
+// grid (ceil(C/32), slabs, N), block (32, 8): sums of g and g*xhat per (n, c)
+__global__ void norm_act_bwd_reduce_kernel(const NormActBwdArgs a) {
+  __shared__ float s1s[8][33], s2s[8][33];
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  const int n = blockIdx.z;
+  const int HW = a.H * a.W;
+  const int per = (HW + gridDim.y - 1) / gridDim.y;
+  const int p0 = blockIdx.y * per, p1 = min(HW, p0 + per);
+  float s1 = 0.f, s2 = 0.f;
+  if (c < a.C) {
+    const float mean = (float)a.stats[((long long)n * a.C + c) * 2];
+    const float rstd = (float)a.stats[((long long)n * a.C + c) * 2 + 1];
+    for (int p = p0 + threadIdx.y; p < p1; p += 8) {
+      float xhat;
+      const float g = grad_xhat(a, n, p, c, mean, rstd, &xhat);
+      s1 += g;
+      s2 += g * xhat;
+    }
+  }
+  s1s[threadIdx.y][threadIdx.x] = s1;
+  s2s[threadIdx.y][threadIdx.x] = s2;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < a.C) {
+    double u = 0.0, v = 0.0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      u += (double)s1s[j][threadIdx.x];
+      v += (double)s2s[j][threadIdx.x];
+    }
+    atomic_add_f64(&a.gstats[((long long)n * a.C + c) * 2 + 0], u);
+    atomic_add_f64(&a.gstats[((long long)n * a.C + c) * 2 + 1], v);
+  }
+}
+
+// grid (slabs, N); block (cx, py)
+__global__ void norm_act_bwd_apply_kernel(const NormActBwdArgs a) {
+  const int n = blockIdx.y;
+  const int HW = a.H * a.W;
+  const int per = (HW + gridDim.x - 1) / gridDim.x;
+  const int p0 = blockIdx.x * per, p1 = min(HW, p0 + per);
+  for (int c = threadIdx.x; c < a.C; c += blockDim.x) {
+    float mean = 0.f, rstd = 1.f, m1 = 0.f, m2 = 0.f;
+    if (a.stats) {
+      mean = (float)a.stats[((long long)n * a.C + c) * 2];
+      rstd = (float)a.stats[((long long)n * a.C + c) * 2 + 1];
+      m1 = (float)a.gstats[((long long)n * a.C + c) * 2];
+      m2 = (float)a.gstats[((long long)n * a.C + c) * 2 + 1];
+    }
+    for (int p = p0 + threadIdx.y; p < p1; p += blockDim.y) {
+      float xhat;
+      float g = grad_xhat(a, n, p, c, mean, rstd, &xhat);
+      if (a.stats) g = rstd * (g - m1 - xhat * m2);
+      const long long off = ((long long)n * HW + p) * a.dy_pitch + a.dy_coff + c;
+      store_split(a.hi, a.lo, off, g);
+    }
+  }
+}
+
+__global__ void sum_grads_kernel(const GradSrcs g, int H, int W, int C, float* dst, int dst_pitch) {
+  const int n = blockIdx.y;
+  const int HW = H * W;
+  const int per = (HW + gridDim.x - 1) / gridDim.x;
+  const int p0 = blockIdx.x * per, p1 = min(HW, p0 + per);
+  for (int c = threadIdx.x; c < C; c += blockDim.x)
+    for (int p = p0 + threadIdx.y; p < p1; p += blockDim.y) {
+      const int h = p / W, w = p - h * W;
+      dst[((long long)n * HW + p) * dst_pitch + c] = gather_grad(g, n, h, w, H, W, c);
+    }
+}
+
+__global__ void tanh_bwd_kernel(const GradSrcs g, const float* __restrict__ out, int out_pitch, int H,
+                                int W, int C, __nv_bfloat16* hi, __nv_bfloat16* lo, int dy_pitch,
+                                int dy_coff) {
+  const int n = blockIdx.y;
+  const int HW = H * W;
+  const int per = (HW + gridDim.x - 1) / gridDim.x;
+  const int p0 = blockIdx.x * per, p1 = min(HW, p0 + per);
+  for (int c = threadIdx.x; c < C; c += blockDim.x)
+    for (int p = p0 + threadIdx.y; p < p1; p += blockDim.y) {
+      const int h = p / W, w = p - h * W;
+      const long long pix = (long long)n * HW + p;
+      const float o = out[pix * out_pitch + c];
+      const float v = gather_grad(g, n, h, w, H, W, c) * (1.f - o * o);
+      store_split(hi, lo, pix * dy_pitch + dy_coff + c, v);
+    }
+}
+
+__global__ void dropout_mask_kernel(unsigned long long seed, uint32_t thresh, long long count,
+                                    uint8_t* out) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < count;
+       i += (long long)gridDim.x * blockDim.x)
+    out[i] = sn_keep(seed, (unsigned long long)i, thresh) ? 1 : 0;
+}
+
+// ---------------------------------------------------------------------------------
+// losses
+// ---------------------------------------------------------------------------------
+__device__ __forceinline__ void block_add_double(double v, double* dst) {
+  __shared__ double red[32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  if (lane == 0) red[warp] = v;
+  __syncthreads();
+  if (warp == 0) {
+    v = lane < (blockDim.x >> 5) ? red[lane] : 0.0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) atomicAdd(dst, v);
+  }
+}
+
+constexpr int kMaxCE = 32;
+__global__ void ce_loss_kernel(const float* __restrict__ logits, int pitch,
+                               const float* __restrict__ target, int N, int H, int W, int C,
+                               float weight, double* loss_acc, float* __restrict__ grad, int gpitch) {
+  const long long npix = (long long)N * H * W;
+  const long long HW = (long long)H * W;
+  double local = 0.0;
+  const float scale = weight / (float)npix;
+  for (long long pix = blockIdx.x * (long long)blockDim.x + threadIdx.x; pix < npix;
+       pix += (long long)gridDim.x * blockDim.x) {
+    const long long n = pix / HW, p = pix - n * HW;
+    float x[kMaxCE];
+    int arg = 0;
+    float best = 0.f, mx = -INFINITY;
+    for (int c = 0; c < C; ++c) {
+      x[c] = logits[pix * pitch + c];
+      mx = fmaxf(mx, x[c]);
+      const float t = target[(n * C + c) * HW + p];
+      if (c == 0 || t > best) {  // first maximum wins (torch.argmax tie-break)
+        best = t;
+        arg = c;
+      }
+    }
+    float se = 0.f;
+    for (int c = 0; c < C; ++c) se += expf(x[c] - mx);
+    const float lse = mx + logf(se);
+    local += (double)(lse - x[arg]);
+    const float inv = 1.f / se;
+    for (int c = 0; c < C; ++c) {
+      float sm = expf(x[c] - mx) * inv;
+      grad[pix * gpitch + c] = scale * (sm - (c == arg ? 1.f : 0.f));
+    }
+  }
+  block_add_double(local * (double)weight / (double)npix, loss_acc);
+}
+
+__global__ void bce_logits_kernel(const float* __restrict__ pred, long long count, int halves, float t0,
+                                  float t1, float gscale, double* loss_acc, float* __restrict__ dpred) {
+  const int half = blockIdx.y;
+  const float t = half == 0 ? t0 : t1;
+  double local = 0.0;
+  const float gs = gscale / (float)count;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < count;
+       i += (long long)gridDim.x * blockDim.x) {
+    const float x = pred[half * count + i];
+    // max(x,0) - x*t + log1p(exp(-|x|))   (ATen binary_cross_entropy_with_logits)
+    const float l = (1.f - t) * x + (fmaxf(-x, 0.f) + log1pf(expf(-fabsf(x))));
+    local += (double)l;
+    const float sg = 1.f / (1.f + expf(-x));
+    if (dpred) dpred[half * count + i] = gs * (sg - t);
+  }
+  (void)halves;
+  block_add_double(local / (double)count, loss_acc + half);
+}
+
+__global__ void l1_loss_kernel(const float* __restrict__ a, int pitch, const float* __restrict__ b,
+                               int N, int H, int W, int C, float weight, double* loss_acc,
+                               float* __restrict__ grad, int gpitch) {
+  const long long HW = (long long)H * W;
+  const long long total = (long long)N * HW * C;
+  double local = 0.0;
+  const float gs = weight / (float)total;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long pix = i / C;
+    const int c = (int)(i - pix * C);
+    const long long n = pix / HW, p = pix - n * HW;
+    const float d = a[pix * pitch + c] - b[(n * C + c) * HW + p];
+    local += (double)fabsf(d);
+    grad[pix * gpitch + c] = d > 0.f ? gs : (d < 0.f ? -gs : 0.f);
+  }
+  block_add_double(local * (double)weight / (double)total, loss_acc);
+}
+
+// ---------------------------------------------------------------------------------
+// SIMT fp32 tap GEMM (test cross-check only)
+// ---------------------------------------------------------------------------------
+struct SimtArgs {
+  const __nv_bfloat16 *a_hi, *a_lo, *b_hi, *b_lo;
+  int a_n, a_h, a_w, a_c, a_pitch, parity;
+  long long b_k;
+  int b_rows;
+  int m_n, m_h, m_w, ntaps, k_per_tap;
+  sn_tap taps[SN_MAX_TAPS];
+  float* out;
+  long long out_sn, out_sh, out_sw;
+  int omh, ooh, omw, oow, n_valid;
+  const float* bias;
+  int act, nsplit;
+};
+__global__ void tap_gemm_simt_kernel(const SimtArgs a) {
+  const long long rows = (long long)a.m_n * a.m_h * a.m_w;
+  const long long total = rows * a.n_valid;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int col = (int)(i % a.n_valid);
+    const long long row = i / a.n_valid;
+    const int w = (int)(row % a.m_w), h = (int)((row / a.m_w) % a.m_h), n = (int)(row / ((long long)a.m_w * a.m_h));
+    float acc = 0.f;
+    for (int t = 0; t < a.ntaps; ++t) {
+      const sn_tap tp = a.taps[t];
+      int sh, sw, cbase;
+      bool inb;
+      if (!a.parity) {
+        sh = h + tp.dh; sw = w + tp.dw; cbase = tp.c_off;
+        inb = sh >= 0 && sh < a.a_h && sw >= 0 && sw < a.a_w;
+      } else {
+        const int h2 = h + tp.dh, w2 = w + tp.dw;
+        const int pw = tp.c_off / a.a_pitch;
+        cbase = tp.c_off - pw * a.a_pitch;
+        inb = h2 >= 0 && h2 < a.a_h / 2 && w2 >= 0 && w2 < a.a_w / 2;
+        sh = 2 * h2 + tp.hp; sw = 2 * w2 + pw;
+      }
+      if (!inb) continue;
+      const long long abase = (((long long)n * a.a_h + sh) * a.a_w + sw) * a.a_pitch + cbase;
+      const long long bbase = (long long)col * a.b_k + tp.kb_off;
+      for (int k = 0; k < a.k_per_tap; ++k) {
+        float av = __bfloat162float(a.a_hi[abase + k]);
+        float bv = col < a.b_rows ? __bfloat162float(a.b_hi[bbase + k]) : 0.f;
+        if (a.nsplit == 3) {
+          av += __bfloat162float(a.a_lo[abase + k]);
+          if (col < a.b_rows) bv += __bfloat162float(a.b_lo[bbase + k]);
+        }
+        acc = fmaf(av, bv, acc);
+      }
+    }
+    if (a.bias) acc += a.bias[col];
+    if (a.act == SN_ACT_TANH) acc = tanhf(acc);
+    a.out[(long long)n * a.out_sn + (long long)(h * a.omh + a.ooh) * a.out_sh +
+          (long long)(w * a.omw + a.oow) * a.out_sw + col] = acc;
+  }
+}
+
+inline int grid_for(long long total, int threads = kEwThreads) {
+  long long g = (total + threads - 1) / threads;
+  if (g > 148 * 16) g = 148 * 16;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+// block (cx, py) with cx*py == 256, cx = min(pow2 >= C, 256)
+inline dim3 cblock(int C) {
+  int cx = 1;
+  while (cx < C && cx < 256) cx <<= 1;
+  return dim3(cx, 256 / cx, 1);
+}
+inline int slabs_for(int hw, int n, int py) {
+  // enough blocks for ~4 waves, at least `py` pixels each
+  int want = (148 * 4 + n - 1) / n;
+  int maxs = (hw + py - 1) / py;
+  if (want > maxs) want = maxs;
+  if (want < 1) want = 1;
+  return want;
+}
+
+}  // namespace
+
+#define LAUNCH_CHECK()                         \
+  do {                                         \
+    sn_count_launch(1);                        \
+    SN_CHECK_CUDA(cudaGetLastError());         \
+  } while (0)
+
+extern "C" {
+
+int sn_pack_planes(const float* src, int src_layout, int src_pitch, int n, int c, int h, int w,
+                   void* dst_hi, void* dst_lo, int dst_pitch, int dst_coff, void* stream) {
+  SN_REQUIRE(src && dst_hi, "null pointer");
+  SN_REQUIRE(dst_coff + c <= dst_pitch, "channel slice exceeds pitch");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (src_layout == SN_LAYOUT_NCHW) {
+    dim3 grid((w + 31) / 32, h, n);
+    size_t smem = (size_t)c * 33 * sizeof(float);
+    SN_REQUIRE(smem <= 48 * 1024, "pack_planes: too many channels for NCHW path (%d)", c);
+    pack_planes_nchw_kernel<<<grid, 256, smem, st>>>(src, n, c, h, w, (__nv_bfloat16*)dst_hi,
+                                                     (__nv_bfloat16*)dst_lo, dst_pitch, dst_coff);
+  } else {
+    const long long npix = (long long)n * h * w;
+    pack_planes_nhwc_kernel<<<grid_for(npix * c), kEwThreads, 0, st>>>(
+        src, src_pitch, npix, c, (__nv_bfloat16*)dst_hi, (__nv_bfloat16*)dst_lo, dst_pitch, dst_coff);
+  }
+  LAUNCH_CHECK();
+  return SN_OK;
+}
+
+int sn_pack_weights(const float* src, long long s_row, long long s_k, int rows, int taps, int k_real,
+                    int k_pad, void* dst_hi, void* dst_lo, void* stream) {
+  SN_REQUIRE(src && dst_hi, "null pointer");
+  SN_REQUIRE(taps >= 1 && taps <= 64 && k_pad >= k_real, "bad pack_weights shape");
+  dim3 grid((k_pad + 31) / 32, rows);
+  size_t smem = (size_t)32 * (taps + 1) * sizeof(float);
+  pack_weights_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(
+      src, s_row, s_k, taps, k_real, k_pad, (__nv_bfloat16*)dst_hi, (__nv_bfloat16*)dst_lo);
+  LAUNCH_CHECK();
+  return SN_OK;
+}
+
+int sn_pack_head_weights(const float* src, int cout, int cin, int rows_pad, int k_pad, int dgrad,
+                         void* dst_hi, void* dst_lo, void* stream) {
+  SN_REQUIRE(src && dst_hi, "null pointer");
+  SN_REQUIRE(dgrad ? (k_pad >= cout) : (k_pad >= cin && rows_pad >= cout), "bad head pack shape");
+  pack_head_weights_kernel<<<grid_for((long long)cout * 25 * cin), kEwThreads, 0, (cudaStream_t)stream>>>(
+      src, cout, cin, rows_pad, k_pad, dgrad, (__nv_bfloat16*)dst_hi, (__nv_bfloat16*)dst_lo);
+  LAUNCH_CHECK();
+  return SN_OK;
+}
+
+int sn_fold_head_wgrad(const float* geff, int cout, int cin, float* dw, void* stream) {
+  fold_head_wgrad_kernel<<<grid_for((long long)cout * cin * 16), kEwThreads, 0, (cudaStream_t)stream>>>(
+      geff, cout, cin, dw);
+  LAUNCH_CHECK();
+  return SN_OK;
+}
+
+int sn_plane_stats(const float* y, int pitch, int n, int hw, int c, float eps, double* stats,
+                   void* stream) {
+  SN_REQUIRE(y && stats, "null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  SN_CHECK_CUDA(cudaMemsetAsync(stats, 0, sizeof(double) * 2 * n * c, st));
+  const int cg = (c + 31) / 32;
+  int slabs = (148 * 4 + n * cg - 1) / (n * cg);
+  if (slabs > (hw + 63) / 64) slabs = (hw + 63) / 64;
+  if (slabs < 1) slabs = 1;
+  plane_stats_kernel<<<dim3(cg, slabs, n), dim3(32, 8), 0, st>>>(y, pitch, hw, c, stats);
+  LAUNCH_CHECK();
+  stats_finalize_kernel<<<(n * c + 255) / 256, 256, 0, st>>>(stats, n * c, hw, (double)eps);
+  LAUNCH_CHECK();
+  return SN_OK;
+}
+
+int sn_norm_act_fwd(const sn_norm_act_desc* d, void* stream) {
+  SN_REQUIRE(d && d->y, "null pointer");
+  SN_REQUIRE(!d->out_reflect_pad || (d->h >= 3 && d->w >= 3), "reflect pad needs h, w >= 3");
+  NormActFwdArgs a;
+  a.y = d->y; a.y_pitch = d->y_pitch;
+  a.H = d->h; a.W = d->w; a.C = d->c;
+  a.stats = d->stats;
+  a.act = d->act; a.slope = d->slope;
+  a.drop_thresh = d->drop_p > 0.f ? drop_thresh(d->drop_p) : 0u;
+  a.drop_scale = d->drop_p > 0.f ? 1.f / (1.f - d->drop_p) : 1.f;
+  a.seed = d->drop_seed;
+  a.residual = d->residual; a.res_pitch = d->res_pitch;
+  a.hi = (__nv_bfloat16*)d->out_hi; a.lo = (__nv_bfloat16*)d->out_lo;
+  a.out_pitch = d->out_pitch; a.out_coff = d->out_coff; a.reflect = d->out_reflect_pad;
+  a.f32 = d->out_f32; a.f32_pitch = d->f32_pitch;
+  dim3 blk = cblock(d->c);
+  dim3 grid(slabs_for(d->h * d->w, d->n, blk.y), d->n);
+  norm_act_fwd_kernel<<<grid, blk, 0, (cudaStream_t)stream>>>(a);
+  LAUNCH_CHECK();
+  return SN_OK;
+}
+
+static int fill_srcs(GradSrcs* g, const sn_grad_src* src, int nsrc) {
+  SN_REQUIRE(nsrc >= 1 && nsrc <= SN_MAX_SRC, "nsrc out of range: %d", nsrc);
+  g->n = nsrc;
+  for (int i = 0; i < nsrc; ++i) {
+    SN_REQUIRE(src[i].ptr, "null gradient source %d", i);
+    g->s[i] = src[i];
+  }
+  return SN_OK;
+}
+
+int sn_norm_act_bwd(const sn_norm_act_bwd_desc* d, void* stream) {
+  SN_REQUIRE(d && d->y && d->dy_hi, "null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  NormActBwdArgs a;
+  int rc = fill_srcs(&a.g, d->src, d->nsrc);
+  if (rc) return rc;
+  a.y = d->y; a.y_pitch = d->y_pitch;
+  a.H = d->h; a.W = d->w; a.C = d->c;
+  a.stats = d->stats;
+  a.act = d->act; a.slope = d->slope;
+  a.drop_thresh = d->drop_p > 0.f ? drop_thresh(d->drop_p) : 0u;
+  a.drop_scale = d->drop_p > 0.f ? 1.f / (1.f - d->drop_p) : 1.f;
+  a.seed = d->drop_seed;
+  a.gstats = d->gstats;
+  a.hi = (__nv_bfloat16*)d->dy_hi; a.lo = (__nv_bfloat16*)d->dy_lo;
+  a.dy_pitch = d->dy_pitch; a.dy_coff = d->dy_coff;
+  const int hw = d->h * d->w;
+  if (d->stats) {
+    SN_REQUIRE(d->gstats, "InstanceNorm backward needs gstats scratch");
+    SN_CHECK_CUDA(cudaMemsetAsync(d->gstats, 0, sizeof(double) * 2 * d->n * d->c, st));
+    const int cg = (d->c + 31) / 32;
+    int slabs = (148 * 4 + d->n * cg - 1) / (d->n * cg);
+    if (slabs > (hw + 63) / 64) slabs = (hw + 63) / 64;
+    if (slabs < 1) slabs = 1;
+    norm_act_bwd_reduce_kernel<<<dim3(cg, slabs, d->n), dim3(32, 8), 0, st>>>(a);
+    LAUNCH_CHECK();
+    gstats_finalize_kernel<<<(d->n * d->c + 255) / 256, 256, 0, st>>>(d->gstats, d->n * d->c, hw);
+    LAUNCH_CHECK();
+  }
+  dim3 blk = cblock(d->c);
+  dim3 grid(slabs_for(hw, d->n, blk.y), d->n);
+  norm_act_bwd_apply_kernel<<<grid, blk, 0, st>>>(a);
+  LAUNCH_CHECK();
+  return SN_OK;
+}
+
+int sn_sum_grads(const sn_grad_src* src, int nsrc, int n, int h, int w, int c, float* dst,
+                 int dst_pitch, void* stream) {
+  GradSrcs g;
+  int rc = fill_srcs(&g, src, nsrc);
+  if (rc) return rc;
+  dim3 blk = cblock(c);
+  dim3 grid(slabs_for(h * w, n, blk.y), n);
+  sum_grads_kernel<<<grid, blk, 0, (cudaStream_t)stream>>>(g, h, w, c, dst, dst_pitch);
+  LAUNCH_CHECK();
+  return SN_OK;
+}
+
+int sn_tanh_bwd(const sn_grad_src* src, int nsrc, const float* out, int out_pitch, int n, int h,
+                int w, int c, void* dy_hi, void* dy_lo, int dy_pitch, int dy_coff, void* stream) {
+  GradSrcs g;
+  int rc = fill_srcs(&g, src, nsrc);
+  if (rc) return rc;
+  dim3 blk = cblock(c);
+  dim3 grid(slabs_for(h * w, n, blk.y), n);
+  tanh_bwd_kernel<<<grid, blk, 0, (cudaStream_t)stream>>>(g, out, out_pitch, h, w, c,
+                                                          (__nv_bfloat16*)dy_hi, (__nv_bfloat16*)dy_lo,
+                                                          dy_pitch, dy_coff);
+  LAUNCH_CHECK();
+  return SN_OK;
+}
+
+int sn_dropout_mask(unsigned long long seed, float p, long long count, uint8_t* out, void* stream) {
+  dropout_mask_kernel<<<grid_for(count), kEwThreads, 0, (cudaStream_t)stream>>>(seed, drop_thresh(p),
+                                                                               count, out);
+  LAUNCH_CHECK();
+  return SN_OK;
+}
+
+int sn_ce_loss_fwd_bwd(const float* logits, int pitch, const float* target_nchw, int n, int h, int w,
+                       int c, float weight, double* loss_acc, float* grad, int grad_pitch, void* stream) {
+  SN_REQUIRE(c <= kMaxCE, "ce loss supports at most %d classes", kMaxCE);
+  ce_loss_kernel<<<grid_for((long long)n * h * w, 128), 128, 0, (cudaStream_t)stream>>>(
+      logits, pitch, target_nchw, n, h, w, c, weight, loss_acc, grad, grad_pitch);
+  LAUNCH_CHECK();
+  return SN_OK;
+}
+
+int sn_bce_logits_fwd_bwd(const float* pred, long long count_per_half, int halves, float t0, float t1,
+                          float gscale, double* loss_acc, float* dpred, void* stream) {
+  SN_REQUIRE(halves == 1 || halves == 2, "halves must be 1 or 2");
+  dim3 grid(grid_for(count_per_half), halves);
+  bce_logits_kernel<<<grid, kEwThreads, 0, (cudaStream_t)stream>>>(pred, count_per_half, halves, t0, t1,
+                                                                   gscale, loss_acc, dpred);
+  LAUNCH_CHECK();
+  return SN_OK;
+}
+
+int sn_l1_loss_fwd_bwd(const float* a, int pitch, const float* b_nchw, int n, int h, int w, int c,
+                       float weight, double* loss_acc, float* grad, int grad_pitch, void* stream) {
+  l1_loss_kernel<<<grid_for((long long)n * h * w * c), kEwThreads, 0, (cudaStream_t)stream>>>(
+      a, pitch, b_nchw, n, h, w, c, weight, loss_acc, grad, grad_pitch);
+  LAUNCH_CHECK();
+  return SN_OK;
+}
+
+int sn_tap_gemm_simt(const sn_tap_gemm_desc* d, void* stream) {
+  SN_REQUIRE(d && d->a_hi && d->b_hi && d->out, "null pointer");
+  SimtArgs a;
+  a.a_hi = (const __nv_bfloat16*)d->a_hi; a.a_lo = (const __nv_bfloat16*)d->a_lo;
+  a.b_hi = (const __nv_bfloat16*)d->b_hi; a.b_lo = (const __nv_bfloat16*)d->b_lo;
+  a.a_n = d->a_n; a.a_h = d->a_h; a.a_w = d->a_w; a.a_c = d->a_c; a.a_pitch = d->a_pitch;
+  a.parity = d->a_parity;
+  a.b_k = d->b_k; a.b_rows = d->b_rows;
+  a.m_n = d->m_n; a.m_h = d->m_h; a.m_w = d->m_w; a.ntaps = d->ntaps; a.k_per_tap = d->k_per_tap;
+  for (int t = 0; t < d->ntaps; ++t) a.taps[t] = d->taps[t];
+  a.out = d->out; a.out_sn = d->out_sn; a.out_sh = d->out_sh; a.out_sw = d->out_sw;
+  a.omh = d->out_mul_h; a.ooh = d->out_off_h; a.omw = d->out_mul_w; a.oow = d->out_off_w;
+  a.n_valid = d->n_valid; a.bias = d->bias; a.act = d->act; a.nsplit = d->nsplit;
+  const long long total = (long long)d->m_n * d->m_h * d->m_w * d->n_valid;
+  tap_gemm_simt_kernel<<<grid_for(total), kEwThreads, 0, (cudaStream_t)stream>>>(a);
+  LAUNCH_CHECK();
+  return SN_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,580 @@
+// swapnet_b200 — tcgen05 implicit-GEMM kernels (sm_100a).
+//
+// Every dense contraction of the SwapNet hot path (reference call sites:
+// modules/layers.py:15,31,131-138  Conv2d 4x4 s2 / ConvTranspose2d 4x4 s2 /
+// reflect-pad Conv2d 3x3; modules/swapnet_modules.py:85-90 upsample+pad+conv
+// head; modules/discriminators.py:111-131 PatchGAN convs; and their autograd
+// dgrad / wgrad) is lowered by the host onto ONE generic contraction:
+//
+//   "tap GEMM" (conv mode, K-major operands)
+//     D[(n,h,w), j] = sum_{t < ntaps} sum_{c < k_per_tap}
+//                       A[n, h + dh_t, w + dw_t, (hp_t), c_off_t + c] * Wp[j, kb_off_t + c]
+//   A is an NHWC activation tensor carried as split-bf16 planes (hi, lo); the
+//   128-row M tile is a th x tw x nb patch of GEMM rows, so the A tile of one
+//   (tap, 64-channel chunk) is a single 5-D TMA box whose out-of-bounds part is
+//   zero-filled by the TMA unit (= the conv zero padding).  Stride-2 gathers go
+//   through a 2x2 "parity view" of the same memory (dims c', w/2, h%2, h/2, n).
+//
+//   "wgrad GEMM" (MN-major operands)
+//     G[i, j] (+)= sum_{pixels (n,h,w)} X[n, h + dh, w + dw, i] * Y[n, h + dh', w + dw', j]
+//   both operands are activation patches; the reduction runs over pixels.
+//
+// Arithmetic: bf16 tensor-core MMAs (tcgen05.mma kind::f16) with fp32
+// accumulation in TMEM.  NSPLIT = 3 evaluates hi*hi + lo*hi + hi*lo, i.e. an
+// fp32-faithful product (~2^-16 relative) as the 1e-3 fp32 parity bar requires;
+// NSPLIT = 1 is the single-pass bf16 fast mode.
+//
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM owner + MMA
+// issuer, warps 2..5 = epilogue (TMEM -> registers -> global).
+#include "common.cuh"
+#include "plan.h"
+
+namespace {
+
+constexpr int kBlockM = 128;
+constexpr int kTileBytes = 16384;  // 128 rows x 128 B (one operand plane of one stage)
+constexpr int kThreads = 192;
+
+template <int NSPLIT>
+struct Cfg {
+  static constexpr int kPlanes = NSPLIT == 3 ? 2 : 1;
+  static constexpr int kStages = NSPLIT == 3 ? 3 : 6;
+  static constexpr int kStageBytes = kPlanes * 2 * kTileBytes;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024;  // + alignment slack
+};
+
+__device__ __forceinline__ float apply_act(float v, int act) {
+  if (act == SN_ACT_TANH) return tanhf(v);
+  return v;
+}
+
+// ============================================================================
+// conv mode
+// ============================================================================
+template <int NSPLIT>
+__global__ void __launch_bounds__(kThreads, 1)
+tap_gemm_kernel(const __grid_constant__ TapGemmParams p) {
+  using C = Cfg<NSPLIT>;
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t full_bar[C::kStages];
+  __shared__ __align__(8) uint64_t empty_bar[C::kStages];
+  __shared__ __align__(8) uint64_t accum_bar;
+  __shared__ uint32_t tmem_base_smem;
+
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (smem_base - smem_u32(smem_raw));
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  // ---- tile coordinates ------------------------------------------------------
+  const int mt = blockIdx.x;
+  const int tw_i = mt % p.tiles_w;
+  const int th_i = (mt / p.tiles_w) % p.tiles_h;
+  const int tn_i = mt / (p.tiles_w * p.tiles_h);
+  const int w0 = tw_i * p.tw, h0 = th_i * p.th, n0 = tn_i * p.nb;
+  const int ncol0 = blockIdx.y * p.block_n;
+  const int k_iters = p.ntaps * p.chunks;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < C::kStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(&accum_bar, 1);
+    mbar_fence_init();
+  }
+  if (warp == 0 && lane == 0) {
+    for (int pl = 0; pl < C::kPlanes; ++pl) {
+      tma_prefetch_desc(&p.tmA[pl]);
+      tma_prefetch_desc(&p.tmB[pl]);
+    }
+  }
+  if (warp == 1) tmem_alloc(&tmem_base_smem, 128);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_smem;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      const uint32_t stage_tx = C::kPlanes * (kTileBytes + p.block_n * 128);
+      for (int it = 0; it < k_iters; ++it) {
+        const int s = it % C::kStages;
+        const uint32_t ph = (it / C::kStages) & 1;
+        mbar_wait(&empty_bar[s], ph ^ 1);
+        mbar_expect_tx(&full_bar[s], stage_tx);
+        const int t = it / p.chunks;
+        const int ch = it - t * p.chunks;
+        const TapDesc tap = p.taps[t];
+        uint8_t* st = smem + s * C::kStageBytes;
+#pragma unroll
+        for (int pl = 0; pl < C::kPlanes; ++pl) {
+          tma_load_5d(&p.tmA[pl], &full_bar[s], st + pl * kTileBytes, tap.c_off + ch * 64,
+                      w0 + tap.dw, tap.hp, h0 + tap.dh, n0);
+          tma_load_2d(&p.tmB[pl], &full_bar[s], st + (C::kPlanes + pl) * kTileBytes,
+                      tap.kb_off + ch * 64, ncol0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc_bf16(kBlockM, p.block_n, 0, 0);
+      uint32_t acc = 0;
+      for (int it = 0; it < k_iters; ++it) {
+        const int s = it % C::kStages;
+        const uint32_t ph = (it / C::kStages) & 1;
+        mbar_wait(&full_bar[s], ph);
+        tc_fence_after();
+        const uint32_t st = smem_base + s * C::kStageBytes;
+        // K-major SWIZZLE_128B: SBO = 1024 B (8 rows x 128 B), LBO unused (1)
+        const uint64_t a_hi = umma_smem_desc(st, 16, 1024);
+        const uint64_t b_hi = umma_smem_desc(st + C::kPlanes * kTileBytes, 16, 1024);
+        const uint64_t a_lo = umma_smem_desc(st + kTileBytes, 16, 1024);
+        const uint64_t b_lo = umma_smem_desc(st + (C::kPlanes + 1) * kTileBytes, 16, 1024);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {  // 4 x (UMMA_K = 16 bf16 = 32 B) per 128-B row
+          const uint64_t adv = (uint64_t)(k * 2);
+          umma_bf16(tmem_base, a_hi + adv, b_hi + adv, idesc, acc);
+          acc = 1;
+          if (NSPLIT == 3) {
+            umma_bf16(tmem_base, a_lo + adv, b_hi + adv, idesc, 1);
+            umma_bf16(tmem_base, a_hi + adv, b_lo + adv, idesc, 1);
+          }
+        }
+        umma_commit(&empty_bar[s]);  // frees the smem stage once these MMAs retire
+      }
+      umma_commit(&accum_bar);
+    }
+  } else {
+    // ===================== epilogue =====================
+    const int q = warp & 3;  // TMEM lane quadrant this warp may read
+    const int row = q * 32 + lane;
+    const int w_i = row % p.tw;
+    const int h_i = (row / p.tw) % p.th;
+    const int n_i = row / (p.tw * p.th);
+    const int gw = w0 + w_i, gh = h0 + h_i, gn = n0 + n_i;
+    const bool valid = (gw < p.m_w) && (gh < p.m_h) && (gn < p.m_n);
+    float* optr = p.out + (long long)gn * p.out_sn + (long long)(gh * p.omh + p.ooh) * p.out_sh +
+                  (long long)(gw * p.omw + p.oow) * p.out_sw + ncol0;
+    mbar_wait(&accum_bar, 0);
+    tc_fence_after();
+    for (int c0 = 0; c0 < p.block_n; c0 += 16) {
+      uint32_t r[16];
+      tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
+      tmem_ld_wait();
+      if (valid) {
+        if (p.vec4 && ncol0 + c0 + 16 <= p.n_valid) {
+#pragma unroll
+          for (int j = 0; j < 16; j += 4) {
+            float4 v;
+            v.x = __uint_as_float(r[j + 0]);
+            v.y = __uint_as_float(r[j + 1]);
+            v.z = __uint_as_float(r[j + 2]);
+            v.w = __uint_as_float(r[j + 3]);
+            if (p.bias) {
+              const float4 b = *reinterpret_cast<const float4*>(p.bias + ncol0 + c0 + j);
+              v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+            }
+            if (p.act) {
+              v.x = apply_act(v.x, p.act); v.y = apply_act(v.y, p.act);
+              v.z = apply_act(v.z, p.act); v.w = apply_act(v.w, p.act);
+            }
+            *reinterpret_cast<float4*>(optr + c0 + j) = v;
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const int col = ncol0 + c0 + j;
+            if (col < p.n_valid) {
+              float v = __uint_as_float(r[j]);
+              if (p.bias) v += p.bias[col];
+              optr[c0 + j] = apply_act(v, p.act);
+            }
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 128);
+}
+
+// ============================================================================
+// wgrad mode
+// ============================================================================
+template <int NSPLIT>
+__global__ void __launch_bounds__(kThreads, 1)
+wgrad_gemm_kernel(const __grid_constant__ WgradParams p) {
+  using C = Cfg<NSPLIT>;
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t full_bar[C::kStages];
+  __shared__ __align__(8) uint64_t empty_bar[C::kStages];
+  __shared__ __align__(8) uint64_t accum_bar;
+  __shared__ uint32_t tmem_base_smem;
+
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (smem_base - smem_u32(smem_raw));
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  const int m_tile = blockIdx.x / p.n_tiles;
+  const int n_tile = blockIdx.x - m_tile * p.n_tiles;
+  const int tap_i = blockIdx.y;
+  const int m0 = m_tile * kBlockM;
+  const int ncol0 = n_tile * p.block_n;
+  const int total = p.tiles_w * p.tiles_h * p.tiles_n;
+  const int kt0 = (int)(((long long)total * blockIdx.z) / gridDim.z);
+  const int kt1 = (int)(((long long)total * (blockIdx.z + 1)) / gridDim.z);
+  const int k_iters = kt1 - kt0;
+  const int y_blocks = p.block_n / 64;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < C::kStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(&accum_bar, 1);
+    mbar_fence_init();
+  }
+  if (warp == 0 && lane == 0) {
+    for (int pl = 0; pl < C::kPlanes; ++pl) {
+      tma_prefetch_desc(&p.tmX[pl]);
+      tma_prefetch_desc(&p.tmY[pl]);
+    }
+  }
+  if (warp == 1) tmem_alloc(&tmem_base_smem, 128);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_smem;
+
+  if (k_iters > 0) {
+    if (warp == 0) {
+      if (lane == 0) {
+        const TapDesc xt = p.xtaps[tap_i];
+        const TapDesc yt = p.ytaps[tap_i];
+        const uint32_t stage_tx = C::kPlanes * (2 + y_blocks) * 8192;
+        for (int it = 0; it < k_iters; ++it) {
+          const int s = it % C::kStages;
+          const uint32_t ph = (it / C::kStages) & 1;
+          mbar_wait(&empty_bar[s], ph ^ 1);
+          mbar_expect_tx(&full_bar[s], stage_tx);
+          const int kt = kt0 + it;
+          const int tw_i = kt % p.tiles_w;
+          const int th_i = (kt / p.tiles_w) % p.tiles_h;
+          const int tn_i = kt / (p.tiles_w * p.tiles_h);
+          const int w0 = tw_i * p.tw, h0 = th_i * p.th, n0 = tn_i * p.nb;
+          uint8_t* st = smem + s * C::kStageBytes;
+#pragma unroll
+          for (int pl = 0; pl < C::kPlanes; ++pl) {
+            for (int b = 0; b < 2; ++b)
+              tma_load_5d(&p.tmX[pl], &full_bar[s], st + pl * kTileBytes + b * 8192,
+                          xt.c_off + m0 + b * 64, w0 + xt.dw, xt.hp, h0 + xt.dh, n0);
+            for (int b = 0; b < y_blocks; ++b)
+              tma_load_5d(&p.tmY[pl], &full_bar[s],
+                          st + (C::kPlanes + pl) * kTileBytes + b * 8192,
+                          yt.c_off + ncol0 + b * 64, w0 + yt.dw, yt.hp, h0 + yt.dh, n0);
+          }
+        }
+      }
+    } else if (warp == 1) {
+      if (lane == 0) {
+        const uint32_t idesc = umma_idesc_bf16(kBlockM, p.block_n, 1, 1);
+        uint32_t acc = 0;
+        for (int it = 0; it < k_iters; ++it) {
+          const int s = it % C::kStages;
+          const uint32_t ph = (it / C::kStages) & 1;
+          mbar_wait(&full_bar[s], ph);
+          tc_fence_after();
+          const uint32_t st = smem_base + s * C::kStageBytes;
+          // MN-major SWIZZLE_128B: LBO = stride between 64-channel blocks (8192 B),
+          // SBO = stride between 8-pixel groups (1024 B)
+          const uint64_t x_hi = umma_smem_desc(st, 8192, 1024);
+          const uint64_t y_hi = umma_smem_desc(st + C::kPlanes * kTileBytes, 8192, 1024);
+          const uint64_t x_lo = umma_smem_desc(st + kTileBytes, 8192, 1024);
+          const uint64_t y_lo = umma_smem_desc(st + (C::kPlanes + 1) * kTileBytes, 8192, 1024);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {  // 4 x 16 pixels; 16 pixel rows = 2048 B
+            const uint64_t adv = (uint64_t)(k * 128);
+            umma_bf16(tmem_base, x_hi + adv, y_hi + adv, idesc, acc);
+            acc = 1;
+            if (NSPLIT == 3) {
+              umma_bf16(tmem_base, x_lo + adv, y_hi + adv, idesc, 1);
+              umma_bf16(tmem_base, x_hi + adv, y_lo + adv, idesc, 1);
+            }
+          }
+          umma_commit(&empty_bar[s]);
+        }
+        umma_commit(&accum_bar);
+      }
+    } else {
+      const int q = warp & 3;
+      const int row = m0 + q * 32 + lane;
+      const bool valid = row < p.rows_valid;
+      float* optr = p.out + (long long)row * p.s_row + p.tap_off[tap_i];
+      mbar_wait(&accum_bar, 0);
+      tc_fence_after();
+      for (int c0 = 0; c0 < p.block_n; c0 += 16) {
+        uint32_t r[16];
+        tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
+        tmem_ld_wait();
+        if (valid) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const int col = ncol0 + c0 + j;
+            if (col < p.cols_valid)
+              atomicAdd(optr + (long long)col * p.s_col, __uint_as_float(r[j]));
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 128);
+}
+
+}  // namespace
+
+// ============================================================================
+// host side
+// ============================================================================
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                    const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                    const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode_fn() {
+  static PFN_encodeTiled fn = nullptr;
+  if (!fn) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres);
+    if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !ptr) return nullptr;
+    fn = reinterpret_cast<PFN_encodeTiled>(ptr);
+  }
+  return fn;
+}
+
+// 5-D map over a split-bf16 NHWC plane.  dims (c', w, hp, h, n); see file header.
+int sn_make_act_map(CUtensorMap* tm, const void* base, int N, int H, int W, int C, int pitch,
+                    int parity, int box_w, int box_h, int box_n) {
+  PFN_encodeTiled enc = get_encode_fn();
+  SN_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled driver entry point unavailable");
+  SN_REQUIRE(pitch % 8 == 0 && ((uintptr_t)base % 16) == 0,
+             "activation plane needs 16-B aligned base and pitch %% 8 == 0 (pitch=%d)", pitch);
+  SN_REQUIRE(box_w >= 1 && box_h >= 1 && box_n >= 1 && box_w <= 256 && box_h <= 256 && box_n <= 256,
+             "bad TMA box %d x %d x %d", box_w, box_h, box_n);
+  cuuint64_t dims[5];
+  cuuint64_t strides[4];
+  const cuuint64_t e = 2;  // bytes per bf16
+  if (!parity) {
+    dims[0] = C; dims[1] = W; dims[2] = 1; dims[3] = H; dims[4] = N;
+    strides[0] = (cuuint64_t)pitch * e;
+    strides[1] = (cuuint64_t)W * pitch * e;
+    strides[2] = (cuuint64_t)W * pitch * e;
+    strides[3] = (cuuint64_t)H * W * pitch * e;
+  } else {
+    SN_REQUIRE(H % 2 == 0 && W % 2 == 0, "parity view needs even H, W (got %d x %d)", H, W);
+    dims[0] = (cuuint64_t)pitch + C; dims[1] = W / 2; dims[2] = 2; dims[3] = H / 2; dims[4] = N;
+    strides[0] = (cuuint64_t)2 * pitch * e;
+    strides[1] = (cuuint64_t)W * pitch * e;
+    strides[2] = (cuuint64_t)2 * W * pitch * e;
+    strides[3] = (cuuint64_t)H * W * pitch * e;
+  }
+  cuuint32_t box[5] = {64, (cuuint32_t)box_w, 1, (cuuint32_t)box_h, (cuuint32_t)box_n};
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(base), dims, strides,
+                   box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  SN_REQUIRE(r == CUDA_SUCCESS,
+             "cuTensorMapEncodeTiled(act) failed: %d (N=%d H=%d W=%d C=%d pitch=%d parity=%d box=%dx%dx%d)",
+             (int)r, N, H, W, C, pitch, parity, box_w, box_h, box_n);
+  return SN_OK;
+}
+
+// 2-D map over packed weights [rows][k_total] bf16, K contiguous.
+int sn_make_weight_map(CUtensorMap* tm, const void* base, int rows, long long k_total, int box_rows) {
+  PFN_encodeTiled enc = get_encode_fn();
+  SN_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled driver entry point unavailable");
+  SN_REQUIRE(k_total % 64 == 0 && ((uintptr_t)base % 16) == 0, "packed weights need K %% 64 == 0");
+  cuuint64_t dims[2] = {(cuuint64_t)k_total, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)k_total * 2};
+  cuuint32_t box[2] = {64, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides,
+                   box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  SN_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(weights) failed: %d (rows=%d K=%lld box_rows=%d)",
+             (int)r, rows, k_total, box_rows);
+  return SN_OK;
+}
+
+static void pick_patch(int m_h, int m_w, int rows, int* th, int* tw, int* nb) {
+  // rows = 128 (conv mode) or 64 (wgrad mode); dims are powers of two except the
+  // PatchGAN 63/62 planes, which take the largest patch and rely on masking.
+  int w = 16;
+  while (w > 1 && w / 2 >= m_w) w /= 2;
+  if (w > rows) w = rows;
+  int h = rows / w;
+  while (h > 1 && h / 2 >= m_h) h /= 2;
+  *tw = w;
+  *th = h;
+  *nb = rows / (w * h);
+}
+
+static int g_smem_attr_done[2][2] = {{0, 0}, {0, 0}};
+
+int sn_tap_gemm_plan_init(TapGemmPlan* plan, const sn_tap_gemm_desc* d) {
+  memset(plan, 0, sizeof(*plan));
+  TapGemmParams& p = plan->p;
+  SN_REQUIRE(d->nsplit == 1 || d->nsplit == 3, "nsplit must be 1 or 3");
+  SN_REQUIRE(d->ntaps >= 1 && d->ntaps <= SN_MAX_TAPS, "ntaps out of range: %d", d->ntaps);
+  SN_REQUIRE(d->k_per_tap > 0 && d->k_per_tap % 64 == 0, "k_per_tap must be a multiple of 64");
+  SN_REQUIRE(d->block_n >= 16 && d->block_n <= 128 && d->block_n % 16 == 0,
+             "block_n must be a multiple of 16 in [16,128]");
+  SN_REQUIRE(d->a_hi && d->b_hi && d->out, "null operand");
+  SN_REQUIRE(d->nsplit == 1 || (d->a_lo && d->b_lo), "nsplit=3 needs lo planes");
+  int th, tw, nb;
+  pick_patch(d->m_h, d->m_w, 128, &th, &tw, &nb);
+  p.tw = tw; p.th = th; p.nb = nb;
+  p.tiles_w = (d->m_w + tw - 1) / tw;
+  p.tiles_h = (d->m_h + th - 1) / th;
+  p.tiles_n = (d->m_n + nb - 1) / nb;
+  p.m_w = d->m_w; p.m_h = d->m_h; p.m_n = d->m_n;
+  p.ntaps = d->ntaps;
+  p.chunks = d->k_per_tap / 64;
+  for (int t = 0; t < d->ntaps; ++t) {
+    p.taps[t].c_off = d->taps[t].c_off;
+    p.taps[t].kb_off = d->taps[t].kb_off;
+    p.taps[t].dw = (short)d->taps[t].dw;
+    p.taps[t].dh = (short)d->taps[t].dh;
+    p.taps[t].hp = (short)d->taps[t].hp;
+  }
+  p.block_n = d->block_n;
+  p.n_valid = d->n_valid;
+  p.out = d->out;
+  p.out_sn = d->out_sn; p.out_sh = d->out_sh; p.out_sw = d->out_sw;
+  p.omh = d->out_mul_h; p.ooh = d->out_off_h; p.omw = d->out_mul_w; p.oow = d->out_off_w;
+  p.bias = d->bias;
+  p.act = d->act;
+  p.vec4 = ((uintptr_t)d->out % 16 == 0) && (d->out_sn % 4 == 0) && (d->out_sh % 4 == 0) &&
+           (d->out_sw % 4 == 0) && (!d->bias || (uintptr_t)d->bias % 16 == 0);
+  int rc;
+  const void* a_pl[2] = {d->a_hi, d->a_lo};
+  const void* b_pl[2] = {d->b_hi, d->b_lo};
+  for (int pl = 0; pl < (d->nsplit == 3 ? 2 : 1); ++pl) {
+    rc = sn_make_act_map(&p.tmA[pl], a_pl[pl], d->a_n, d->a_h, d->a_w, d->a_c, d->a_pitch,
+                         d->a_parity, tw, th, nb);
+    if (rc) return rc;
+    rc = sn_make_weight_map(&p.tmB[pl], b_pl[pl], d->b_rows, d->b_k, d->block_n);
+    if (rc) return rc;
+  }
+  plan->nsplit = d->nsplit;
+  plan->grid = dim3(p.tiles_w * p.tiles_h * p.tiles_n, (d->n_valid + d->block_n - 1) / d->block_n, 1);
+  return SN_OK;
+}
+
+int sn_tap_gemm_plan_launch(const TapGemmPlan* plan, cudaStream_t stream) {
+  const int idx = plan->nsplit == 3 ? 1 : 0;
+  if (plan->nsplit == 3) {
+    if (!g_smem_attr_done[0][idx]) {
+      SN_CHECK_CUDA(cudaFuncSetAttribute(tap_gemm_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         Cfg<3>::kSmemBytes));
+      g_smem_attr_done[0][idx] = 1;
+    }
+    tap_gemm_kernel<3><<<plan->grid, kThreads, Cfg<3>::kSmemBytes, stream>>>(plan->p);
+  } else {
+    if (!g_smem_attr_done[0][idx]) {
+      SN_CHECK_CUDA(cudaFuncSetAttribute(tap_gemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         Cfg<1>::kSmemBytes));
+      g_smem_attr_done[0][idx] = 1;
+    }
+    tap_gemm_kernel<1><<<plan->grid, kThreads, Cfg<1>::kSmemBytes, stream>>>(plan->p);
+  }
+  SN_CHECK_CUDA(cudaGetLastError());
+  return SN_OK;
+}
+
+int sn_wgrad_plan_init(WgradPlan* plan, const sn_wgrad_desc* d, int sm_count) {
+  memset(plan, 0, sizeof(*plan));
+  WgradParams& p = plan->p;
+  SN_REQUIRE(d->nsplit == 1 || d->nsplit == 3, "nsplit must be 1 or 3");
+  SN_REQUIRE(d->ntaps >= 1 && d->ntaps <= SN_MAX_TAPS, "ntaps out of range: %d", d->ntaps);
+  SN_REQUIRE(d->block_n == 64 || d->block_n == 128, "wgrad block_n must be 64 or 128");
+  SN_REQUIRE(d->x_hi && d->y_hi && d->out, "null operand");
+  SN_REQUIRE(d->nsplit == 1 || (d->x_lo && d->y_lo), "nsplit=3 needs lo planes");
+  int th, tw, nb;
+  pick_patch(d->m_h, d->m_w, 64, &th, &tw, &nb);
+  p.tw = tw; p.th = th; p.nb = nb;
+  p.tiles_w = (d->m_w + tw - 1) / tw;
+  p.tiles_h = (d->m_h + th - 1) / th;
+  p.tiles_n = (d->m_n + nb - 1) / nb;
+  p.ntaps = d->ntaps;
+  for (int t = 0; t < d->ntaps; ++t) {
+    p.xtaps[t].c_off = d->xtaps[t].c_off; p.xtaps[t].dw = (short)d->xtaps[t].dw;
+    p.xtaps[t].dh = (short)d->xtaps[t].dh; p.xtaps[t].hp = (short)d->xtaps[t].hp;
+    p.ytaps[t].c_off = d->ytaps[t].c_off; p.ytaps[t].dw = (short)d->ytaps[t].dw;
+    p.ytaps[t].dh = (short)d->ytaps[t].dh; p.ytaps[t].hp = (short)d->ytaps[t].hp;
+    p.tap_off[t] = d->tap_off[t];
+  }
+  p.block_n = d->block_n;
+  p.m_tiles = (d->rows_valid + kBlockM - 1) / kBlockM;
+  p.n_tiles = (d->cols_valid + d->block_n - 1) / d->block_n;
+  p.rows_valid = d->rows_valid;
+  p.cols_valid = d->cols_valid;
+  p.out = d->out;
+  p.s_row = d->s_row;
+  p.s_col = d->s_col;
+  int rc;
+  const void* x_pl[2] = {d->x_hi, d->x_lo};
+  const void* y_pl[2] = {d->y_hi, d->y_lo};
+  for (int pl = 0; pl < (d->nsplit == 3 ? 2 : 1); ++pl) {
+    rc = sn_make_act_map(&p.tmX[pl], x_pl[pl], d->x_n, d->x_h, d->x_w, d->x_c, d->x_pitch,
+                         d->x_parity, tw, th, nb);
+    if (rc) return rc;
+    rc = sn_make_act_map(&p.tmY[pl], y_pl[pl], d->y_n, d->y_h, d->y_w, d->y_c, d->y_pitch,
+                         d->y_parity, tw, th, nb);
+    if (rc) return rc;
+  }
+  plan->nsplit = d->nsplit;
+  const int base_ctas = p.m_tiles * p.n_tiles * d->ntaps;
+  const int total = p.tiles_w * p.tiles_h * p.tiles_n;
+  int ks = d->ksplit;
+  if (ks <= 0) {  // aim for ~3 waves, at least 8 k-iterations per CTA
+    ks = (3 * sm_count + base_ctas - 1) / base_ctas;
+    int max_ks = total / 8;
+    if (max_ks < 1) max_ks = 1;
+    if (ks > max_ks) ks = max_ks;
+    if (ks < 1) ks = 1;
+  }
+  if (ks > total) ks = total;
+  plan->grid = dim3(p.m_tiles * p.n_tiles, d->ntaps, ks);
+  return SN_OK;
+}
+
+int sn_wgrad_plan_launch(const WgradPlan* plan, cudaStream_t stream) {
+  const int idx = plan->nsplit == 3 ? 1 : 0;
+  if (plan->nsplit == 3) {
+    if (!g_smem_attr_done[1][idx]) {
+      SN_CHECK_CUDA(cudaFuncSetAttribute(wgrad_gemm_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         Cfg<3>::kSmemBytes));
+      g_smem_attr_done[1][idx] = 1;
+    }
+    wgrad_gemm_kernel<3><<<plan->grid, kThreads, Cfg<3>::kSmemBytes, stream>>>(plan->p);
+  } else {
+    if (!g_smem_attr_done[1][idx]) {
+      SN_CHECK_CUDA(cudaFuncSetAttribute(wgrad_gemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         Cfg<1>::kSmemBytes));
+      g_smem_attr_done[1][idx] = 1;
+    }
+    wgrad_gemm_kernel<1><<<plan->grid, kThreads, Cfg<1>::kSmemBytes, stream>>>(plan->p);
+  }
+  SN_CHECK_CUDA(cudaGetLastError());
+  return SN_OK;
+}

@@ -1,0 +1,59 @@
+// swapnet_b200 — internal kernel-parameter structs and plan objects.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include "../../include/swapnet_b200.h"
+
+struct TapDesc {
+  int c_off;   // channel (c') offset of this tap inside the A tensor map
+  int kb_off;  // K offset of this tap inside the packed weight matrix
+  short dw, dh, hp, _pad;
+};
+
+struct alignas(64) TapGemmParams {
+  CUtensorMap tmA[2];  // hi, lo activation planes
+  CUtensorMap tmB[2];  // hi, lo packed weights
+  TapDesc taps[SN_MAX_TAPS];
+  int ntaps, chunks;
+  int tiles_w, tiles_h, tiles_n;
+  int tw, th, nb;
+  int m_w, m_h, m_n;
+  int block_n, n_valid;
+  float* out;
+  long long out_sn, out_sh, out_sw;
+  int omh, ooh, omw, oow;
+  const float* bias;
+  int act;
+  int vec4;
+};
+
+struct alignas(64) WgradParams {
+  CUtensorMap tmX[2];
+  CUtensorMap tmY[2];
+  TapDesc xtaps[SN_MAX_TAPS];
+  TapDesc ytaps[SN_MAX_TAPS];
+  long long tap_off[SN_MAX_TAPS];
+  int ntaps;
+  int tiles_w, tiles_h, tiles_n;
+  int tw, th, nb;
+  int m_tiles, n_tiles, block_n;
+  int rows_valid, cols_valid;
+  float* out;
+  long long s_row, s_col;
+};
+
+struct TapGemmPlan {
+  TapGemmParams p;
+  dim3 grid;
+  int nsplit;
+};
+struct WgradPlan {
+  WgradParams p;
+  dim3 grid;
+  int nsplit;
+};
+
+int sn_tap_gemm_plan_init(TapGemmPlan* plan, const sn_tap_gemm_desc* d);
+int sn_tap_gemm_plan_launch(const TapGemmPlan* plan, cudaStream_t stream);
+int sn_wgrad_plan_init(WgradPlan* plan, const sn_wgrad_desc* d, int sm_count);
+int sn_wgrad_plan_launch(const WgradPlan* plan, cudaStream_t stream);

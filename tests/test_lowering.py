@@ -1,0 +1,122 @@
+"""CPU proof that swapnet_b200/lowering.py maps each reference conv layer, its input gradient
+and its weight gradient onto the generic tap-GEMM / wgrad-GEMM contractions exactly (fp64)."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import emulate as E
+from swapnet_b200 import lowering as L
+
+torch.manual_seed(0)
+
+
+def ref_forward(kind, x, w, b=None):
+    """x NCHW fp64 -> NCHW, with torch's own ops exactly as the reference modules call them."""
+    if kind == "conv4s2":
+        return F.conv2d(x, w, b, 2, 1)
+    if kind == "convT4s2":
+        return F.conv_transpose2d(x, w, b, 2, 1)
+    if kind == "conv3r":
+        return F.conv2d(F.pad(x, (1, 1, 1, 1), mode="reflect"), w, b)
+    if kind == "conv4s1":
+        return F.conv2d(x, w, b, 1, 1)
+    if kind == "head":
+        u = F.interpolate(x, scale_factor=2)  # nn.Upsample default = nearest
+        u = F.pad(u, (1, 0, 1, 0))            # ZeroPad2d((1,0,1,0))
+        return F.conv2d(u, w, b, 1, 1)
+    raise ValueError(kind)
+
+
+CASES = [
+    ("conv4s2", 3, 5, 8, 8), ("conv4s2", 4, 6, 12, 16),
+    ("convT4s2", 5, 3, 4, 4), ("convT4s2", 6, 4, 6, 8),
+    ("conv3r", 4, 5, 6, 6), ("conv3r", 3, 3, 8, 10),
+    ("conv4s1", 4, 3, 7, 9), ("conv4s1", 5, 1, 8, 8),
+    ("head", 6, 5, 4, 4), ("head", 4, 3, 6, 8),
+]
+
+
+def nhwc(x):
+    return x.permute(0, 2, 3, 1).contiguous()
+
+
+def to_planes(x_nchw, kind, pitch):
+    """layer input NCHW -> dense A [N, H', W', pitch] as the planes buffer would hold it."""
+    if kind == "conv3r":
+        x_nchw = F.pad(x_nchw, (1, 1, 1, 1), mode="reflect")
+    a = nhwc(x_nchw)
+    out = a.new_zeros(*a.shape[:3], pitch)
+    out[..., : a.shape[3]] = a
+    return out
+
+
+@pytest.mark.parametrize("kind,cin,cout,h,w", CASES)
+def test_forward_dgrad_wgrad(kind, cin, cout, h, w):
+    N = 2
+    k_pad = 8  # emulator has no 64-alignment requirement
+    x = torch.randn(N, cin, h, w, dtype=torch.float64, requires_grad=True)
+    wshape = (cin, cout, 4, 4) if kind == "convT4s2" else (cout, cin, 3 if kind == "conv3r" else 4,) * 1
+    if kind != "convT4s2":
+        k = 3 if kind == "conv3r" else 4
+        wshape = (cout, cin, k, k)
+    wt = torch.randn(*wshape, dtype=torch.float64, requires_grad=True)
+    bias = torch.randn(cout, dtype=torch.float64)
+    y = ref_forward(kind, x, wt, bias)
+    gy = torch.randn_like(y)
+    gx, gw = torch.autograd.grad(y, (x, wt), gy)
+    oh, ow = L.out_hw(kind, h, w)
+    assert y.shape[2:] == (oh, ow)
+
+    # ---- forward ----
+    A = to_planes(x.detach(), kind, pitch=k_pad + 3)
+    out = torch.zeros(N, oh, ow, cout, dtype=torch.float64)
+    specs = L.forward_specs(kind, h, w)
+    if kind == "head":
+        mats = E.pack_head_ref(wt.detach(), rows_pad=cout + 2, k_pad=k_pad, dgrad=False)
+    else:
+        Wp = E.pack_weights_ref(wt.detach(), kind, False, k_pad)
+    for s in specs:
+        assert s.a_hw == tuple(A.shape[1:3])
+        E.emul_tap_gemm(A, s, mats[s.w_phase] if kind == "head" else Wp, k_pad, cout, out, bias=bias)
+    torch.testing.assert_close(out, nhwc(y.detach()), rtol=1e-10, atol=1e-10)
+
+    # ---- dgrad ----
+    DY = torch.zeros(N, oh, ow, k_pad + 5, dtype=torch.float64)
+    DY[..., :cout] = nhwc(gy)
+    if kind == "head":
+        Wd = E.pack_head_ref(wt.detach(), 0, k_pad, dgrad=True)
+    else:
+        Wd = E.pack_weights_ref(wt.detach(), kind, True, k_pad)
+    ih, iw = (h + 2, w + 2) if kind == "conv3r" else (h, w)
+    dx = torch.zeros(N, ih, iw, cin, dtype=torch.float64)
+    for s in L.dgrad_specs(kind, h, w):
+        assert s.a_hw == (oh, ow)
+        E.emul_tap_gemm(DY, s, Wd, k_pad, cin, dx)
+    if kind == "conv3r":  # fold the reflect padding back (adjoint of ReflectionPad2d(1))
+        xp = F.pad(x.detach(), (1, 1, 1, 1), mode="reflect").requires_grad_()
+        ref = torch.autograd.grad(F.conv2d(xp, wt.detach()), xp, gy)[0]
+        torch.testing.assert_close(dx, nhwc(ref), rtol=1e-10, atol=1e-10)
+    else:
+        torch.testing.assert_close(dx, nhwc(gx), rtol=1e-10, atol=1e-10)
+
+    # ---- wgrad ----
+    (ws,) = L.wgrad_specs(kind, h, w)
+    Xd, Yd = (DY, A) if ws.x_is == "dy" else (A, DY)
+    cx, cy = (cout, cin) if ws.x_is == "dy" else (cin, cout)
+    G = E.emul_wgrad(Xd, Yd, ws, cx, cy)  # [taps, cx, cy]
+    s_row, s_col = L.wgrad_out_strides(kind, cin, cout, ws.x_is == "dy")
+    if kind == "head":
+        flat = torch.zeros(cout * 25 * cin, dtype=torch.float64)
+        tap_off = [t * cin for t in ws.tap_ids]
+    else:
+        flat = torch.zeros(wt.numel(), dtype=torch.float64)
+        tap_off = list(ws.tap_ids)
+    r = torch.arange(cx)[:, None] * s_row
+    c = torch.arange(cy)[None, :] * s_col
+    for t, off in enumerate(tap_off):
+        flat.index_add_(0, (r + c + off).reshape(-1), G[t].reshape(-1))
+    if kind == "head":
+        got = E.fold_head_wgrad_ref(flat.reshape(cout, 25, cin))
+    else:
+        got = flat.reshape(wt.shape)
+    torch.testing.assert_close(got, gw, rtol=1e-9, atol=1e-9)
