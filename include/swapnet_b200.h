@@ -161,6 +161,10 @@ typedef struct sn_norm_act_bwd_desc {
 } sn_norm_act_bwd_desc;
 int sn_norm_act_bwd(const sn_norm_act_bwd_desc* d, void* stream);
 
+/* bias gradient db[c] = sum over the npix pixels of dL/dy (split planes); scratch: double[c] */
+int sn_bias_grad(const void* dy_hi, const void* dy_lo, int pitch, int coff, long long npix, int c,
+                 double* scratch, float* db, void* stream);
+
 /* dst[n,h,w,c] = sum_i src_i (fp32), e.g. the residual-stream gradient of a ResidualBlock */
 int sn_sum_grads(const sn_grad_src* src, int nsrc, int n, int h, int w, int c, float* dst,
                  int dst_pitch, void* stream);

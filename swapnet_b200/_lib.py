@@ -105,6 +105,7 @@ SIGNATURES = {
     "sn_plane_stats": (_I, [_VP, _I, _I, _I, _I, _F, _VP, _VP]),
     "sn_norm_act_fwd": (_I, [C.POINTER(SnNormActDesc), _VP]),
     "sn_norm_act_bwd": (_I, [C.POINTER(SnNormActBwdDesc), _VP]),
+    "sn_bias_grad": (_I, [_VP, _VP, _I, _I, _LL, _I, _VP, _VP, _VP]),
     "sn_sum_grads": (_I, [C.POINTER(SnGradSrc), _I, _I, _I, _I, _I, _VP, _I, _VP]),
     "sn_tanh_bwd": (_I, [C.POINTER(SnGradSrc), _I, _VP, _I, _I, _I, _I, _I, _VP, _VP, _I, _I, _VP]),
     "sn_dropout_mask": (_I, [_ULL, _F, _LL, _VP, _VP]),

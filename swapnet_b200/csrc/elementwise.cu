@@ -243,6 +243,41 @@ __global__ void gstats_finalize_kernel(double* g, int count, int hw) {
   }
 }
 
+
+// bias gradient: db[c] = sum over pixels of dy (dy carried as split planes)
+__global__ void bias_grad_kernel(const __nv_bfloat16* __restrict__ hi, const __nv_bfloat16* __restrict__ lo,
+                                 int pitch, long long npix, int C, double* __restrict__ acc) {
+  __shared__ float s1s[8][33];
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  const long long per = (npix + gridDim.y - 1) / gridDim.y;
+  const long long p0 = blockIdx.y * per;
+  const long long p1 = p0 + per < npix ? p0 + per : npix;
+  double s = 0.0;
+  if (c < C) {
+    float part = 0.f;
+    int cnt = 0;
+    for (long long p = p0 + threadIdx.y; p < p1; p += 8) {
+      float v = __bfloat162float(hi[p * pitch + c]);
+      if (lo) v += __bfloat162float(lo[p * pitch + c]);
+      part += v;
+      if (++cnt == 64) { s += (double)part; part = 0.f; cnt = 0; }
+    }
+    s += (double)part;
+  }
+  s1s[threadIdx.y][threadIdx.x] = (float)s;  // per-thread partial (<= per/8 terms) fits fp32 well
+  __syncthreads();
+  if (threadIdx.y == 0 && c < C) {
+    double a = 0.0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) a += (double)s1s[j][threadIdx.x];
+    atomic_add_f64(&acc[c], a);
+  }
+}
+__global__ void bias_grad_finalize_kernel(const double* acc, int C, float* db) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < C) db[i] = (float)acc[i];
+}
+
 // ---------------------------------------------------------------------------------
 // InstanceNorm-apply + activation + dropout (+ residual) forward
 // grid (slabs, N); block (cx, py): cx threads over channels, py over pixels
@@ -786,6 +821,25 @@ int sn_norm_act_bwd(const sn_norm_act_bwd_desc* d, void* stream) {
   dim3 blk = cblock(d->c);
   dim3 grid(slabs_for(hw, d->n, blk.y), d->n);
   norm_act_bwd_apply_kernel<<<grid, blk, 0, st>>>(a);
+  LAUNCH_CHECK();
+  return SN_OK;
+}
+
+
+int sn_bias_grad(const void* dy_hi, const void* dy_lo, int pitch, int coff, long long npix, int c,
+                 double* scratch, float* db, void* stream) {
+  SN_REQUIRE(dy_hi && scratch && db, "null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  SN_CHECK_CUDA(cudaMemsetAsync(scratch, 0, sizeof(double) * c, st));
+  const int cg = (c + 31) / 32;
+  long long slabs = (148 * 4 + cg - 1) / cg;
+  if (slabs > (npix + 63) / 64) slabs = (npix + 63) / 64;
+  if (slabs < 1) slabs = 1;
+  const __nv_bfloat16* hi = (const __nv_bfloat16*)dy_hi + coff;
+  const __nv_bfloat16* lo = dy_lo ? (const __nv_bfloat16*)dy_lo + coff : nullptr;
+  bias_grad_kernel<<<dim3(cg, (int)slabs), dim3(32, 8), 0, st>>>(hi, lo, pitch, npix, c, scratch);
+  LAUNCH_CHECK();
+  bias_grad_finalize_kernel<<<(c + 255) / 256, 256, 0, st>>>(scratch, c, db);
   LAUNCH_CHECK();
   return SN_OK;
 }

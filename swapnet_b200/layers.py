@@ -1,0 +1,148 @@
+"""Conv layers of the hot path as bundles of pre-built tensor-core plans.
+
+A `ConvLayer` owns, for one reference conv (kinds in lowering.py), the packed split-bf16 weight
+matrices and the sn_plan handles of its forward, input-gradient and weight-gradient launches.
+All buffers are allocated once (shapes are static per model/batch), so a training step is a
+fixed sequence of launches: `pack()` once per step after the optimizer update, then
+`forward()`, `backward()`.
+"""
+from __future__ import annotations
+
+from typing import List, Optional
+
+import torch
+
+from . import lowering as L
+from . import ops
+from .ops import ACT_NONE, ACT_TANH, PackedWeights, Planes
+
+
+class ConvLayer:
+    def __init__(self, kind: str, weight: torch.Tensor, bias: Optional[torch.Tensor], x: Planes, *,
+                 nsplit: int = 3, act: int = ACT_NONE, name: str = ""):
+        """x: input operand planes (for 'conv3r' the reflect-padded [h+2, w+2] planes).
+        weight / bias: the torch parameters (torch layout, fp32, on the same device)."""
+        assert kind in L.KINDS
+        self.kind, self.name, self.nsplit, self.act = kind, name, nsplit, act
+        self.weight, self.bias = weight, bias
+        self.x = x
+        dev = weight.device
+        if kind == "convT4s2":
+            self.cin, self.cout = weight.shape[0], weight.shape[1]
+        else:
+            self.cout, self.cin = weight.shape[0], weight.shape[1]
+        self.in_h, self.in_w = (x.h - 2, x.w - 2) if kind == "conv3r" else (x.h, x.w)
+        self.out_h, self.out_w = L.out_hw(kind, self.in_h, self.in_w)
+        self.n = x.n
+        self.k_pad = x.c                       # input channels as the planes carry them (multiple of 64)
+        assert self.k_pad % 64 == 0 and self.k_pad >= self.cin, (name, x.c, self.cin)
+        self.block_n = L.pick_block_n(self.cout)
+        self.t = L.ntaps(kind)
+        if kind == "head":
+            self.rows_pad = (self.cout + self.block_n - 1) // self.block_n * self.block_n
+            self.wp = PackedWeights(self.rows_pad, 25 * self.k_pad, dev)
+        else:
+            self.wp = PackedWeights(self.cout, self.t * self.k_pad, dev)
+        self.fwd_plans: List[ops.Plan] = []
+        self.y: Optional[torch.Tensor] = None
+        # backward state
+        self.wd: Optional[PackedWeights] = None
+        self.dy: Optional[Planes] = None
+        self.dgrad_plans: List[ops.Plan] = []
+        self.wgrad_plan: Optional[ops.Plan] = None
+        self.dx: Optional[torch.Tensor] = None
+        self.wgrad_out: Optional[torch.Tensor] = None
+        self.bgrad_out: Optional[torch.Tensor] = None
+        self._geff: Optional[torch.Tensor] = None
+        self._bscratch: Optional[torch.Tensor] = None
+
+    # ---- forward --------------------------------------------------------------------------
+    def bind_forward(self, y: torch.Tensor, y_c_off: int = 0) -> None:
+        """y: fp32 NHWC [n, out_h, out_w, pitch]; the conv output (+bias, +act) is written to
+        channels [y_c_off, y_c_off + cout)."""
+        assert y.shape[:3] == (self.n, self.out_h, self.out_w), (self.name, y.shape, self.out_h, self.out_w)
+        self.y = y
+        self.fwd_plans = []
+        for spec in L.forward_specs(self.kind, self.in_h, self.in_w):
+            kw = {}
+            if self.kind == "head":
+                p = spec.w_phase
+                nt = L.head_neff(p >> 1) * L.head_neff(p & 1)
+                kw = dict(w_elem_off=self.rows_pad * self.k_pad * L.HEAD_PHASE_OFF[p], w_rows=self.rows_pad,
+                          w_k=nt * self.k_pad)
+            d = ops.tap_gemm_desc(self.x, spec, self.wp, self.k_pad, y, self.cout, bias=self.bias,
+                                  act=self.act, nsplit=self.nsplit, block_n=self.block_n, out_c_off=y_c_off, **kw)
+            self.fwd_plans.append(ops.tap_gemm_plan(d, keep=(self.x.hi, self.x.lo, self.wp.hi, self.wp.lo, y)))
+
+    def pack(self) -> None:
+        """Re-pack the (updated) torch weights into the kernel layouts."""
+        if self.kind == "head":
+            ops.pack_head_weights(self.weight, self.rows_pad, self.k_pad, False, self.wp)
+            if self.wd is not None and self.dgrad_plans:
+                ops.pack_head_weights(self.weight, 0, self.dy.c, True, self.wd)
+        else:
+            ops.pack_weights(self.weight, self.kind, False, self.k_pad, self.wp)
+            if self.wd is not None and self.dgrad_plans:
+                ops.pack_weights(self.weight, self.kind, True, self.dy.c, self.wd)
+
+    def forward(self) -> None:
+        for p in self.fwd_plans:
+            p.run()
+
+    # ---- backward -------------------------------------------------------------------------
+    def bind_backward(self, dy: Planes, dx: Optional[torch.Tensor], wgrad: Optional[torch.Tensor],
+                      bgrad: Optional[torch.Tensor] = None, dx_c_off: int = 0) -> None:
+        """dy: split planes of dL/d(conv output) [n, out_h, out_w, pad64(cout)].
+        dx: fp32 NHWC gradient w.r.t. the input operand ([n, h+2, w+2, .] for conv3r) or None.
+        wgrad / bgrad: fp32 tensors in torch layout that receive (+=) the parameter gradients
+        (must be zeroed by the caller once per step)."""
+        dev = self.weight.device
+        assert (dy.n, dy.h, dy.w) == (self.n, self.out_h, self.out_w), (self.name, dy.h, dy.w)
+        assert dy.c % 64 == 0 and dy.c >= self.cout
+        self.dy = dy
+        self.dx = dx
+        self.dgrad_plans = []
+        if dx is not None:
+            if self.kind == "head":
+                self.wd = PackedWeights(self.cin, 25 * dy.c, dev)
+            else:
+                self.wd = PackedWeights(self.cin, self.t * dy.c, dev)
+            bn = L.pick_block_n(self.cin)
+            for spec in L.dgrad_specs(self.kind, self.in_h, self.in_w):
+                d = ops.tap_gemm_desc(dy, spec, self.wd, dy.c, dx, self.cin, nsplit=self.nsplit, block_n=bn,
+                                      out_c_off=dx_c_off)
+                self.dgrad_plans.append(ops.tap_gemm_plan(d, keep=(dy.hi, dy.lo, self.wd.hi, self.wd.lo, dx)))
+        self.wgrad_out = wgrad
+        self.wgrad_plan = None
+        if wgrad is not None:
+            assert wgrad.shape == self.weight.shape and wgrad.is_contiguous()
+            (ws,) = L.wgrad_specs(self.kind, self.in_h, self.in_w)
+            x_is_dy = ws.x_is == "dy"
+            xs, ys = (dy, self.x) if x_is_dy else (self.x, dy)
+            cx, cy = (self.cout, self.cin) if x_is_dy else (self.cin, self.cout)
+            s_row, s_col = L.wgrad_out_strides(self.kind, self.cin, self.cout, x_is_dy)
+            if self.kind == "head":
+                self._geff = torch.zeros(self.cout, 25, self.cin, dtype=torch.float32, device=dev)
+                out, tap_off = self._geff, [t * self.cin for t in ws.tap_ids]
+            else:
+                out, tap_off = wgrad, list(ws.tap_ids)
+            # the 128-row M side should be the operand with more channels
+            swap = cy > cx
+            d = ops.wgrad_desc(xs, ys, ws, out, s_row, s_col, tap_off, cx, cy, swap=swap, nsplit=self.nsplit)
+            self.wgrad_plan = ops.wgrad_plan(d, keep=(xs.hi, xs.lo, ys.hi, ys.lo, out))
+        self.bgrad_out = bgrad
+        if bgrad is not None:
+            self._bscratch = torch.zeros(self.cout, dtype=torch.float64, device=dev)
+
+    def backward(self, dgrad: bool = True, wgrad: bool = True) -> None:
+        if dgrad:
+            for p in self.dgrad_plans:
+                p.run()
+        if wgrad and self.wgrad_plan is not None:
+            if self._geff is not None:
+                self._geff.zero_()
+            self.wgrad_plan.run()
+            if self._geff is not None:
+                ops.fold_head_wgrad(self._geff, self.cout, self.cin, self.wgrad_out)
+        if wgrad and self.bgrad_out is not None:
+            ops.bias_grad(self.dy, self.cout, self._bscratch, self.bgrad_out)

@@ -1,0 +1,363 @@
+"""Python face of the C ABI: torch tensors in, kernel launches on torch's current stream out.
+
+torch is used for device memory and streams only; every function here ends in a call into
+libswapnet_b200.so and raises if that fails (no eager fallback).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import List, Optional, Sequence
+
+import torch
+
+from . import _lib
+from . import lowering as L
+from ._lib import (ACT_LRELU, ACT_NONE, ACT_RELU, ACT_TANH, LAYOUT_NCHW, LAYOUT_NHWC, SnGradSrc,
+                   SnNormActBwdDesc, SnNormActDesc, SnTap, SnTapGemmDesc, SnWgradDesc, check)
+
+IN_EPS = 1e-5  # nn.InstanceNorm2d default (modules/__init__.py:67-69)
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+# ---------------------------------------------------------------------------------------------
+# split-plane operand buffers
+# ---------------------------------------------------------------------------------------------
+class Planes:
+    """A split-bf16 NHWC operand [n, h, w, c] living at channel offset `c_off` of a (possibly
+    wider) buffer with `pitch` channels per pixel.  Padding channels stay zero forever."""
+
+    def __init__(self, n: int, h: int, w: int, pitch: int, device, c: Optional[int] = None, c_off: int = 0,
+                 hi: Optional[torch.Tensor] = None, lo: Optional[torch.Tensor] = None):
+        assert pitch % 8 == 0 and c_off % 8 == 0
+        self.n, self.h, self.w, self.pitch = n, h, w, pitch
+        self.c = pitch if c is None else c
+        self.c_off = c_off
+        self.hi = hi if hi is not None else torch.zeros(n, h, w, pitch, dtype=torch.bfloat16, device=device)
+        self.lo = lo if lo is not None else torch.zeros(n, h, w, pitch, dtype=torch.bfloat16, device=device)
+
+    def slice(self, c_off: int, c: int) -> "Planes":
+        assert c_off + c <= self.pitch
+        return Planes(self.n, self.h, self.w, self.pitch, self.hi.device, c, self.c_off + c_off, self.hi, self.lo)
+
+    def batch_slice(self, n0: int, n: int) -> "Planes":
+        return Planes(n, self.h, self.w, self.pitch, self.hi.device, self.c, self.c_off, self.hi[n0:n0 + n],
+                      self.lo[n0:n0 + n])
+
+    @property
+    def hi_ptr(self) -> int:
+        return self.hi.data_ptr() + 2 * self.c_off
+
+    @property
+    def lo_ptr(self) -> int:
+        return self.lo.data_ptr() + 2 * self.c_off
+
+    def dense(self) -> torch.Tensor:
+        """fp32 reconstruction hi + lo of the logical [n,h,w,c] tensor (tests / debugging)."""
+        s = slice(self.c_off, self.c_off + self.c)
+        return self.hi[..., s].float() + self.lo[..., s].float()
+
+
+class PackedWeights:
+    """[rows][k_total] split-bf16 weight matrix (K contiguous)."""
+
+    def __init__(self, rows: int, k_total: int, device):
+        self.rows, self.k_total = rows, k_total
+        self.hi = torch.zeros(rows, k_total, dtype=torch.bfloat16, device=device)
+        self.lo = torch.zeros(rows, k_total, dtype=torch.bfloat16, device=device)
+
+
+class Plan:
+    """Owns one sn_plan handle (encoded TMA descriptors + launch geometry)."""
+
+    def __init__(self, handle: int, keep: Sequence):
+        self.handle = handle
+        self._keep = list(keep)  # tensors whose addresses are baked into the plan
+
+    def run(self) -> None:
+        check(_lib.load().sn_plan_run(self.handle, _stream()))
+
+    def __del__(self):
+        try:
+            if self.handle:
+                _lib.load().sn_plan_destroy(self.handle)
+        except Exception:
+            pass
+
+
+def _fill_tap(dst: SnTap, tap: L.Tap, pitch: int, k_pad: int, c_base: int = 0) -> None:
+    dst.c_off = tap.pw * pitch + c_base
+    dst.kb_off = tap.kb * k_pad
+    dst.dw, dst.dh, dst.hp = tap.dw, tap.dh, tap.hp
+
+
+def tap_gemm_desc(a: Planes, spec: L.GemmSpec, w: PackedWeights, k_per_tap: int, out: torch.Tensor,
+                  n_valid: int, *, w_row_off: int = 0, w_rows: Optional[int] = None,
+                  w_k: Optional[int] = None, w_elem_off: int = 0, bias: Optional[torch.Tensor] = None,
+                  act: int = ACT_NONE, nsplit: int = 3, block_n: Optional[int] = None,
+                  out_c_off: int = 0) -> SnTapGemmDesc:
+    """out: fp32 NHWC tensor [n, OH, OW, pitch_out]; rows (h, w) land on pixel
+    (h*mul_h + off_h, w*mul_w + off_w)."""
+    assert (a.h, a.w) == tuple(spec.a_hw), f"operand is {a.h}x{a.w}, spec wants {spec.a_hw}"
+    assert k_per_tap % 64 == 0 and k_per_tap <= a.c
+    d = SnTapGemmDesc()
+    d.a_hi, d.a_lo = a.hi_ptr, a.lo_ptr
+    d.a_n, d.a_h, d.a_w, d.a_c, d.a_pitch = a.n, a.h, a.w, a.c, a.pitch
+    d.a_parity = 1 if spec.parity else 0
+    d.b_hi = w.hi.data_ptr() + 2 * w_elem_off
+    d.b_lo = w.lo.data_ptr() + 2 * w_elem_off
+    d.b_rows = w.rows if w_rows is None else w_rows
+    d.b_k = w.k_total if w_k is None else w_k
+    d.m_n, d.m_h, d.m_w = a.n, spec.m_h, spec.m_w
+    d.ntaps, d.k_per_tap = len(spec.taps), k_per_tap
+    for i, t in enumerate(spec.taps):
+        _fill_tap(d.taps[i], t, a.pitch, k_per_tap)
+    assert out.dtype == torch.float32 and out.dim() == 4 and (out.shape[3] == 1 or out.stride(3) == 1)
+    d.out = out.data_ptr() + 4 * out_c_off
+    d.out_sn, d.out_sh, d.out_sw = out.stride(0), out.stride(1), out.stride(2)
+    d.out_mul_h, d.out_mul_w = spec.out_mul
+    d.out_off_h, d.out_off_w = spec.out_off
+    d.n_valid = n_valid
+    d.block_n = block_n or L.pick_block_n(n_valid)
+    d.bias = _ptr(bias)
+    d.act = act
+    d.nsplit = nsplit
+    return d
+
+
+def tap_gemm_plan(desc: SnTapGemmDesc, keep: Sequence = ()) -> Plan:
+    h = C.c_void_p()
+    check(_lib.load().sn_tap_gemm_plan_create(C.byref(desc), C.byref(h)))
+    return Plan(h.value, keep)
+
+
+def tap_gemm_simt(desc: SnTapGemmDesc) -> None:
+    check(_lib.load().sn_tap_gemm_simt(C.byref(desc), _stream()))
+
+
+def wgrad_desc(x: Planes, y: Planes, spec: L.WgradSpec, out: torch.Tensor, s_row: int, s_col: int,
+               tap_off: Sequence[int], rows_valid: int, cols_valid: int, *, swap: bool = False,
+               nsplit: int = 3, block_n: Optional[int] = None, ksplit: int = 0) -> SnWgradDesc:
+    """x / y follow the spec orientation; swap=True exchanges the roles (rows <-> cols)."""
+    xt, yt = spec.xtaps, spec.ytaps
+    xp, yp = spec.x_parity, spec.y_parity
+    if swap:
+        x, y, xt, yt, xp, yp = y, x, yt, xt, yp, xp
+        s_row, s_col = s_col, s_row
+        rows_valid, cols_valid = cols_valid, rows_valid
+    d = SnWgradDesc()
+    d.x_hi, d.x_lo = x.hi_ptr, x.lo_ptr
+    d.x_n, d.x_h, d.x_w, d.x_c, d.x_pitch, d.x_parity = x.n, x.h, x.w, x.c, x.pitch, int(xp)
+    d.y_hi, d.y_lo = y.hi_ptr, y.lo_ptr
+    d.y_n, d.y_h, d.y_w, d.y_c, d.y_pitch, d.y_parity = y.n, y.h, y.w, y.c, y.pitch, int(yp)
+    d.m_n, d.m_h, d.m_w = x.n, spec.m_h, spec.m_w
+    d.ntaps = len(xt)
+    for i in range(len(xt)):
+        _fill_tap(d.xtaps[i], xt[i], x.pitch, 0)
+        _fill_tap(d.ytaps[i], yt[i], y.pitch, 0)
+        d.tap_off[i] = tap_off[i]
+    assert out.dtype == torch.float32
+    d.out = out.data_ptr()
+    d.s_row, d.s_col = s_row, s_col
+    d.rows_valid, d.cols_valid = rows_valid, cols_valid
+    d.block_n = block_n or (128 if cols_valid > 64 else 64)
+    d.ksplit = ksplit
+    d.nsplit = nsplit
+    return d
+
+
+def wgrad_plan(desc: SnWgradDesc, keep: Sequence = ()) -> Plan:
+    h = C.c_void_p()
+    check(_lib.load().sn_wgrad_plan_create(C.byref(desc), C.byref(h)))
+    return Plan(h.value, keep)
+
+
+# ---------------------------------------------------------------------------------------------
+# packing
+# ---------------------------------------------------------------------------------------------
+def pack_planes(src: torch.Tensor, dst: Planes, *, nhwc: bool = False) -> None:
+    """src: fp32 NCHW contiguous [n,c,h,w] (or NHWC [n,h,w,pitch] with nhwc=True, first dst.c channels)."""
+    assert src.dtype == torch.float32
+    if nhwc:
+        n, h, w, sp = src.shape
+        assert src.stride(3) == 1 and src.stride(2) == sp
+        c = dst.c
+        check(_lib.load().sn_pack_planes(src.data_ptr(), LAYOUT_NHWC, sp, n, c, h, w, dst.hi_ptr, dst.lo_ptr,
+                                         dst.pitch, 0, _stream()))
+    else:
+        assert src.is_contiguous()
+        n, c, h, w = src.shape
+        assert c <= dst.c
+        check(_lib.load().sn_pack_planes(src.data_ptr(), LAYOUT_NCHW, 0, n, c, h, w, dst.hi_ptr, dst.lo_ptr,
+                                         dst.pitch, 0, _stream()))
+    assert (n, h, w) == (dst.n, dst.h, dst.w)
+
+
+def pack_weights(weight: torch.Tensor, kind: str, dgrad: bool, k_pad: int, dst: PackedWeights) -> None:
+    assert weight.is_contiguous() and weight.dtype == torch.float32
+    if kind == "convT4s2":
+        cin, cout = weight.shape[0], weight.shape[1]
+    else:
+        cout, cin = weight.shape[0], weight.shape[1]
+    s_row, s_k, rows, k_real = L.pack_strides(kind, cin, cout, dgrad)
+    t = L.ntaps(kind)
+    assert dst.rows >= rows and dst.k_total == t * k_pad and k_pad >= k_real
+    check(_lib.load().sn_pack_weights(weight.data_ptr(), s_row, s_k, rows, t, k_real, k_pad, dst.hi.data_ptr(),
+                                      dst.lo.data_ptr(), _stream()))
+
+
+def pack_head_weights(weight: torch.Tensor, rows_pad: int, k_pad: int, dgrad: bool, dst: PackedWeights) -> None:
+    cout, cin = weight.shape[:2]
+    assert dst.hi.numel() >= (cin * 25 * k_pad if dgrad else rows_pad * 25 * k_pad)
+    check(_lib.load().sn_pack_head_weights(weight.data_ptr(), cout, cin, rows_pad, k_pad, int(dgrad),
+                                           dst.hi.data_ptr(), dst.lo.data_ptr(), _stream()))
+
+
+def fold_head_wgrad(geff: torch.Tensor, cout: int, cin: int, dw: torch.Tensor) -> None:
+    check(_lib.load().sn_fold_head_wgrad(geff.data_ptr(), cout, cin, dw.data_ptr(), _stream()))
+
+
+# ---------------------------------------------------------------------------------------------
+# InstanceNorm / activation blocks
+# ---------------------------------------------------------------------------------------------
+def plane_stats(y: torch.Tensor, c: int, stats: torch.Tensor, eps: float = IN_EPS) -> None:
+    """y fp32 NHWC [n,h,w,pitch]; stats float64 [n, c, 2] <- (mean, rstd)."""
+    n, h, w, pitch = y.shape
+    assert stats.dtype == torch.float64 and stats.numel() >= n * c * 2
+    check(_lib.load().sn_plane_stats(y.data_ptr(), pitch, n, h * w, c, eps, stats.data_ptr(), _stream()))
+
+
+def norm_act_fwd(y: torch.Tensor, c: int, stats: Optional[torch.Tensor], act: int, slope: float = 0.2,
+                 drop_p: float = 0.0, drop_seed: int = 0, residual: Optional[torch.Tensor] = None,
+                 out: Optional[Planes] = None, reflect_pad: bool = False,
+                 out_f32: Optional[torch.Tensor] = None) -> None:
+    n, h, w, pitch = y.shape
+    d = SnNormActDesc()
+    d.y, d.y_pitch = y.data_ptr(), pitch
+    d.n, d.h, d.w, d.c = n, h, w, c
+    d.stats = _ptr(stats)
+    d.act, d.slope = act, slope
+    d.drop_p, d.drop_seed = drop_p, drop_seed
+    if residual is not None:
+        d.residual, d.res_pitch = residual.data_ptr(), residual.shape[3]
+    if out is not None:
+        if reflect_pad:
+            assert (out.h, out.w) == (h + 2, w + 2)
+        else:
+            assert (out.h, out.w) == (h, w)
+        assert out.c >= c and out.n == n
+        d.out_hi, d.out_lo, d.out_pitch, d.out_coff = out.hi.data_ptr(), out.lo.data_ptr(), out.pitch, out.c_off
+        d.out_reflect_pad = int(reflect_pad)
+    if out_f32 is not None:
+        d.out_f32, d.f32_pitch = out_f32.data_ptr(), out_f32.shape[3]
+    check(_lib.load().sn_norm_act_fwd(C.byref(d), _stream()))
+
+
+@dataclass
+class GradSrc:
+    t: torch.Tensor          # fp32 NHWC [n, h(+2), w(+2), pitch]
+    c_off: int = 0
+    reflect_padded: bool = False
+
+
+def _fill_srcs(arr, srcs: Sequence[GradSrc]) -> None:
+    assert 1 <= len(srcs) <= _lib.SN_MAX_SRC
+    for i, s in enumerate(srcs):
+        assert s.t.dtype == torch.float32 and (s.t.shape[3] == 1 or s.t.stride(3) == 1)
+        arr[i].ptr = s.t.data_ptr()
+        arr[i].pitch = s.t.shape[3]
+        arr[i].c_off = s.c_off
+        arr[i].reflect_padded = int(s.reflect_padded)
+
+
+def norm_act_bwd(srcs: Sequence[GradSrc], y: torch.Tensor, c: int, stats: Optional[torch.Tensor], act: int,
+                 dy: Planes, gstats: Optional[torch.Tensor] = None, slope: float = 0.2, drop_p: float = 0.0,
+                 drop_seed: int = 0) -> None:
+    n, h, w, pitch = y.shape
+    d = SnNormActBwdDesc()
+    _fill_srcs(d.src, srcs)
+    d.nsrc = len(srcs)
+    d.y, d.y_pitch = y.data_ptr(), pitch
+    d.n, d.h, d.w, d.c = n, h, w, c
+    d.stats = _ptr(stats)
+    d.act, d.slope = act, slope
+    d.drop_p, d.drop_seed = drop_p, drop_seed
+    d.gstats = _ptr(gstats)
+    assert (dy.n, dy.h, dy.w) == (n, h, w) and dy.c >= c
+    d.dy_hi, d.dy_lo, d.dy_pitch, d.dy_coff = dy.hi.data_ptr(), dy.lo.data_ptr(), dy.pitch, dy.c_off
+    check(_lib.load().sn_norm_act_bwd(C.byref(d), _stream()))
+
+
+def bias_grad(dy: Planes, c: int, scratch: torch.Tensor, db: torch.Tensor) -> None:
+    assert scratch.dtype == torch.float64 and scratch.numel() >= c and db.dtype == torch.float32
+    check(_lib.load().sn_bias_grad(dy.hi.data_ptr(), dy.lo.data_ptr(), dy.pitch, dy.c_off, dy.n * dy.h * dy.w, c,
+                                   scratch.data_ptr(), db.data_ptr(), _stream()))
+
+
+def sum_grads(srcs: Sequence[GradSrc], n: int, h: int, w: int, c: int, dst: torch.Tensor) -> None:
+    arr = (SnGradSrc * _lib.SN_MAX_SRC)()
+    _fill_srcs(arr, srcs)
+    check(_lib.load().sn_sum_grads(arr, len(srcs), n, h, w, c, dst.data_ptr(), dst.shape[3], _stream()))
+
+
+def tanh_bwd(srcs: Sequence[GradSrc], out: torch.Tensor, c: int, dy: Planes) -> None:
+    n, h, w, pitch = out.shape
+    arr = (SnGradSrc * _lib.SN_MAX_SRC)()
+    _fill_srcs(arr, srcs)
+    check(_lib.load().sn_tanh_bwd(arr, len(srcs), out.data_ptr(), pitch, n, h, w, c, dy.hi.data_ptr(),
+                                  dy.lo.data_ptr(), dy.pitch, dy.c_off, _stream()))
+
+
+def dropout_mask(seed: int, p: float, count: int, device) -> torch.Tensor:
+    out = torch.empty(count, dtype=torch.uint8, device=device)
+    check(_lib.load().sn_dropout_mask(seed, p, count, out.data_ptr(), _stream()))
+    return out
+
+
+# ---------------------------------------------------------------------------------------------
+# losses
+# ---------------------------------------------------------------------------------------------
+def ce_loss_fwd_bwd(logits: torch.Tensor, c: int, target_nchw: torch.Tensor, weight: float,
+                    loss_acc: torch.Tensor, grad: torch.Tensor) -> None:
+    n, h, w, pitch = logits.shape
+    assert target_nchw.is_contiguous() and target_nchw.shape == (n, c, h, w)
+    check(_lib.load().sn_ce_loss_fwd_bwd(logits.data_ptr(), pitch, target_nchw.data_ptr(), n, h, w, c, weight,
+                                         loss_acc.data_ptr(), grad.data_ptr(), grad.shape[3], _stream()))
+
+
+def bce_logits_fwd_bwd(pred: torch.Tensor, halves: int, t0: float, t1: float, gscale: float,
+                       loss_acc: torch.Tensor, dpred: Optional[torch.Tensor]) -> None:
+    count = pred.numel() // halves
+    check(_lib.load().sn_bce_logits_fwd_bwd(pred.data_ptr(), count, halves, t0, t1, gscale, loss_acc.data_ptr(),
+                                            _ptr(dpred), _stream()))
+
+
+def l1_loss_fwd_bwd(a: torch.Tensor, c: int, b_nchw: torch.Tensor, weight: float, loss_acc: torch.Tensor,
+                    grad: torch.Tensor) -> None:
+    n, h, w, pitch = a.shape
+    check(_lib.load().sn_l1_loss_fwd_bwd(a.data_ptr(), pitch, b_nchw.data_ptr(), n, h, w, c, weight,
+                                         loss_acc.data_ptr(), grad.data_ptr(), grad.shape[3], _stream()))
+
+
+def roi_align_pack(tex_nchw: torch.Tensor, rois: torch.Tensor, pool: int, out_f32: Optional[torch.Tensor],
+                   out_planes: Optional[Planes]) -> None:
+    b, ch, h, w = tex_nchw.shape
+    nroi = rois.shape[1]
+    assert rois.shape == (b, nroi, 4) and rois.is_contiguous() and tex_nchw.is_contiguous()
+    check(_lib.load().sn_roi_align_pack_fwd(
+        tex_nchw.data_ptr(), b, ch, h, w, rois.data_ptr(), nroi, pool, _ptr(out_f32),
+        0 if out_f32 is None else out_f32.shape[3],
+        None if out_planes is None else out_planes.hi.data_ptr(),
+        None if out_planes is None else out_planes.lo.data_ptr(),
+        0 if out_planes is None else out_planes.pitch, 0 if out_planes is None else out_planes.c_off, _stream()))
+
+
+def launch_count() -> int:
+    return int(_lib.load().sn_launch_count())

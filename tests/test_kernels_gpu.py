@@ -1,0 +1,323 @@
+"""GPU parity of every CUDA kernel behind the C ABI, one op at a time, against fp64 torch
+restatements of the reference ops (and the numpy ROI oracle).
+
+Tolerances: split-bf16 x3 tensor-core products are fp32-faithful -> 1e-4 of the output scale
+(the north-star bar is 1e-3 relative fp32); single-pass bf16 is reported at 3e-2.
+"""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+from oracle import roi_align as R  # noqa: E402
+from swapnet_b200 import lowering as L  # noqa: E402
+
+
+def dev():
+    return torch.device("cuda:0")
+
+
+def relmax(a, b):
+    return ((a.double() - b.double()).abs().max() / b.double().abs().max().clamp_min(1e-30)).item()
+
+
+def ref_forward(kind, x, w, b=None):
+    if kind == "conv4s2":
+        return F.conv2d(x, w, b, 2, 1)
+    if kind == "convT4s2":
+        return F.conv_transpose2d(x, w, b, 2, 1)
+    if kind == "conv3r":
+        return F.conv2d(F.pad(x, (1, 1, 1, 1), mode="reflect"), w, b)
+    if kind == "conv4s1":
+        return F.conv2d(x, w, b, 1, 1)
+    if kind == "head":
+        return F.conv2d(F.pad(F.interpolate(x, scale_factor=2), (1, 0, 1, 0)), w, b, 1, 1)
+    raise ValueError(kind)
+
+
+def nhwc(x):
+    return x.permute(0, 2, 3, 1).contiguous()
+
+
+# (kind, n, cin, cout, h, w) — shapes chosen to hit: multi M-tile, multi N-tile, partial tiles
+# (63/62 PatchGAN planes), tiny planes (nb > 1), padded channels (3/19/22 -> 64), block_n 16/32/64/128
+CONV_CASES = [
+    ("conv4s2", 2, 3, 64, 32, 32),
+    ("conv4s2", 2, 64, 128, 32, 64),
+    ("conv4s2", 3, 128, 192, 16, 16),
+    ("conv4s2", 5, 64, 64, 4, 4),
+    ("conv4s2", 2, 22, 64, 64, 64),
+    ("convT4s2", 2, 128, 64, 8, 8),
+    ("convT4s2", 2, 192, 128, 16, 32),
+    ("convT4s2", 3, 64, 3, 16, 16),
+    ("conv3r", 2, 128, 128, 32, 32),
+    ("conv3r", 1, 64, 192, 16, 16),
+    ("conv4s1", 2, 128, 256, 64, 64),
+    ("conv4s1", 2, 64, 1, 63, 63),
+    ("conv4s1", 1, 64, 64, 8, 8),
+    ("head", 2, 192, 19, 32, 32),
+    ("head", 1, 64, 19, 16, 48),
+]
+
+
+def make_layer(kind, n, cin, cout, h, w, nsplit, with_bias=True):
+    from swapnet_b200 import ops
+    from swapnet_b200.layers import ConvLayer
+
+    g = torch.Generator().manual_seed(1234 + n * 7 + cin + cout + h)
+    x = torch.randn(n, cin, h, w, generator=g)
+    k = 3 if kind == "conv3r" else 4
+    wshape = (cin, cout, k, k) if kind == "convT4s2" else (cout, cin, k, k)
+    wt = torch.randn(*wshape, generator=g) * (1.0 / (cin * k * k) ** 0.5)
+    bias = torch.randn(cout, generator=g) if with_bias else None
+    cp = L.pad64(cin)
+    if kind == "conv3r":
+        xp = F.pad(x, (1, 1, 1, 1), mode="reflect")
+        planes = ops.Planes(n, h + 2, w + 2, cp + 64, dev(), c=cp, c_off=64)  # inside a wider buffer
+        ops.pack_planes(xp.to(dev()), planes)
+    else:
+        planes = ops.Planes(n, h, w, cp + 64, dev(), c=cp, c_off=0)
+        ops.pack_planes(x.to(dev()), planes)
+    wd = wt.to(dev()).contiguous()
+    bd = None if bias is None else bias.to(dev())
+    layer = ConvLayer(kind, wd, bd, planes, nsplit=nsplit, name=f"{kind}-{cin}-{cout}")
+    return layer, x, wt, bias
+
+
+@pytest.mark.parametrize("nsplit", [3, 1])
+@pytest.mark.parametrize("kind,n,cin,cout,h,w", CONV_CASES)
+def test_conv_forward(kind, n, cin, cout, h, w, nsplit):
+    from swapnet_b200 import ops
+
+    layer, x, wt, bias = make_layer(kind, n, cin, cout, h, w, nsplit)
+    oh, ow = L.out_hw(kind, h, w)
+    y = torch.full((n, oh, ow, cout + 5), 7.0, device=dev())  # sentinel in the pad channels
+    layer.bind_forward(y, y_c_off=2)
+    layer.pack()
+    layer.forward()
+    torch.cuda.synchronize()
+    ref = nhwc(ref_forward(kind, x.double(), wt.double(), bias.double()))
+    got = y[..., 2:2 + cout].cpu()
+    err = relmax(got, ref)
+    tol = 1e-4 if nsplit == 3 else 3e-2
+    assert err < tol, f"{kind} fwd nsplit={nsplit}: relmax {err:.3e}"
+    assert torch.all(y[..., :2] == 7.0) and torch.all(y[..., 2 + cout:] == 7.0), "wrote outside its channel slice"
+    if nsplit == 3:  # SIMT cross-check of the same descriptors (same split operands)
+        y2 = torch.zeros_like(y)
+        for spec in L.forward_specs(kind, h, w):
+            kw = {}
+            if kind == "head":
+                p = spec.w_phase
+                nt = L.head_neff(p >> 1) * L.head_neff(p & 1)
+                kw = dict(w_elem_off=layer.rows_pad * layer.k_pad * L.HEAD_PHASE_OFF[p], w_rows=layer.rows_pad,
+                          w_k=nt * layer.k_pad)
+            d = ops.tap_gemm_desc(layer.x, spec, layer.wp, layer.k_pad, y2, cout, bias=layer.bias, nsplit=3,
+                                  block_n=layer.block_n, out_c_off=2, **kw)
+            ops.tap_gemm_simt(d)
+        torch.cuda.synchronize()
+        assert relmax(y2[..., 2:2 + cout].cpu(), ref) < 1e-4
+
+
+@pytest.mark.parametrize("kind,n,cin,cout,h,w", CONV_CASES)
+def test_conv_backward(kind, n, cin, cout, h, w):
+    from swapnet_b200 import ops
+
+    layer, x, wt, bias = make_layer(kind, n, cin, cout, h, w, 3)
+    oh, ow = L.out_hw(kind, h, w)
+    xr = x.double().requires_grad_()
+    wr = wt.double().requires_grad_()
+    br = bias.double().requires_grad_()
+    yr = ref_forward(kind, xr, wr, br)
+    g = torch.Generator().manual_seed(99)
+    gy = torch.randn(yr.shape, generator=g)
+    if kind == "conv3r":  # compare against the gradient w.r.t. the PADDED input
+        xp = F.pad(x.double(), (1, 1, 1, 1), mode="reflect").requires_grad_()
+        gx = torch.autograd.grad(F.conv2d(xp, wt.double()), xp, gy.double())[0]
+        gw, gb = torch.autograd.grad(yr, (wr, br), gy.double())
+    else:
+        gx, gw, gb = torch.autograd.grad(yr, (xr, wr, br), gy.double())
+    dy = ops.Planes(n, oh, ow, L.pad64(cout), dev())
+    ops.pack_planes(gy.to(dev()), dy)
+    ih, iw = (h + 2, w + 2) if kind == "conv3r" else (h, w)
+    dx = torch.full((n, ih, iw, cin + 3), 5.0, device=dev())
+    wg = torch.zeros_like(layer.weight)
+    bg = torch.zeros(cout, device=dev())
+    layer.bind_backward(dy, dx, wg, bg, dx_c_off=1)
+    layer.pack()
+    layer.backward()
+    torch.cuda.synchronize()
+    e_dx = relmax(dx[..., 1:1 + cin].cpu(), nhwc(gx))
+    e_w = relmax(wg.cpu(), gw)
+    e_b = relmax(bg.cpu(), gb)
+    assert e_dx < 1e-4, f"{kind} dgrad relmax {e_dx:.3e}"
+    assert e_w < 1e-4, f"{kind} wgrad relmax {e_w:.3e}"
+    assert e_b < 1e-4, f"{kind} bias grad relmax {e_b:.3e}"
+    assert torch.all(dx[..., 0] == 5.0) and torch.all(dx[..., 1 + cin:] == 5.0)
+
+
+def test_pack_planes_roundtrip():
+    from swapnet_b200 import ops
+
+    x = torch.randn(2, 19, 24, 40)
+    p = ops.Planes(2, 24, 40, 128, dev(), c=64, c_off=64)
+    ops.pack_planes(x.to(dev()), p)
+    torch.cuda.synchronize()
+    got = p.dense().cpu()
+    assert relmax(got[..., :19], nhwc(x)) < 2e-5
+    assert torch.all(got[..., 19:] == 0) and torch.all(p.hi[..., :64] == 0)
+    # hi is exactly bf16(x)
+    assert torch.equal(p.hi[..., 64:64 + 19].cpu(), nhwc(x).to(torch.bfloat16))
+    y = torch.randn(2, 24, 40, 32)
+    q = ops.Planes(2, 24, 40, 64, dev(), c=24, c_off=8)
+    ops.pack_planes(y.to(dev()), q, nhwc=True)
+    torch.cuda.synchronize()
+    assert relmax(q.dense().cpu(), y[..., :24]) < 2e-5
+
+
+@pytest.mark.parametrize("c,h,w", [(64, 32, 32), (19, 16, 8), (256, 8, 8), (1, 62, 62), (1024, 4, 4)])
+def test_instance_norm_block_fwd_bwd(c, h, w):
+    """stats + IN-apply + LeakyReLU + dropout, forward and backward, vs torch autograd (fp64)."""
+    from swapnet_b200 import ops
+
+    n = 3
+    g = torch.Generator().manual_seed(5)
+    y = torch.randn(n, c, h, w, generator=g) * 2.0 + 0.5
+    seed, p = 77, 0.5
+    mask = ops.dropout_mask(seed, p, n * h * w * c, dev()).cpu().view(n, h, w, c).permute(0, 3, 1, 2).double()
+    assert 0.4 < mask.mean().item() < 0.6 or mask.numel() < 2000
+    yr = y.double().requires_grad_()
+    a_ref = F.leaky_relu(F.instance_norm(yr, eps=1e-5), 0.2) * mask * 2.0
+    ga = torch.randn(a_ref.shape, generator=g).double()
+    (gy_ref,) = torch.autograd.grad(a_ref, yr, ga)
+
+    yd = nhwc(y).to(dev())
+    stats = torch.zeros(n, c, 2, dtype=torch.float64, device=dev())
+    ops.plane_stats(yd, c, stats)
+    out = ops.Planes(n, h, w, L.pad64(c) + 64, dev(), c=L.pad64(c), c_off=64)
+    f32 = torch.zeros(n, h, w, c, device=dev())
+    ops.norm_act_fwd(yd, c, stats, ops.ACT_LRELU, 0.2, p, seed, out=out, out_f32=f32)
+    torch.cuda.synchronize()
+    mean_ref = y.double().mean((2, 3))
+    assert relmax(stats[..., 0].cpu(), mean_ref) < 1e-6
+    assert relmax(f32.cpu(), nhwc(a_ref.detach())) < 1e-5
+    assert relmax(out.dense().cpu()[..., :c], nhwc(a_ref.detach())) < 3e-5
+
+    gad = nhwc(ga.float()).to(dev())
+    half = (gad * 0.25).contiguous()
+    dy = ops.Planes(n, h, w, L.pad64(c), dev())
+    gst = torch.zeros(n, c, 2, dtype=torch.float64, device=dev())
+    # two sources that sum to ga (exercises the multi-source gather)
+    ops.norm_act_bwd([ops.GradSrc(half), ops.GradSrc((gad - half).contiguous())], yd, c, stats, ops.ACT_LRELU, dy,
+                     gst, 0.2, p, seed)
+    torch.cuda.synchronize()
+    assert relmax(dy.dense().cpu()[..., :c], nhwc(gy_ref)) < 1e-4
+
+
+def test_residual_tail_and_reflect_pad():
+    """ResidualBlock tail: out = x + IN(y2), written as reflect-padded planes + fp32 stream."""
+    from swapnet_b200 import ops
+
+    n, c, h, w = 2, 64, 8, 8
+    y = torch.randn(n, c, h, w)
+    xres = torch.randn(n, c, h, w)
+    ref = xres.double() + F.instance_norm(y.double(), eps=1e-5)
+    yd, xd = nhwc(y).to(dev()), nhwc(xres).to(dev())
+    stats = torch.zeros(n, c, 2, dtype=torch.float64, device=dev())
+    ops.plane_stats(yd, c, stats)
+    pl = ops.Planes(n, h + 2, w + 2, 64, dev())
+    f32 = torch.zeros(n, h, w, c, device=dev())
+    ops.norm_act_fwd(yd, c, stats, ops.ACT_NONE, residual=xd, out=pl, reflect_pad=True, out_f32=f32)
+    torch.cuda.synchronize()
+    assert relmax(f32.cpu(), nhwc(ref)) < 1e-5
+    pad_ref = nhwc(F.pad(ref, (1, 1, 1, 1), mode="reflect"))
+    assert relmax(pl.dense().cpu(), pad_ref) < 3e-5
+    # adjoint: reflect-padded gradient source folds back onto the interior
+    gp = torch.randn(n, c, h + 2, w + 2)
+    xin = torch.randn(n, c, h, w).double().requires_grad_()
+    (gref,) = torch.autograd.grad(F.pad(xin, (1, 1, 1, 1), mode="reflect"), xin, gp.double())
+    dst = torch.zeros(n, h, w, c, device=dev())
+    ops.sum_grads([ops.GradSrc(nhwc(gp).to(dev()), 0, True)], n, h, w, c, dst)
+    torch.cuda.synchronize()
+    assert relmax(dst.cpu(), nhwc(gref)) < 1e-6
+
+
+def test_tanh_bwd():
+    from swapnet_b200 import ops
+
+    n, c, h, w = 2, 19, 16, 16
+    z = torch.randn(n, h, w, c).double().requires_grad_()
+    out = torch.tanh(z)
+    g1, g2 = torch.randn(n, h, w, 24), torch.randn(n, h, w, c)
+    (ref,) = torch.autograd.grad(out, z, g1[..., 3:3 + c].double() + g2.double())
+    dy = ops.Planes(n, h, w, 64, dev())
+    ops.tanh_bwd([ops.GradSrc(g1.to(dev()), 3), ops.GradSrc(g2.to(dev()))], out.detach().float().to(dev()), c, dy)
+    torch.cuda.synchronize()
+    assert relmax(dy.dense().cpu()[..., :c], ref) < 1e-4
+
+
+def test_losses():
+    from swapnet_b200 import ops
+
+    n, c, h, w = 2, 19, 32, 32
+    g = torch.Generator().manual_seed(3)
+    logits = torch.tanh(torch.randn(n, c, h, w, generator=g))
+    lab = torch.randint(0, c, (n, h, w), generator=g)
+    tgt = torch.zeros(n, c, h, w)
+    for k in range(1, c):
+        tgt[:, k] = (lab == k).float()  # label 0 -> all-zero vector (argmax tie -> index 0)
+    lr = logits.double().requires_grad_()
+    loss_ref = F.cross_entropy(lr, tgt.argmax(1)) * 100
+    (g_ref,) = torch.autograd.grad(loss_ref, lr)
+    acc = torch.zeros(1, dtype=torch.float64, device=dev())
+    grad = torch.zeros(n, h, w, c, device=dev())
+    ops.ce_loss_fwd_bwd(nhwc(logits).to(dev()), c, tgt.to(dev()), 100.0, acc, grad)
+    torch.cuda.synchronize()
+    assert abs(acc.item() - loss_ref.item()) / loss_ref.item() < 1e-6
+    assert relmax(grad.cpu(), nhwc(g_ref)) < 1e-5
+
+    pred = torch.randn(2 * 4, 1, 30, 30, generator=g) * 3
+    pr = pred.double().requires_grad_()
+    lf = F.binary_cross_entropy_with_logits(pr[:4], torch.full_like(pr[:4], 0.83))
+    lr_ = F.binary_cross_entropy_with_logits(pr[4:], torch.full_like(pr[4:], 1.02))
+    (gp,) = torch.autograd.grad(0.5 * (lf + lr_), pr)
+    acc2 = torch.zeros(2, dtype=torch.float64, device=dev())
+    dp = torch.zeros_like(pred, device=dev())
+    ops.bce_logits_fwd_bwd(pred.to(dev()), 2, 0.83, 1.02, 0.5, acc2, dp)
+    torch.cuda.synchronize()
+    assert abs(acc2[0].item() - lf.item()) < 1e-6 and abs(acc2[1].item() - lr_.item()) < 1e-6
+    assert relmax(dp.cpu(), gp) < 1e-5
+
+    a = torch.randn(n, 3, h, w, generator=g)
+    b = torch.randn(n, 3, h, w, generator=g)
+    ar = a.double().requires_grad_()
+    l1 = F.l1_loss(ar, b.double()) * 10
+    (ga,) = torch.autograd.grad(l1, ar)
+    acc3 = torch.zeros(1, dtype=torch.float64, device=dev())
+    g3 = torch.zeros(n, h, w, 3, device=dev())
+    ops.l1_loss_fwd_bwd(nhwc(a).to(dev()), 3, b.to(dev()), 10.0, acc3, g3)
+    torch.cuda.synchronize()
+    assert abs(acc3.item() - l1.item()) / l1.item() < 1e-6
+    assert relmax(g3.cpu(), nhwc(ga)) < 1e-6
+
+
+def test_roi_align_pack_bit_exact():
+    """ROI bookkeeping must be bit-exact: values equal the numpy oracle bit for bit."""
+    from swapnet_b200 import ops
+
+    S, B = 256, 3
+    base = np.concatenate([R.NOTEBOOK_ROIS_256, R.NOTEBOOK_EXTRA_256])
+    rois = np.stack([np.roll(base, b, axis=0)[:12] for b in range(B)]).astype(np.float32)
+    rois[2, 5] = [-30, -20, 40, 50]
+    rois[1, 3] = [S + 5, S + 7, S + 40, S + 50]
+    rois[0, 7] = [10.5, 20.25, 11.0, 20.5]
+    tex = torch.randn(B, 3, S, S, generator=torch.Generator().manual_seed(0))
+    ref = R.roi_align_pack(tex.numpy(), rois, 128)  # [B, 36, 128, 128]
+    out = torch.zeros(B, 128, 128, 40, device=dev())
+    planes = ops.Planes(B, 128, 128, 64, dev())
+    ops.roi_align_pack(tex.to(dev()), torch.from_numpy(rois).to(dev()), 128, out, planes)
+    torch.cuda.synchronize()
+    got = out[..., :36].permute(0, 3, 1, 2).cpu().numpy()
+    assert np.array_equal(got, ref), f"max abs diff {np.abs(got - ref).max()}"
+    assert relmax(planes.dense().cpu()[..., :36], torch.from_numpy(ref).permute(0, 2, 3, 1)) < 3e-5
