@@ -1,0 +1,297 @@
+"""Forward/backward engines of the SwapNet networks on the B200 library.
+
+An engine turns one parameter container (swapnet_b200.modules) into a static launch plan for a
+fixed (batch, size): every activation buffer, packed weight matrix and TMA-backed sn_plan is
+created once; a training step is then a fixed sequence of kernel launches with no allocation
+and no host synchronisation.
+
+Dataflow conventions
+  * activations that feed a conv live as split-bf16 NHWC `Planes`; the producer stage writes
+    straight into the channel slice of the consumer's concat buffer, so torch.cat
+    (swapnet_modules.py:131, layers.py:42,61, pix2pix_modules.py:262) never materialises;
+  * every stage keeps its raw conv output `y` (fp32 NHWC) + InstanceNorm statistics; the
+    normalise/activate/dropout step is one fused kernel forward and two backward;
+  * gradients w.r.t. activations are fp32 NHWC tensors; a stage's backward takes a list of
+    (tensor, channel offset) sources and sums them on the fly.
+
+Reference graphs: WarpModule.forward swapnet_modules.py:92-151; NLayerDiscriminator
+discriminators.py:111-136; TextureModule.forward swapnet_modules.py:231-260 + UnetGenerator
+pix2pix_modules.py:113-262.
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+from torch import nn
+
+from . import lowering as L
+from . import modules as M
+from . import ops
+from .layers import ConvLayer
+from .ops import ACT_LRELU, ACT_NONE, ACT_RELU, ACT_TANH, GradSrc, Planes
+
+
+def _mix_seed(step_seed: int, stage_id: int) -> int:
+    return (step_seed * 0x9E3779B1 + stage_id * 0x85EBCA77 + 0x165667B1) & 0xFFFFFFFFFFFF
+
+
+class Stage:
+    """conv -> [InstanceNorm] -> activation -> [dropout] (-> + residual), output written as operand
+    planes (and/or fp32).  `plain=True`: the conv output itself (after the epilogue activation) is
+    the stage output (head conv with tanh, PatchGAN logits)."""
+
+    def __init__(self, eng: "Engine", name: str, kind: str, conv: nn.Module, x: Planes, *,
+                 out: Optional[Planes] = None, norm: bool = False, act: int = ACT_NONE, slope: float = 0.2,
+                 drop_p: float = 0.0, reflect_out: bool = False, residual: Optional[torch.Tensor] = None,
+                 out_f32: Optional[torch.Tensor] = None, plain: bool = False, epi_act: int = ACT_NONE,
+                 need_dx: bool = True, y: Optional[torch.Tensor] = None):
+        self.eng, self.name, self.kind = eng, name, kind
+        self.id = len(eng.stages)
+        eng.stages.append(self)
+        dev = eng.device
+        self.layer = ConvLayer(kind, conv.weight.data, None if conv.bias is None else conv.bias.data, x,
+                               nsplit=eng.nsplit, act=epi_act, name=name)
+        self.conv = conv
+        ly = self.layer
+        self.n, self.oh, self.ow, self.cout = ly.n, ly.out_h, ly.out_w, ly.cout
+        self.y = y if y is not None else torch.zeros(self.n, self.oh, self.ow, self.cout, device=dev)
+        ly.bind_forward(self.y)
+        self.norm, self.act, self.slope, self.drop_p = norm, act, slope, drop_p
+        self.out, self.reflect_out, self.residual, self.out_f32 = out, reflect_out, residual, out_f32
+        self.plain, self.epi_act, self.need_dx = plain, epi_act, need_dx
+        self.stats = torch.zeros(self.n, self.cout, 2, dtype=torch.float64, device=dev) if norm else None
+        self.dy: Optional[Planes] = None
+        self.dx: Optional[torch.Tensor] = None
+        self.gstats = None
+
+    # ---- forward ----
+    def forward(self) -> None:
+        self.layer.forward()
+        if self.plain:
+            return
+        if self.norm:
+            ops.plane_stats(self.y, self.cout, self.stats)
+        p = self.drop_p if self.eng.training else 0.0
+        ops.norm_act_fwd(self.y, self.cout, self.stats, self.act, self.slope, p,
+                         _mix_seed(self.eng.seed, self.id), residual=self.residual, out=self.out,
+                         reflect_pad=self.reflect_out, out_f32=self.out_f32)
+
+    # ---- backward ----
+    def bind_backward(self, wgrad: bool = True) -> None:
+        dev = self.eng.device
+        ly = self.layer
+        self.dy = Planes(self.n, self.oh, self.ow, L.pad64(self.cout), dev)
+        if self.need_dx:
+            ih, iw = (ly.in_h + 2, ly.in_w + 2) if self.kind == "conv3r" else (ly.in_h, ly.in_w)
+            self.dx = torch.zeros(self.n, ih, iw, ly.cin, device=dev)
+        wg = self.conv.weight.grad if wgrad else None
+        bg = self.conv.bias.grad if (wgrad and self.conv.bias is not None) else None
+        ly.bind_backward(self.dy, self.dx, wg, bg)
+        if self.norm:
+            self.gstats = torch.zeros(self.n, self.cout, 2, dtype=torch.float64, device=dev)
+
+    def backward(self, srcs: Sequence[GradSrc], wgrad: bool = True) -> None:
+        if self.plain and self.epi_act == ACT_TANH:
+            ops.tanh_bwd(srcs, self.y, self.cout, self.dy)
+        else:
+            p = 0.0 if self.plain else (self.drop_p if self.eng.training else 0.0)
+            ops.norm_act_bwd(srcs, self.y, self.cout, None if self.plain else self.stats,
+                             ACT_NONE if self.plain else self.act, self.dy, self.gstats, self.slope, p,
+                             _mix_seed(self.eng.seed, self.id))
+        self.layer.backward(dgrad=self.need_dx, wgrad=wgrad)
+
+
+class Engine:
+    """Common plumbing: stage list, flat gradient buffer, packing."""
+
+    def __init__(self, net: nn.Module, device, nsplit: int):
+        self.net, self.device, self.nsplit = net, torch.device(device), nsplit
+        self.stages: List[Stage] = []
+        self.training = True
+        self.seed = 0
+        self.flat_grad: Optional[torch.Tensor] = None
+
+    def alloc_grads(self, share_with: Optional["Engine"] = None) -> None:
+        """One flat fp32 buffer for all parameter gradients (a single all-reduce under DP);
+        p.grad are views into it."""
+        if share_with is not None:
+            self.flat_grad = share_with.flat_grad
+            return
+        params = [p for p in self.net.parameters()]
+        total = sum(p.numel() for p in params)
+        self.flat_grad = torch.zeros(total, device=self.device)
+        off = 0
+        for p in params:
+            p.grad = self.flat_grad[off:off + p.numel()].view_as(p)
+            off += p.numel()
+
+    def zero_grad(self) -> None:
+        self.flat_grad.zero_()
+        # the optimizer may have dropped .grad (zero_grad(set_to_none=True)): re-attach the views
+        off = 0
+        for p in self.net.parameters():
+            if p.grad is None or p.grad.data_ptr() != self.flat_grad.data_ptr() + 4 * off:
+                p.grad = self.flat_grad[off:off + p.numel()].view_as(p)
+            off += p.numel()
+
+    def pack(self) -> None:
+        for s in self.stages:
+            s.layer.pack()
+
+    def bind_backward(self, wgrad: bool = True) -> None:
+        for s in self.stages:
+            s.bind_backward(wgrad=wgrad)
+
+
+# =============================================================================================
+# WarpModule
+# =============================================================================================
+class WarpEngine(Engine):
+    def __init__(self, net: M.WarpModule, batch: int, size: int, device, nsplit: int = 3):
+        super().__init__(net, device, nsplit)
+        assert size % 64 == 0 and size >= 64, "WarpModule needs H = W = 64k (cloth_down6 is H/64)"
+        B, S, dev = batch, size, self.device
+        self.batch, self.size = B, S
+        self.cb, self.cc = net.body_channels, net.cloth_channels
+        dp = net.dropout
+        self.in_body = Planes(B, S, S, 64, dev)
+        self.in_cloth = Planes(B, S, S, 64, dev)
+        cat3 = Planes(B, S // 2, S // 2, 192, dev)
+        cat2 = Planes(B, S // 4, S // 4, 384, dev)
+        cat1 = Planes(B, S // 8, S // 8, 768, dev)
+        h16 = S // 16
+        xpad = [Planes(B, h16 + 2, h16 + 2, 1024, dev) for _ in range(4)]   # reflect-padded resblock inputs
+        xf32 = [torch.zeros(B, h16, h16, 1024, device=dev) for _ in range(5)]  # fp32 residual stream
+        a_c4 = Planes(B, h16, h16, 512, dev)
+        a_c5 = Planes(B, S // 32, S // 32, 1024, dev)
+        a_c6 = Planes(B, S // 64, S // 64, 1024, dev)
+        a_u1 = Planes(B, S // 32, S // 32, 1024, dev)
+        x4 = Planes(B, h16, h16, 1024, dev)
+        self.cat3, self.cat2, self.cat1, self.xf32 = cat3, cat2, cat1, xf32
+        St = lambda *a, **k: Stage(self, *a, **k)  # noqa: E731
+        n = net
+        lre = dict(act=ACT_LRELU, slope=0.2)
+        self.b1 = St("body_down1", "conv4s2", n.body_down1.model[0], self.in_body, out=cat3.slice(64, 64), need_dx=False, **lre)
+        self.b2 = St("body_down2", "conv4s2", n.body_down2.model[0], cat3.slice(64, 64), out=cat2.slice(128, 128), norm=True, **lre)
+        self.b3 = St("body_down3", "conv4s2", n.body_down3.model[0], cat2.slice(128, 128), out=cat1.slice(256, 256), norm=True, **lre)
+        self.b4 = St("body_down4", "conv4s2", n.body_down4.model[0], cat1.slice(256, 256), out=xpad[0].slice(0, 512),
+                     reflect_out=True, out_f32=xf32[0][..., :512], norm=True, drop_p=dp, **lre)
+        self.c1 = St("cloth_down1", "conv4s2", n.cloth_down1.model[0], self.in_cloth, out=cat3.slice(128, 64), need_dx=False, **lre)
+        self.c2 = St("cloth_down2", "conv4s2", n.cloth_down2.model[0], cat3.slice(128, 64), out=cat2.slice(256, 128), norm=True, **lre)
+        self.c3 = St("cloth_down3", "conv4s2", n.cloth_down3.model[0], cat2.slice(256, 128), out=cat1.slice(512, 256), norm=True, **lre)
+        self.c4 = St("cloth_down4", "conv4s2", n.cloth_down4.model[0], cat1.slice(512, 256), out=a_c4, norm=True, **lre)
+        self.c5 = St("cloth_down5", "conv4s2", n.cloth_down5.model[0], a_c4, out=a_c5, norm=True, drop_p=dp, **lre)
+        self.c6 = St("cloth_down6", "conv4s2", n.cloth_down6.model[0], a_c5, out=a_c6, drop_p=dp, **lre)
+        self.u1 = St("cloth_up1", "convT4s2", n.cloth_up1.model[0], a_c6, out=a_u1, norm=True, act=ACT_RELU)
+        self.u2 = St("cloth_up2", "convT4s2", n.cloth_up2.model[0], a_u1, out=xpad[0].slice(512, 512), reflect_out=True,
+                     out_f32=xf32[0][..., 512:], norm=True, act=ACT_RELU)
+        self.res: List[Tuple[Stage, Stage]] = []
+        for k in range(4):
+            blk = n.resblocks[k].conv_block
+            p1 = Planes(B, h16 + 2, h16 + 2, 1024, dev)
+            r1 = St(f"resblocks.{k}.conv1", "conv3r", blk[1], xpad[k], out=p1, reflect_out=True, norm=True, act=ACT_RELU,
+                    drop_p=dp)
+            last = k == 3
+            r2 = St(f"resblocks.{k}.conv2", "conv3r", blk[6], p1, out=x4 if last else xpad[k + 1], reflect_out=not last,
+                    norm=True, act=ACT_NONE, residual=xf32[k], out_f32=xf32[k + 1])
+            self.res.append((r1, r2))
+        self.d1 = St("dual_up1", "convT4s2", n.dual_up1.model[0], x4, out=cat1.slice(0, 256), norm=True, act=ACT_RELU)
+        self.d2 = St("dual_up2", "convT4s2", n.dual_up2.model[0], cat1, out=cat2.slice(0, 128), norm=True, act=ACT_RELU)
+        self.d3 = St("dual_up3", "convT4s2", n.dual_up3.model[0], cat2, out=cat3.slice(0, 64), norm=True, act=ACT_RELU)
+        self.fakes = torch.zeros(B, S, S, self.cc, device=dev)   # NHWC; fakes.permute(0,3,1,2) is the NCHW view
+        self.head = St("upsample_and_pad", "head", n.upsample_and_pad[2], cat3, plain=True, epi_act=ACT_TANH, y=self.fakes)
+        self._fwd_order = [self.b1, self.b2, self.b3, self.b4, self.c1, self.c2, self.c3, self.c4, self.c5, self.c6,
+                           self.u1, self.u2] + [s for pair in self.res for s in pair] + [self.d1, self.d2, self.d3, self.head]
+        self._dres: List[torch.Tensor] = []
+
+    def forward(self, body: torch.Tensor, cloth: torch.Tensor, training: bool = True, seed: int = 0) -> torch.Tensor:
+        """body [B,cb,S,S], cloth [B,cc,S,S] fp32 NCHW on device -> fakes [B,S,S,cc] (NHWC storage)."""
+        self.training, self.seed = training, seed
+        ops.pack_planes(body, self.in_body)
+        ops.pack_planes(cloth, self.in_cloth)
+        for s in self._fwd_order:
+            s.forward()
+        return self.fakes
+
+    def bind_backward(self, wgrad: bool = True) -> None:
+        super().bind_backward(wgrad)
+        h16 = self.size // 16
+        self._dres = [torch.zeros(self.batch, h16, h16, 1024, device=self.device) for _ in range(4)]
+
+    def backward(self, srcs: Sequence[GradSrc]) -> None:
+        """srcs: gradient(s) w.r.t. fakes (NHWC fp32).  Accumulates parameter grads into flat_grad."""
+        B, h16 = self.batch, self.size // 16
+        self.head.backward(srcs)
+        g3 = self.head.dx                                     # d cat3 [.,192]
+        self.d3.backward([GradSrc(g3, 0)])
+        g2 = self.d3.dx                                       # d cat2 [.,384]
+        self.d2.backward([GradSrc(g2, 0)])
+        g1 = self.d2.dx                                       # d cat1 [.,768]
+        self.d1.backward([GradSrc(g1, 0)])
+        gx = self.d1.dx                                       # d x4 [.,1024]
+        for k in (3, 2, 1, 0):
+            r1, r2 = self.res[k]
+            r2.backward([GradSrc(gx)])                        # IN(y2) branch; identity branch handled below
+            r1.backward([GradSrc(r2.dx, 0, True)])
+            ops.sum_grads([GradSrc(gx), GradSrc(r1.dx, 0, True)], B, h16, h16, 1024, self._dres[k])
+            gx = self._dres[k]
+        self.u2.backward([GradSrc(gx, 512)])
+        self.u1.backward([GradSrc(self.u2.dx)])
+        self.c6.backward([GradSrc(self.u1.dx)])
+        self.c5.backward([GradSrc(self.c6.dx)])
+        self.c4.backward([GradSrc(self.c5.dx)])
+        self.c3.backward([GradSrc(self.c4.dx), GradSrc(g1, 512)])
+        self.c2.backward([GradSrc(self.c3.dx), GradSrc(g2, 256)])
+        self.c1.backward([GradSrc(self.c2.dx), GradSrc(g3, 128)])
+        self.b4.backward([GradSrc(gx, 0)])
+        self.b3.backward([GradSrc(self.b4.dx), GradSrc(g1, 256)])
+        self.b2.backward([GradSrc(self.b3.dx), GradSrc(g2, 128)])
+        self.b1.backward([GradSrc(self.b2.dx), GradSrc(g3, 64)])
+
+
+# =============================================================================================
+# PatchGAN
+# =============================================================================================
+class PatchGANEngine(Engine):
+    """NLayerDiscriminator on a [batch, S, S, pad64(input_nc)] operand (`self.din`)."""
+
+    def __init__(self, net: M.NLayerDiscriminator, batch: int, size: int, device, nsplit: int = 3,
+                 din: Optional[Planes] = None, input_grad: bool = False):
+        super().__init__(net, device, nsplit)
+        B, S, dev = batch, size, self.device
+        self.batch, self.size = B, S
+        self.din = din if din is not None else Planes(B, S, S, L.pad64(net.input_nc), dev)
+        assert (self.din.n, self.din.h, self.din.w) == (B, S, S)
+        convs = net.convs()
+        use_norm = net.norm == "instance"
+        x = self.din
+        self.chain: List[Stage] = []
+        h = S
+        for i, conv in enumerate(convs[:-1]):
+            kind = "conv4s2" if conv.stride[0] == 2 else "conv4s1"
+            oh = h // 2 if kind == "conv4s2" else h - 1
+            out = Planes(B, oh, oh, L.pad64(conv.out_channels), dev)
+            st = Stage(self, f"model.{net.conv_index[i]}", kind, conv, x, out=out, norm=use_norm and i > 0,
+                       act=ACT_LRELU, slope=0.2, need_dx=(i > 0) or input_grad)
+            self.chain.append(st)
+            x, h = out, oh
+        self.last = Stage(self, f"model.{net.conv_index[-1]}", "conv4s1", convs[-1], x, plain=True)
+        self.pred = self.last.y                                # [B, S/8-2, S/8-2, 1]
+
+    def forward(self) -> torch.Tensor:
+        for s in self.chain:
+            s.forward()
+        self.last.forward()
+        return self.pred
+
+    def backward(self, dpred: torch.Tensor, wgrad: bool = True) -> None:
+        self.last.backward([GradSrc(dpred)], wgrad=wgrad)
+        g = self.last.dx
+        for s in reversed(self.chain):
+            s.backward([GradSrc(g)], wgrad=wgrad)
+            g = s.dx
+
+    @property
+    def dx_in(self) -> torch.Tensor:
+        return self.chain[0].dx

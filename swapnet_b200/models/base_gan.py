@@ -1,0 +1,230 @@
+"""GAN training-step framework on the B200 engines.
+
+Keeps the option surface and step order of /root/reference/models/base_gan.py:16-231:
+    forward -> zero/backward/step D -> zero/backward/step G        (base_gan.py:194-203)
+with G = a generator engine, D = the conditional PatchGAN (define_D 'basic' / 'n_layers',
+discriminators.py:45-88), GANLoss = vanilla BCE-with-logits with the reference's smooth labels
+(loss.py:65-122, including the "fake target drawn from the real range" quirk, loss.py:102) and
+torch.optim.AdamW exactly as optimizers/__init__.py:37-60 builds it.
+
+What runs differently from the eager reference (results unchanged):
+  * D's fake and real passes of the D step run as ONE batch of 2B (InstanceNorm is per sample,
+    so this is exact) with per-half targets;
+  * D's weight gradients are not computed in the G step (the reference computes and discards
+    them);
+  * losses stay on the device until get_current_losses() is called.
+Unsupported option values raise (there is no eager fallback): --gan_mode other than vanilla,
+--gan_label_mode hard (crashes in the reference too), --discriminator pixel, --norm batch,
+--optimizer AdaBound.
+"""
+from __future__ import annotations
+
+from abc import ABC, abstractmethod
+from argparse import ArgumentParser
+from typing import Optional
+
+import torch
+
+from .. import engine as E
+from .. import modules as M
+from .. import ops
+from .base_model import BaseModel, LazyLoss
+
+
+def adam_modifier(parser: ArgumentParser, *_):
+    """optimizers/__init__.py:25-28 (contributed by the options code when the reference's
+    `optimizers` package is importable; provided here for standalone use)."""
+    parser.add_argument("--b1", type=float, default=0.9, help="Adam b1")
+    parser.add_argument("--b2", type=float, default=0.999, help="Adam b2")
+    return parser
+
+
+def define_optimizer(parameters, opt, net: str) -> torch.optim.Optimizer:
+    """optimizers/__init__.py:37-60 for the AdamW choice."""
+    if net not in ("D", "G"):
+        raise ValueError(f"net arg must be 'D' or 'G', received {net}")
+    choice = getattr(opt, "optimizer_" + net)
+    if choice != "AdamW":
+        raise NotImplementedError(f"optimizer {choice}: only AdamW is available on the B200 plugin")
+    lr = opt.d_lr if net == "D" else opt.lr
+    wd = opt.d_weight_decay if net == "D" else opt.weight_decay
+    return torch.optim.AdamW(parameters, lr=lr, weight_decay=wd, betas=(opt.b1, opt.b2))
+
+
+class BaseGAN(BaseModel, ABC):
+    @staticmethod
+    def modify_commandline_options(parser: ArgumentParser, is_train):
+        """Same flags, defaults and aliases as base_gan.py:16-128, plus the engine precision switch."""
+        if is_train:
+            parser.add_argument("--gan_mode", default="vanilla", help="gan regularization to use",
+                                choices=("vanilla", "wgan", "wgan-gp", "lsgan", "dragan-gp", "dragan-lp",
+                                         "mescheder-r1-gp", "mescheder-r2-gp"))
+            parser.add_argument("--lambda_gan", type=float, default=1.0, help="weight for adversarial loss")
+            parser.add_argument("--lambda_discriminator", type=float, default=1.0, help="weight for discriminator loss")
+            parser.add_argument("--lambda_gp", type=float, default=10, help="weight parameter for gradient penalty")
+            parser.add_argument("--discriminator", default="basic", choices=("basic", "pixel", "n_layers"),
+                                help="what discriminator type to use")
+            parser.add_argument("--n_layers_D", type=int, default=3, help="only used if discriminator==n_layers")
+            parser.add_argument("--norm", type=str, default="instance",
+                                help="instance normalization or batch normalization [instance | batch | none]")
+            parser.add_argument("--optimizer_G", "--opt_G", "--optim_G", default="AdamW", choices=("AdamW", "AdaBound"),
+                                help="optimizer for generator")
+            parser.add_argument("--lr", "--g_lr", "--learning_rate", type=float, default=0.0001,
+                                help="initial learning rate for generator")
+            parser.add_argument("--beta1", type=float, default=0.5, help="momentum term of adam")
+            parser.add_argument("--optimizer_D", "--opt_D", "--optim_D", default="AdamW", choices=("AdamW", "AdaBound"),
+                                help="optimizer for discriminator")
+            parser.add_argument("--d_lr", type=float, default=0.0004, help="initial learning rate for Discriminator")
+            parser.add_argument("--d_wt_decay", "--d_weight_decay", dest="d_weight_decay", default=0.01, type=float,
+                                help="optimizer L2 weight decay")
+            parser.add_argument("--gan_label_mode", default="smooth", choices=("hard", "smooth"),
+                                help="whether to use hard (real 1.0 and fake 0.0) or smooth "
+                                     "(real [0.7, 1.1] and fake [0., 0.3]) values for labels")
+        parser.add_argument("--b200_precision", default="fp32x3", choices=("fp32x3", "bf16"),
+                            help="tensor-core arithmetic of the B200 engines: fp32x3 = split-bf16 3-pass "
+                                 "(fp32-faithful, parity mode); bf16 = single pass (fast, ~1e-2 relative)")
+        return parser
+
+    def __init__(self, opt):
+        super().__init__(opt)
+        self.nsplit = 1 if getattr(opt, "b200_precision", "fp32x3") == "bf16" else 3
+        self.net_generator = self.define_G().to(self.device)
+        M.init_weights(self.net_generator, opt.init_type, opt.init_gain)
+        self.model_names = ["generator"]
+        self._eng_G = None          # built lazily for the (batch, size) of the first input
+        self._eng_key = None
+        self._eng_Dd = self._eng_Dg = None
+        self._step = 0
+        self._seed_base = int(getattr(opt, "b200_seed", 0))
+        self._world = torch.distributed.get_world_size() if torch.distributed.is_available() and \
+            torch.distributed.is_initialized() else 1
+        # smooth-label draws: the CPU default generator like the reference (loss.py:74-77); under DP a
+        # dedicated, identically seeded generator so that every rank sees the same label (SURVEY §8e i)
+        self._label_gen = torch.Generator().manual_seed(1234) if self._world > 1 else None
+        if self.is_train:
+            if opt.gan_mode != "vanilla":
+                raise NotImplementedError(f"--gan_mode {opt.gan_mode}: only vanilla runs on the B200 engines")
+            if opt.gan_label_mode != "smooth":
+                raise NotImplementedError("--gan_label_mode hard crashes in the reference (loss.py:92,101) and is "
+                                          "not provided")
+            if opt.discriminator == "pixel":
+                raise NotImplementedError("--discriminator pixel is not provided on the B200 engines")
+            n_layers = 3 if opt.discriminator == "basic" else opt.n_layers_D
+            self.net_discriminator = M.NLayerDiscriminator(self.get_D_inchannels(), 64, n_layers, opt.norm).to(self.device)
+            M.init_weights(self.net_discriminator, opt.init_type, opt.init_gain)
+            self.model_names.append("discriminator")
+            if opt.lambda_discriminator:
+                self.loss_names = ["D", "D_real", "D_fake"]
+            self.loss_names += ["G"]
+            if opt.lambda_gan:
+                self.loss_names += ["G_gan"]
+            self.optimizer_G = define_optimizer(self.net_generator.parameters(), opt, "G")
+            self.optimizer_D = define_optimizer(self.net_discriminator.parameters(), opt, "D")
+            self.optimizer_names = ("G", "D")
+            self._acc = torch.zeros(8, dtype=torch.float64, device=self.device)  # device-side loss sums
+            lam = float(opt.lambda_gan)
+            self.loss_D_fake = LazyLoss(lambda: self._acc[0].item())
+            self.loss_D_real = LazyLoss(lambda: self._acc[1].item())
+            self.loss_D = LazyLoss(lambda: 0.5 * (self._acc[0].item() + self._acc[1].item()))
+            self.loss_G_gan = LazyLoss(lambda: lam * self._acc[2].item())
+            if self._world > 1:
+                for p in list(self.net_generator.parameters()) + list(self.net_discriminator.parameters()):
+                    torch.distributed.broadcast(p.data, 0)
+
+    # ---- to be provided by the plugin ----
+    @abstractmethod
+    def get_D_inchannels(self):
+        ...
+
+    @abstractmethod
+    def define_G(self):
+        ...
+
+    @abstractmethod
+    def build_generator_engine(self, batch: int, size: int):
+        ...
+
+    @abstractmethod
+    def backward_G(self):
+        ...
+
+    # ---- engines ----
+    def ensure_engines(self, batch: int, size: int) -> None:
+        key = (batch, size)
+        if self._eng_key == key:
+            return
+        self._eng_key = key
+        self._eng_G = self.build_generator_engine(batch, size)
+        if self.is_train:
+            self._eng_G.alloc_grads()
+            self._eng_G.bind_backward()
+        self._eng_Dd = self._eng_Dg = None
+        if self.is_train and hasattr(self, "net_discriminator"):
+            dn = self.net_discriminator
+            self._eng_Dd = E.PatchGANEngine(dn, 2 * batch, size, self.device, self.nsplit)
+            self._eng_Dd.alloc_grads()
+            self._eng_Dd.bind_backward()
+            self._eng_Dg = E.PatchGANEngine(dn, batch, size, self.device, self.nsplit,
+                                            din=self._eng_Dd.din.batch_slice(0, batch), input_grad=True)
+            self._eng_Dg.alloc_grads(share_with=self._eng_Dd)
+            self._eng_Dg.bind_backward(wgrad=False)
+            p = self._eng_Dd.pred
+            self._dpred_d = torch.zeros_like(p)
+            self._dpred_g = torch.zeros_like(self._eng_Dg.pred)
+
+    def step_seed(self) -> int:
+        return (self._seed_base * 1000003 + self._step) & 0xFFFFFFFF
+
+    def draw_label(self) -> float:
+        """One smooth-label scalar exactly as GANLoss.get_target_tensor computes it (loss.py:65-107):
+        fp32 `rand(1) * (1.1 - 0.7) + 0.7`, for real AND fake targets."""
+        low, high = torch.tensor((0.7, 1.1))
+        r = torch.rand(1, generator=self._label_gen) if self._label_gen is not None else torch.rand(1)
+        return float(r * (high - low) + low)
+
+    def allreduce_grads(self, eng) -> None:
+        if self._world > 1:
+            torch.distributed.all_reduce(eng.flat_grad, op=torch.distributed.ReduceOp.SUM)
+            eng.flat_grad.mul_(1.0 / self._world)
+
+    # ---- discriminator phases (conditioning supplied by the plugin through pack_D_inputs) ----
+    @abstractmethod
+    def pack_D_inputs(self, din_fake: ops.Planes, din_real: Optional[ops.Planes]) -> None:
+        """Write the conditioned fake (and real) discriminator inputs into the operand planes."""
+
+    def backward_D(self):
+        """D(fake.detach()) and D(real) as one 2B batch; loss_D = 0.5 * (fake + real)
+        (warp_model.py:109-139, texture_model.py:127-155)."""
+        B = self._eng_key[0]
+        d = self._eng_Dd
+        d.training = self.training
+        d.pack()
+        self.pack_D_inputs(d.din.batch_slice(0, B), d.din.batch_slice(B, B))
+        pred = d.forward()
+        t_fake, t_real = self.draw_label(), self.draw_label()   # order: D_fake, D_real (loss.py:117,121)
+        ops.bce_logits_fwd_bwd(pred, 2, t_fake, t_real, 0.5, self._acc[0:2], self._dpred_d)
+        d.backward(self._dpred_d)
+        self.allreduce_grads(d)
+
+    def gan_backward_through_D(self) -> torch.Tensor:
+        """G phase: D(fake) with the updated D, BCE against a 'real' label, gradient back to the
+        discriminator input.  Returns d(loss_G_gan)/d(din) [B,S,S,pad64(cin)] (fp32 NHWC)."""
+        g = self._eng_Dg
+        g.training = self.training
+        g.pack()
+        pred = g.forward()
+        t = self.draw_label()
+        ops.bce_logits_fwd_bwd(pred, 1, t, t, float(self.opt.lambda_gan), self._acc[2:3], self._dpred_g)
+        g.backward(self._dpred_g, wgrad=False)
+        return g.dx_in
+
+    def optimize_parameters(self):
+        self._acc.zero_()
+        self.forward()
+        self._eng_Dd.zero_grad()
+        self.backward_D()
+        self.optimizer_D.step()
+        self._eng_G.zero_grad()
+        self.backward_G()
+        self.optimizer_G.step()
+        self._step += 1

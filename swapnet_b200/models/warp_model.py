@@ -1,0 +1,119 @@
+"""Warp-stage plugin (`--model warp`) on the B200 engines.
+
+Same options, attributes and step semantics as /root/reference/models/warp_model.py:14-183:
+generator = WarpModule(body 3ch, cloth 19ch), conditional PatchGAN on cat(body, cloth) (22 ch),
+loss_G = lambda_ce * CE(fakes, argmax(targets)) + lambda_gan * GAN (or CE only with
+--warp_mode ce).
+"""
+from __future__ import annotations
+
+from argparse import ArgumentParser
+
+import torch
+
+from .. import engine as E
+from .. import modules as M
+from .. import ops
+from ..ops import GradSrc
+from .base_gan import BaseGAN
+from .base_model import LazyLoss
+
+
+class WarpModel(BaseGAN):
+    @staticmethod
+    def modify_commandline_options(parser: ArgumentParser, is_train):
+        if is_train:
+            parser.add_argument("--warp_mode", default="gan", choices=("gan", "ce"))
+            parser.add_argument("--lambda_ce", type=float, default=100,
+                                help="weight for cross entropy loss in final term")
+            parser.set_defaults(display_ncols=4)
+        return super(WarpModel, WarpModel).modify_commandline_options(parser, is_train)
+
+    def __init__(self, opt):
+        self.body_channels = opt.body_channels if opt.body_representation == "labels" else 3
+        self.cloth_channels = opt.cloth_channels if opt.cloth_representation == "labels" else 3
+        BaseGAN.__init__(self, opt)
+        self.visual_names = ["inputs_decoded", "bodys_unnormalized", "fakes_decoded"]
+        if self.is_train:
+            self.visual_names.append("targets_decoded")
+            self.loss_G_ce = LazyLoss(lambda: self._acc[3].item())
+            if opt.warp_mode != "gan":
+                self.model_names = ["generator"]
+                self.loss_names = "G"   # (sic) warp_model.py:71 — a str; get_current_losses iterates its chars
+                del self.net_discriminator
+                del self.optimizer_D
+                self.optimizer_names = ["G"]
+                self.loss_G = self.loss_G_ce
+            else:
+                self.loss_names += ["G_ce"]
+                lam = float(opt.lambda_gan)
+                self.loss_G = LazyLoss(lambda: lam * self._acc[2].item() + self._acc[3].item())
+
+    # ---- visuals: off the hot path; reuse the reference's helpers when they are importable ----
+    def compute_visuals(self):
+        from datasets.data_utils import unnormalize
+        from util.decode_labels import decode_cloth_labels
+
+        self.inputs_decoded = decode_cloth_labels(self.inputs)
+        self.bodys_unnormalized = unnormalize(self.bodys, *self.opt.body_norm_stats)
+        self.targets_decoded = decode_cloth_labels(self.targets)
+        self.fakes_decoded = decode_cloth_labels(self.fakes)
+
+    def define_G(self):
+        return M.WarpModule(body_channels=self.body_channels, cloth_channels=self.cloth_channels)
+
+    def get_D_inchannels(self):
+        return self.cloth_channels + self.body_channels
+
+    def build_generator_engine(self, batch, size):
+        return E.WarpEngine(self.net_generator, batch, size, self.device, self.nsplit)
+
+    def set_input(self, input):
+        f32 = dict(device=self.device, dtype=torch.float32, non_blocking=True)
+        self.bodys = input["bodys"].to(**f32).contiguous()
+        self.inputs = input["input_cloths"].to(**f32).contiguous()
+        self.targets = input["target_cloths"].to(**f32).contiguous()
+        self.image_paths = tuple(zip(input["cloth_paths"], input["body_paths"]))
+
+    def forward(self):
+        B, _, S, S2 = self.bodys.shape
+        assert S == S2, "square inputs expected"
+        self.ensure_engines(B, S)
+        g = self._eng_G
+        g.pack()
+        out = g.forward(self.bodys, self.inputs, training=self.training and self.is_train, seed=self.step_seed())
+        self.fakes = out.permute(0, 3, 1, 2)   # [B,19,S,S] view of the NHWC storage
+
+    def pack_D_inputs(self, din_fake, din_real):
+        """conditioned = cat((bodys, cloth), 1): body first (warp_model.py:115,119,157)."""
+        cb, cc = self.body_channels, self.cloth_channels
+        ops.pack_planes(self.bodys, din_fake.slice(0, cb))
+        ops.pack_planes(self._eng_G.fakes, din_fake.slice(cb, cc), nhwc=True)
+        if din_real is not None:
+            ops.pack_planes(self.bodys, din_real.slice(0, cb))
+            ops.pack_planes(self.targets, din_real.slice(cb, cc))
+
+    def backward_G(self):
+        g = self._eng_G
+        B, S = self._eng_key
+        if not hasattr(self, "_dce") or self._dce.shape[0] != B or self._dce.shape[1] != S:
+            self._dce = torch.zeros(B, S, S, self.cloth_channels, device=self.device)
+        ops.ce_loss_fwd_bwd(g.fakes, self.cloth_channels, self.targets, float(self.opt.lambda_ce), self._acc[3:4],
+                            self._dce)
+        srcs = [GradSrc(self._dce)]
+        if self.opt.warp_mode == "gan":
+            dx = self.gan_backward_through_D()
+            srcs.append(GradSrc(dx, self.body_channels))
+        g.backward(srcs)
+        self.allreduce_grads(g)
+
+    def optimize_parameters(self):
+        if self.opt.warp_mode == "gan":
+            super().optimize_parameters()
+        else:
+            self._acc.zero_()
+            self.forward()
+            self._eng_G.zero_grad()
+            self.backward_G()
+            self.optimizer_G.step()
+            self._step += 1

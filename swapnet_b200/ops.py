@@ -36,7 +36,7 @@ class Planes:
 
     def __init__(self, n: int, h: int, w: int, pitch: int, device, c: Optional[int] = None, c_off: int = 0,
                  hi: Optional[torch.Tensor] = None, lo: Optional[torch.Tensor] = None):
-        assert pitch % 8 == 0 and c_off % 8 == 0
+        assert pitch % 8 == 0
         self.n, self.h, self.w, self.pitch = n, h, w, pitch
         self.c = pitch if c is None else c
         self.c_off = c_off
@@ -106,7 +106,7 @@ def tap_gemm_desc(a: Planes, spec: L.GemmSpec, w: PackedWeights, k_per_tap: int,
     """out: fp32 NHWC tensor [n, OH, OW, pitch_out]; rows (h, w) land on pixel
     (h*mul_h + off_h, w*mul_w + off_w)."""
     assert (a.h, a.w) == tuple(spec.a_hw), f"operand is {a.h}x{a.w}, spec wants {spec.a_hw}"
-    assert k_per_tap % 64 == 0 and k_per_tap <= a.c
+    assert k_per_tap % 64 == 0 and k_per_tap <= a.c and a.c_off % 8 == 0
     d = SnTapGemmDesc()
     d.a_hi, d.a_lo = a.hi_ptr, a.lo_ptr
     d.a_n, d.a_h, d.a_w, d.a_c, d.a_pitch = a.n, a.h, a.w, a.c, a.pitch
@@ -152,6 +152,7 @@ def wgrad_desc(x: Planes, y: Planes, spec: L.WgradSpec, out: torch.Tensor, s_row
         x, y, xt, yt, xp, yp = y, x, yt, xt, yp, xp
         s_row, s_col = s_col, s_row
         rows_valid, cols_valid = cols_valid, rows_valid
+    assert x.c_off % 8 == 0 and y.c_off % 8 == 0
     d = SnWgradDesc()
     d.x_hi, d.x_lo = x.hi_ptr, x.lo_ptr
     d.x_n, d.x_h, d.x_w, d.x_c, d.x_pitch, d.x_parity = x.n, x.h, x.w, x.c, x.pitch, int(xp)
@@ -227,9 +228,27 @@ def fold_head_wgrad(geff: torch.Tensor, cout: int, cin: int, dw: torch.Tensor) -
 # ---------------------------------------------------------------------------------------------
 # InstanceNorm / activation blocks
 # ---------------------------------------------------------------------------------------------
+def _pitch(t: torch.Tensor) -> int:
+    """pixel pitch (elements) of an NHWC fp32 tensor or channel-slice view of one"""
+    assert t.dim() == 4 and (t.shape[3] == 1 or t.stride(3) == 1)
+    n, h, w, c = t.shape
+    if w > 1:
+        p = t.stride(2)
+    elif h > 1:
+        p = t.stride(1)
+    elif n > 1:
+        p = t.stride(0)
+    else:
+        p = c
+    assert t.stride(1) == w * p or h == 1, "not an NHWC-contiguous pixel grid"
+    assert t.stride(0) == h * w * p or n == 1, "not an NHWC-contiguous pixel grid"
+    return p
+
+
 def plane_stats(y: torch.Tensor, c: int, stats: torch.Tensor, eps: float = IN_EPS) -> None:
     """y fp32 NHWC [n,h,w,pitch]; stats float64 [n, c, 2] <- (mean, rstd)."""
-    n, h, w, pitch = y.shape
+    n, h, w, _ = y.shape
+    pitch = _pitch(y)
     assert stats.dtype == torch.float64 and stats.numel() >= n * c * 2
     check(_lib.load().sn_plane_stats(y.data_ptr(), pitch, n, h * w, c, eps, stats.data_ptr(), _stream()))
 
@@ -238,7 +257,8 @@ def norm_act_fwd(y: torch.Tensor, c: int, stats: Optional[torch.Tensor], act: in
                  drop_p: float = 0.0, drop_seed: int = 0, residual: Optional[torch.Tensor] = None,
                  out: Optional[Planes] = None, reflect_pad: bool = False,
                  out_f32: Optional[torch.Tensor] = None) -> None:
-    n, h, w, pitch = y.shape
+    n, h, w, _ = y.shape
+    pitch = _pitch(y)
     d = SnNormActDesc()
     d.y, d.y_pitch = y.data_ptr(), pitch
     d.n, d.h, d.w, d.c = n, h, w, c
@@ -246,7 +266,7 @@ def norm_act_fwd(y: torch.Tensor, c: int, stats: Optional[torch.Tensor], act: in
     d.act, d.slope = act, slope
     d.drop_p, d.drop_seed = drop_p, drop_seed
     if residual is not None:
-        d.residual, d.res_pitch = residual.data_ptr(), residual.shape[3]
+        d.residual, d.res_pitch = residual.data_ptr(), _pitch(residual)
     if out is not None:
         if reflect_pad:
             assert (out.h, out.w) == (h + 2, w + 2)
@@ -256,7 +276,7 @@ def norm_act_fwd(y: torch.Tensor, c: int, stats: Optional[torch.Tensor], act: in
         d.out_hi, d.out_lo, d.out_pitch, d.out_coff = out.hi.data_ptr(), out.lo.data_ptr(), out.pitch, out.c_off
         d.out_reflect_pad = int(reflect_pad)
     if out_f32 is not None:
-        d.out_f32, d.f32_pitch = out_f32.data_ptr(), out_f32.shape[3]
+        d.out_f32, d.f32_pitch = out_f32.data_ptr(), _pitch(out_f32)
     check(_lib.load().sn_norm_act_fwd(C.byref(d), _stream()))
 
 
@@ -272,7 +292,7 @@ def _fill_srcs(arr, srcs: Sequence[GradSrc]) -> None:
     for i, s in enumerate(srcs):
         assert s.t.dtype == torch.float32 and (s.t.shape[3] == 1 or s.t.stride(3) == 1)
         arr[i].ptr = s.t.data_ptr()
-        arr[i].pitch = s.t.shape[3]
+        arr[i].pitch = _pitch(s.t)
         arr[i].c_off = s.c_off
         arr[i].reflect_padded = int(s.reflect_padded)
 
@@ -280,7 +300,8 @@ def _fill_srcs(arr, srcs: Sequence[GradSrc]) -> None:
 def norm_act_bwd(srcs: Sequence[GradSrc], y: torch.Tensor, c: int, stats: Optional[torch.Tensor], act: int,
                  dy: Planes, gstats: Optional[torch.Tensor] = None, slope: float = 0.2, drop_p: float = 0.0,
                  drop_seed: int = 0) -> None:
-    n, h, w, pitch = y.shape
+    n, h, w, _ = y.shape
+    pitch = _pitch(y)
     d = SnNormActBwdDesc()
     _fill_srcs(d.src, srcs)
     d.nsrc = len(srcs)
@@ -304,11 +325,12 @@ def bias_grad(dy: Planes, c: int, scratch: torch.Tensor, db: torch.Tensor) -> No
 def sum_grads(srcs: Sequence[GradSrc], n: int, h: int, w: int, c: int, dst: torch.Tensor) -> None:
     arr = (SnGradSrc * _lib.SN_MAX_SRC)()
     _fill_srcs(arr, srcs)
-    check(_lib.load().sn_sum_grads(arr, len(srcs), n, h, w, c, dst.data_ptr(), dst.shape[3], _stream()))
+    check(_lib.load().sn_sum_grads(arr, len(srcs), n, h, w, c, dst.data_ptr(), _pitch(dst), _stream()))
 
 
 def tanh_bwd(srcs: Sequence[GradSrc], out: torch.Tensor, c: int, dy: Planes) -> None:
-    n, h, w, pitch = out.shape
+    n, h, w, _ = out.shape
+    pitch = _pitch(out)
     arr = (SnGradSrc * _lib.SN_MAX_SRC)()
     _fill_srcs(arr, srcs)
     check(_lib.load().sn_tanh_bwd(arr, len(srcs), out.data_ptr(), pitch, n, h, w, c, dy.hi.data_ptr(),
