@@ -1,0 +1,73 @@
+"""Stage-by-stage comparison of the engines against the CPU oracle (fp64): conv outputs y,
+dL/dy, dL/d(input) — prints relmax per stage.  Diagnostic; run on the GPU box."""
+import sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
+import torch
+import torch.nn.functional as F
+from oracle import nets as ON
+from swapnet_b200 import engine as E, ops
+from test_engine_gpu import make_nets, synth_warp_batch, relmax
+
+dev = torch.device("cuda:0")
+B, S = 2, int(sys.argv[1]) if len(sys.argv) > 1 else 64
+G, D = make_nets()
+sdG = {k: v.clone().double().requires_grad_() for k, v in G.state_dict().items()}
+sdD = {k: v.clone().double().requires_grad_() for k, v in D.state_dict().items()}
+body, inp, tgt = synth_warp_batch(B, S)
+G.to(dev); D.to(dev)
+nhwc = lambda t: t.permute(0, 2, 3, 1)
+
+# ---------------- generator ----------------
+eng = E.WarpEngine(G, B, S, dev); eng.alloc_grads(); eng.bind_backward(); eng.pack()
+fakes = eng.forward(body.to(dev), inp.to(dev), training=False)
+rec = {}
+ON.record_into(rec)
+ref = ON.warp_forward(sdG, body.double(), inp.double())
+ON.record_into(None)
+gout = torch.randn(ref.shape, generator=torch.Generator().manual_seed(5)).double() * 1e-3
+ref.backward(gout)
+eng.zero_grad()
+eng.backward([ops.GradSrc(nhwc(gout).float().contiguous().to(dev))])
+torch.cuda.synchronize()
+print(f"== WarpEngine S={S}: fakes relmax {relmax(fakes.cpu(), nhwc(ref.detach())):.2e}")
+for st in eng.stages:
+    key = st.name + ".y"
+    r = rec[key]
+    line = f"{st.name:28s} y {relmax(st.y.cpu(), nhwc(r.detach())):.2e}"
+    if st.plain:
+        pass
+    else:
+        line += f"  dy {relmax(st.dy.dense().cpu()[..., :st.cout], nhwc(r.grad)):.2e}"
+    wkey = [k for k in sdG if k.startswith(st.name.replace('.conv1', '.conv_block.1').replace('.conv2', '.conv_block.6')) and k.endswith("weight")]
+    if wkey:
+        line += f"  wgrad {relmax(st.conv.weight.grad.cpu(), sdG[wkey[0]].grad):.2e}"
+    print(line)
+
+# ---------------- discriminator ----------------
+x = torch.cat((body, ref.detach().float()), 1)
+Dd = E.PatchGANEngine(D, B, S, dev, input_grad=True); Dd.alloc_grads(); Dd.bind_backward(); Dd.pack()
+ops.pack_planes(x.to(dev), Dd.din.slice(0, 22))
+pred = Dd.forward()
+rec = {}
+ON.record_into(rec)
+xr = x.double().requires_grad_()
+pr = ON.patchgan_forward(sdD, xr)
+ON.record_into(None)
+gp = torch.randn(pr.shape, generator=torch.Generator().manual_seed(6)).double() * 1e-3
+pr.backward(gp)
+Dd.zero_grad()
+Dd.backward(nhwc(gp).float().contiguous().to(dev))
+torch.cuda.synchronize()
+print(f"== PatchGAN: pred relmax {relmax(pred.cpu(), nhwc(pr.detach())):.2e}  dx_in {relmax(Dd.dx_in.cpu()[..., :22], nhwc(xr.grad)):.2e}")
+for st in Dd.stages:
+    r = rec[st.name + ".y"]
+    line = f"{st.name:28s} y {relmax(st.y.cpu(), nhwc(r.detach())):.2e}"
+    line += f"  dy {relmax(st.dy.dense().cpu()[..., :st.cout], nhwc(r.grad)):.2e}"
+    line += f"  wgrad {relmax(st.conv.weight.grad.cpu(), sdD[st.name + '.weight'].grad):.2e}"
+    if st.conv.bias is not None:
+        bref = sdD[st.name + '.bias'].grad
+        line += f"  bgrad abs {float((st.conv.bias.grad.cpu().double() - bref).abs().max()):.2e} (ref max {float(bref.abs().max()):.2e})"
+    if st.dx is not None and not st.plain:
+        pass
+    print(line)
