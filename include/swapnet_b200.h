@@ -19,9 +19,9 @@
  *   - activations are NHWC ("channels-last") fp32 with an explicit pixel pitch (elements per
  *     pixel in memory >= channels) so that a tensor can live inside a channel slice of a
  *     wider concat buffer;
- *   - a GEMM operand is a "split plane pair": two bf16 NHWC tensors hi = bf16(v),
- *     lo = bf16(v - hi) (fp32 carried as 2 x bf16; products are evaluated as
- *     hi*hi + lo*hi + hi*lo on the tcgen05 tensor cores with fp32 accumulation).
+ *   - a GEMM operand is a "split plane pair": two 16-bit-float NHWC tensors hi = r16(v),
+ *     lo = r16(v - hi) in format SN_FMT_F16 or SN_FMT_BF16 (fp32 carried as 2 x 16 bit; products are
+ *     evaluated as hi*hi + lo*hi + hi*lo on the tcgen05 tensor cores with fp32 accumulation).
  */
 #ifndef SWAPNET_B200_H
 #define SWAPNET_B200_H
@@ -37,6 +37,10 @@ extern "C" {
 
 enum { SN_ACT_NONE = 0, SN_ACT_TANH = 1, SN_ACT_LRELU = 2, SN_ACT_RELU = 3 };
 enum { SN_LAYOUT_NCHW = 0, SN_LAYOUT_NHWC = 1 };
+/* 16-bit float format of a split plane pair: bf16 (8+8 mantissa bits, fp32 range: gradients) or
+ * fp16 (11+11 bits: activations, pre-scaled weights).  The two may meet in one MMA. */
+#define SN_FMT_BF16 0
+#define SN_FMT_F16 1
 
 const char* sn_version(void);
 const char* sn_last_error(void);
@@ -59,8 +63,13 @@ typedef struct sn_tap_gemm_desc {
   const void* a_hi; const void* a_lo;   /* split planes, logical [a_n, a_h, a_w, a_c], pitch a_pitch */
   int a_n, a_h, a_w, a_c, a_pitch;
   int a_parity;                          /* 1: address through the 2x2 parity view (stride-2) */
-  const void* b_hi; const void* b_lo;   /* packed weights [b_rows][b_k] bf16, K contiguous */
+  int a_fmt;                             /* SN_FMT_* of the A planes */
+  const void* b_hi; const void* b_lo;   /* packed weights [b_rows][b_k] 16-bit, K contiguous */
   int b_rows; long long b_k;
+  int b_fmt;                             /* SN_FMT_* of the packed weights */
+  const float* b_scale;                  /* optional device float[2] = (s, 1/s) written by
+                                            sn_weight_scale: weights were packed as w*s, the
+                                            epilogue multiplies the accumulator by 1/s */
   int m_n, m_h, m_w;                     /* GEMM row grid */
   int ntaps; int k_per_tap;              /* k_per_tap % 64 == 0 */
   sn_tap taps[SN_MAX_TAPS];
@@ -78,8 +87,8 @@ typedef struct sn_tap_gemm_desc {
  * Lowers every weight gradient (atomic accumulation into a zeroed fp32 buffer, which can be the
  * torch-layout .grad tensor itself). */
 typedef struct sn_wgrad_desc {
-  const void* x_hi; const void* x_lo; int x_n, x_h, x_w, x_c, x_pitch, x_parity;
-  const void* y_hi; const void* y_lo; int y_n, y_h, y_w, y_c, y_pitch, y_parity;
+  const void* x_hi; const void* x_lo; int x_n, x_h, x_w, x_c, x_pitch, x_parity, x_fmt;
+  const void* y_hi; const void* y_lo; int y_n, y_h, y_w, y_c, y_pitch, y_parity, y_fmt;
   int m_n, m_h, m_w;                     /* pixel grid the reduction runs over */
   int ntaps;
   sn_tap xtaps[SN_MAX_TAPS];
@@ -106,12 +115,15 @@ void sn_plan_destroy(sn_plan* plan);
  * offset dst_coff of an NHWC plane pair with pitch dst_pitch.  Replaces the torch.cat /
  * .to(device) glue of warp_model.py:99-116 and swapnet_modules.py:258. */
 int sn_pack_planes(const float* src, int src_layout, int src_pitch, int n, int c, int h, int w,
-                   void* dst_hi, void* dst_lo, int dst_pitch, int dst_coff, void* stream);
+                   void* dst_hi, void* dst_lo, int dst_pitch, int dst_coff, int fmt, void* stream);
+
+/* exact power-of-two scale that brings max|w| into [2^13, 2^14): scale2 <- (s, 1/s). */
+int sn_weight_scale(const float* w, long long count, float* scale2, void* stream);
 
 /* weights -> packed [rows][taps][k_pad] split planes.  Source element (row r, tap t, k) is read
  * at src[r*s_row + k*s_k + t] (taps contiguous, as in torch OIHW / IOHW).  k >= k_real is zero. */
 int sn_pack_weights(const float* src, long long s_row, long long s_k, int rows, int taps, int k_real,
-                    int k_pad, void* dst_hi, void* dst_lo, void* stream);
+                    int k_pad, void* dst_hi, void* dst_lo, int fmt, const float* scale2, void* stream);
 
 /* head conv (swapnet_modules.py:85-90): nearest x2 upsample + ZeroPad2d((1,0,1,0)) + Conv2d(k4,p1)
  * folded into 4 output-parity phases with 2/3 effective taps per dim (25 taps in total).
@@ -119,7 +131,7 @@ int sn_pack_weights(const float* src, long long s_row, long long s_k, int rows, 
  *   dgrad pack: dst[row=ci][ (phase,teff) ][co (k_pad)]
  * src is torch OIHW [cout][cin][4][4]. */
 int sn_pack_head_weights(const float* src, int cout, int cin, int rows_pad, int k_pad, int dgrad,
-                         void* dst_hi, void* dst_lo, void* stream);
+                         void* dst_hi, void* dst_lo, int fmt, const float* scale2, void* stream);
 /* fold the 25 effective-tap gradients [cout][25][cin] back onto dW [cout][cin][4][4] (+=) */
 int sn_fold_head_wgrad(const float* geff, int cout, int cin, float* dw, void* stream);
 
@@ -139,6 +151,7 @@ typedef struct sn_norm_act_desc {
   float drop_p; unsigned long long drop_seed; /* drop_p == 0: no dropout */
   const float* residual; int res_pitch;  /* optional: out = residual + xhat (ResidualBlock tail) */
   void* out_hi; void* out_lo; int out_pitch, out_coff; /* optional split planes */
+  int out_fmt;
   int out_reflect_pad;                   /* 1: planes are [n, h+2, w+2] with ReflectionPad2d(1) */
   float* out_f32; int f32_pitch;         /* optional fp32 copy (residual stream) */
 } sn_norm_act_desc;
@@ -158,11 +171,12 @@ typedef struct sn_norm_act_bwd_desc {
   float drop_p; unsigned long long drop_seed;
   double* gstats;                        /* scratch [n][c][2] (needed when stats != NULL) */
   void* dy_hi; void* dy_lo; int dy_pitch, dy_coff; /* split planes of dL/dy */
+  int dy_fmt;
 } sn_norm_act_bwd_desc;
 int sn_norm_act_bwd(const sn_norm_act_bwd_desc* d, void* stream);
 
 /* bias gradient db[c] = sum over the npix pixels of dL/dy (split planes); scratch: double[c] */
-int sn_bias_grad(const void* dy_hi, const void* dy_lo, int pitch, int coff, long long npix, int c,
+int sn_bias_grad(const void* dy_hi, const void* dy_lo, int pitch, int coff, int fmt, long long npix, int c,
                  double* scratch, float* db, void* stream);
 
 /* dst[n,h,w,c] = sum_i src_i (fp32), e.g. the residual-stream gradient of a ResidualBlock */
@@ -171,7 +185,7 @@ int sn_sum_grads(const sn_grad_src* src, int nsrc, int n, int h, int w, int c, f
 
 /* dL/dy of a tanh output: (sum_i src_i) * (1 - out^2) -> split planes */
 int sn_tanh_bwd(const sn_grad_src* src, int nsrc, const float* out, int out_pitch, int n, int h,
-                int w, int c, void* dy_hi, void* dy_lo, int dy_pitch, int dy_coff, void* stream);
+                int w, int c, void* dy_hi, void* dy_lo, int dy_pitch, int dy_coff, int dy_fmt, void* stream);
 
 /* deterministic dropout keep-mask shared by forward, backward and the test oracle:
  * keep(seed, idx) with idx the linear NHWC element index; returns 0/1 bytes. */
@@ -200,7 +214,7 @@ int sn_l1_loss_fwd_bwd(const float* a, int pitch, const float* b_nchw, int n, in
  * ---------------------------------------------------------------------------------------- */
 int sn_roi_align_pack_fwd(const float* tex_nchw, int b, int ch, int h, int w, const float* rois,
                           int nroi, int pool, float* out_f32, int out_pitch, void* out_hi,
-                          void* out_lo, int plane_pitch, int plane_coff, void* stream);
+                          void* out_lo, int plane_pitch, int plane_coff, int plane_fmt, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * reference-free fp32 CUDA-core contraction with the tap-GEMM semantics (no tensor cores).

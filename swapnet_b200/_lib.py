@@ -15,6 +15,7 @@ SN_MAX_TAPS = 32
 SN_MAX_SRC = 3
 ACT_NONE, ACT_TANH, ACT_LRELU, ACT_RELU = 0, 1, 2, 3
 LAYOUT_NCHW, LAYOUT_NHWC = 0, 1
+FMT_BF16, FMT_F16 = 0, 1
 
 
 class SnTap(C.Structure):
@@ -25,9 +26,9 @@ class SnTapGemmDesc(C.Structure):
     _fields_ = [
         ("a_hi", C.c_void_p), ("a_lo", C.c_void_p),
         ("a_n", C.c_int), ("a_h", C.c_int), ("a_w", C.c_int), ("a_c", C.c_int), ("a_pitch", C.c_int),
-        ("a_parity", C.c_int),
+        ("a_parity", C.c_int), ("a_fmt", C.c_int),
         ("b_hi", C.c_void_p), ("b_lo", C.c_void_p),
-        ("b_rows", C.c_int), ("b_k", C.c_longlong),
+        ("b_rows", C.c_int), ("b_k", C.c_longlong), ("b_fmt", C.c_int), ("b_scale", C.c_void_p),
         ("m_n", C.c_int), ("m_h", C.c_int), ("m_w", C.c_int),
         ("ntaps", C.c_int), ("k_per_tap", C.c_int),
         ("taps", SnTap * SN_MAX_TAPS),
@@ -43,10 +44,10 @@ class SnWgradDesc(C.Structure):
     _fields_ = [
         ("x_hi", C.c_void_p), ("x_lo", C.c_void_p),
         ("x_n", C.c_int), ("x_h", C.c_int), ("x_w", C.c_int), ("x_c", C.c_int), ("x_pitch", C.c_int),
-        ("x_parity", C.c_int),
+        ("x_parity", C.c_int), ("x_fmt", C.c_int),
         ("y_hi", C.c_void_p), ("y_lo", C.c_void_p),
         ("y_n", C.c_int), ("y_h", C.c_int), ("y_w", C.c_int), ("y_c", C.c_int), ("y_pitch", C.c_int),
-        ("y_parity", C.c_int),
+        ("y_parity", C.c_int), ("y_fmt", C.c_int),
         ("m_n", C.c_int), ("m_h", C.c_int), ("m_w", C.c_int),
         ("ntaps", C.c_int),
         ("xtaps", SnTap * SN_MAX_TAPS), ("ytaps", SnTap * SN_MAX_TAPS),
@@ -66,7 +67,7 @@ class SnNormActDesc(C.Structure):
         ("drop_p", C.c_float), ("drop_seed", C.c_ulonglong),
         ("residual", C.c_void_p), ("res_pitch", C.c_int),
         ("out_hi", C.c_void_p), ("out_lo", C.c_void_p), ("out_pitch", C.c_int), ("out_coff", C.c_int),
-        ("out_reflect_pad", C.c_int),
+        ("out_fmt", C.c_int), ("out_reflect_pad", C.c_int),
         ("out_f32", C.c_void_p), ("f32_pitch", C.c_int),
     ]
 
@@ -85,6 +86,7 @@ class SnNormActBwdDesc(C.Structure):
         ("drop_p", C.c_float), ("drop_seed", C.c_ulonglong),
         ("gstats", C.c_void_p),
         ("dy_hi", C.c_void_p), ("dy_lo", C.c_void_p), ("dy_pitch", C.c_int), ("dy_coff", C.c_int),
+        ("dy_fmt", C.c_int),
     ]
 
 
@@ -98,21 +100,22 @@ SIGNATURES = {
     "sn_wgrad_plan_create": (_I, [C.POINTER(SnWgradDesc), C.POINTER(_VP)]),
     "sn_plan_run": (_I, [_VP, _VP]),
     "sn_plan_destroy": (None, [_VP]),
-    "sn_pack_planes": (_I, [_VP, _I, _I, _I, _I, _I, _I, _VP, _VP, _I, _I, _VP]),
-    "sn_pack_weights": (_I, [_VP, _LL, _LL, _I, _I, _I, _I, _VP, _VP, _VP]),
-    "sn_pack_head_weights": (_I, [_VP, _I, _I, _I, _I, _I, _VP, _VP, _VP]),
+    "sn_pack_planes": (_I, [_VP, _I, _I, _I, _I, _I, _I, _VP, _VP, _I, _I, _I, _VP]),
+    "sn_weight_scale": (_I, [_VP, _LL, _VP, _VP]),
+    "sn_pack_weights": (_I, [_VP, _LL, _LL, _I, _I, _I, _I, _VP, _VP, _I, _VP, _VP]),
+    "sn_pack_head_weights": (_I, [_VP, _I, _I, _I, _I, _I, _VP, _VP, _I, _VP, _VP]),
     "sn_fold_head_wgrad": (_I, [_VP, _I, _I, _VP, _VP]),
     "sn_plane_stats": (_I, [_VP, _I, _I, _I, _I, _F, _VP, _VP]),
     "sn_norm_act_fwd": (_I, [C.POINTER(SnNormActDesc), _VP]),
     "sn_norm_act_bwd": (_I, [C.POINTER(SnNormActBwdDesc), _VP]),
-    "sn_bias_grad": (_I, [_VP, _VP, _I, _I, _LL, _I, _VP, _VP, _VP]),
+    "sn_bias_grad": (_I, [_VP, _VP, _I, _I, _I, _LL, _I, _VP, _VP, _VP]),
     "sn_sum_grads": (_I, [C.POINTER(SnGradSrc), _I, _I, _I, _I, _I, _VP, _I, _VP]),
-    "sn_tanh_bwd": (_I, [C.POINTER(SnGradSrc), _I, _VP, _I, _I, _I, _I, _I, _VP, _VP, _I, _I, _VP]),
+    "sn_tanh_bwd": (_I, [C.POINTER(SnGradSrc), _I, _VP, _I, _I, _I, _I, _I, _VP, _VP, _I, _I, _I, _VP]),
     "sn_dropout_mask": (_I, [_ULL, _F, _LL, _VP, _VP]),
     "sn_ce_loss_fwd_bwd": (_I, [_VP, _I, _VP, _I, _I, _I, _I, _F, _VP, _VP, _I, _VP]),
     "sn_bce_logits_fwd_bwd": (_I, [_VP, _LL, _I, _F, _F, _F, _VP, _VP, _VP]),
     "sn_l1_loss_fwd_bwd": (_I, [_VP, _I, _VP, _I, _I, _I, _I, _F, _VP, _VP, _I, _VP]),
-    "sn_roi_align_pack_fwd": (_I, [_VP, _I, _I, _I, _I, _VP, _I, _I, _VP, _I, _VP, _VP, _I, _I, _VP]),
+    "sn_roi_align_pack_fwd": (_I, [_VP, _I, _I, _I, _I, _VP, _I, _I, _VP, _I, _VP, _VP, _I, _I, _I, _VP]),
     "sn_tap_gemm_simt": (_I, [C.POINTER(SnTapGemmDesc), _VP]),
 }
 

@@ -7,6 +7,7 @@
 #include <cuda_runtime.h>
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <string.h>
@@ -20,6 +21,10 @@ void sn_set_error(const char* fmt, ...);
 #define SN_ERR_INVALID (-1)
 #define SN_ERR_CUDA (-2)
 #define SN_ERR_UNSUPPORTED (-3)
+#ifndef SN_FMT_BF16
+#define SN_FMT_BF16 0
+#define SN_FMT_F16 1
+#endif
 
 #define SN_CHECK_CUDA(expr)                                                        \
   do {                                                                             \
@@ -196,13 +201,15 @@ __device__ __forceinline__ uint64_t umma_smem_desc(uint32_t smem_addr, uint32_t 
 // Instruction descriptor (cute::UMMA::InstrDescriptor), kind::f16, bf16 x bf16 -> f32.
 //   c_format[4,6)=1(F32) a_format[7,10)=1(BF16) b_format[10,13)=1(BF16)
 //   a_major bit15, b_major bit16 (0 = K-major, 1 = MN-major), n>>3 at [17,23), m>>4 at [24,29)
-__host__ __device__ __forceinline__ uint32_t umma_idesc_bf16(uint32_t m, uint32_t n,
-                                                             uint32_t a_mn_major,
-                                                             uint32_t b_mn_major) {
+//   a_format / b_format: 0 = F16, 1 = BF16 — independent, so an fp16-split activation can meet a
+//   bf16-split gradient in one instruction.
+__host__ __device__ __forceinline__ uint32_t umma_idesc_16(uint32_t m, uint32_t n, uint32_t a_fmt,
+                                                           uint32_t b_fmt, uint32_t a_mn_major,
+                                                           uint32_t b_mn_major) {
   uint32_t d = 0;
   d |= 1u << 4;
-  d |= 1u << 7;
-  d |= 1u << 10;
+  d |= (a_fmt == SN_FMT_F16 ? 0u : 1u) << 7;
+  d |= (b_fmt == SN_FMT_F16 ? 0u : 1u) << 10;
   d |= (a_mn_major & 1u) << 15;
   d |= (b_mn_major & 1u) << 16;
   d |= ((n >> 3) & 0x3Fu) << 17;
@@ -210,12 +217,30 @@ __host__ __device__ __forceinline__ uint32_t umma_idesc_bf16(uint32_t m, uint32_
   return d;
 }
 
-// ---- split-bf16 representation ---------------------------------------------------
-// An fp32 value v is carried as hi = bf16(v), lo = bf16(v - hi); hi + lo
-// reproduces v to ~2^-17 relative.  Products use hi*hi + lo*hi + hi*lo.
-__device__ __forceinline__ void split_bf16(float v, __nv_bfloat16& hi, __nv_bfloat16& lo) {
-  hi = __float2bfloat16_rn(v);
-  lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+// ---- split 16-bit representation --------------------------------------------------
+// An fp32 value v is carried as two 16-bit floats hi = r16(v), lo = r16(v - hi); products use
+// hi*hi + lo*hi + hi*lo with fp32 accumulation.
+//   SN_FMT_BF16: 8+8 mantissa bits (~2^-17 relative), fp32 exponent range — used for gradients;
+//   SN_FMT_F16 : 11+11 bits (~2^-23 relative for |v| >~ 2^-3, absolute floor 2^-24) — used for
+//                activations (O(1) after InstanceNorm) and for weights (pre-scaled by an exact
+//                power of two, undone in the epilogue).  fp32-level forward accuracy is what keeps
+//                the ReLU / LeakyReLU gates identical to the reference's.
+__device__ __forceinline__ void split16(float v, int fmt, uint16_t& hi, uint16_t& lo) {
+  if (fmt == SN_FMT_F16) {
+    v = fminf(fmaxf(v, -65504.f), 65504.f);
+    const __half h = __float2half_rn(v);
+    const __half l = __float2half_rn(v - __half2float(h));
+    hi = __half_as_ushort(h);
+    lo = __half_as_ushort(l);
+  } else {
+    const __nv_bfloat16 h = __float2bfloat16_rn(v);
+    const __nv_bfloat16 l = __float2bfloat16_rn(v - __bfloat162float(h));
+    hi = __bfloat16_as_ushort(h);
+    lo = __bfloat16_as_ushort(l);
+  }
+}
+__device__ __forceinline__ float decode16(uint16_t x, int fmt) {
+  return fmt == SN_FMT_F16 ? __half2float(__ushort_as_half(x)) : __bfloat162float(__ushort_as_bfloat16(x));
 }
 
 __device__ __forceinline__ float warp_sum(float v) {

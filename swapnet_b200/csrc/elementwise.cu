@@ -40,9 +40,9 @@ __host__ __device__ __forceinline__ uint32_t drop_thresh(float p) {
   return (uint32_t)t;
 }
 
-__device__ __forceinline__ void store_split(__nv_bfloat16* hi, __nv_bfloat16* lo, long long off, float v) {
-  __nv_bfloat16 h, l;
-  split_bf16(v, h, l);
+__device__ __forceinline__ void store_split(uint16_t* hi, uint16_t* lo, long long off, float v, int fmt) {
+  uint16_t h, l;
+  split16(v, fmt, h, l);
   hi[off] = h;
   if (lo) lo[off] = l;
 }
@@ -52,8 +52,8 @@ __device__ __forceinline__ void store_split(__nv_bfloat16* hi, __nv_bfloat16* lo
 // ---------------------------------------------------------------------------------
 // NCHW source: one block per (n, h, 32-pixel run); smem transposes [c][w] -> [w][c].
 __global__ void pack_planes_nchw_kernel(const float* __restrict__ src, int N, int C, int H, int W,
-                                        __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo,
-                                        int pitch, int coff) {
+                                        uint16_t* __restrict__ hi, uint16_t* __restrict__ lo,
+                                        int pitch, int coff, int fmt) {
   extern __shared__ float tile[];  // [C][33]
   const int w0 = blockIdx.x * 32;
   const int h = blockIdx.y;
@@ -69,19 +69,19 @@ __global__ void pack_planes_nchw_kernel(const float* __restrict__ src, int N, in
     const int w = i / C, c = i % C;
     if (w0 + w < W) {
       const long long off = (((long long)n * H + h) * W + w0 + w) * pitch + coff + c;
-      store_split(hi, lo, off, tile[c * 33 + w]);
+      store_split(hi, lo, off, tile[c * 33 + w], fmt);
     }
   }
 }
 __global__ void pack_planes_nhwc_kernel(const float* __restrict__ src, int src_pitch, long long npix,
-                                        int C, __nv_bfloat16* __restrict__ hi,
-                                        __nv_bfloat16* __restrict__ lo, int pitch, int coff) {
+                                        int C, uint16_t* __restrict__ hi,
+                                        uint16_t* __restrict__ lo, int pitch, int coff, int fmt) {
   const long long total = npix * C;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
     const long long pix = i / C;
     const int c = (int)(i - pix * C);
-    store_split(hi, lo, pix * pitch + coff + c, src[pix * src_pitch + c]);
+    store_split(hi, lo, pix * pitch + coff + c, src[pix * src_pitch + c], fmt);
   }
 }
 
@@ -89,9 +89,10 @@ __global__ void pack_planes_nhwc_kernel(const float* __restrict__ src, int src_p
 // pack_weights: dst[r][t][k] <- src[r*s_row + k*s_k + t]
 // ---------------------------------------------------------------------------------
 __global__ void pack_weights_kernel(const float* __restrict__ src, long long s_row, long long s_k,
-                                    int taps, int k_real, int k_pad, __nv_bfloat16* __restrict__ hi,
-                                    __nv_bfloat16* __restrict__ lo) {
+                                    int taps, int k_real, int k_pad, uint16_t* __restrict__ hi,
+                                    uint16_t* __restrict__ lo, int fmt, const float* __restrict__ scale2) {
   extern __shared__ float tile[];  // [32][taps + 1]
+  const float sc = scale2 ? scale2[0] : 1.f;
   const int r = blockIdx.y;
   const int k0 = blockIdx.x * 32;
   const int T1 = taps + 1;
@@ -106,7 +107,7 @@ __global__ void pack_weights_kernel(const float* __restrict__ src, long long s_r
     const int t = i / 32, kk = i % 32;
     if (k0 + kk < k_pad) {
       const long long off = ((long long)r * taps + t) * k_pad + k0 + kk;
-      store_split(hi, lo, off, tile[kk * T1 + t]);
+      store_split(hi, lo, off, tile[kk * T1 + t] * sc, fmt);
     }
   }
 }
@@ -136,9 +137,11 @@ __host__ __device__ __forceinline__ int head_taps_of(int par, int e, int ks[2]) 
   return 1;
 }
 __global__ void pack_head_weights_kernel(const float* __restrict__ w, int cout, int cin, int rows_pad,
-                                         int k_pad, int dgrad, __nv_bfloat16* __restrict__ hi,
-                                         __nv_bfloat16* __restrict__ lo) {
+                                         int k_pad, int dgrad, uint16_t* __restrict__ hi,
+                                         uint16_t* __restrict__ lo, int fmt,
+                                         const float* __restrict__ scale2) {
   // one thread per (co, te, ci) with te the global effective tap 0..24
+  const float sc = scale2 ? scale2[0] : 1.f;
   const long long total = (long long)cout * 25 * cin;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -163,7 +166,7 @@ __global__ void pack_head_weights_kernel(const float* __restrict__ w, int cout, 
     } else {
       off = ((long long)ci * 25 + te) * k_pad + co;  // [ci][25][k_pad]
     }
-    store_split(hi, lo, off, acc);
+    store_split(hi, lo, off, acc * sc, fmt);
   }
 }
 __global__ void fold_head_wgrad_kernel(const float* __restrict__ geff, int cout, int cin,
@@ -184,6 +187,30 @@ __global__ void fold_head_wgrad_kernel(const float* __restrict__ geff, int cout,
     }
     dw[i] += acc;
   }
+}
+
+// ---------------------------------------------------------------------------------
+// per-tensor power-of-two weight scale (fp16-split operands): s = 2^k with max|w|*s in [2^13, 2^14)
+// ---------------------------------------------------------------------------------
+__global__ void absmax_kernel(const float* __restrict__ w, long long count, unsigned int* out) {
+  float m = 0.f;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < count;
+       i += (long long)gridDim.x * blockDim.x)
+    m = fmaxf(m, fabsf(w[i]));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) atomicMax(out, __float_as_uint(m));  // non-negative floats order as uints
+}
+__global__ void weight_scale_finalize_kernel(const unsigned int* amax, float* scale2) {
+  const float m = __uint_as_float(*amax);
+  float s = 1.f;
+  if (m > 0.f && isfinite(m)) {
+    int e;
+    frexpf(m, &e);          // m = f * 2^e, f in [0.5, 1)
+    s = ldexpf(1.f, 14 - e);  // m * s in [2^13, 2^14)
+  }
+  scale2[0] = s;
+  scale2[1] = 1.f / s;
 }
 
 // ---------------------------------------------------------------------------------
@@ -245,8 +272,8 @@ __global__ void gstats_finalize_kernel(double* g, int count, int hw) {
 
 
 // bias gradient: db[c] = sum over pixels of dy (dy carried as split planes)
-__global__ void bias_grad_kernel(const __nv_bfloat16* __restrict__ hi, const __nv_bfloat16* __restrict__ lo,
-                                 int pitch, long long npix, int C, double* __restrict__ acc) {
+__global__ void bias_grad_kernel(const uint16_t* __restrict__ hi, const uint16_t* __restrict__ lo,
+                                 int pitch, int fmt, long long npix, int C, double* __restrict__ acc) {
   __shared__ float s1s[8][33];
   const int c = blockIdx.x * 32 + threadIdx.x;
   const long long per = (npix + gridDim.y - 1) / gridDim.y;
@@ -257,8 +284,8 @@ __global__ void bias_grad_kernel(const __nv_bfloat16* __restrict__ hi, const __n
     float part = 0.f;
     int cnt = 0;
     for (long long p = p0 + threadIdx.y; p < p1; p += 8) {
-      float v = __bfloat162float(hi[p * pitch + c]);
-      if (lo) v += __bfloat162float(lo[p * pitch + c]);
+      float v = decode16(hi[p * pitch + c], fmt);
+      if (lo) v += decode16(lo[p * pitch + c], fmt);
       part += v;
       if (++cnt == 64) { s += (double)part; part = 0.f; cnt = 0; }
     }
@@ -289,7 +316,7 @@ struct NormActFwdArgs {
   int act; float slope;
   uint32_t drop_thresh; float drop_scale; unsigned long long seed;
   const float* residual; int res_pitch;
-  __nv_bfloat16* hi; __nv_bfloat16* lo; int out_pitch, out_coff, reflect;
+  uint16_t* hi; uint16_t* lo; int out_pitch, out_coff, reflect, fmt;
   float* f32; int f32_pitch;
 };
 
@@ -327,8 +354,8 @@ __global__ void norm_act_fwd_kernel(const NormActFwdArgs a) {
       if (a.residual) v += a.residual[pix * a.res_pitch + c];
       if (a.f32) a.f32[pix * a.f32_pitch + c] = v;
       if (a.hi) {
-        __nv_bfloat16 h, l;
-        split_bf16(v, h, l);
+        uint16_t h, l;
+        split16(v, a.fmt, h, l);
         if (!a.reflect) {
           const long long off = pix * a.out_pitch + a.out_coff + c;
           a.hi[off] = h;
@@ -396,7 +423,7 @@ struct NormActBwdArgs {
   int act; float slope;
   uint32_t drop_thresh; float drop_scale; unsigned long long seed;
   double* gstats;
-  __nv_bfloat16* hi; __nv_bfloat16* lo; int dy_pitch, dy_coff;
+  uint16_t* hi; uint16_t* lo; int dy_pitch, dy_coff, fmt;
 };
 
 // gradient w.r.t. xhat (before the InstanceNorm backward), and xhat itself
@@ -469,7 +496,7 @@ __global__ void norm_act_bwd_apply_kernel(const NormActBwdArgs a) {
       float g = grad_xhat(a, n, p, c, mean, rstd, &xhat);
       if (a.stats) g = rstd * (g - m1 - xhat * m2);
       const long long off = ((long long)n * HW + p) * a.dy_pitch + a.dy_coff + c;
-      store_split(a.hi, a.lo, off, g);
+      store_split(a.hi, a.lo, off, g, a.fmt);
     }
   }
 }
@@ -487,8 +514,8 @@ __global__ void sum_grads_kernel(const GradSrcs g, int H, int W, int C, float* d
 }
 
 __global__ void tanh_bwd_kernel(const GradSrcs g, const float* __restrict__ out, int out_pitch, int H,
-                                int W, int C, __nv_bfloat16* hi, __nv_bfloat16* lo, int dy_pitch,
-                                int dy_coff) {
+                                int W, int C, uint16_t* hi, uint16_t* lo, int dy_pitch,
+                                int dy_coff, int fmt) {
   const int n = blockIdx.y;
   const int HW = H * W;
   const int per = (HW + gridDim.x - 1) / gridDim.x;
@@ -499,7 +526,7 @@ __global__ void tanh_bwd_kernel(const GradSrcs g, const float* __restrict__ out,
       const long long pix = (long long)n * HW + p;
       const float o = out[pix * out_pitch + c];
       const float v = gather_grad(g, n, h, w, H, W, c) * (1.f - o * o);
-      store_split(hi, lo, pix * dy_pitch + dy_coff + c, v);
+      store_split(hi, lo, pix * dy_pitch + dy_coff + c, v, fmt);
     }
 }
 
@@ -606,7 +633,9 @@ __global__ void l1_loss_kernel(const float* __restrict__ a, int pitch, const flo
 // SIMT fp32 tap GEMM (test cross-check only)
 // ---------------------------------------------------------------------------------
 struct SimtArgs {
-  const __nv_bfloat16 *a_hi, *a_lo, *b_hi, *b_lo;
+  const uint16_t *a_hi, *a_lo, *b_hi, *b_lo;
+  int a_fmt, b_fmt;
+  const float* b_scale;
   int a_n, a_h, a_w, a_c, a_pitch, parity;
   long long b_k;
   int b_rows;
@@ -645,15 +674,16 @@ __global__ void tap_gemm_simt_kernel(const SimtArgs a) {
       const long long abase = (((long long)n * a.a_h + sh) * a.a_w + sw) * a.a_pitch + cbase;
       const long long bbase = (long long)col * a.b_k + tp.kb_off;
       for (int k = 0; k < a.k_per_tap; ++k) {
-        float av = __bfloat162float(a.a_hi[abase + k]);
-        float bv = col < a.b_rows ? __bfloat162float(a.b_hi[bbase + k]) : 0.f;
+        float av = decode16(a.a_hi[abase + k], a.a_fmt);
+        float bv = col < a.b_rows ? decode16(a.b_hi[bbase + k], a.b_fmt) : 0.f;
         if (a.nsplit == 3) {
-          av += __bfloat162float(a.a_lo[abase + k]);
-          if (col < a.b_rows) bv += __bfloat162float(a.b_lo[bbase + k]);
+          av += decode16(a.a_lo[abase + k], a.a_fmt);
+          if (col < a.b_rows) bv += decode16(a.b_lo[bbase + k], a.b_fmt);
         }
         acc = fmaf(av, bv, acc);
       }
     }
+    if (a.b_scale) acc *= a.b_scale[1];
     if (a.bias) acc += a.bias[col];
     if (a.act == SN_ACT_TANH) acc = tanhf(acc);
     a.out[(long long)n * a.out_sn + (long long)(h * a.omh + a.ooh) * a.out_sh +
@@ -693,7 +723,7 @@ inline int slabs_for(int hw, int n, int py) {
 extern "C" {
 
 int sn_pack_planes(const float* src, int src_layout, int src_pitch, int n, int c, int h, int w,
-                   void* dst_hi, void* dst_lo, int dst_pitch, int dst_coff, void* stream) {
+                   void* dst_hi, void* dst_lo, int dst_pitch, int dst_coff, int fmt, void* stream) {
   SN_REQUIRE(src && dst_hi, "null pointer");
   SN_REQUIRE(dst_coff + c <= dst_pitch, "channel slice exceeds pitch");
   cudaStream_t st = (cudaStream_t)stream;
@@ -701,35 +731,48 @@ int sn_pack_planes(const float* src, int src_layout, int src_pitch, int n, int c
     dim3 grid((w + 31) / 32, h, n);
     size_t smem = (size_t)c * 33 * sizeof(float);
     SN_REQUIRE(smem <= 48 * 1024, "pack_planes: too many channels for NCHW path (%d)", c);
-    pack_planes_nchw_kernel<<<grid, 256, smem, st>>>(src, n, c, h, w, (__nv_bfloat16*)dst_hi,
-                                                     (__nv_bfloat16*)dst_lo, dst_pitch, dst_coff);
+    pack_planes_nchw_kernel<<<grid, 256, smem, st>>>(src, n, c, h, w, (uint16_t*)dst_hi,
+                                                     (uint16_t*)dst_lo, dst_pitch, dst_coff, fmt);
   } else {
     const long long npix = (long long)n * h * w;
     pack_planes_nhwc_kernel<<<grid_for(npix * c), kEwThreads, 0, st>>>(
-        src, src_pitch, npix, c, (__nv_bfloat16*)dst_hi, (__nv_bfloat16*)dst_lo, dst_pitch, dst_coff);
+        src, src_pitch, npix, c, (uint16_t*)dst_hi, (uint16_t*)dst_lo, dst_pitch, dst_coff, fmt);
   }
   LAUNCH_CHECK();
   return SN_OK;
 }
 
 int sn_pack_weights(const float* src, long long s_row, long long s_k, int rows, int taps, int k_real,
-                    int k_pad, void* dst_hi, void* dst_lo, void* stream) {
+                    int k_pad, void* dst_hi, void* dst_lo, int fmt, const float* scale2, void* stream) {
   SN_REQUIRE(src && dst_hi, "null pointer");
   SN_REQUIRE(taps >= 1 && taps <= 64 && k_pad >= k_real, "bad pack_weights shape");
   dim3 grid((k_pad + 31) / 32, rows);
   size_t smem = (size_t)32 * (taps + 1) * sizeof(float);
   pack_weights_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(
-      src, s_row, s_k, taps, k_real, k_pad, (__nv_bfloat16*)dst_hi, (__nv_bfloat16*)dst_lo);
+      src, s_row, s_k, taps, k_real, k_pad, (uint16_t*)dst_hi, (uint16_t*)dst_lo, fmt, scale2);
   LAUNCH_CHECK();
   return SN_OK;
 }
 
 int sn_pack_head_weights(const float* src, int cout, int cin, int rows_pad, int k_pad, int dgrad,
-                         void* dst_hi, void* dst_lo, void* stream) {
+                         void* dst_hi, void* dst_lo, int fmt, const float* scale2, void* stream) {
   SN_REQUIRE(src && dst_hi, "null pointer");
   SN_REQUIRE(dgrad ? (k_pad >= cout) : (k_pad >= cin && rows_pad >= cout), "bad head pack shape");
   pack_head_weights_kernel<<<grid_for((long long)cout * 25 * cin), kEwThreads, 0, (cudaStream_t)stream>>>(
-      src, cout, cin, rows_pad, k_pad, dgrad, (__nv_bfloat16*)dst_hi, (__nv_bfloat16*)dst_lo);
+      src, cout, cin, rows_pad, k_pad, dgrad, (uint16_t*)dst_hi, (uint16_t*)dst_lo, fmt, scale2);
+  LAUNCH_CHECK();
+  return SN_OK;
+}
+
+int sn_weight_scale(const float* w, long long count, float* scale2, void* stream) {
+  SN_REQUIRE(w && scale2, "null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  // scale2[1] doubles as the atomicMax scratch before the finalize kernel overwrites it
+  unsigned int* scratch = reinterpret_cast<unsigned int*>(scale2 + 1);
+  SN_CHECK_CUDA(cudaMemsetAsync(scratch, 0, sizeof(unsigned int), st));
+  absmax_kernel<<<grid_for(count), kEwThreads, 0, st>>>(w, count, scratch);
+  LAUNCH_CHECK();
+  weight_scale_finalize_kernel<<<1, 1, 0, st>>>(scratch, scale2);
   LAUNCH_CHECK();
   return SN_OK;
 }
@@ -769,8 +812,9 @@ int sn_norm_act_fwd(const sn_norm_act_desc* d, void* stream) {
   a.drop_scale = d->drop_p > 0.f ? 1.f / (1.f - d->drop_p) : 1.f;
   a.seed = d->drop_seed;
   a.residual = d->residual; a.res_pitch = d->res_pitch;
-  a.hi = (__nv_bfloat16*)d->out_hi; a.lo = (__nv_bfloat16*)d->out_lo;
+  a.hi = (uint16_t*)d->out_hi; a.lo = (uint16_t*)d->out_lo;
   a.out_pitch = d->out_pitch; a.out_coff = d->out_coff; a.reflect = d->out_reflect_pad;
+  a.fmt = d->out_fmt;
   a.f32 = d->out_f32; a.f32_pitch = d->f32_pitch;
   dim3 blk = cblock(d->c);
   dim3 grid(slabs_for(d->h * d->w, d->n, blk.y), d->n);
@@ -803,8 +847,8 @@ int sn_norm_act_bwd(const sn_norm_act_bwd_desc* d, void* stream) {
   a.drop_scale = d->drop_p > 0.f ? 1.f / (1.f - d->drop_p) : 1.f;
   a.seed = d->drop_seed;
   a.gstats = d->gstats;
-  a.hi = (__nv_bfloat16*)d->dy_hi; a.lo = (__nv_bfloat16*)d->dy_lo;
-  a.dy_pitch = d->dy_pitch; a.dy_coff = d->dy_coff;
+  a.hi = (uint16_t*)d->dy_hi; a.lo = (uint16_t*)d->dy_lo;
+  a.dy_pitch = d->dy_pitch; a.dy_coff = d->dy_coff; a.fmt = d->dy_fmt;
   const int hw = d->h * d->w;
   if (d->stats) {
     SN_REQUIRE(d->gstats, "InstanceNorm backward needs gstats scratch");
@@ -826,7 +870,7 @@ int sn_norm_act_bwd(const sn_norm_act_bwd_desc* d, void* stream) {
 }
 
 
-int sn_bias_grad(const void* dy_hi, const void* dy_lo, int pitch, int coff, long long npix, int c,
+int sn_bias_grad(const void* dy_hi, const void* dy_lo, int pitch, int coff, int fmt, long long npix, int c,
                  double* scratch, float* db, void* stream) {
   SN_REQUIRE(dy_hi && scratch && db, "null pointer");
   cudaStream_t st = (cudaStream_t)stream;
@@ -835,9 +879,9 @@ int sn_bias_grad(const void* dy_hi, const void* dy_lo, int pitch, int coff, long
   long long slabs = (148 * 4 + cg - 1) / cg;
   if (slabs > (npix + 63) / 64) slabs = (npix + 63) / 64;
   if (slabs < 1) slabs = 1;
-  const __nv_bfloat16* hi = (const __nv_bfloat16*)dy_hi + coff;
-  const __nv_bfloat16* lo = dy_lo ? (const __nv_bfloat16*)dy_lo + coff : nullptr;
-  bias_grad_kernel<<<dim3(cg, (int)slabs), dim3(32, 8), 0, st>>>(hi, lo, pitch, npix, c, scratch);
+  const uint16_t* hi = (const uint16_t*)dy_hi + coff;
+  const uint16_t* lo = dy_lo ? (const uint16_t*)dy_lo + coff : nullptr;
+  bias_grad_kernel<<<dim3(cg, (int)slabs), dim3(32, 8), 0, st>>>(hi, lo, pitch, fmt, npix, c, scratch);
   LAUNCH_CHECK();
   bias_grad_finalize_kernel<<<(c + 255) / 256, 256, 0, st>>>(scratch, c, db);
   LAUNCH_CHECK();
@@ -857,15 +901,15 @@ int sn_sum_grads(const sn_grad_src* src, int nsrc, int n, int h, int w, int c, f
 }
 
 int sn_tanh_bwd(const sn_grad_src* src, int nsrc, const float* out, int out_pitch, int n, int h,
-                int w, int c, void* dy_hi, void* dy_lo, int dy_pitch, int dy_coff, void* stream) {
+                int w, int c, void* dy_hi, void* dy_lo, int dy_pitch, int dy_coff, int dy_fmt, void* stream) {
   GradSrcs g;
   int rc = fill_srcs(&g, src, nsrc);
   if (rc) return rc;
   dim3 blk = cblock(c);
   dim3 grid(slabs_for(h * w, n, blk.y), n);
   tanh_bwd_kernel<<<grid, blk, 0, (cudaStream_t)stream>>>(g, out, out_pitch, h, w, c,
-                                                          (__nv_bfloat16*)dy_hi, (__nv_bfloat16*)dy_lo,
-                                                          dy_pitch, dy_coff);
+                                                          (uint16_t*)dy_hi, (uint16_t*)dy_lo,
+                                                          dy_pitch, dy_coff, dy_fmt);
   LAUNCH_CHECK();
   return SN_OK;
 }
@@ -907,8 +951,9 @@ int sn_l1_loss_fwd_bwd(const float* a, int pitch, const float* b_nchw, int n, in
 int sn_tap_gemm_simt(const sn_tap_gemm_desc* d, void* stream) {
   SN_REQUIRE(d && d->a_hi && d->b_hi && d->out, "null pointer");
   SimtArgs a;
-  a.a_hi = (const __nv_bfloat16*)d->a_hi; a.a_lo = (const __nv_bfloat16*)d->a_lo;
-  a.b_hi = (const __nv_bfloat16*)d->b_hi; a.b_lo = (const __nv_bfloat16*)d->b_lo;
+  a.a_hi = (const uint16_t*)d->a_hi; a.a_lo = (const uint16_t*)d->a_lo;
+  a.b_hi = (const uint16_t*)d->b_hi; a.b_lo = (const uint16_t*)d->b_lo;
+  a.a_fmt = d->a_fmt; a.b_fmt = d->b_fmt; a.b_scale = d->b_scale;
   a.a_n = d->a_n; a.a_h = d->a_h; a.a_w = d->a_w; a.a_c = d->a_c; a.a_pitch = d->a_pitch;
   a.parity = d->a_parity;
   a.b_k = d->b_k; a.b_rows = d->b_rows;

@@ -120,7 +120,7 @@ tap_gemm_kernel(const __grid_constant__ TapGemmParams p) {
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
-      const uint32_t idesc = umma_idesc_bf16(kBlockM, p.block_n, 0, 0);
+      const uint32_t idesc = umma_idesc_16(kBlockM, p.block_n, p.a_fmt, p.b_fmt, 0, 0);
       uint32_t acc = 0;
       for (int it = 0; it < k_iters; ++it) {
         const int s = it % C::kStages;
@@ -158,6 +158,7 @@ tap_gemm_kernel(const __grid_constant__ TapGemmParams p) {
     const bool valid = (gw < p.m_w) && (gh < p.m_h) && (gn < p.m_n);
     float* optr = p.out + (long long)gn * p.out_sn + (long long)(gh * p.omh + p.ooh) * p.out_sh +
                   (long long)(gw * p.omw + p.oow) * p.out_sw + ncol0;
+    const float oscale = p.b_scale ? p.b_scale[1] : 1.f;  // undo the power-of-two weight scale (exact)
     mbar_wait(&accum_bar, 0);
     tc_fence_after();
     for (int c0 = 0; c0 < p.block_n; c0 += 16) {
@@ -169,10 +170,10 @@ tap_gemm_kernel(const __grid_constant__ TapGemmParams p) {
 #pragma unroll
           for (int j = 0; j < 16; j += 4) {
             float4 v;
-            v.x = __uint_as_float(r[j + 0]);
-            v.y = __uint_as_float(r[j + 1]);
-            v.z = __uint_as_float(r[j + 2]);
-            v.w = __uint_as_float(r[j + 3]);
+            v.x = __uint_as_float(r[j + 0]) * oscale;
+            v.y = __uint_as_float(r[j + 1]) * oscale;
+            v.z = __uint_as_float(r[j + 2]) * oscale;
+            v.w = __uint_as_float(r[j + 3]) * oscale;
             if (p.bias) {
               const float4 b = *reinterpret_cast<const float4*>(p.bias + ncol0 + c0 + j);
               v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
@@ -188,7 +189,7 @@ tap_gemm_kernel(const __grid_constant__ TapGemmParams p) {
           for (int j = 0; j < 16; ++j) {
             const int col = ncol0 + c0 + j;
             if (col < p.n_valid) {
-              float v = __uint_as_float(r[j]);
+              float v = __uint_as_float(r[j]) * oscale;
               if (p.bias) v += p.bias[col];
               optr[c0 + j] = apply_act(v, p.act);
             }
@@ -283,7 +284,7 @@ wgrad_gemm_kernel(const __grid_constant__ WgradParams p) {
       }
     } else if (warp == 1) {
       if (lane == 0) {
-        const uint32_t idesc = umma_idesc_bf16(kBlockM, p.block_n, 1, 1);
+        const uint32_t idesc = umma_idesc_16(kBlockM, p.block_n, p.x_fmt, p.y_fmt, 1, 1);
         uint32_t acc = 0;
         for (int it = 0; it < k_iters; ++it) {
           const int s = it % C::kStages;
@@ -462,6 +463,9 @@ int sn_tap_gemm_plan_init(TapGemmPlan* plan, const sn_tap_gemm_desc* d) {
   p.out_sn = d->out_sn; p.out_sh = d->out_sh; p.out_sw = d->out_sw;
   p.omh = d->out_mul_h; p.ooh = d->out_off_h; p.omw = d->out_mul_w; p.oow = d->out_off_w;
   p.bias = d->bias;
+  p.b_scale = d->b_scale;
+  p.a_fmt = d->a_fmt;
+  p.b_fmt = d->b_fmt;
   p.act = d->act;
   p.vec4 = ((uintptr_t)d->out % 16 == 0) && (d->out_sn % 4 == 0) && (d->out_sh % 4 == 0) &&
            (d->out_sw % 4 == 0) && (!d->bias || (uintptr_t)d->bias % 16 == 0);
@@ -531,6 +535,8 @@ int sn_wgrad_plan_init(WgradPlan* plan, const sn_wgrad_desc* d, int sm_count) {
   p.out = d->out;
   p.s_row = d->s_row;
   p.s_col = d->s_col;
+  p.x_fmt = d->x_fmt;
+  p.y_fmt = d->y_fmt;
   int rc;
   const void* x_pl[2] = {d->x_hi, d->x_lo};
   const void* y_pl[2] = {d->y_hi, d->y_lo};

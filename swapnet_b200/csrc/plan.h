@@ -23,8 +23,10 @@ struct alignas(64) TapGemmParams {
   long long out_sn, out_sh, out_sw;
   int omh, ooh, omw, oow;
   const float* bias;
+  const float* b_scale;  // device (s, 1/s) of the packed weights, or null
   int act;
   int vec4;
+  int a_fmt, b_fmt;
 };
 
 struct alignas(64) WgradParams {
@@ -40,6 +42,7 @@ struct alignas(64) WgradParams {
   int rows_valid, cols_valid;
   float* out;
   long long s_row, s_col;
+  int x_fmt, y_fmt;
 };
 
 struct TapGemmPlan {

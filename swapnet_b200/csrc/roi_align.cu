@@ -21,7 +21,7 @@ struct RoiArgs {
   const float* tex; int B, CH, H, W;
   const float* rois; int nroi, pool;
   float* out; int out_pitch;
-  __nv_bfloat16* hi; __nv_bfloat16* lo; int ppitch, pcoff;
+  uint16_t* hi; uint16_t* lo; int ppitch, pcoff, fmt;
 };
 
 // thread = one (b, ph, pw, roi); writes CH consecutive output channels
@@ -88,8 +88,8 @@ __global__ void roi_align_pack_kernel(const RoiArgs a) {
       const int oc = a.CH * r + c;
       if (a.out) a.out[opix * a.out_pitch + oc] = v;
       if (a.hi) {
-        __nv_bfloat16 h, l;
-        split_bf16(v, h, l);
+        uint16_t h, l;
+        split16(v, a.fmt, h, l);
         a.hi[opix * a.ppitch + a.pcoff + oc] = h;
         if (a.lo) a.lo[opix * a.ppitch + a.pcoff + oc] = l;
       }
@@ -102,14 +102,14 @@ __global__ void roi_align_pack_kernel(const RoiArgs a) {
 extern "C" int sn_roi_align_pack_fwd(const float* tex_nchw, int b, int ch, int h, int w,
                                      const float* rois, int nroi, int pool, float* out_f32,
                                      int out_pitch, void* out_hi, void* out_lo, int plane_pitch,
-                                     int plane_coff, void* stream) {
+                                     int plane_coff, int plane_fmt, void* stream) {
   SN_REQUIRE(tex_nchw && rois && (out_f32 || out_hi), "null pointer");
   RoiArgs a;
   a.tex = tex_nchw; a.B = b; a.CH = ch; a.H = h; a.W = w;
   a.rois = rois; a.nroi = nroi; a.pool = pool;
   a.out = out_f32; a.out_pitch = out_pitch;
-  a.hi = (__nv_bfloat16*)out_hi; a.lo = (__nv_bfloat16*)out_lo;
-  a.ppitch = plane_pitch; a.pcoff = plane_coff;
+  a.hi = (uint16_t*)out_hi; a.lo = (uint16_t*)out_lo;
+  a.ppitch = plane_pitch; a.pcoff = plane_coff; a.fmt = plane_fmt;
   const long long total = (long long)b * pool * pool * nroi;
   long long grid = (total + 255) / 256;
   if (grid > 148 * 16) grid = 148 * 16;

@@ -29,7 +29,7 @@ from . import lowering as L
 from . import modules as M
 from . import ops
 from .layers import ConvLayer
-from .ops import ACT_LRELU, ACT_NONE, ACT_RELU, ACT_TANH, GradSrc, Planes
+from .ops import ACT_LRELU, ACT_NONE, ACT_RELU, ACT_TANH, FMT_BF16, GradSrc, Planes
 
 
 def _mix_seed(step_seed: int, stage_id: int) -> int:
@@ -81,7 +81,7 @@ class Stage:
     def bind_backward(self, wgrad: bool = True) -> None:
         dev = self.eng.device
         ly = self.layer
-        self.dy = Planes(self.n, self.oh, self.ow, L.pad64(self.cout), dev)
+        self.dy = Planes(self.n, self.oh, self.ow, L.pad64(self.cout), dev, fmt=FMT_BF16)  # gradients: fp32 range
         if self.need_dx:
             ih, iw = (ly.in_h + 2, ly.in_w + 2) if self.kind == "conv3r" else (ly.in_h, ly.in_w)
             self.dx = torch.zeros(self.n, ih, iw, ly.cin, device=dev)

@@ -14,7 +14,7 @@ import torch
 
 from . import lowering as L
 from . import ops
-from .ops import ACT_NONE, ACT_TANH, PackedWeights, Planes
+from .ops import ACT_NONE, ACT_TANH, FMT_BF16, FMT_F16, PackedWeights, Planes
 
 
 class ConvLayer:
@@ -38,11 +38,12 @@ class ConvLayer:
         assert self.k_pad % 64 == 0 and self.k_pad >= self.cin, (name, x.c, self.cin)
         self.block_n = L.pick_block_n(self.cout)
         self.t = L.ntaps(kind)
+        self.wscale = torch.ones(2, dtype=torch.float32, device=dev)  # (s, 1/s), shared by fwd and dgrad packs
         if kind == "head":
             self.rows_pad = (self.cout + self.block_n - 1) // self.block_n * self.block_n
-            self.wp = PackedWeights(self.rows_pad, 25 * self.k_pad, dev)
+            self.wp = PackedWeights(self.rows_pad, 25 * self.k_pad, dev, self.wscale)
         else:
-            self.wp = PackedWeights(self.cout, self.t * self.k_pad, dev)
+            self.wp = PackedWeights(self.cout, self.t * self.k_pad, dev, self.wscale)
         self.fwd_plans: List[ops.Plan] = []
         self.y: Optional[torch.Tensor] = None
         # backward state
@@ -76,6 +77,7 @@ class ConvLayer:
 
     def pack(self) -> None:
         """Re-pack the (updated) torch weights into the kernel layouts."""
+        ops.weight_scale(self.weight, self.wscale)
         if self.kind == "head":
             ops.pack_head_weights(self.weight, self.rows_pad, self.k_pad, False, self.wp)
             if self.wd is not None and self.dgrad_plans:
@@ -104,9 +106,9 @@ class ConvLayer:
         self.dgrad_plans = []
         if dx is not None:
             if self.kind == "head":
-                self.wd = PackedWeights(self.cin, 25 * dy.c, dev)
+                self.wd = PackedWeights(self.cin, 25 * dy.c, dev, self.wscale)
             else:
-                self.wd = PackedWeights(self.cin, self.t * dy.c, dev)
+                self.wd = PackedWeights(self.cin, self.t * dy.c, dev, self.wscale)
             bn = L.pick_block_n(self.cin)
             for spec in L.dgrad_specs(self.kind, self.in_h, self.in_w):
                 d = ops.tap_gemm_desc(dy, spec, self.wd, dy.c, dx, self.cin, nsplit=self.nsplit, block_n=bn,

@@ -13,7 +13,8 @@ import torch
 
 from . import _lib
 from . import lowering as L
-from ._lib import (ACT_LRELU, ACT_NONE, ACT_RELU, ACT_TANH, LAYOUT_NCHW, LAYOUT_NHWC, SnGradSrc,
+
+from ._lib import (ACT_LRELU, ACT_NONE, ACT_RELU, ACT_TANH, FMT_BF16, FMT_F16, LAYOUT_NCHW, LAYOUT_NHWC, SnGradSrc,
                    SnNormActBwdDesc, SnNormActDesc, SnTap, SnTapGemmDesc, SnWgradDesc, check)
 
 IN_EPS = 1e-5  # nn.InstanceNorm2d default (modules/__init__.py:67-69)
@@ -35,8 +36,11 @@ class Planes:
     wider) buffer with `pitch` channels per pixel.  Padding channels stay zero forever."""
 
     def __init__(self, n: int, h: int, w: int, pitch: int, device, c: Optional[int] = None, c_off: int = 0,
-                 hi: Optional[torch.Tensor] = None, lo: Optional[torch.Tensor] = None):
+                 hi: Optional[torch.Tensor] = None, lo: Optional[torch.Tensor] = None, fmt: int = FMT_F16):
+        """fmt: FMT_F16 (activations: 22-bit split) or FMT_BF16 (gradients: fp32 range).  The storage
+        dtype is bfloat16 either way — the planes are opaque 16-bit words to torch."""
         assert pitch % 8 == 0
+        self.fmt = fmt
         self.n, self.h, self.w, self.pitch = n, h, w, pitch
         self.c = pitch if c is None else c
         self.c_off = c_off
@@ -45,11 +49,12 @@ class Planes:
 
     def slice(self, c_off: int, c: int) -> "Planes":
         assert c_off + c <= self.pitch
-        return Planes(self.n, self.h, self.w, self.pitch, self.hi.device, c, self.c_off + c_off, self.hi, self.lo)
+        return Planes(self.n, self.h, self.w, self.pitch, self.hi.device, c, self.c_off + c_off, self.hi, self.lo,
+                      self.fmt)
 
     def batch_slice(self, n0: int, n: int) -> "Planes":
         return Planes(n, self.h, self.w, self.pitch, self.hi.device, self.c, self.c_off, self.hi[n0:n0 + n],
-                      self.lo[n0:n0 + n])
+                      self.lo[n0:n0 + n], self.fmt)
 
     @property
     def hi_ptr(self) -> int:
@@ -62,14 +67,19 @@ class Planes:
     def dense(self) -> torch.Tensor:
         """fp32 reconstruction hi + lo of the logical [n,h,w,c] tensor (tests / debugging)."""
         s = slice(self.c_off, self.c_off + self.c)
+        if self.fmt == FMT_F16:
+            return self.hi[..., s].view(torch.float16).float() + self.lo[..., s].view(torch.float16).float()
         return self.hi[..., s].float() + self.lo[..., s].float()
 
 
 class PackedWeights:
-    """[rows][k_total] split-bf16 weight matrix (K contiguous)."""
+    """[rows][k_total] split 16-bit weight matrix (K contiguous), fp16-split with an exact
+    power-of-two scale (`scale` = device (s, 1/s), set by weight_scale())."""
 
-    def __init__(self, rows: int, k_total: int, device):
+    def __init__(self, rows: int, k_total: int, device, scale: Optional[torch.Tensor] = None):
         self.rows, self.k_total = rows, k_total
+        self.fmt = FMT_F16
+        self.scale = scale if scale is not None else torch.ones(2, dtype=torch.float32, device=device)
         self.hi = torch.zeros(rows, k_total, dtype=torch.bfloat16, device=device)
         self.lo = torch.zeros(rows, k_total, dtype=torch.bfloat16, device=device)
 
@@ -111,6 +121,8 @@ def tap_gemm_desc(a: Planes, spec: L.GemmSpec, w: PackedWeights, k_per_tap: int,
     d.a_hi, d.a_lo = a.hi_ptr, a.lo_ptr
     d.a_n, d.a_h, d.a_w, d.a_c, d.a_pitch = a.n, a.h, a.w, a.c, a.pitch
     d.a_parity = 1 if spec.parity else 0
+    d.a_fmt, d.b_fmt = a.fmt, w.fmt
+    d.b_scale = w.scale.data_ptr()
     d.b_hi = w.hi.data_ptr() + 2 * w_elem_off
     d.b_lo = w.lo.data_ptr() + 2 * w_elem_off
     d.b_rows = w.rows if w_rows is None else w_rows
@@ -156,6 +168,7 @@ def wgrad_desc(x: Planes, y: Planes, spec: L.WgradSpec, out: torch.Tensor, s_row
     d = SnWgradDesc()
     d.x_hi, d.x_lo = x.hi_ptr, x.lo_ptr
     d.x_n, d.x_h, d.x_w, d.x_c, d.x_pitch, d.x_parity = x.n, x.h, x.w, x.c, x.pitch, int(xp)
+    d.x_fmt, d.y_fmt = x.fmt, y.fmt
     d.y_hi, d.y_lo = y.hi_ptr, y.lo_ptr
     d.y_n, d.y_h, d.y_w, d.y_c, d.y_pitch, d.y_parity = y.n, y.h, y.w, y.c, y.pitch, int(yp)
     d.m_n, d.m_h, d.m_w = x.n, spec.m_h, spec.m_w
@@ -191,14 +204,19 @@ def pack_planes(src: torch.Tensor, dst: Planes, *, nhwc: bool = False) -> None:
         assert src.stride(3) == 1 and src.stride(2) == sp
         c = dst.c
         check(_lib.load().sn_pack_planes(src.data_ptr(), LAYOUT_NHWC, sp, n, c, h, w, dst.hi_ptr, dst.lo_ptr,
-                                         dst.pitch, 0, _stream()))
+                                         dst.pitch, 0, dst.fmt, _stream()))
     else:
         assert src.is_contiguous()
         n, c, h, w = src.shape
         assert c <= dst.c
         check(_lib.load().sn_pack_planes(src.data_ptr(), LAYOUT_NCHW, 0, n, c, h, w, dst.hi_ptr, dst.lo_ptr,
-                                         dst.pitch, 0, _stream()))
+                                         dst.pitch, 0, dst.fmt, _stream()))
     assert (n, h, w) == (dst.n, dst.h, dst.w)
+
+
+def weight_scale(weight: torch.Tensor, scale: torch.Tensor) -> None:
+    """scale <- (s, 1/s), s = 2^k with max|w| * s in [2^13, 2^14) (device side, no sync)."""
+    check(_lib.load().sn_weight_scale(weight.data_ptr(), weight.numel(), scale.data_ptr(), _stream()))
 
 
 def pack_weights(weight: torch.Tensor, kind: str, dgrad: bool, k_pad: int, dst: PackedWeights) -> None:
@@ -211,14 +229,15 @@ def pack_weights(weight: torch.Tensor, kind: str, dgrad: bool, k_pad: int, dst: 
     t = L.ntaps(kind)
     assert dst.rows >= rows and dst.k_total == t * k_pad and k_pad >= k_real
     check(_lib.load().sn_pack_weights(weight.data_ptr(), s_row, s_k, rows, t, k_real, k_pad, dst.hi.data_ptr(),
-                                      dst.lo.data_ptr(), _stream()))
+                                      dst.lo.data_ptr(), dst.fmt, dst.scale.data_ptr(), _stream()))
 
 
 def pack_head_weights(weight: torch.Tensor, rows_pad: int, k_pad: int, dgrad: bool, dst: PackedWeights) -> None:
     cout, cin = weight.shape[:2]
     assert dst.hi.numel() >= (cin * 25 * k_pad if dgrad else rows_pad * 25 * k_pad)
     check(_lib.load().sn_pack_head_weights(weight.data_ptr(), cout, cin, rows_pad, k_pad, int(dgrad),
-                                           dst.hi.data_ptr(), dst.lo.data_ptr(), _stream()))
+                                           dst.hi.data_ptr(), dst.lo.data_ptr(), dst.fmt, dst.scale.data_ptr(),
+                                           _stream()))
 
 
 def fold_head_wgrad(geff: torch.Tensor, cout: int, cin: int, dw: torch.Tensor) -> None:
@@ -275,6 +294,7 @@ def norm_act_fwd(y: torch.Tensor, c: int, stats: Optional[torch.Tensor], act: in
         assert out.c >= c and out.n == n
         d.out_hi, d.out_lo, d.out_pitch, d.out_coff = out.hi.data_ptr(), out.lo.data_ptr(), out.pitch, out.c_off
         d.out_reflect_pad = int(reflect_pad)
+        d.out_fmt = out.fmt
     if out_f32 is not None:
         d.out_f32, d.f32_pitch = out_f32.data_ptr(), _pitch(out_f32)
     check(_lib.load().sn_norm_act_fwd(C.byref(d), _stream()))
@@ -313,12 +333,13 @@ def norm_act_bwd(srcs: Sequence[GradSrc], y: torch.Tensor, c: int, stats: Option
     d.gstats = _ptr(gstats)
     assert (dy.n, dy.h, dy.w) == (n, h, w) and dy.c >= c
     d.dy_hi, d.dy_lo, d.dy_pitch, d.dy_coff = dy.hi.data_ptr(), dy.lo.data_ptr(), dy.pitch, dy.c_off
+    d.dy_fmt = dy.fmt
     check(_lib.load().sn_norm_act_bwd(C.byref(d), _stream()))
 
 
 def bias_grad(dy: Planes, c: int, scratch: torch.Tensor, db: torch.Tensor) -> None:
     assert scratch.dtype == torch.float64 and scratch.numel() >= c and db.dtype == torch.float32
-    check(_lib.load().sn_bias_grad(dy.hi.data_ptr(), dy.lo.data_ptr(), dy.pitch, dy.c_off, dy.n * dy.h * dy.w, c,
+    check(_lib.load().sn_bias_grad(dy.hi.data_ptr(), dy.lo.data_ptr(), dy.pitch, dy.c_off, dy.fmt, dy.n * dy.h * dy.w, c,
                                    scratch.data_ptr(), db.data_ptr(), _stream()))
 
 
@@ -334,7 +355,7 @@ def tanh_bwd(srcs: Sequence[GradSrc], out: torch.Tensor, c: int, dy: Planes) -> 
     arr = (SnGradSrc * _lib.SN_MAX_SRC)()
     _fill_srcs(arr, srcs)
     check(_lib.load().sn_tanh_bwd(arr, len(srcs), out.data_ptr(), pitch, n, h, w, c, dy.hi.data_ptr(),
-                                  dy.lo.data_ptr(), dy.pitch, dy.c_off, _stream()))
+                                  dy.lo.data_ptr(), dy.pitch, dy.c_off, dy.fmt, _stream()))
 
 
 def dropout_mask(seed: int, p: float, count: int, device) -> torch.Tensor:
@@ -378,7 +399,8 @@ def roi_align_pack(tex_nchw: torch.Tensor, rois: torch.Tensor, pool: int, out_f3
         0 if out_f32 is None else out_f32.shape[3],
         None if out_planes is None else out_planes.hi.data_ptr(),
         None if out_planes is None else out_planes.lo.data_ptr(),
-        0 if out_planes is None else out_planes.pitch, 0 if out_planes is None else out_planes.c_off, _stream()))
+        0 if out_planes is None else out_planes.pitch, 0 if out_planes is None else out_planes.c_off,
+        FMT_F16 if out_planes is None else out_planes.fmt, _stream()))
 
 
 def launch_count() -> int:

@@ -8,6 +8,17 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 
+def record(name: str, value) -> None:
+    """Append a measured parity number to gpurun_out/parity.log (kept with the round's evidence)."""
+    try:
+        d = os.path.join(ROOT, "gpurun_out")
+        os.makedirs(d, exist_ok=True)
+        with open(os.path.join(d, "parity.log"), "a") as f:
+            f.write(f"{name} {value}\n")
+    except OSError:
+        pass
+
+
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
 

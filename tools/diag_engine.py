@@ -27,6 +27,7 @@ ref = ON.warp_forward(sdG, body.double(), inp.double())
 ON.record_into(None)
 gout = torch.randn(ref.shape, generator=torch.Generator().manual_seed(5)).double() * 1e-3
 ref.backward(gout)
+rec_G = rec
 eng.zero_grad()
 eng.backward([ops.GradSrc(nhwc(gout).float().contiguous().to(dev))])
 torch.cuda.synchronize()
@@ -71,3 +72,20 @@ for st in Dd.stages:
     if st.dx is not None and not st.plain:
         pass
     print(line)
+
+# ---------------- focus: dual_up2 backward ----------------
+if "--focus" in sys.argv:
+    st = eng.d2
+    g_in = eng.d3.dx[..., :128].cpu()
+    ra = rec_G["dual_up2.a"].grad
+    print(f"upstream grad into dual_up2 (d3.dx[:128]) relmax {relmax(g_in, nhwc(ra)):.2e}")
+    ry = rec_G["dual_up2.y"]
+    ref_dy = nhwc(ry.grad)
+    got = st.dy.dense().cpu()[..., :st.cout].double()
+    err_c = (got - ref_dy).abs().amax((0, 1, 2))
+    top = torch.topk(err_c, 5).indices.tolist()
+    mean_ref = ry.detach().mean((2, 3)); var_ref = ry.detach().var((2, 3), unbiased=False)
+    print("worst channels", top, "err", [f"{err_c[c]:.2e}" for c in top], "ref max|dy|", f"{ref_dy.abs().max():.2e}")
+    for c in top:
+        print(f" ch {c}: ref mean {mean_ref[:, c].tolist()} var {var_ref[:, c].tolist()} | eng mean {st.stats[:, c, 0].tolist()} rstd {st.stats[:, c, 1].tolist()} (ref rstd {(var_ref[:, c] + 1e-5).rsqrt().tolist()})")
+        print(f"        ref dy absmax per n {ref_dy[..., c].abs().amax((1,2)).tolist()}  got {got[..., c].abs().amax((1,2)).tolist()}")
