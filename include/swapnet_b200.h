@@ -22,6 +22,8 @@
  *   - a GEMM operand is a "split plane pair": two 16-bit-float NHWC tensors hi = r16(v),
  *     lo = r16(v - hi) in format SN_FMT_F16 or SN_FMT_BF16 (fp32 carried as 2 x 16 bit; products are
  *     evaluated as hi*hi + lo*hi + hi*lo on the tcgen05 tensor cores with fp32 accumulation).
+ *     Both operands of one contraction must use the same format: forward GEMMs run fp16-split
+ *     (activations x scaled weights), backward GEMMs bf16-split (gradients x bf16 copies).
  */
 #ifndef SWAPNET_B200_H
 #define SWAPNET_B200_H
@@ -38,7 +40,7 @@ extern "C" {
 enum { SN_ACT_NONE = 0, SN_ACT_TANH = 1, SN_ACT_LRELU = 2, SN_ACT_RELU = 3 };
 enum { SN_LAYOUT_NCHW = 0, SN_LAYOUT_NHWC = 1 };
 /* 16-bit float format of a split plane pair: bf16 (8+8 mantissa bits, fp32 range: gradients) or
- * fp16 (11+11 bits: activations, pre-scaled weights).  The two may meet in one MMA. */
+ * fp16 (11+11 bits: activations, pre-scaled weights).  A and B of one GEMM must agree. */
 #define SN_FMT_BF16 0
 #define SN_FMT_F16 1
 
@@ -152,6 +154,9 @@ typedef struct sn_norm_act_desc {
   const float* residual; int res_pitch;  /* optional: out = residual + xhat (ResidualBlock tail) */
   void* out_hi; void* out_lo; int out_pitch, out_coff; /* optional split planes */
   int out_fmt;
+  void* out2_hi; void* out2_lo; int out2_fmt; /* optional companion planes, same geometry (the
+                                            bf16-split copy read by the weight-gradient GEMM: A and B
+                                            of one tcgen05.mma must share a format) */
   int out_reflect_pad;                   /* 1: planes are [n, h+2, w+2] with ReflectionPad2d(1) */
   float* out_f32; int f32_pitch;         /* optional fp32 copy (residual stream) */
 } sn_norm_act_desc;

@@ -67,7 +67,8 @@ class SnNormActDesc(C.Structure):
         ("drop_p", C.c_float), ("drop_seed", C.c_ulonglong),
         ("residual", C.c_void_p), ("res_pitch", C.c_int),
         ("out_hi", C.c_void_p), ("out_lo", C.c_void_p), ("out_pitch", C.c_int), ("out_coff", C.c_int),
-        ("out_fmt", C.c_int), ("out_reflect_pad", C.c_int),
+        ("out_fmt", C.c_int), ("out2_hi", C.c_void_p), ("out2_lo", C.c_void_p), ("out2_fmt", C.c_int),
+        ("out_reflect_pad", C.c_int),
         ("out_f32", C.c_void_p), ("f32_pitch", C.c_int),
     ]
 

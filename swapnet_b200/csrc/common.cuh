@@ -201,8 +201,8 @@ __device__ __forceinline__ uint64_t umma_smem_desc(uint32_t smem_addr, uint32_t 
 // Instruction descriptor (cute::UMMA::InstrDescriptor), kind::f16, bf16 x bf16 -> f32.
 //   c_format[4,6)=1(F32) a_format[7,10)=1(BF16) b_format[10,13)=1(BF16)
 //   a_major bit15, b_major bit16 (0 = K-major, 1 = MN-major), n>>3 at [17,23), m>>4 at [24,29)
-//   a_format / b_format: 0 = F16, 1 = BF16 — independent, so an fp16-split activation can meet a
-//   bf16-split gradient in one instruction.
+//   a_format / b_format: 0 = F16, 1 = BF16.  (Mixing the two in one instruction raises
+//   "illegal instruction" on B200 — measured — so the host enforces a_fmt == b_fmt.)
 __host__ __device__ __forceinline__ uint32_t umma_idesc_16(uint32_t m, uint32_t n, uint32_t a_fmt,
                                                            uint32_t b_fmt, uint32_t a_mn_major,
                                                            uint32_t b_mn_major) {

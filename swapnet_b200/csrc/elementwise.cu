@@ -317,6 +317,7 @@ struct NormActFwdArgs {
   uint32_t drop_thresh; float drop_scale; unsigned long long seed;
   const float* residual; int res_pitch;
   uint16_t* hi; uint16_t* lo; int out_pitch, out_coff, reflect, fmt;
+  uint16_t* hi2; uint16_t* lo2; int fmt2;
   float* f32; int f32_pitch;
 };
 
@@ -354,12 +355,17 @@ __global__ void norm_act_fwd_kernel(const NormActFwdArgs a) {
       if (a.residual) v += a.residual[pix * a.res_pitch + c];
       if (a.f32) a.f32[pix * a.f32_pitch + c] = v;
       if (a.hi) {
-        uint16_t h, l;
+        uint16_t h, l, h2 = 0, l2 = 0;
         split16(v, a.fmt, h, l);
+        if (a.hi2) split16(v, a.fmt2, h2, l2);
         if (!a.reflect) {
           const long long off = pix * a.out_pitch + a.out_coff + c;
           a.hi[off] = h;
           if (a.lo) a.lo[off] = l;
+          if (a.hi2) {
+            a.hi2[off] = h2;
+            if (a.lo2) a.lo2[off] = l2;
+          }
         } else {
           const int hh = p / a.W, ww = p - hh * a.W;
           const int Hp = a.H + 2, Wp = a.W + 2;
@@ -376,6 +382,10 @@ __global__ void norm_act_fwd_kernel(const NormActFwdArgs a) {
                   (((long long)n * Hp + rows[i]) * Wp + cols[j]) * a.out_pitch + a.out_coff + c;
               a.hi[off] = h;
               if (a.lo) a.lo[off] = l;
+              if (a.hi2) {
+                a.hi2[off] = h2;
+                if (a.lo2) a.lo2[off] = l2;
+              }
             }
         }
       }
@@ -815,6 +825,7 @@ int sn_norm_act_fwd(const sn_norm_act_desc* d, void* stream) {
   a.hi = (uint16_t*)d->out_hi; a.lo = (uint16_t*)d->out_lo;
   a.out_pitch = d->out_pitch; a.out_coff = d->out_coff; a.reflect = d->out_reflect_pad;
   a.fmt = d->out_fmt;
+  a.hi2 = (uint16_t*)d->out2_hi; a.lo2 = (uint16_t*)d->out2_lo; a.fmt2 = d->out2_fmt;
   a.f32 = d->out_f32; a.f32_pitch = d->f32_pitch;
   dim3 blk = cblock(d->c);
   dim3 grid(slabs_for(d->h * d->w, d->n, blk.y), d->n);

@@ -441,6 +441,8 @@ int sn_tap_gemm_plan_init(TapGemmPlan* plan, const sn_tap_gemm_desc* d) {
              "block_n must be a multiple of 16 in [16,128]");
   SN_REQUIRE(d->a_hi && d->b_hi && d->out, "null operand");
   SN_REQUIRE(d->nsplit == 1 || (d->a_lo && d->b_lo), "nsplit=3 needs lo planes");
+  SN_REQUIRE(d->a_fmt == d->b_fmt, "A and B of one tcgen05.mma must share a 16-bit format (a=%d b=%d)",
+             d->a_fmt, d->b_fmt);
   int th, tw, nb;
   pick_patch(d->m_h, d->m_w, 128, &th, &tw, &nb);
   p.tw = tw; p.th = th; p.nb = nb;
@@ -513,6 +515,8 @@ int sn_wgrad_plan_init(WgradPlan* plan, const sn_wgrad_desc* d, int sm_count) {
   SN_REQUIRE(d->block_n == 64 || d->block_n == 128, "wgrad block_n must be 64 or 128");
   SN_REQUIRE(d->x_hi && d->y_hi && d->out, "null operand");
   SN_REQUIRE(d->nsplit == 1 || (d->x_lo && d->y_lo), "nsplit=3 needs lo planes");
+  SN_REQUIRE(d->x_fmt == d->y_fmt, "X and Y of one tcgen05.mma must share a 16-bit format (x=%d y=%d)",
+             d->x_fmt, d->y_fmt);
   int th, tw, nb;
   pick_patch(d->m_h, d->m_w, 64, &th, &tw, &nb);
   p.tw = tw; p.th = th; p.nb = nb;

@@ -105,12 +105,17 @@ class Stage:
 class Engine:
     """Common plumbing: stage list, flat gradient buffer, packing."""
 
-    def __init__(self, net: nn.Module, device, nsplit: int):
+    def __init__(self, net: nn.Module, device, nsplit: int, train: bool = True):
         self.net, self.device, self.nsplit = net, torch.device(device), nsplit
+        self.dual = train   # activation planes carry a bf16-split twin for the weight-gradient GEMMs
         self.stages: List[Stage] = []
         self.training = True
         self.seed = 0
         self.flat_grad: Optional[torch.Tensor] = None
+
+    def planes(self, n: int, h: int, w: int, c: int) -> Planes:
+        """fp16-split activation operand (+ bf16 twin when training)."""
+        return Planes(n, h, w, c, self.device, dual=self.dual)
 
     def alloc_grads(self, share_with: Optional["Engine"] = None) -> None:
         """One flat fp32 buffer for all parameter gradients (a single all-reduce under DP);
@@ -148,26 +153,26 @@ class Engine:
 # WarpModule
 # =============================================================================================
 class WarpEngine(Engine):
-    def __init__(self, net: M.WarpModule, batch: int, size: int, device, nsplit: int = 3):
-        super().__init__(net, device, nsplit)
+    def __init__(self, net: M.WarpModule, batch: int, size: int, device, nsplit: int = 3, train: bool = True):
+        super().__init__(net, device, nsplit, train)
         assert size % 64 == 0 and size >= 64, "WarpModule needs H = W = 64k (cloth_down6 is H/64)"
         B, S, dev = batch, size, self.device
         self.batch, self.size = B, S
         self.cb, self.cc = net.body_channels, net.cloth_channels
         dp = net.dropout
-        self.in_body = Planes(B, S, S, 64, dev)
-        self.in_cloth = Planes(B, S, S, 64, dev)
-        cat3 = Planes(B, S // 2, S // 2, 192, dev)
-        cat2 = Planes(B, S // 4, S // 4, 384, dev)
-        cat1 = Planes(B, S // 8, S // 8, 768, dev)
+        self.in_body = self.planes(B, S, S, 64)
+        self.in_cloth = self.planes(B, S, S, 64)
+        cat3 = self.planes(B, S // 2, S // 2, 192)
+        cat2 = self.planes(B, S // 4, S // 4, 384)
+        cat1 = self.planes(B, S // 8, S // 8, 768)
         h16 = S // 16
-        xpad = [Planes(B, h16 + 2, h16 + 2, 1024, dev) for _ in range(4)]   # reflect-padded resblock inputs
+        xpad = [self.planes(B, h16 + 2, h16 + 2, 1024) for _ in range(4)]   # reflect-padded resblock inputs
         xf32 = [torch.zeros(B, h16, h16, 1024, device=dev) for _ in range(5)]  # fp32 residual stream
-        a_c4 = Planes(B, h16, h16, 512, dev)
-        a_c5 = Planes(B, S // 32, S // 32, 1024, dev)
-        a_c6 = Planes(B, S // 64, S // 64, 1024, dev)
-        a_u1 = Planes(B, S // 32, S // 32, 1024, dev)
-        x4 = Planes(B, h16, h16, 1024, dev)
+        a_c4 = self.planes(B, h16, h16, 512)
+        a_c5 = self.planes(B, S // 32, S // 32, 1024)
+        a_c6 = self.planes(B, S // 64, S // 64, 1024)
+        a_u1 = self.planes(B, S // 32, S // 32, 1024)
+        x4 = self.planes(B, h16, h16, 1024)
         self.cat3, self.cat2, self.cat1, self.xf32 = cat3, cat2, cat1, xf32
         St = lambda *a, **k: Stage(self, *a, **k)  # noqa: E731
         n = net
@@ -189,7 +194,7 @@ class WarpEngine(Engine):
         self.res: List[Tuple[Stage, Stage]] = []
         for k in range(4):
             blk = n.resblocks[k].conv_block
-            p1 = Planes(B, h16 + 2, h16 + 2, 1024, dev)
+            p1 = self.planes(B, h16 + 2, h16 + 2, 1024)
             r1 = St(f"resblocks.{k}.conv1", "conv3r", blk[1], xpad[k], out=p1, reflect_out=True, norm=True, act=ACT_RELU,
                     drop_p=dp)
             last = k == 3
@@ -257,11 +262,11 @@ class PatchGANEngine(Engine):
     """NLayerDiscriminator on a [batch, S, S, pad64(input_nc)] operand (`self.din`)."""
 
     def __init__(self, net: M.NLayerDiscriminator, batch: int, size: int, device, nsplit: int = 3,
-                 din: Optional[Planes] = None, input_grad: bool = False):
-        super().__init__(net, device, nsplit)
+                 din: Optional[Planes] = None, input_grad: bool = False, train: bool = True):
+        super().__init__(net, device, nsplit, train)
         B, S, dev = batch, size, self.device
         self.batch, self.size = B, S
-        self.din = din if din is not None else Planes(B, S, S, L.pad64(net.input_nc), dev)
+        self.din = din if din is not None else self.planes(B, S, S, L.pad64(net.input_nc))
         assert (self.din.n, self.din.h, self.din.w) == (B, S, S)
         convs = net.convs()
         use_norm = net.norm == "instance"
@@ -271,7 +276,7 @@ class PatchGANEngine(Engine):
         for i, conv in enumerate(convs[:-1]):
             kind = "conv4s2" if conv.stride[0] == 2 else "conv4s1"
             oh = h // 2 if kind == "conv4s2" else h - 1
-            out = Planes(B, oh, oh, L.pad64(conv.out_channels), dev)
+            out = self.planes(B, oh, oh, L.pad64(conv.out_channels))
             st = Stage(self, f"model.{net.conv_index[i]}", kind, conv, x, out=out, norm=use_norm and i > 0,
                        act=ACT_LRELU, slope=0.2, need_dx=(i > 0) or input_grad)
             self.chain.append(st)

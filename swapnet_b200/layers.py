@@ -106,9 +106,9 @@ class ConvLayer:
         self.dgrad_plans = []
         if dx is not None:
             if self.kind == "head":
-                self.wd = PackedWeights(self.cin, 25 * dy.c, dev, self.wscale)
+                self.wd = PackedWeights(self.cin, 25 * dy.c, dev, fmt=dy.fmt)
             else:
-                self.wd = PackedWeights(self.cin, self.t * dy.c, dev, self.wscale)
+                self.wd = PackedWeights(self.cin, self.t * dy.c, dev, fmt=dy.fmt)
             bn = L.pick_block_n(self.cin)
             for spec in L.dgrad_specs(self.kind, self.in_h, self.in_w):
                 d = ops.tap_gemm_desc(dy, spec, self.wd, dy.c, dx, self.cin, nsplit=self.nsplit, block_n=bn,
@@ -120,7 +120,10 @@ class ConvLayer:
             assert wgrad.shape == self.weight.shape and wgrad.is_contiguous()
             (ws,) = L.wgrad_specs(self.kind, self.in_h, self.in_w)
             x_is_dy = ws.x_is == "dy"
-            xs, ys = (dy, self.x) if x_is_dy else (self.x, dy)
+            # the activation operand must come in the gradient's format: its bf16-split twin
+            xin = self.x if self.x.fmt == dy.fmt else self.x.twin
+            assert xin is not None, f"{self.name}: wgrad needs a {dy.fmt}-format twin of the input planes (dual=True)"
+            xs, ys = (dy, xin) if x_is_dy else (xin, dy)
             cx, cy = (self.cout, self.cin) if x_is_dy else (self.cin, self.cout)
             s_row, s_col = L.wgrad_out_strides(self.kind, self.cin, self.cout, x_is_dy)
             if self.kind == "head":

@@ -36,11 +36,17 @@ class Planes:
     wider) buffer with `pitch` channels per pixel.  Padding channels stay zero forever."""
 
     def __init__(self, n: int, h: int, w: int, pitch: int, device, c: Optional[int] = None, c_off: int = 0,
-                 hi: Optional[torch.Tensor] = None, lo: Optional[torch.Tensor] = None, fmt: int = FMT_F16):
+                 hi: Optional[torch.Tensor] = None, lo: Optional[torch.Tensor] = None, fmt: int = FMT_F16,
+                 dual: bool = False, twin: Optional["Planes"] = None):
         """fmt: FMT_F16 (activations: 22-bit split) or FMT_BF16 (gradients: fp32 range).  The storage
-        dtype is bfloat16 either way — the planes are opaque 16-bit words to torch."""
+        dtype is bfloat16 either way — the planes are opaque 16-bit words to torch.
+        dual=True also allocates a bf16-split twin of the same geometry (`self.twin`): forward GEMMs
+        read the fp16 planes, the weight-gradient GEMM reads the twin (one MMA = one format)."""
         assert pitch % 8 == 0
         self.fmt = fmt
+        self.twin = twin
+        if dual and twin is None:
+            self.twin = Planes(n, h, w, pitch, device, c, c_off, fmt=FMT_BF16)
         self.n, self.h, self.w, self.pitch = n, h, w, pitch
         self.c = pitch if c is None else c
         self.c_off = c_off
@@ -50,11 +56,11 @@ class Planes:
     def slice(self, c_off: int, c: int) -> "Planes":
         assert c_off + c <= self.pitch
         return Planes(self.n, self.h, self.w, self.pitch, self.hi.device, c, self.c_off + c_off, self.hi, self.lo,
-                      self.fmt)
+                      self.fmt, twin=None if self.twin is None else self.twin.slice(c_off, c))
 
     def batch_slice(self, n0: int, n: int) -> "Planes":
         return Planes(n, self.h, self.w, self.pitch, self.hi.device, self.c, self.c_off, self.hi[n0:n0 + n],
-                      self.lo[n0:n0 + n], self.fmt)
+                      self.lo[n0:n0 + n], self.fmt, twin=None if self.twin is None else self.twin.batch_slice(n0, n))
 
     @property
     def hi_ptr(self) -> int:
@@ -76,10 +82,11 @@ class PackedWeights:
     """[rows][k_total] split 16-bit weight matrix (K contiguous), fp16-split with an exact
     power-of-two scale (`scale` = device (s, 1/s), set by weight_scale())."""
 
-    def __init__(self, rows: int, k_total: int, device, scale: Optional[torch.Tensor] = None):
+    def __init__(self, rows: int, k_total: int, device, scale: Optional[torch.Tensor] = None, fmt: int = FMT_F16):
         self.rows, self.k_total = rows, k_total
-        self.fmt = FMT_F16
-        self.scale = scale if scale is not None else torch.ones(2, dtype=torch.float32, device=device)
+        self.fmt = fmt
+        # bf16-split packs (backward GEMMs) are unscaled; fp16-split packs carry the per-tensor 2^k
+        self.scale = scale if (scale is not None and fmt == FMT_F16) else None
         self.hi = torch.zeros(rows, k_total, dtype=torch.bfloat16, device=device)
         self.lo = torch.zeros(rows, k_total, dtype=torch.bfloat16, device=device)
 
@@ -122,7 +129,7 @@ def tap_gemm_desc(a: Planes, spec: L.GemmSpec, w: PackedWeights, k_per_tap: int,
     d.a_n, d.a_h, d.a_w, d.a_c, d.a_pitch = a.n, a.h, a.w, a.c, a.pitch
     d.a_parity = 1 if spec.parity else 0
     d.a_fmt, d.b_fmt = a.fmt, w.fmt
-    d.b_scale = w.scale.data_ptr()
+    d.b_scale = None if w.scale is None else w.scale.data_ptr()
     d.b_hi = w.hi.data_ptr() + 2 * w_elem_off
     d.b_lo = w.lo.data_ptr() + 2 * w_elem_off
     d.b_rows = w.rows if w_rows is None else w_rows
@@ -203,14 +210,16 @@ def pack_planes(src: torch.Tensor, dst: Planes, *, nhwc: bool = False) -> None:
         n, h, w, sp = src.shape
         assert src.stride(3) == 1 and src.stride(2) == sp
         c = dst.c
-        check(_lib.load().sn_pack_planes(src.data_ptr(), LAYOUT_NHWC, sp, n, c, h, w, dst.hi_ptr, dst.lo_ptr,
-                                         dst.pitch, 0, dst.fmt, _stream()))
+        for d_ in ((dst,) if dst.twin is None else (dst, dst.twin)):
+            check(_lib.load().sn_pack_planes(src.data_ptr(), LAYOUT_NHWC, sp, n, c, h, w, d_.hi_ptr, d_.lo_ptr,
+                                             d_.pitch, 0, d_.fmt, _stream()))
     else:
         assert src.is_contiguous()
         n, c, h, w = src.shape
         assert c <= dst.c
-        check(_lib.load().sn_pack_planes(src.data_ptr(), LAYOUT_NCHW, 0, n, c, h, w, dst.hi_ptr, dst.lo_ptr,
-                                         dst.pitch, 0, dst.fmt, _stream()))
+        for d_ in ((dst,) if dst.twin is None else (dst, dst.twin)):
+            check(_lib.load().sn_pack_planes(src.data_ptr(), LAYOUT_NCHW, 0, n, c, h, w, d_.hi_ptr, d_.lo_ptr,
+                                             d_.pitch, 0, d_.fmt, _stream()))
     assert (n, h, w) == (dst.n, dst.h, dst.w)
 
 
@@ -229,15 +238,16 @@ def pack_weights(weight: torch.Tensor, kind: str, dgrad: bool, k_pad: int, dst: 
     t = L.ntaps(kind)
     assert dst.rows >= rows and dst.k_total == t * k_pad and k_pad >= k_real
     check(_lib.load().sn_pack_weights(weight.data_ptr(), s_row, s_k, rows, t, k_real, k_pad, dst.hi.data_ptr(),
-                                      dst.lo.data_ptr(), dst.fmt, dst.scale.data_ptr(), _stream()))
+                                      dst.lo.data_ptr(), dst.fmt, None if dst.scale is None else dst.scale.data_ptr(),
+                                      _stream()))
 
 
 def pack_head_weights(weight: torch.Tensor, rows_pad: int, k_pad: int, dgrad: bool, dst: PackedWeights) -> None:
     cout, cin = weight.shape[:2]
     assert dst.hi.numel() >= (cin * 25 * k_pad if dgrad else rows_pad * 25 * k_pad)
     check(_lib.load().sn_pack_head_weights(weight.data_ptr(), cout, cin, rows_pad, k_pad, int(dgrad),
-                                           dst.hi.data_ptr(), dst.lo.data_ptr(), dst.fmt, dst.scale.data_ptr(),
-                                           _stream()))
+                                           dst.hi.data_ptr(), dst.lo.data_ptr(), dst.fmt,
+                                           None if dst.scale is None else dst.scale.data_ptr(), _stream()))
 
 
 def fold_head_wgrad(geff: torch.Tensor, cout: int, cin: int, dw: torch.Tensor) -> None:
@@ -295,6 +305,8 @@ def norm_act_fwd(y: torch.Tensor, c: int, stats: Optional[torch.Tensor], act: in
         d.out_hi, d.out_lo, d.out_pitch, d.out_coff = out.hi.data_ptr(), out.lo.data_ptr(), out.pitch, out.c_off
         d.out_reflect_pad = int(reflect_pad)
         d.out_fmt = out.fmt
+        if out.twin is not None:
+            d.out2_hi, d.out2_lo, d.out2_fmt = out.twin.hi.data_ptr(), out.twin.lo.data_ptr(), out.twin.fmt
     if out_f32 is not None:
         d.out_f32, d.f32_pitch = out_f32.data_ptr(), _pitch(out_f32)
     check(_lib.load().sn_norm_act_fwd(C.byref(d), _stream()))

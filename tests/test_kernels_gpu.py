@@ -1,8 +1,8 @@
 """GPU parity of every CUDA kernel behind the C ABI, one op at a time, against fp64 torch
 restatements of the reference ops (and the numpy ROI oracle).
 
-Tolerances: split-bf16 x3 tensor-core products are fp32-faithful -> 1e-4 of the output scale
-(the north-star bar is 1e-3 relative fp32); single-pass bf16 is reported at 3e-2.
+Tolerances (max|err| / max|ref|; the north-star bar is 1e-3 relative fp32): forward GEMMs run
+fp16-split x3 -> < 1.5e-5; backward GEMMs run bf16-split x3 -> < 1e-4; single-pass fp16 < 5e-3.
 """
 import numpy as np
 import pytest
@@ -81,10 +81,10 @@ def make_layer(kind, n, cin, cout, h, w, nsplit, with_bias=True):
     cp = L.pad64(cin)
     if kind == "conv3r":
         xp = F.pad(x, (1, 1, 1, 1), mode="reflect")
-        planes = ops.Planes(n, h + 2, w + 2, cp + 64, dev(), c=cp, c_off=64)  # inside a wider buffer
+        planes = ops.Planes(n, h + 2, w + 2, cp + 64, dev(), c=cp, c_off=64, dual=True)  # inside a wider buffer
         ops.pack_planes(xp.to(dev()), planes)
     else:
-        planes = ops.Planes(n, h, w, cp + 64, dev(), c=cp, c_off=0)
+        planes = ops.Planes(n, h, w, cp + 64, dev(), c=cp, c_off=0, dual=True)
         ops.pack_planes(x.to(dev()), planes)
     wd = wt.to(dev()).contiguous()
     bd = None if bias is None else bias.to(dev())
@@ -107,7 +107,9 @@ def test_conv_forward(kind, n, cin, cout, h, w, nsplit):
     ref = nhwc(ref_forward(kind, x.double(), wt.double(), bias.double()))
     got = y[..., 2:2 + cout].cpu()
     err = relmax(got, ref)
-    tol = 5e-6 if nsplit == 3 else 5e-3   # fp16-split x3 is fp32-level; single-pass fp16 ~2^-11
+    # fp16-split x3: operands carry 22 bits; what remains (~3e-6) is the tensor core's fp32
+    # accumulation (truncating adds).  Single-pass fp16 ~2^-11.
+    tol = 1.5e-5 if nsplit == 3 else 5e-3
     record(f"conv_fwd[{kind},{n},{cin},{cout},{h}x{w},nsplit={nsplit}]", f"{err:.3e}")
     assert err < tol, f"{kind} fwd nsplit={nsplit}: relmax {err:.3e}"
     assert torch.all(y[..., :2] == 7.0) and torch.all(y[..., 2 + cout:] == 7.0), "wrote outside its channel slice"
@@ -124,7 +126,7 @@ def test_conv_forward(kind, n, cin, cout, h, w, nsplit):
                                   block_n=layer.block_n, out_c_off=2, **kw)
             ops.tap_gemm_simt(d)
         torch.cuda.synchronize()
-        assert relmax(y2[..., 2:2 + cout].cpu(), ref) < 5e-6
+        assert relmax(y2[..., 2:2 + cout].cpu(), ref) < 2e-6
 
 
 @pytest.mark.parametrize("kind,n,cin,cout,h,w", CONV_CASES)
