@@ -30,6 +30,22 @@ def record(name, value):
     _r(name, value)
 
 
+def stage_gates(eng, n0=0, n1=None):
+    """name -> bool NCHW mask (CPU) of the activation gates the device used: xhat > 0 <=> y > mean."""
+    out = {}
+    for st in eng.stages:
+        if st.plain or st.act == 0:
+            continue
+        y = st.y[n0:n1]
+        if st.stats is not None:
+            mean = st.stats[n0:n1, :, 0].float()[:, None, None, :]
+            m = y > mean
+        else:
+            m = y > 0
+        out[st.name] = m.permute(0, 3, 1, 2).cpu()
+    return out
+
+
 def synth_warp_batch(B, S, seed=1234):
     """normalised-RGB-like body, 16x16-block one-hot cloth labels (label 0 = all-zero)."""
     g = torch.Generator().manual_seed(seed)
@@ -128,7 +144,26 @@ def test_warp_model_step_matches_oracle():
 
     torch.manual_seed(123)
     draws = [torch.rand(1) for _ in range(3)]
+    # gradients are compared at the gates the device used (see oracle/nets.py: _GATE); D is called three
+    # times by the oracle: fake half, real half (D step), fake again (G step, same weights here)
+    gates_G = stage_gates(model._eng_G)
+    gates_D = [stage_gates(model._eng_Dd, 0, B), stage_gates(model._eng_Dd, B, 2 * B), stage_gates(model._eng_Dg)]
+    calls = {}
+
+    def gate(name, x):
+        if name in gates_G:
+            return gates_G[name]
+        k = calls.get(name, 0)
+        calls[name] = k + 1
+        return gates_D[k][name]
+
+    ON.gate_with(gate)
     o = ON.warp_step_losses(sdG, sdD, body.double(), inp.double(), tgt.double(), draws)
+    ON.gate_with(None)
+    flips = {k: v for k, v in ON.GATE_STATS.items() if k != "__total__" and v}
+    total = ON.GATE_STATS.get("__total__", 1)
+    record("warp_step_gate_flips", f"{sum(flips.values())} of {total} gates differ from the fp64 oracle: {flips}")
+    assert sum(flips.values()) <= 2e-5 * total, f"too many activation gates differ: {flips}"
     refD = torch.autograd.grad(o["D"], list(sdD.values()), retain_graph=True)
     refG = torch.autograd.grad(o["G"], list(sdG.values()), allow_unused=True)
     for k in ("D", "D_real", "D_fake", "G", "G_gan", "G_ce"):
