@@ -65,6 +65,16 @@ class Stage:
         self.dx: Optional[torch.Tensor] = None
         self.gstats = None
 
+    def nominal_macs(self) -> int:
+        """Dense multiply-accumulates of the reference op for this stage's batch (SURVEY §8d:
+        Conv2d out_elems*Cin*k*k, ConvTranspose2d in_elems*Cout*k*k; zero taps of padding and
+        up-sampling counted)."""
+        ly = self.layer
+        k2 = 9 if self.kind == "conv3r" else 16
+        if self.kind == "convT4s2":
+            return self.n * ly.in_h * ly.in_w * ly.cin * ly.cout * k2
+        return self.n * self.oh * self.ow * ly.cout * ly.cin * k2
+
     # ---- forward ----
     def forward(self) -> None:
         self.layer.forward()

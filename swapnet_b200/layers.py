@@ -74,6 +74,7 @@ class ConvLayer:
             d = ops.tap_gemm_desc(self.x, spec, self.wp, self.k_pad, y, self.cout, bias=self.bias,
                                   act=self.act, nsplit=self.nsplit, block_n=self.block_n, out_c_off=y_c_off, **kw)
             self.fwd_plans.append(ops.tap_gemm_plan(d, keep=(self.x.hi, self.x.lo, self.wp.hi, self.wp.lo, y)))
+            self.fwd_plans[-1].tag = ("fwd", self.name)
 
     def pack(self) -> None:
         """Re-pack the (updated) torch weights into the kernel layouts."""
@@ -114,6 +115,7 @@ class ConvLayer:
                 d = ops.tap_gemm_desc(dy, spec, self.wd, dy.c, dx, self.cin, nsplit=self.nsplit, block_n=bn,
                                       out_c_off=dx_c_off)
                 self.dgrad_plans.append(ops.tap_gemm_plan(d, keep=(dy.hi, dy.lo, self.wd.hi, self.wd.lo, dx)))
+                self.dgrad_plans[-1].tag = ("dgrad", self.name)
         self.wgrad_out = wgrad
         self.wgrad_plan = None
         if wgrad is not None:
@@ -135,6 +137,7 @@ class ConvLayer:
             swap = cy > cx
             d = ops.wgrad_desc(xs, ys, ws, out, s_row, s_col, tap_off, cx, cy, swap=swap, nsplit=self.nsplit)
             self.wgrad_plan = ops.wgrad_plan(d, keep=(xs.hi, xs.lo, ys.hi, ys.lo, out))
+            self.wgrad_plan.tag = ("wgrad", self.name)
         self.bgrad_out = bgrad
         if bgrad is not None:
             self._bscratch = torch.zeros(self.cout, dtype=torch.float64, device=dev)

@@ -94,12 +94,24 @@ class PackedWeights:
 class Plan:
     """Owns one sn_plan handle (encoded TMA descriptors + launch geometry)."""
 
-    def __init__(self, handle: int, keep: Sequence):
+    def __init__(self, handle: int, keep: Sequence, tag=None):
         self.handle = handle
+        self.tag = tag
         self._keep = list(keep)  # tensors whose addresses are baked into the plan
 
+    # bench.py's roofline pass: when a list is installed here every plan launch is bracketed by CUDA
+    # events on the launching stream and (tag, start, end) is appended
+    trace = None
+
     def run(self) -> None:
+        if Plan.trace is None:
+            check(_lib.load().sn_plan_run(self.handle, _stream()))
+            return
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
         check(_lib.load().sn_plan_run(self.handle, _stream()))
+        e1.record()
+        Plan.trace.append((self, e0, e1))
 
     def __del__(self):
         try:

@@ -159,9 +159,10 @@ def test_warp_model_step_matches_oracle():
 
     ON.gate_with(gate)
     o = ON.warp_step_losses(sdG, sdD, body.double(), inp.double(), tgt.double(), draws)
+    stats = dict(ON.GATE_STATS)
     ON.gate_with(None)
-    flips = {k: v for k, v in ON.GATE_STATS.items() if k != "__total__" and v}
-    total = ON.GATE_STATS.get("__total__", 1)
+    flips = {k: v for k, v in stats.items() if k != "__total__" and v}
+    total = stats.get("__total__", 1)
     record("warp_step_gate_flips", f"{sum(flips.values())} of {total} gates differ from the fp64 oracle: {flips}")
     assert sum(flips.values()) <= 2e-5 * total, f"too many activation gates differ: {flips}"
     refD = torch.autograd.grad(o["D"], list(sdD.values()), retain_graph=True)
