@@ -71,13 +71,13 @@ class ClockSampler(threading.Thread):
 
     def __init__(self, index: int):
         super().__init__(daemon=True)
-        self.index, self.rows, self._stop = index, [], threading.Event()
+        self.index, self.rows, self._halt = index, [], threading.Event()
 
     def run(self):
         q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
              "clocks_event_reasons.sw_power_cap")
-        while not self._stop.is_set():
+        while not self._halt.is_set():
             try:
                 out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}",
                                       "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
@@ -86,10 +86,10 @@ class ClockSampler(threading.Thread):
                     self.rows.append(f)
             except Exception:
                 pass
-            self._stop.wait(0.2)
+            self._halt.wait(0.05)
 
     def stop(self):
-        self._stop.set()
+        self._halt.set()
         self.join(timeout=5)
         if not self.rows:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}

@@ -701,6 +701,242 @@ __global__ void tap_gemm_simt_kernel(const SimtArgs a) {
   }
 }
 
+
+// =================================================================================
+// 4-channel vectorised variants (C % 4 == 0, 16-B aligned fp32 rows, 8-B aligned plane rows).
+// One block = one image n and one slab of pixels, all channels; the per-channel statistics sit
+// in shared memory; threads walk the flattened (pixel, channel-quad) index so that a warp
+// touches 512 contiguous bytes.
+// =================================================================================
+__device__ __forceinline__ void store_split4(uint16_t* hi, uint16_t* lo, long long off, const float v[4], int fmt) {
+  uint16_t h[4], l[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) split16(v[j], fmt, h[j], l[j]);
+  uint2 ph, pl;
+  ph.x = (uint32_t)h[0] | ((uint32_t)h[1] << 16); ph.y = (uint32_t)h[2] | ((uint32_t)h[3] << 16);
+  pl.x = (uint32_t)l[0] | ((uint32_t)l[1] << 16); pl.y = (uint32_t)l[2] | ((uint32_t)l[3] << 16);
+  *reinterpret_cast<uint2*>(hi + off) = ph;
+  if (lo) *reinterpret_cast<uint2*>(lo + off) = pl;
+}
+
+__global__ void norm_act_fwd_v4_kernel(const NormActFwdArgs a) {
+  extern __shared__ float sm[];  // mean[C], rstd[C]
+  float* s_mean = sm;
+  float* s_rstd = sm + a.C;
+  const int n = blockIdx.y;
+  for (int c = threadIdx.x; c < a.C; c += blockDim.x) {
+    s_mean[c] = a.stats ? (float)a.stats[((long long)n * a.C + c) * 2] : 0.f;
+    s_rstd[c] = a.stats ? (float)a.stats[((long long)n * a.C + c) * 2 + 1] : 1.f;
+  }
+  __syncthreads();
+  const int HW = a.H * a.W, Q = a.C >> 2;
+  const int per = (HW + gridDim.x - 1) / gridDim.x;
+  const int p0 = blockIdx.x * per, p1 = min(HW, p0 + per);
+  const long long i1 = (long long)p1 * Q;
+  for (long long i = (long long)p0 * Q + threadIdx.x; i < i1; i += blockDim.x) {
+    const int p = (int)(i / Q);
+    const int c = ((int)(i - (long long)p * Q)) << 2;
+    const long long pix = (long long)n * HW + p;
+    const float4 yv = *reinterpret_cast<const float4*>(a.y + pix * a.y_pitch + c);
+    float v[4] = {yv.x, yv.y, yv.z, yv.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float t = (v[j] - s_mean[c + j]) * s_rstd[c + j];
+      t = act_fwd(t, a.act, a.slope);
+      if (a.drop_thresh) {
+        const bool keep = sn_keep(a.seed, (unsigned long long)pix * a.C + c + j, a.drop_thresh);
+        t = keep ? t * a.drop_scale : 0.f;
+      }
+      v[j] = t;
+    }
+    if (a.residual) {
+      const float4 r = *reinterpret_cast<const float4*>(a.residual + pix * a.res_pitch + c);
+      v[0] += r.x; v[1] += r.y; v[2] += r.z; v[3] += r.w;
+    }
+    if (a.f32) *reinterpret_cast<float4*>(a.f32 + pix * a.f32_pitch + c) = make_float4(v[0], v[1], v[2], v[3]);
+    if (a.hi) {
+      if (!a.reflect) {
+        const long long off = pix * a.out_pitch + a.out_coff + c;
+        store_split4(a.hi, a.lo, off, v, a.fmt);
+        if (a.hi2) store_split4(a.hi2, a.lo2, off, v, a.fmt2);
+      } else {
+        const int hh = p / a.W, ww = p - hh * a.W;
+        const int Hp = a.H + 2, Wp = a.W + 2;
+        int rows[2], cols[2], nr = 1, nc = 1;
+        rows[0] = hh + 1;
+        cols[0] = ww + 1;
+        if (hh == 1) rows[nr++] = 0;
+        if (hh == a.H - 2) rows[nr++] = a.H + 1;
+        if (ww == 1) cols[nc++] = 0;
+        if (ww == a.W - 2) cols[nc++] = a.W + 1;
+        for (int ii = 0; ii < nr; ++ii)
+          for (int jj = 0; jj < nc; ++jj) {
+            const long long off = (((long long)n * Hp + rows[ii]) * Wp + cols[jj]) * a.out_pitch + a.out_coff + c;
+            store_split4(a.hi, a.lo, off, v, a.fmt);
+            if (a.hi2) store_split4(a.hi2, a.lo2, off, v, a.fmt2);
+          }
+      }
+    }
+  }
+}
+
+__device__ __forceinline__ float4 gather_grad4(const GradSrcs& g, int n, int h, int w, int H, int W, int c) {
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int i = 0; i < g.n; ++i) {
+    const sn_grad_src& s = g.s[i];
+    if (!s.reflect_padded) {
+      const float4 v = *reinterpret_cast<const float4*>(s.ptr + (((long long)n * H + h) * W + w) * s.pitch + s.c_off + c);
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    } else {
+      const int Hp = H + 2, Wp = W + 2;
+      int rows[2], cols[2], nr = 1, nc = 1;
+      rows[0] = h + 1;
+      cols[0] = w + 1;
+      if (h == 1) rows[nr++] = 0;
+      if (h == H - 2) rows[nr++] = H + 1;
+      if (w == 1) cols[nc++] = 0;
+      if (w == W - 2) cols[nc++] = W + 1;
+      for (int a = 0; a < nr; ++a)
+        for (int b = 0; b < nc; ++b) {
+          const float4 v = *reinterpret_cast<const float4*>(
+              s.ptr + (((long long)n * Hp + rows[a]) * Wp + cols[b]) * s.pitch + s.c_off + c);
+          acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+        }
+    }
+  }
+  return acc;
+}
+
+// g (w.r.t. xhat) and xhat for a channel quad
+__device__ __forceinline__ void grad_xhat4(const NormActBwdArgs& a, int n, int p, int c, const float* mean,
+                                           const float* rstd, float g[4], float xh[4]) {
+  const int HW = a.H * a.W;
+  const long long pix = (long long)n * HW + p;
+  const int h = p / a.W, w = p - h * a.W;
+  const float4 gv = gather_grad4(a.g, n, h, w, a.H, a.W, c);
+  const float4 yv = *reinterpret_cast<const float4*>(a.y + pix * a.y_pitch + c);
+  const float gg[4] = {gv.x, gv.y, gv.z, gv.w};
+  const float yy[4] = {yv.x, yv.y, yv.z, yv.w};
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float xhat = (yy[j] - mean[j]) * rstd[j];
+    float t = gg[j];
+    if (a.drop_thresh) {
+      const bool keep = sn_keep(a.seed, (unsigned long long)pix * a.C + c + j, a.drop_thresh);
+      t = keep ? t * a.drop_scale : 0.f;
+    }
+    g[j] = t * act_grad(xhat, a.act, a.slope);
+    xh[j] = xhat;
+  }
+}
+
+// grid (ceil(Q/32), slabs, N), block (32, 8): thread = channel quad, strided over pixels
+__global__ void norm_act_bwd_reduce_v4_kernel(const NormActBwdArgs a) {
+  __shared__ float red[8][32][8];
+  const int q = blockIdx.x * 32 + threadIdx.x;
+  const int c = q << 2;
+  const int n = blockIdx.z;
+  const int HW = a.H * a.W;
+  const int per = (HW + gridDim.y - 1) / gridDim.y;
+  const int p0 = blockIdx.y * per, p1 = min(HW, p0 + per);
+  float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
+  if (c < a.C) {
+    float mean[4], rstd[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      mean[j] = (float)a.stats[((long long)n * a.C + c + j) * 2];
+      rstd[j] = (float)a.stats[((long long)n * a.C + c + j) * 2 + 1];
+    }
+    for (int p = p0 + threadIdx.y; p < p1; p += 8) {
+      float g[4], xh[4];
+      grad_xhat4(a, n, p, c, mean, rstd, g, xh);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        s1[j] += g[j];
+        s2[j] += g[j] * xh[j];
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    red[threadIdx.y][threadIdx.x][j] = s1[j];
+    red[threadIdx.y][threadIdx.x][4 + j] = s2[j];
+  }
+  __syncthreads();
+  if (threadIdx.y == 0 && c < a.C) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      double u = 0.0, v = 0.0;
+#pragma unroll
+      for (int r = 0; r < 8; ++r) {
+        u += (double)red[r][threadIdx.x][j];
+        v += (double)red[r][threadIdx.x][4 + j];
+      }
+      atomic_add_f64(&a.gstats[((long long)n * a.C + c + j) * 2 + 0], u);
+      atomic_add_f64(&a.gstats[((long long)n * a.C + c + j) * 2 + 1], v);
+    }
+  }
+}
+
+__global__ void norm_act_bwd_apply_v4_kernel(const NormActBwdArgs a) {
+  extern __shared__ float sm[];  // mean, rstd, m1, m2 : 4 x C
+  float* s_mean = sm;
+  float* s_rstd = sm + a.C;
+  float* s_m1 = sm + 2 * a.C;
+  float* s_m2 = sm + 3 * a.C;
+  const int n = blockIdx.y;
+  for (int c = threadIdx.x; c < a.C; c += blockDim.x) {
+    const long long k = ((long long)n * a.C + c) * 2;
+    s_mean[c] = a.stats ? (float)a.stats[k] : 0.f;
+    s_rstd[c] = a.stats ? (float)a.stats[k + 1] : 1.f;
+    s_m1[c] = a.stats ? (float)a.gstats[k] : 0.f;
+    s_m2[c] = a.stats ? (float)a.gstats[k + 1] : 0.f;
+  }
+  __syncthreads();
+  const int HW = a.H * a.W, Q = a.C >> 2;
+  const int per = (HW + gridDim.x - 1) / gridDim.x;
+  const int p0 = blockIdx.x * per, p1 = min(HW, p0 + per);
+  const long long i1 = (long long)p1 * Q;
+  for (long long i = (long long)p0 * Q + threadIdx.x; i < i1; i += blockDim.x) {
+    const int p = (int)(i / Q);
+    const int c = ((int)(i - (long long)p * Q)) << 2;
+    float g[4], xh[4];
+    grad_xhat4(a, n, p, c, s_mean + c, s_rstd + c, g, xh);
+    if (a.stats) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) g[j] = s_rstd[c + j] * (g[j] - s_m1[c + j] - xh[j] * s_m2[c + j]);
+    }
+    store_split4(a.hi, a.lo, ((long long)n * HW + p) * a.dy_pitch + a.dy_coff + c, g, a.fmt);
+  }
+}
+
+__global__ void sum_grads_v4_kernel(const GradSrcs g, int H, int W, int C, float* dst, int dst_pitch) {
+  const int n = blockIdx.y;
+  const int HW = H * W, Q = C >> 2;
+  const int per = (HW + gridDim.x - 1) / gridDim.x;
+  const int p0 = blockIdx.x * per, p1 = min(HW, p0 + per);
+  const long long i1 = (long long)p1 * Q;
+  for (long long i = (long long)p0 * Q + threadIdx.x; i < i1; i += blockDim.x) {
+    const int p = (int)(i / Q);
+    const int c = ((int)(i - (long long)p * Q)) << 2;
+    const int h = p / W, w = p - h * W;
+    *reinterpret_cast<float4*>(dst + ((long long)n * HW + p) * dst_pitch + c) = gather_grad4(g, n, h, w, H, W, c);
+  }
+}
+
+inline bool al16(const void* p) { return ((uintptr_t)p & 15) == 0; }
+inline bool srcs_vec_ok(const GradSrcs& g) {
+  for (int i = 0; i < g.n; ++i)
+    if (!al16(g.s[i].ptr) || (g.s[i].pitch & 3) || (g.s[i].c_off & 3)) return false;
+  return true;
+}
+inline int vslabs(int hw, int n) {  // ~6 waves of 256-thread blocks, at least 32 pixels per block
+  int want = (148 * 6 + n - 1) / n;
+  int maxs = (hw + 31) / 32;
+  if (want > maxs) want = maxs;
+  return want < 1 ? 1 : want;
+}
+
 inline int grid_for(long long total, int threads = kEwThreads) {
   long long g = (total + threads - 1) / threads;
   if (g > 148 * 16) g = 148 * 16;
@@ -827,9 +1063,21 @@ int sn_norm_act_fwd(const sn_norm_act_desc* d, void* stream) {
   a.fmt = d->out_fmt;
   a.hi2 = (uint16_t*)d->out2_hi; a.lo2 = (uint16_t*)d->out2_lo; a.fmt2 = d->out2_fmt;
   a.f32 = d->out_f32; a.f32_pitch = d->f32_pitch;
-  dim3 blk = cblock(d->c);
-  dim3 grid(slabs_for(d->h * d->w, d->n, blk.y), d->n);
-  norm_act_fwd_kernel<<<grid, blk, 0, (cudaStream_t)stream>>>(a);
+  const bool vec = (d->c % 4 == 0) && al16(d->y) && (d->y_pitch % 4 == 0) &&
+                   (!d->residual || (al16(d->residual) && d->res_pitch % 4 == 0)) &&
+                   (!d->out_f32 || (al16(d->out_f32) && d->f32_pitch % 4 == 0)) &&
+                   (!d->out_hi || (d->out_pitch % 4 == 0 && d->out_coff % 4 == 0 && ((uintptr_t)d->out_hi & 7) == 0 &&
+                                   ((uintptr_t)d->out_lo & 7) == 0 && ((uintptr_t)d->out2_hi & 7) == 0 &&
+                                   ((uintptr_t)d->out2_lo & 7) == 0)) &&
+                   d->c <= 4096;
+  if (vec) {
+    dim3 grid(vslabs(d->h * d->w, d->n), d->n);
+    norm_act_fwd_v4_kernel<<<grid, 256, 2 * d->c * sizeof(float), (cudaStream_t)stream>>>(a);
+  } else {
+    dim3 blk = cblock(d->c);
+    dim3 grid(slabs_for(d->h * d->w, d->n, blk.y), d->n);
+    norm_act_fwd_kernel<<<grid, blk, 0, (cudaStream_t)stream>>>(a);
+  }
   LAUNCH_CHECK();
   return SN_OK;
 }
@@ -861,21 +1109,37 @@ int sn_norm_act_bwd(const sn_norm_act_bwd_desc* d, void* stream) {
   a.hi = (uint16_t*)d->dy_hi; a.lo = (uint16_t*)d->dy_lo;
   a.dy_pitch = d->dy_pitch; a.dy_coff = d->dy_coff; a.fmt = d->dy_fmt;
   const int hw = d->h * d->w;
+  const bool vec = (d->c % 4 == 0) && al16(d->y) && (d->y_pitch % 4 == 0) && srcs_vec_ok(a.g) &&
+                   (d->dy_pitch % 4 == 0) && (d->dy_coff % 4 == 0) && ((uintptr_t)d->dy_hi & 7) == 0 &&
+                   ((uintptr_t)d->dy_lo & 7) == 0 && d->c <= 2048;
   if (d->stats) {
     SN_REQUIRE(d->gstats, "InstanceNorm backward needs gstats scratch");
     SN_CHECK_CUDA(cudaMemsetAsync(d->gstats, 0, sizeof(double) * 2 * d->n * d->c, st));
-    const int cg = (d->c + 31) / 32;
-    int slabs = (148 * 4 + d->n * cg - 1) / (d->n * cg);
-    if (slabs > (hw + 63) / 64) slabs = (hw + 63) / 64;
-    if (slabs < 1) slabs = 1;
-    norm_act_bwd_reduce_kernel<<<dim3(cg, slabs, d->n), dim3(32, 8), 0, st>>>(a);
+    if (vec) {
+      const int qg = (d->c / 4 + 31) / 32;
+      int slabs = (148 * 6 + d->n * qg - 1) / (d->n * qg);
+      if (slabs > (hw + 63) / 64) slabs = (hw + 63) / 64;
+      if (slabs < 1) slabs = 1;
+      norm_act_bwd_reduce_v4_kernel<<<dim3(qg, slabs, d->n), dim3(32, 8), 0, st>>>(a);
+    } else {
+      const int cg = (d->c + 31) / 32;
+      int slabs = (148 * 4 + d->n * cg - 1) / (d->n * cg);
+      if (slabs > (hw + 63) / 64) slabs = (hw + 63) / 64;
+      if (slabs < 1) slabs = 1;
+      norm_act_bwd_reduce_kernel<<<dim3(cg, slabs, d->n), dim3(32, 8), 0, st>>>(a);
+    }
     LAUNCH_CHECK();
     gstats_finalize_kernel<<<(d->n * d->c + 255) / 256, 256, 0, st>>>(d->gstats, d->n * d->c, hw);
     LAUNCH_CHECK();
   }
-  dim3 blk = cblock(d->c);
-  dim3 grid(slabs_for(hw, d->n, blk.y), d->n);
-  norm_act_bwd_apply_kernel<<<grid, blk, 0, st>>>(a);
+  if (vec) {
+    dim3 grid(vslabs(hw, d->n), d->n);
+    norm_act_bwd_apply_v4_kernel<<<grid, 256, 4 * d->c * sizeof(float), st>>>(a);
+  } else {
+    dim3 blk = cblock(d->c);
+    dim3 grid(slabs_for(hw, d->n, blk.y), d->n);
+    norm_act_bwd_apply_kernel<<<grid, blk, 0, st>>>(a);
+  }
   LAUNCH_CHECK();
   return SN_OK;
 }
@@ -904,9 +1168,13 @@ int sn_sum_grads(const sn_grad_src* src, int nsrc, int n, int h, int w, int c, f
   GradSrcs g;
   int rc = fill_srcs(&g, src, nsrc);
   if (rc) return rc;
-  dim3 blk = cblock(c);
-  dim3 grid(slabs_for(h * w, n, blk.y), n);
-  sum_grads_kernel<<<grid, blk, 0, (cudaStream_t)stream>>>(g, h, w, c, dst, dst_pitch);
+  if ((c % 4 == 0) && srcs_vec_ok(g) && al16(dst) && (dst_pitch % 4 == 0)) {
+    sum_grads_v4_kernel<<<dim3(vslabs(h * w, n), n), 256, 0, (cudaStream_t)stream>>>(g, h, w, c, dst, dst_pitch);
+  } else {
+    dim3 blk = cblock(c);
+    dim3 grid(slabs_for(h * w, n, blk.y), n);
+    sum_grads_kernel<<<grid, blk, 0, (cudaStream_t)stream>>>(g, h, w, c, dst, dst_pitch);
+  }
   LAUNCH_CHECK();
   return SN_OK;
 }
