@@ -116,12 +116,15 @@ def cpu_reference_run(S, B, steps, warmup):
     from oracle import nets as ON
     from swapnet_b200 import modules as M
 
+    import contextlib
+
     torch.set_num_threads(os.cpu_count() or 1)
     torch.manual_seed(0)
-    G = M.WarpModule()
-    M.init_weights(G, "kaiming")
-    D = M.NLayerDiscriminator(22, 64, 3, "instance")
-    M.init_weights(D, "kaiming")
+    with contextlib.redirect_stdout(sys.stderr):
+        G = M.WarpModule()
+        M.init_weights(G, "kaiming")
+        D = M.NLayerDiscriminator(22, 64, 3, "instance")
+        M.init_weights(D, "kaiming")
     sdG = {k: v.detach().clone().requires_grad_() for k, v in G.state_dict().items()}
     sdD = {k: v.detach().clone().requires_grad_() for k, v in D.state_dict().items()}
     optG = torch.optim.AdamW(list(sdG.values()), lr=1e-4, weight_decay=0, betas=(0.9, 0.999))
@@ -146,7 +149,7 @@ def cpu_reference_run(S, B, steps, warmup):
         gan = ON.gan_loss(ON.patchgan_forward(sdD, torch.cat((body, fakes), 1)), t[2])
         (ce + gan).backward()
         optG.step()
-        return float(ce + gan)
+        return float((ce + gan).detach())
 
     for _ in range(warmup):
         step()
@@ -204,8 +207,11 @@ def main():
     from swapnet_b200.models import create_model
 
     torch.manual_seed(0)
-    model = create_model(warp_opt(B, S, args.precision))
-    model.setup(model.opt)
+    import contextlib
+
+    with contextlib.redirect_stdout(sys.stderr):   # stdout carries exactly one JSON line
+        model = create_model(warp_opt(B, S, args.precision))
+        model.setup(model.opt)
     host = synth_batch(B, S, 1234 + rank)
     for k in ("bodys", "input_cloths", "target_cloths"):
         host[k] = host[k].pin_memory()

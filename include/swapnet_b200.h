@@ -165,6 +165,11 @@ int sn_norm_act_fwd(const sn_norm_act_desc* d, void* stream);
 typedef struct sn_grad_src {
   const float* ptr; int pitch; int c_off;
   int reflect_padded;                    /* 1: [n, h+2, w+2] gradient of a reflect-padded operand */
+  int up;                                /* >1: source is [n, h*up, w*up]; gradient of a nearest-upsampled
+                                            copy (F.interpolate, swapnet_modules.py:244-247): block-summed */
+  int act;                               /* -1: the block's activation; else SN_ACT_* of THIS consumer: the
+                                            pix2pix skip reads relu() of a tensor whose other consumer reads
+                                            leaky_relu() (pix2pix_modules.py:220-222,262) */
 } sn_grad_src;
 
 typedef struct sn_norm_act_bwd_desc {
@@ -191,6 +196,11 @@ int sn_sum_grads(const sn_grad_src* src, int nsrc, int n, int h, int w, int c, f
 /* dL/dy of a tanh output: (sum_i src_i) * (1 - out^2) -> split planes */
 int sn_tanh_bwd(const sn_grad_src* src, int nsrc, const float* out, int out_pitch, int n, int h,
                 int w, int c, void* dy_hi, void* dy_lo, int dy_pitch, int dy_coff, int dy_fmt, void* stream);
+
+/* nearest-neighbour up-sampling of split planes (16-bit words are copied, hi and lo):
+ * dst[n, h, w, dst_coff + c] = src[n, h / f, w / f, src_coff + c] */
+int sn_upsample_planes(const void* src_hi, const void* src_lo, int src_pitch, int src_coff, int n, int h, int w,
+                       int c, int factor, void* dst_hi, void* dst_lo, int dst_pitch, int dst_coff, void* stream);
 
 /* deterministic dropout keep-mask shared by forward, backward and the test oracle:
  * keep(seed, idx) with idx the linear NHWC element index; returns 0/1 bytes. */

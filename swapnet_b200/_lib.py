@@ -74,7 +74,8 @@ class SnNormActDesc(C.Structure):
 
 
 class SnGradSrc(C.Structure):
-    _fields_ = [("ptr", C.c_void_p), ("pitch", C.c_int), ("c_off", C.c_int), ("reflect_padded", C.c_int)]
+    _fields_ = [("ptr", C.c_void_p), ("pitch", C.c_int), ("c_off", C.c_int), ("reflect_padded", C.c_int),
+                ("up", C.c_int), ("act", C.c_int)]
 
 
 class SnNormActBwdDesc(C.Structure):
@@ -112,6 +113,7 @@ SIGNATURES = {
     "sn_bias_grad": (_I, [_VP, _VP, _I, _I, _I, _LL, _I, _VP, _VP, _VP]),
     "sn_sum_grads": (_I, [C.POINTER(SnGradSrc), _I, _I, _I, _I, _I, _VP, _I, _VP]),
     "sn_tanh_bwd": (_I, [C.POINTER(SnGradSrc), _I, _VP, _I, _I, _I, _I, _I, _VP, _VP, _I, _I, _I, _VP]),
+    "sn_upsample_planes": (_I, [_VP, _VP, _I, _I, _I, _I, _I, _I, _I, _VP, _VP, _I, _I, _VP]),
     "sn_dropout_mask": (_I, [_ULL, _F, _LL, _VP, _VP]),
     "sn_ce_loss_fwd_bwd": (_I, [_VP, _I, _VP, _I, _I, _I, _I, _F, _VP, _VP, _I, _VP]),
     "sn_bce_logits_fwd_bwd": (_I, [_VP, _LL, _I, _F, _F, _F, _VP, _VP, _VP]),

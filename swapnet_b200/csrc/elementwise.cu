@@ -402,11 +402,15 @@ struct GradSrcs {
 };
 // upstream gradient at (n, h, w, c): sum of sources; a reflect-padded source folds its
 // mirrored border rows/cols back onto the interior pixel (adjoint of ReflectionPad2d(1)).
-__device__ __forceinline__ float gather_grad(const GradSrcs& g, int n, int h, int w, int H, int W, int c) {
+__device__ __forceinline__ float gather_one(const sn_grad_src& s, int n, int h, int w, int H, int W, int c) {
   float acc = 0.f;
-  for (int i = 0; i < g.n; ++i) {
-    const sn_grad_src& s = g.s[i];
-    if (!s.reflect_padded) {
+  {
+    if (s.up > 1) {
+      const int u = s.up;
+      for (int a = 0; a < u; ++a)
+        for (int b = 0; b < u; ++b)
+          acc += s.ptr[(((long long)n * H * u + h * u + a) * W * u + w * u + b) * s.pitch + s.c_off + c];
+    } else if (!s.reflect_padded) {
       acc += s.ptr[(((long long)n * H + h) * W + w) * s.pitch + s.c_off + c];
     } else {
       const int Hp = H + 2, Wp = W + 2;
@@ -422,6 +426,11 @@ __device__ __forceinline__ float gather_grad(const GradSrcs& g, int n, int h, in
           acc += s.ptr[(((long long)n * Hp + rows[a]) * Wp + cols[b]) * s.pitch + s.c_off + c];
     }
   }
+  return acc;
+}
+__device__ __forceinline__ float gather_grad(const GradSrcs& g, int n, int h, int w, int H, int W, int c) {
+  float acc = 0.f;
+  for (int i = 0; i < g.n; ++i) acc += gather_one(g.s[i], n, h, w, H, W, c);
   return acc;
 }
 
@@ -442,13 +451,16 @@ __device__ __forceinline__ float grad_xhat(const NormActBwdArgs& a, int n, int p
   const int HW = a.H * a.W;
   const long long pix = (long long)n * HW + p;
   const int h = p / a.W, w = p - h * a.W;
-  float g = gather_grad(a.g, n, h, w, a.H, a.W, c);
   const float xhat = (a.y[pix * a.y_pitch + c] - mean) * rstd;
+  float g = 0.f;
+  for (int i = 0; i < a.g.n; ++i) {
+    const sn_grad_src& s = a.g.s[i];
+    g += gather_one(s, n, h, w, a.H, a.W, c) * act_grad(xhat, s.act >= 0 ? s.act : a.act, a.slope);
+  }
   if (a.drop_thresh) {
     const bool keep = sn_keep(a.seed, (unsigned long long)pix * a.C + c, a.drop_thresh);
     g = keep ? g * a.drop_scale : 0.f;
   }
-  g *= act_grad(xhat, a.act, a.slope);
   *xhat_out = xhat;
   return g;
 }
@@ -538,6 +550,21 @@ __global__ void tanh_bwd_kernel(const GradSrcs g, const float* __restrict__ out,
       const float v = gather_grad(g, n, h, w, H, W, c) * (1.f - o * o);
       store_split(hi, lo, pix * dy_pitch + dy_coff + c, v, fmt);
     }
+}
+
+__global__ void upsample_planes_kernel(const uint16_t* __restrict__ shi, const uint16_t* __restrict__ slo,
+                                       int spitch, int H, int W, int C, int f, uint16_t* __restrict__ dhi,
+                                       uint16_t* __restrict__ dlo, int dpitch, long long total) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    const long long pix = i / C;
+    const int w = (int)(pix % W), h = (int)((pix / W) % H);
+    const long long n = pix / ((long long)W * H);
+    const long long sp = (n * (H / f) + h / f) * (W / f) + w / f;
+    dhi[pix * dpitch + c] = shi[sp * spitch + c];
+    if (dlo) dlo[pix * dpitch + c] = slo[sp * spitch + c];
+  }
 }
 
 __global__ void dropout_mask_kernel(unsigned long long seed, uint32_t thresh, long long count,
@@ -780,11 +807,18 @@ __global__ void norm_act_fwd_v4_kernel(const NormActFwdArgs a) {
   }
 }
 
-__device__ __forceinline__ float4 gather_grad4(const GradSrcs& g, int n, int h, int w, int H, int W, int c) {
+__device__ __forceinline__ float4 gather_one4(const sn_grad_src& s, int n, int h, int w, int H, int W, int c) {
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (int i = 0; i < g.n; ++i) {
-    const sn_grad_src& s = g.s[i];
-    if (!s.reflect_padded) {
+  {
+    if (s.up > 1) {
+      const int u = s.up;
+      for (int a = 0; a < u; ++a)
+        for (int b = 0; b < u; ++b) {
+          const float4 v = *reinterpret_cast<const float4*>(
+              s.ptr + (((long long)n * H * u + h * u + a) * W * u + w * u + b) * s.pitch + s.c_off + c);
+          acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+        }
+    } else if (!s.reflect_padded) {
       const float4 v = *reinterpret_cast<const float4*>(s.ptr + (((long long)n * H + h) * W + w) * s.pitch + s.c_off + c);
       acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
     } else {
@@ -806,6 +840,14 @@ __device__ __forceinline__ float4 gather_grad4(const GradSrcs& g, int n, int h, 
   }
   return acc;
 }
+__device__ __forceinline__ float4 gather_grad4(const GradSrcs& g, int n, int h, int w, int H, int W, int c) {
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int i = 0; i < g.n; ++i) {
+    const float4 v = gather_one4(g.s[i], n, h, w, H, W, c);
+    acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+  }
+  return acc;
+}
 
 // g (w.r.t. xhat) and xhat for a channel quad
 __device__ __forceinline__ void grad_xhat4(const NormActBwdArgs& a, int n, int p, int c, const float* mean,
@@ -813,20 +855,27 @@ __device__ __forceinline__ void grad_xhat4(const NormActBwdArgs& a, int n, int p
   const int HW = a.H * a.W;
   const long long pix = (long long)n * HW + p;
   const int h = p / a.W, w = p - h * a.W;
-  const float4 gv = gather_grad4(a.g, n, h, w, a.H, a.W, c);
   const float4 yv = *reinterpret_cast<const float4*>(a.y + pix * a.y_pitch + c);
-  const float gg[4] = {gv.x, gv.y, gv.z, gv.w};
   const float yy[4] = {yv.x, yv.y, yv.z, yv.w};
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
-    const float xhat = (yy[j] - mean[j]) * rstd[j];
-    float t = gg[j];
-    if (a.drop_thresh) {
+    xh[j] = (yy[j] - mean[j]) * rstd[j];
+    g[j] = 0.f;
+  }
+  for (int i = 0; i < a.g.n; ++i) {
+    const sn_grad_src& s = a.g.s[i];
+    const float4 gv = gather_one4(s, n, h, w, a.H, a.W, c);
+    const float gg[4] = {gv.x, gv.y, gv.z, gv.w};
+    const int act = s.act >= 0 ? s.act : a.act;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) g[j] += gg[j] * act_grad(xh[j], act, a.slope);
+  }
+  if (a.drop_thresh) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
       const bool keep = sn_keep(a.seed, (unsigned long long)pix * a.C + c + j, a.drop_thresh);
-      t = keep ? t * a.drop_scale : 0.f;
+      g[j] = keep ? g[j] * a.drop_scale : 0.f;
     }
-    g[j] = t * act_grad(xhat, a.act, a.slope);
-    xh[j] = xhat;
   }
 }
 
@@ -1087,6 +1136,7 @@ static int fill_srcs(GradSrcs* g, const sn_grad_src* src, int nsrc) {
   g->n = nsrc;
   for (int i = 0; i < nsrc; ++i) {
     SN_REQUIRE(src[i].ptr, "null gradient source %d", i);
+    SN_REQUIRE(!(src[i].up > 1 && src[i].reflect_padded), "gradient source %d: up and reflect_padded are exclusive", i);
     g->s[i] = src[i];
   }
   return SN_OK;
@@ -1189,6 +1239,17 @@ int sn_tanh_bwd(const sn_grad_src* src, int nsrc, const float* out, int out_pitc
   tanh_bwd_kernel<<<grid, blk, 0, (cudaStream_t)stream>>>(g, out, out_pitch, h, w, c,
                                                           (uint16_t*)dy_hi, (uint16_t*)dy_lo,
                                                           dy_pitch, dy_coff, dy_fmt);
+  LAUNCH_CHECK();
+  return SN_OK;
+}
+
+int sn_upsample_planes(const void* src_hi, const void* src_lo, int src_pitch, int src_coff, int n, int h, int w,
+                       int c, int factor, void* dst_hi, void* dst_lo, int dst_pitch, int dst_coff, void* stream) {
+  SN_REQUIRE(src_hi && dst_hi && factor >= 1 && h % factor == 0 && w % factor == 0, "bad upsample arguments");
+  const long long total = (long long)n * h * w * c;
+  upsample_planes_kernel<<<grid_for(total), kEwThreads, 0, (cudaStream_t)stream>>>(
+      (const uint16_t*)src_hi + src_coff, src_lo ? (const uint16_t*)src_lo + src_coff : nullptr, src_pitch, h, w, c,
+      factor, (uint16_t*)dst_hi + dst_coff, dst_lo ? (uint16_t*)dst_lo + dst_coff : nullptr, dst_pitch, total);
   LAUNCH_CHECK();
   return SN_OK;
 }

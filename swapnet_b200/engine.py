@@ -45,7 +45,7 @@ class Stage:
                  out: Optional[Planes] = None, norm: bool = False, act: int = ACT_NONE, slope: float = 0.2,
                  drop_p: float = 0.0, reflect_out: bool = False, residual: Optional[torch.Tensor] = None,
                  out_f32: Optional[torch.Tensor] = None, plain: bool = False, epi_act: int = ACT_NONE,
-                 need_dx: bool = True, y: Optional[torch.Tensor] = None):
+                 need_dx: bool = True, y: Optional[torch.Tensor] = None, out_relu: Optional[Planes] = None):
         self.eng, self.name, self.kind = eng, name, kind
         self.id = len(eng.stages)
         eng.stages.append(self)
@@ -60,6 +60,7 @@ class Stage:
         self.norm, self.act, self.slope, self.drop_p = norm, act, slope, drop_p
         self.out, self.reflect_out, self.residual, self.out_f32 = out, reflect_out, residual, out_f32
         self.plain, self.epi_act, self.need_dx = plain, epi_act, need_dx
+        self.out_relu = out_relu   # pix2pix skip: a second consumer reads relu() of the same pre-activation
         self.stats = torch.zeros(self.n, self.cout, 2, dtype=torch.float64, device=dev) if norm else None
         self.dy: Optional[Planes] = None
         self.dx: Optional[torch.Tensor] = None
@@ -86,6 +87,8 @@ class Stage:
         ops.norm_act_fwd(self.y, self.cout, self.stats, self.act, self.slope, p,
                          _mix_seed(self.eng.seed, self.id), residual=self.residual, out=self.out,
                          reflect_pad=self.reflect_out, out_f32=self.out_f32)
+        if self.out_relu is not None:
+            ops.norm_act_fwd(self.y, self.cout, self.stats, ACT_RELU, 0.0, 0.0, 0, out=self.out_relu)
 
     # ---- backward ----
     def bind_backward(self, wgrad: bool = True) -> None:
@@ -94,7 +97,7 @@ class Stage:
         self.dy = Planes(self.n, self.oh, self.ow, L.pad64(self.cout), dev, fmt=FMT_BF16)  # gradients: fp32 range
         if self.need_dx:
             ih, iw = (ly.in_h + 2, ly.in_w + 2) if self.kind == "conv3r" else (ly.in_h, ly.in_w)
-            self.dx = torch.zeros(self.n, ih, iw, ly.cin, device=dev)
+            self.dx = torch.zeros(self.n, ih, iw, (ly.cin + 3) // 4 * 4, device=dev)[..., :ly.cin]
         wg = self.conv.weight.grad if wgrad else None
         bg = self.conv.bias.grad if (wgrad and self.conv.bias is not None) else None
         ly.bind_backward(self.dy, self.dx, wg, bg)
@@ -310,3 +313,98 @@ class PatchGANEngine(Engine):
     @property
     def dx_in(self) -> torch.Tensor:
         return self.chain[0].dx
+
+
+# =============================================================================================
+# TextureModule
+# =============================================================================================
+class TextureEngine(Engine):
+    """ROIAlign+repack -> encode (UNetDown 36->36) -> nearest upsample -> cat cloth -> pix2pix U-Net
+    (swapnet_modules.py:231-260, pix2pix_modules.py:113-262, norm = instance => bias on every conv).
+
+    U-Net bookkeeping (depth j = 0 outermost .. nd-1 innermost; D_j / U_j = its down / up conv):
+      L_{j+1} = leaky_relu([IN](D_j(.)))  is both the operand of D_{j+1} and, because the reference's
+                LeakyReLU is in place, the skip half of block j+1's output (App. B #1);
+      the parent applies ReLU to the whole concat, so U_j reads cat(relu(L_{j+1}), relu(V_{j+1})) with
+      V = dropout?(IN(U(.))) — buffer `cu[j]`, written in place by the producing stages.
+    """
+
+    def __init__(self, net: M.TextureModule, batch: int, size: int, device, nsplit: int = 3, train: bool = True):
+        super().__init__(net, device, nsplit, train)
+        B, S = batch, size
+        assert S >= 64 and (S & (S - 1)) == 0, "texture stage: power-of-two size >= 64"
+        self.batch, self.size = B, S
+        self.ct, self.cc, self.nroi = net.texture_channels, net.cloth_channels, net.num_roi
+        ch = self.ct * self.nroi
+        self.ch = ch
+        unet = net.unet
+        nd = unet.num_downs
+        blocks = unet.blocks()
+        assert len(blocks) == nd
+        self.pool = 128
+        self.pooled = self.planes(B, self.pool, self.pool, L.pad64(ch))
+        self.enc = self.planes(B, self.pool // 2, self.pool // 2, L.pad64(ch))
+        self.in_unet = self.planes(B, S, S, L.pad64(ch + self.cc))
+        self.up_factor = S // (self.pool // 2)
+        St = lambda *a, **k: Stage(self, *a, **k)  # noqa: E731
+        self.encode = St("encode", "conv4s2", net.encode.model[0], self.pooled, out=self.enc, norm=True,
+                         act=ACT_LRELU, need_dx=False)
+        chans = [blocks[j].down.out_channels for j in range(nd)]          # channels of x_{j+1}
+        self.cu = [self.planes(B, S >> (j + 1), S >> (j + 1), 2 * chans[j]) for j in range(nd - 1)]
+        self.down: List[Stage] = []
+        x = self.in_unet
+        for j in range(nd):
+            h = S >> (j + 1)
+            last = j == nd - 1
+            if last:
+                out = self.planes(B, h, h, L.pad64(chans[j]))
+                st = St(f"unet.D{j}", "conv4s2", blocks[j].down, x, out=out, norm=False, act=ACT_RELU)
+            else:
+                out = self.planes(B, h, h, L.pad64(chans[j]))
+                st = St(f"unet.D{j}", "conv4s2", blocks[j].down, x, out=out, norm=(j >= 1), act=ACT_LRELU,
+                        out_relu=self.cu[j].slice(0, chans[j]))
+            self.down.append(st)
+            x = out
+        self.up: List[Optional[Stage]] = [None] * nd
+        for j in range(nd - 1, 0, -1):
+            src = self.down[nd - 1].out if j == nd - 1 else self.cu[j]
+            cout = blocks[j].up.out_channels
+            drop = 0.5 if (blocks[j].use_dropout and not blocks[j].innermost) else 0.0
+            self.up[j] = St(f"unet.U{j}", "convT4s2", blocks[j].up, src, out=self.cu[j - 1].slice(chans[j - 1], cout),
+                            norm=True, act=ACT_RELU, drop_p=drop)
+        self.fakes = torch.zeros(B, S, S, self.ct, device=self.device)
+        self.up[0] = St("unet.U0", "convT4s2", blocks[0].up, self.cu[0], plain=True, epi_act=ACT_TANH, y=self.fakes)
+
+    def forward(self, tex: torch.Tensor, rois: torch.Tensor, cloth: torch.Tensor, training: bool = True,
+                seed: int = 0) -> torch.Tensor:
+        """tex [B,3,S,S], rois [B,12,4], cloth [B,19,S,S] (fp32, device) -> fakes [B,S,S,3] NHWC."""
+        self.training, self.seed = training, seed
+        ops.roi_align_pack(tex, rois, self.pool, None, self.pooled.slice(0, self.ch))
+        if self.pooled.twin is not None:
+            ops.roi_align_pack(tex, rois, self.pool, None, self.pooled.twin.slice(0, self.ch))
+        self.encode.forward()
+        ops.upsample_planes(self.enc.slice(0, self.ch), self.in_unet.slice(0, self.ch), self.up_factor)
+        ops.pack_planes(cloth, self.in_unet.slice(self.ch, self.cc))
+        for st in self.down:
+            st.forward()
+        for j in range(len(self.up) - 1, -1, -1):
+            self.up[j].forward()
+        return self.fakes
+
+    def backward(self, srcs: Sequence[GradSrc]) -> None:
+        nd = len(self.down)
+        self.up[0].backward(srcs)
+        g = self.up[0].dx                                           # d cu[0]
+        gcu = [None] * (nd - 1)
+        gcu[0] = g
+        for j in range(1, nd):
+            cprev = self.down[j - 1].cout
+            self.up[j].backward([GradSrc(gcu[j - 1], cprev)])
+            if j < nd - 1:
+                gcu[j] = self.up[j].dx
+        # innermost down conv: its relu() output only feeds U_{nd-1}
+        self.down[nd - 1].backward([GradSrc(self.up[nd - 1].dx)])
+        for j in range(nd - 2, -1, -1):
+            # L_{j+1} feeds D_{j+1} (as leaky_relu) and the skip slot of cu[j] (as relu)
+            self.down[j].backward([GradSrc(self.down[j + 1].dx), GradSrc(gcu[j], 0, act=ACT_RELU)])
+        self.encode.backward([GradSrc(self.down[0].dx, 0, up=self.up_factor)])

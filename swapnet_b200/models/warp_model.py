@@ -66,7 +66,7 @@ class WarpModel(BaseGAN):
         return self.cloth_channels + self.body_channels
 
     def build_generator_engine(self, batch, size):
-        return E.WarpEngine(self.net_generator, batch, size, self.device, self.nsplit)
+        return E.WarpEngine(self.net_generator, batch, size, self.device, self.nsplit, train=self.is_train)
 
     def set_input(self, input):
         f32 = dict(device=self.device, dtype=torch.float32, non_blocking=True)

@@ -329,6 +329,8 @@ class GradSrc:
     t: torch.Tensor          # fp32 NHWC [n, h(+2), w(+2), pitch]
     c_off: int = 0
     reflect_padded: bool = False
+    up: int = 1              # >1: t is [n, h*up, w*up, .] (gradient of a nearest-upsampled copy)
+    act: int = -1            # activation of THIS consumer (-1: the stage's own)
 
 
 def _fill_srcs(arr, srcs: Sequence[GradSrc]) -> None:
@@ -339,6 +341,8 @@ def _fill_srcs(arr, srcs: Sequence[GradSrc]) -> None:
         arr[i].pitch = _pitch(s.t)
         arr[i].c_off = s.c_off
         arr[i].reflect_padded = int(s.reflect_padded)
+        arr[i].up = s.up
+        arr[i].act = s.act
 
 
 def norm_act_bwd(srcs: Sequence[GradSrc], y: torch.Tensor, c: int, stats: Optional[torch.Tensor], act: int,
@@ -380,6 +384,18 @@ def tanh_bwd(srcs: Sequence[GradSrc], out: torch.Tensor, c: int, dy: Planes) -> 
     _fill_srcs(arr, srcs)
     check(_lib.load().sn_tanh_bwd(arr, len(srcs), out.data_ptr(), pitch, n, h, w, c, dy.hi.data_ptr(),
                                   dy.lo.data_ptr(), dy.pitch, dy.c_off, dy.fmt, _stream()))
+
+
+def upsample_planes(src: Planes, dst: Planes, factor: int) -> None:
+    """dst[n,h,w,:src.c] = src[n,h//f,w//f,:] on the 16-bit words (and on the bf16 twins if both have one)."""
+    assert (dst.h, dst.w) == (src.h * factor, src.w * factor) and dst.c >= src.c and src.fmt == dst.fmt
+    pairs = [(src, dst)]
+    if src.twin is not None and dst.twin is not None:
+        pairs.append((src.twin, dst.twin))
+    for s_, d_ in pairs:
+        check(_lib.load().sn_upsample_planes(s_.hi.data_ptr(), s_.lo.data_ptr(), s_.pitch, s_.c_off, dst.n, dst.h,
+                                             dst.w, src.c, factor, d_.hi.data_ptr(), d_.lo.data_ptr(), d_.pitch,
+                                             d_.c_off, _stream()))
 
 
 def dropout_mask(seed: int, p: float, count: int, device) -> torch.Tensor:

@@ -212,3 +212,130 @@ def test_warp_model_two_steps_run_and_change_weights():
     assert not torch.equal(w0, model.net_generator.body_down2.model[0].weight)
     model.save_checkpoint("latest")
     model.load_checkpoint_dir("latest")
+
+
+# ------------------------------------------------------------------------------------------------
+# texture stage
+# ------------------------------------------------------------------------------------------------
+def synth_texture_batch(B, S, seed=1234):
+    import numpy as np
+
+    from oracle import roi_align as R
+
+    g = torch.Generator().manual_seed(seed)
+    tex = torch.rand(B, 3, S, S, generator=g) * 4.5 - 2.0
+    tgt = torch.rand(B, 3, S, S, generator=g) * 4.5 - 2.0
+    lab = torch.randint(0, 19, (B, S // 16, S // 16), generator=g).repeat_interleave(16, 1).repeat_interleave(16, 2)
+    cloth = torch.zeros(B, 19, S, S)
+    for c in range(1, 19):
+        cloth[:, c] = (lab == c).float()
+    base = np.concatenate([R.NOTEBOOK_ROIS_256, R.NOTEBOOK_EXTRA_256])
+    rois = torch.from_numpy(np.stack([np.roll(base, b, axis=0)[:12] for b in range(B)]) * (S / 256.0)).float()
+    return tex, rois, cloth, tgt
+
+
+def make_texture_net(S, seed=0):
+    from swapnet_b200 import modules as M
+
+    torch.manual_seed(seed)
+    T = M.TextureModule(3, 19, 12, "instance", 0.5, S)
+    M.init_weights(T, "kaiming")
+    g = torch.Generator().manual_seed(9)
+    for n, p in T.named_parameters():
+        if n.endswith("bias"):
+            p.data.copy_(torch.randn(p.shape, generator=g) * 0.1)
+    return T
+
+
+@pytest.mark.parametrize("S", [64, 128])
+def test_texture_engine_forward(S):
+    from swapnet_b200 import engine as E
+
+    B = 2
+    T = make_texture_net(S)
+    tex, rois, cloth, _ = synth_texture_batch(B, S)
+    sd = {k: v.clone().double() for k, v in T.state_dict().items()}
+    eng = E.TextureEngine(T.to(dev()), B, S, dev())
+    eng.pack()
+    out = eng.forward(tex.to(dev()), rois.to(dev()), cloth.to(dev()), training=False)
+    torch.cuda.synchronize()
+    with torch.no_grad():
+        ref = ON.texture_forward(sd, tex.double(), rois.double(), cloth.double())
+    err = relmax(out.permute(0, 3, 1, 2).cpu(), ref)
+    record(f"texture_engine_forward[{S}]", f"{err:.3e}")
+    assert err < 1e-3, f"texture forward relmax {err:.3e}"
+
+
+def test_texture_model_step_matches_oracle():
+    from swapnet_b200.models import create_model
+
+    B, S = 2, 128
+    torch.manual_seed(0)
+    opt = _opt(B, S, model="texture", name="texture", netG="swapnet", lambda_l1=10, lambda_content=0, lambda_style=0)
+    model = create_model(opt)
+    model.setup(opt)
+    model.eval()
+    g = torch.Generator().manual_seed(9)
+    for net in (model.net_generator, model.net_discriminator):
+        for n, p in net.named_parameters():
+            if n.endswith("bias"):
+                p.data.copy_((torch.randn(p.shape, generator=g) * 0.1).to(p.device))
+    sdG = {k: v.detach().cpu().double().requires_grad_() for k, v in model.net_generator.state_dict().items()}
+    sdD = {k: v.detach().cpu().double().requires_grad_() for k, v in model.net_discriminator.state_dict().items()}
+    tex, rois, cloth, tgt = synth_texture_batch(B, S)
+    batch = dict(input_textures=tex, rois=rois, cloths=cloth, target_textures=tgt, cloth_paths=["c"] * B,
+                 texture_paths=["t"] * B)
+    torch.manual_seed(321)
+    model.set_input(batch)
+    model._acc.zero_()
+    model.forward()
+    model._eng_Dd.zero_grad()
+    model.backward_D()
+    gD = {k: p.grad.detach().cpu().clone() for k, p in model.net_discriminator.named_parameters()}
+    model._eng_G.zero_grad()
+    model.backward_G()
+    torch.cuda.synchronize()
+    gG = {k: p.grad.detach().cpu().clone() for k, p in model.net_generator.named_parameters()}
+    losses = model.get_current_losses()
+
+    torch.manual_seed(321)
+    draws = [torch.rand(1) for _ in range(3)]
+    gates_G = stage_gates(model._eng_G)
+    gates_D = [stage_gates(model._eng_Dd, 0, B), stage_gates(model._eng_Dd, B, 2 * B), stage_gates(model._eng_Dg)]
+    calls = {}
+
+    def gate(name, x):
+        if name in gates_G:
+            return gates_G[name]
+        k = calls.get(name, 0)
+        calls[name] = k + 1
+        return gates_D[k][name]
+
+    ON.gate_with(gate)
+    o = ON.texture_step_losses(sdG, sdD, tex.double(), rois.double(), cloth.double(), tgt.double(), draws)
+    stats = dict(ON.GATE_STATS)
+    ON.gate_with(None)
+    flips = {k: v for k, v in stats.items() if k != "__total__" and v}
+    record("texture_step_gate_flips", f"{sum(flips.values())} of {stats.get('__total__', 1)}: {flips}")
+    refD = torch.autograd.grad(o["D"], list(sdD.values()), retain_graph=True)
+    refG = torch.autograd.grad(o["G"], list(sdG.values()), allow_unused=True)
+    for k in ("D", "D_real", "D_fake", "G", "G_gan", "G_l1"):
+        ref = o[k].item()
+        assert abs(losses[k] - ref) <= 1e-3 * abs(ref), f"loss_{k}: {losses[k]} vs {ref}"
+    err_f = relmax(model.fakes.cpu(), o["fakes"].detach())
+    assert err_f < 1e-3, f"fakes relmax {err_f:.3e}"
+    worst = {}
+    for name, got, sd, refs in (("D.", gD, sdD, refD), ("G.", gG, sdG, refG)):
+        mx = max(r.abs().max().item() for r in refs if r is not None)
+        for (k, _), r in zip(sd.items(), refs):
+            if r is None:
+                continue
+            if r.abs().max().item() < 1e-6 * mx:
+                assert got[k].abs().max().item() < 1e-4 * mx, k
+                continue
+            worst[name + k] = relmax(got[k], r)
+    record("texture_step_worst_grads", sorted(worst.items(), key=lambda kv: -kv[1])[:5])
+    record("texture_step_fakes", f"{err_f:.3e}")
+    bad = {k: v for k, v in worst.items() if v >= 1e-3}
+    assert not bad, f"parameter gradients beyond 1e-3: {bad}"
+    assert sum(flips.values()) <= 2e-5 * stats.get("__total__", 1), f"too many activation gates differ: {flips}"

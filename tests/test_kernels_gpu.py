@@ -126,7 +126,7 @@ def test_conv_forward(kind, n, cin, cout, h, w, nsplit):
                                   block_n=layer.block_n, out_c_off=2, **kw)
             ops.tap_gemm_simt(d)
         torch.cuda.synchronize()
-        assert relmax(y2[..., 2:2 + cout].cpu(), ref) < 2e-6
+        assert relmax(y2[..., 2:2 + cout].cpu(), ref) < 5e-6   # fp32 FMA chain over K up to 2048
 
 
 @pytest.mark.parametrize("kind,n,cin,cout,h,w", CONV_CASES)
