@@ -312,7 +312,12 @@ def test_texture_model_step_matches_oracle():
         return gates_D[k][name]
 
     ON.gate_with(gate)
-    o = ON.texture_step_losses(sdG, sdD, tex.double(), rois.double(), cloth.double(), tgt.double(), draws)
+    d = model.fakes.detach() - tgt.to(dev())                     # same fp32 subtraction as the L1 kernel
+    l1_sign = torch.sign(d).cpu().double()
+    o = ON.texture_step_losses(sdG, sdD, tex.double(), rois.double(), cloth.double(), tgt.double(), draws,
+                               l1_sign=l1_sign)
+    ref_sign = torch.sign(o["fakes"].detach() - tgt.double())
+    record("texture_step_l1_sign_flips", f"{int((ref_sign != l1_sign).sum())} of {l1_sign.numel()}")
     stats = dict(ON.GATE_STATS)
     ON.gate_with(None)
     flips = {k: v for k, v in stats.items() if k != "__total__" and v}
