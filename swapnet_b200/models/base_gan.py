@@ -28,6 +28,7 @@ import torch
 from .. import engine as E
 from .. import modules as M
 from .. import ops
+from .. import parallel
 from .base_model import BaseModel, LazyLoss
 
 
@@ -96,11 +97,10 @@ class BaseGAN(BaseModel, ABC):
         self._eng_Dd = self._eng_Dg = None
         self._step = 0
         self._seed_base = int(getattr(opt, "b200_seed", 0))
-        self._world = torch.distributed.get_world_size() if torch.distributed.is_available() and \
-            torch.distributed.is_initialized() else 1
+        self._world = parallel.world_size()
         # smooth-label draws: the CPU default generator like the reference (loss.py:74-77); under DP a
         # dedicated, identically seeded generator so that every rank sees the same label (SURVEY §8e i)
-        self._label_gen = torch.Generator().manual_seed(1234) if self._world > 1 else None
+        self._labels = parallel.LabelDraws(1234 if self._world > 1 else None)
         if self.is_train:
             if opt.gan_mode != "vanilla":
                 raise NotImplementedError(f"--gan_mode {opt.gan_mode}: only vanilla runs on the B200 engines")
@@ -127,9 +127,8 @@ class BaseGAN(BaseModel, ABC):
             self.loss_D_real = LazyLoss(lambda: self._acc[1].item())
             self.loss_D = LazyLoss(lambda: 0.5 * (self._acc[0].item() + self._acc[1].item()))
             self.loss_G_gan = LazyLoss(lambda: lam * self._acc[2].item())
-            if self._world > 1:
-                for p in list(self.net_generator.parameters()) + list(self.net_discriminator.parameters()):
-                    torch.distributed.broadcast(p.data, 0)
+            parallel.broadcast_parameters(list(self.net_generator.parameters()) +
+                                          list(self.net_discriminator.parameters()))
 
     # ---- to be provided by the plugin ----
     @abstractmethod
@@ -178,14 +177,10 @@ class BaseGAN(BaseModel, ABC):
     def draw_label(self) -> float:
         """One smooth-label scalar exactly as GANLoss.get_target_tensor computes it (loss.py:65-107):
         fp32 `rand(1) * (1.1 - 0.7) + 0.7`, for real AND fake targets."""
-        low, high = torch.tensor((0.7, 1.1))
-        r = torch.rand(1, generator=self._label_gen) if self._label_gen is not None else torch.rand(1)
-        return float(r * (high - low) + low)
+        return self._labels.draw()
 
     def allreduce_grads(self, eng) -> None:
-        if self._world > 1:
-            torch.distributed.all_reduce(eng.flat_grad, op=torch.distributed.ReduceOp.SUM)
-            eng.flat_grad.mul_(1.0 / self._world)
+        parallel.average_gradients(eng.flat_grad)
 
     # ---- discriminator phases (conditioning supplied by the plugin through pack_D_inputs) ----
     @abstractmethod

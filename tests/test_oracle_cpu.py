@@ -1,0 +1,132 @@
+"""Pins the CPU oracle (oracle/) against the reference: golden vectors generated from the UNMODIFIED
+reference by tools/make_golden.py (committed under tests/golden/), and — when /root/reference is
+mounted (build container) — the reference modules themselves, bit for bit."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import dropout as OD
+from oracle import nets as ON
+from oracle import ref_harness as RH
+from oracle import roi_align as R
+from swapnet_b200 import modules as M
+from test_engine_gpu import synth_texture_batch, synth_warp_batch
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def relmax(a, b):
+    return ((a.double() - b.double()).abs().max() / b.double().abs().max().clamp_min(1e-30)).item()
+
+
+def checksums(sd):
+    return {k: (float(v.double().sum()), float(v.double().abs().sum())) for k, v in sd.items()}
+
+
+def close_checksums(a, b, tol):
+    assert a.keys() == b.keys()
+    for k in a:
+        for x, y in zip(a[k], b[k]):
+            assert abs(x - y) <= tol * max(1.0, abs(y)), (k, x, y)
+
+
+def test_warp_forward_and_step_match_golden():
+    g = torch.load(os.path.join(GOLD, "warp_64.pt"))
+    torch.manual_seed(0)
+    G = M.WarpModule(); M.init_weights(G, "kaiming")
+    D = M.NLayerDiscriminator(22, 64, 3, "instance"); M.init_weights(D, "kaiming")
+    # our parameter containers reproduce the reference's seeded init exactly
+    close_checksums(checksums(G.state_dict()), g["init_checksums_G"], 0.0)
+    close_checksums(checksums(D.state_dict()), g["init_checksums_D"], 0.0)
+    body, inp, tgt = synth_warp_batch(1, 64)
+    with torch.no_grad():
+        fakes = ON.warp_forward(G.state_dict(), body, inp)
+        pred = ON.patchgan_forward(D.state_dict(), torch.cat((body, fakes), 1))
+    assert relmax(fakes, g["fakes"]) < 1e-5 and relmax(pred, g["pred"]) < 1e-5
+    # one full optimize_parameters(): D step, then G step against the UPDATED discriminator
+    sdG = {k: v.detach().clone().requires_grad_() for k, v in G.state_dict().items()}
+    sdD = {k: v.detach().clone().requires_grad_() for k, v in D.state_dict().items()}
+    optG = torch.optim.AdamW(list(sdG.values()), lr=1e-4, weight_decay=0, betas=(0.9, 0.999))
+    optD = torch.optim.AdamW(list(sdD.values()), lr=4e-4, weight_decay=0.01, betas=(0.9, 0.999))
+    torch.manual_seed(123)
+    fk = ON.warp_forward(sdG, body, inp)
+    t_fake, t_real = ON.smooth_label(torch.rand(1)), ON.smooth_label(torch.rand(1))
+    lf = ON.gan_loss(ON.patchgan_forward(sdD, torch.cat((body, fk), 1).detach()), t_fake)
+    lr = ON.gan_loss(ON.patchgan_forward(sdD, torch.cat((body, tgt), 1)), t_real)
+    lD = 0.5 * (lf + lr)
+    lD.backward()
+    optD.step()
+    ce = torch.nn.functional.cross_entropy(fk, torch.argmax(tgt, 1)) * 100
+    gan = ON.gan_loss(ON.patchgan_forward(sdD, torch.cat((body, fk), 1)), ON.smooth_label(torch.rand(1)))
+    (ce + gan).backward()
+    optG.step()
+    got = dict(D=lD.item(), D_real=lr.item(), D_fake=lf.item(), G=(ce + gan).item(), G_gan=gan.item(), G_ce=ce.item())
+    for k, v in g["step_losses"].items():
+        assert abs(got[k] - v) <= 1e-5 * abs(v), (k, got[k], v)
+    close_checksums(checksums({k: v.detach() for k, v in sdG.items()}), g["step_checksums_G"], 2e-6)
+    close_checksums(checksums({k: v.detach() for k, v in sdD.items()}), g["step_checksums_D"], 2e-6)
+
+
+def test_texture_forward_matches_golden():
+    g = torch.load(os.path.join(GOLD, "texture_64.pt"))
+    torch.manual_seed(0)
+    T = M.TextureModule(3, 19, 12, "instance", 0.5, 64); M.init_weights(T, "kaiming")
+    close_checksums(checksums(T.state_dict()), g["init_checksums"], 0.0)
+    tex, rois, cloth, _ = synth_texture_batch(2, 64)
+    # ROI bookkeeping: bit-exact
+    assert np.array_equal(R.reshape_rois(rois.numpy()), g["reshaped_rois"].numpy())
+    pooled = R.roi_align_pack(tex.numpy(), rois.numpy(), 128)
+    assert np.array_equal(pooled[:, :, ::8, ::8], g["pooled_sub"].numpy())
+    with torch.no_grad():
+        out = ON.texture_forward(T.state_dict(), tex, rois, cloth)
+    assert relmax(out, g["fakes"]) < 1e-5
+
+
+def test_roi_align_known_answer_notebook_fixture():
+    """test/Test TextureDataset Draw ROIs.ipynb ROI tensor (incl. zero-area and out-of-bounds rows)."""
+    g = torch.load(os.path.join(GOLD, "roi_256.pt"))
+    tex = torch.randn(3, 3, 256, 256, generator=torch.Generator().manual_seed(0))
+    out = R.roi_align_pack(tex.numpy(), g["rois"].numpy(), 128)
+    assert np.array_equal(out[:, :, ::8, ::8], g["sub"].numpy())
+    assert np.allclose(out.astype(np.float64).sum((2, 3)), g["sums"].numpy(), rtol=0, atol=1e-9)
+
+
+def test_dropout_restatement_is_deterministic_and_balanced():
+    m = OD.keep_mask(77, 0.5, 1 << 16)
+    assert np.array_equal(m, OD.keep_mask(77, 0.5, 1 << 16))
+    assert 0.49 < m.mean() < 0.51
+    assert not np.array_equal(m, OD.keep_mask(78, 0.5, 1 << 16))
+    assert OD.keep_mask(5, 0.0, 1000).all()
+
+
+@pytest.mark.skipif(not RH.available(), reason="/root/reference not mounted (GPU box)")
+def test_oracle_is_bit_identical_to_reference_modules():
+    RH.import_reference()
+    from modules import init_weights
+    from modules.discriminators import define_D
+    from modules.swapnet_modules import TextureModule, WarpModule
+
+    torch.manual_seed(0)
+    G = WarpModule(); init_weights(G, "kaiming")
+    D = define_D(22, 64, "basic", 3, "instance"); init_weights(D, "kaiming")
+    G.eval(); D.eval()
+    body, inp, _ = synth_warp_batch(2, 64)
+    with torch.no_grad():
+        ref = G(body, inp)
+        assert torch.equal(ref, ON.warp_forward(G.state_dict(), body, inp))
+        x = torch.cat((body, ref), 1)
+        assert torch.equal(D(x.clone()), ON.patchgan_forward(D.state_dict(), x))
+    torch.manual_seed(0)
+    T = TextureModule(3, 19, 12, "instance", 0.5, "pix2pix", 128); init_weights(T, "kaiming"); T.eval()
+    tex, rois, cloth, _ = synth_texture_batch(2, 128)
+    with torch.no_grad():
+        assert torch.equal(T(tex, rois, cloth.clone()), ON.texture_forward(T.state_dict(), tex, rois, cloth))
+    # state_dict keys / seeded init of our containers == the reference's
+    torch.manual_seed(3)
+    a = WarpModule(); init_weights(a, "kaiming")
+    torch.manual_seed(3)
+    b = M.WarpModule(); M.init_weights(b, "kaiming")
+    assert list(a.state_dict()) == list(b.state_dict())
+    assert all(torch.equal(a.state_dict()[k], b.state_dict()[k]) for k in a.state_dict())
