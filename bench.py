@@ -254,12 +254,13 @@ def main():
 
     # ---- roofline pass (untimed): per-launch CUDA events on the tap-GEMM kernel ----
     roof = None
+    # every rank runs the traced step (it contains the gradient all-reduces); rank 0 evaluates it
+    ops.Plan.trace = []
+    model.set_input(dev_batch)
+    model.optimize_parameters()
+    torch.cuda.synchronize()
+    trace, ops.Plan.trace = ops.Plan.trace, None
     if rank == 0:
-        ops.Plan.trace = []
-        model.set_input(dev_batch)
-        model.optimize_parameters()
-        torch.cuda.synchronize()
-        trace, ops.Plan.trace = ops.Plan.trace, None
         info = {}
         for eng in (model._eng_G, model._eng_Dd, model._eng_Dg):
             for st in eng.stages:
@@ -291,6 +292,7 @@ def main():
                                  "share_of_step": tot["wgrad"][1] / step_ms, "launches_per_step": tot["wgrad"][2]}}
 
     if rank != 0:
+        torch.distributed.destroy_process_group()
         return
     cpu = None
     if not args.no_cpu_baseline and args.gpus == 1:
