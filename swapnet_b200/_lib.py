@@ -103,6 +103,7 @@ SIGNATURES = {
     "sn_plan_run": (_I, [_VP, _VP]),
     "sn_plan_destroy": (None, [_VP]),
     "sn_pack_planes": (_I, [_VP, _I, _I, _I, _I, _I, _I, _VP, _VP, _I, _I, _I, _VP]),
+    "sn_pack_concat": (_I, [_VP, _I, _I, _I, _VP, _I, _I, _I, _I, _I, _I, _I, _VP, _VP, _VP, _VP, _I, _I, _I, _I, _VP]),
     "sn_weight_scale": (_I, [_VP, _LL, _VP, _VP]),
     "sn_pack_weights": (_I, [_VP, _LL, _LL, _I, _I, _I, _I, _VP, _VP, _I, _VP, _VP]),
     "sn_pack_head_weights": (_I, [_VP, _I, _I, _I, _I, _I, _VP, _VP, _I, _VP, _VP]),

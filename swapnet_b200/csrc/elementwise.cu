@@ -85,6 +85,63 @@ __global__ void pack_planes_nhwc_kernel(const float* __restrict__ src, int src_p
   }
 }
 
+// pack_concat: up to two fp32 sources (NCHW or NHWC) concatenated along channels, zero-filled up to
+// c_fill channels, written as full 16-byte groups of 8 channels into the fp16 planes AND their bf16
+// twin in one pass.  One block = one (n, h, 32-pixel run).
+struct PackSrc { const float* p; int layout, pitch, c; };
+struct PackConcatArgs {
+  PackSrc s[2]; int nsrc;
+  int N, H, W, c_fill;
+  uint16_t *hi, *lo, *hi2, *lo2; int pitch, coff, fmt, fmt2;
+};
+__global__ void __launch_bounds__(256) pack_concat_kernel(const PackConcatArgs a) {
+  extern __shared__ float tile[];  // [c_fill][33]
+  const int w0 = blockIdx.x * 32, h = blockIdx.y, n = blockIdx.z;
+  int cbase = 0;
+  for (int si = 0; si < a.nsrc; ++si) {
+    const PackSrc s = a.s[si];
+    if (s.layout == SN_LAYOUT_NCHW) {
+      for (int i = threadIdx.x; i < s.c * 32; i += blockDim.x) {
+        const int c = i >> 5, w = i & 31;
+        tile[(cbase + c) * 33 + w] = (w0 + w < a.W) ? s.p[(((long long)n * s.c + c) * a.H + h) * a.W + w0 + w] : 0.f;
+      }
+    } else {
+      for (int i = threadIdx.x; i < s.c * 32; i += blockDim.x) {
+        const int w = i / s.c, c = i - w * s.c;
+        tile[(cbase + c) * 33 + w] = (w0 + w < a.W) ? s.p[(((long long)n * a.H + h) * a.W + w0 + w) * s.pitch + c] : 0.f;
+      }
+    }
+    cbase += s.c;
+  }
+  for (int i = threadIdx.x; i < (a.c_fill - cbase) * 32; i += blockDim.x) tile[(cbase + (i >> 5)) * 33 + (i & 31)] = 0.f;
+  __syncthreads();
+  const int G = a.c_fill >> 3;
+  for (int i = threadIdx.x; i < 32 * G; i += blockDim.x) {
+    const int w = i / G, g = i - w * G;
+    if (w0 + w >= a.W) continue;
+    uint16_t h1[8], l1[8], h2[8], l2[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float v = tile[(g * 8 + j) * 33 + w];
+      split16(v, a.fmt, h1[j], l1[j]);
+      if (a.hi2) split16(v, a.fmt2, h2[j], l2[j]);
+    }
+    const long long off = (((long long)n * a.H + h) * a.W + w0 + w) * a.pitch + a.coff + g * 8;
+    auto pk = [](const uint16_t* x) {
+      uint4 r;
+      r.x = x[0] | ((uint32_t)x[1] << 16); r.y = x[2] | ((uint32_t)x[3] << 16);
+      r.z = x[4] | ((uint32_t)x[5] << 16); r.w = x[6] | ((uint32_t)x[7] << 16);
+      return r;
+    };
+    *reinterpret_cast<uint4*>(a.hi + off) = pk(h1);
+    if (a.lo) *reinterpret_cast<uint4*>(a.lo + off) = pk(l1);
+    if (a.hi2) {
+      *reinterpret_cast<uint4*>(a.hi2 + off) = pk(h2);
+      if (a.lo2) *reinterpret_cast<uint4*>(a.lo2 + off) = pk(l2);
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------
 // pack_weights: dst[r][t][k] <- src[r*s_row + k*s_k + t]
 // ---------------------------------------------------------------------------------
@@ -430,7 +487,11 @@ __device__ __forceinline__ float gather_one(const sn_grad_src& s, int n, int h, 
 }
 __device__ __forceinline__ float gather_grad(const GradSrcs& g, int n, int h, int w, int H, int W, int c) {
   float acc = 0.f;
-  for (int i = 0; i < g.n; ++i) acc += gather_one(g.s[i], n, h, w, H, W, c);
+#pragma unroll
+  for (int i = 0; i < SN_MAX_SRC; ++i) {
+    if (i >= g.n) break;
+    acc += gather_one(g.s[i], n, h, w, H, W, c);
+  }
   return acc;
 }
 
@@ -453,7 +514,9 @@ __device__ __forceinline__ float grad_xhat(const NormActBwdArgs& a, int n, int p
   const int h = p / a.W, w = p - h * a.W;
   const float xhat = (a.y[pix * a.y_pitch + c] - mean) * rstd;
   float g = 0.f;
-  for (int i = 0; i < a.g.n; ++i) {
+#pragma unroll
+  for (int i = 0; i < SN_MAX_SRC; ++i) {
+    if (i >= a.g.n) break;
     const sn_grad_src& s = a.g.s[i];
     g += gather_one(s, n, h, w, a.H, a.W, c) * act_grad(xhat, s.act >= 0 ? s.act : a.act, a.slope);
   }
@@ -746,7 +809,7 @@ __device__ __forceinline__ void store_split4(uint16_t* hi, uint16_t* lo, long lo
   if (lo) *reinterpret_cast<uint2*>(lo + off) = pl;
 }
 
-__global__ void norm_act_fwd_v4_kernel(const NormActFwdArgs a) {
+__global__ void __launch_bounds__(256, 4) norm_act_fwd_v4_kernel(const NormActFwdArgs a) {
   extern __shared__ float sm[];  // mean[C], rstd[C]
   float* s_mean = sm;
   float* s_rstd = sm + a.C;
@@ -842,7 +905,9 @@ __device__ __forceinline__ float4 gather_one4(const sn_grad_src& s, int n, int h
 }
 __device__ __forceinline__ float4 gather_grad4(const GradSrcs& g, int n, int h, int w, int H, int W, int c) {
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (int i = 0; i < g.n; ++i) {
+#pragma unroll
+  for (int i = 0; i < SN_MAX_SRC; ++i) {
+    if (i >= g.n) break;
     const float4 v = gather_one4(g.s[i], n, h, w, H, W, c);
     acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
   }
@@ -862,7 +927,9 @@ __device__ __forceinline__ void grad_xhat4(const NormActBwdArgs& a, int n, int p
     xh[j] = (yy[j] - mean[j]) * rstd[j];
     g[j] = 0.f;
   }
-  for (int i = 0; i < a.g.n; ++i) {
+#pragma unroll
+  for (int i = 0; i < SN_MAX_SRC; ++i) {
+    if (i >= a.g.n) break;
     const sn_grad_src& s = a.g.s[i];
     const float4 gv = gather_one4(s, n, h, w, a.H, a.W, c);
     const float gg[4] = {gv.x, gv.y, gv.z, gv.w};
@@ -880,7 +947,7 @@ __device__ __forceinline__ void grad_xhat4(const NormActBwdArgs& a, int n, int p
 }
 
 // grid (ceil(Q/32), slabs, N), block (32, 8): thread = channel quad, strided over pixels
-__global__ void norm_act_bwd_reduce_v4_kernel(const NormActBwdArgs a) {
+__global__ void __launch_bounds__(256, 4) norm_act_bwd_reduce_v4_kernel(const NormActBwdArgs a) {
   __shared__ float red[8][32][8];
   const int q = blockIdx.x * 32 + threadIdx.x;
   const int c = q << 2;
@@ -927,7 +994,7 @@ __global__ void norm_act_bwd_reduce_v4_kernel(const NormActBwdArgs a) {
   }
 }
 
-__global__ void norm_act_bwd_apply_v4_kernel(const NormActBwdArgs a) {
+__global__ void __launch_bounds__(256, 4) norm_act_bwd_apply_v4_kernel(const NormActBwdArgs a) {
   extern __shared__ float sm[];  // mean, rstd, m1, m2 : 4 x C
   float* s_mean = sm;
   float* s_rstd = sm + a.C;
@@ -1033,6 +1100,30 @@ int sn_pack_planes(const float* src, int src_layout, int src_pitch, int n, int c
     pack_planes_nhwc_kernel<<<grid_for(npix * c), kEwThreads, 0, st>>>(
         src, src_pitch, npix, c, (uint16_t*)dst_hi, (uint16_t*)dst_lo, dst_pitch, dst_coff, fmt);
   }
+  LAUNCH_CHECK();
+  return SN_OK;
+}
+
+int sn_pack_concat(const float* src0, int layout0, int pitch0, int c0, const float* src1, int layout1, int pitch1,
+                   int c1, int n, int h, int w, int c_fill, void* dst_hi, void* dst_lo, void* dst2_hi, void* dst2_lo,
+                   int dst_pitch, int dst_coff, int fmt, int fmt2, void* stream) {
+  SN_REQUIRE(src0 && dst_hi, "null pointer");
+  SN_REQUIRE(c_fill % 8 == 0 && dst_coff % 8 == 0 && dst_pitch % 8 == 0 && c0 + (src1 ? c1 : 0) <= c_fill &&
+                 dst_coff + c_fill <= dst_pitch,
+             "pack_concat: channel slice must be 8-aligned and fit (coff=%d fill=%d pitch=%d)", dst_coff, c_fill,
+             dst_pitch);
+  SN_REQUIRE((((uintptr_t)dst_hi | (uintptr_t)dst_lo | (uintptr_t)dst2_hi | (uintptr_t)dst2_lo) & 15) == 0,
+             "pack_concat: planes must be 16-byte aligned");
+  PackConcatArgs a;
+  a.s[0] = PackSrc{src0, layout0, pitch0, c0};
+  a.s[1] = PackSrc{src1, layout1, pitch1, src1 ? c1 : 0};
+  a.nsrc = src1 ? 2 : 1;
+  a.N = n; a.H = h; a.W = w; a.c_fill = c_fill;
+  a.hi = (uint16_t*)dst_hi; a.lo = (uint16_t*)dst_lo; a.hi2 = (uint16_t*)dst2_hi; a.lo2 = (uint16_t*)dst2_lo;
+  a.pitch = dst_pitch; a.coff = dst_coff; a.fmt = fmt; a.fmt2 = fmt2;
+  const size_t smem = (size_t)c_fill * 33 * sizeof(float);
+  SN_REQUIRE(smem <= 48 * 1024, "pack_concat: c_fill too large (%d)", c_fill);
+  pack_concat_kernel<<<dim3((w + 31) / 32, h, n), 256, smem, (cudaStream_t)stream>>>(a);
   LAUNCH_CHECK();
   return SN_OK;
 }

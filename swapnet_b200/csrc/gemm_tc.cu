@@ -98,7 +98,7 @@ tap_gemm_kernel(const __grid_constant__ TapGemmParams p) {
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
-      const uint32_t stage_tx = C::kPlanes * (kTileBytes + p.block_n * 128);
+      const uint32_t stage_tx = C::kPlanes * (p.a_rows * 128 + p.block_n * 128);
       for (int it = 0; it < k_iters; ++it) {
         const int s = it % C::kStages;
         const uint32_t ph = (it / C::kStages) & 1;
@@ -155,7 +155,7 @@ tap_gemm_kernel(const __grid_constant__ TapGemmParams p) {
     const int h_i = (row / p.tw) % p.th;
     const int n_i = row / (p.tw * p.th);
     const int gw = w0 + w_i, gh = h0 + h_i, gn = n0 + n_i;
-    const bool valid = (gw < p.m_w) && (gh < p.m_h) && (gn < p.m_n);
+    const bool valid = (row < p.a_rows) && (gw < p.m_w) && (gh < p.m_h) && (gn < p.m_n);
     float* optr = p.out + (long long)gn * p.out_sn + (long long)(gh * p.omh + p.ooh) * p.out_sh +
                   (long long)(gw * p.omw + p.oow) * p.out_sw + ncol0;
     const float oscale = p.b_scale ? p.b_scale[1] : 1.f;  // undo the power-of-two weight scale (exact)
@@ -429,6 +429,42 @@ static void pick_patch(int m_h, int m_w, int rows, int* th, int* tw, int* nb) {
   *nb = rows / (w * h);
 }
 
+// conv mode: any th x tw x nb patch with <= 128 GEMM rows works (rows the TMA box does not write
+// are never stored), so pick the patch that wastes the fewest rows on this plane — e.g. 7 x 17 on the
+// 34 x 34 padded resblock-gradient grid (90 % instead of 60 % with 8 x 16).  Ties: squarer patch
+// (smaller halo re-read across taps).
+static void pick_patch_conv(int m_n, int m_h, int m_w, int* th, int* tw, int* nb) {
+  double best_eff = -1.0;
+  int best_perim = 1 << 30, best_rows = 0, best_area = 0;
+  const long long useful = (long long)m_n * m_h * m_w;
+  for (int w = 1; w <= m_w && w <= 128; ++w) {
+    for (int h = 1; h <= m_h && h * w <= 128; ++h) {
+      // planes of >= 128 pixels: purely spatial patches (halo locality); smaller planes: whole
+      // planes of several images per tile
+      int n = 1;
+      if (m_h * m_w < 128) {
+        if (w != m_w || h != m_h) continue;
+        n = 128 / (w * h);
+        if (n > m_n) n = m_n;
+        if (n > 256) n = 256;
+      }
+      const long long tiles = (long long)((m_w + w - 1) / w) * ((m_h + h - 1) / h) * ((m_n + n - 1) / n);
+      const double eff = (double)useful / (double)(tiles * 128);
+      const int rows = w * h * n, perim = w + h, area = w * h;
+      // ties: more rows per tile, then the larger spatial patch (fewer images per tile), then the squarer one
+      const bool better =
+          eff > best_eff + 1e-9 ||
+          (eff > best_eff - 1e-9 &&
+           (rows > best_rows ||
+            (rows == best_rows && (area > best_area || (area == best_area && (perim < best_perim || (perim == best_perim && w > *tw)))))));
+      if (better) {
+        best_eff = eff; best_rows = rows; best_perim = perim; best_area = area;
+        *tw = w; *th = h; *nb = n;
+      }
+    }
+  }
+}
+
 static int g_smem_attr_done[2][2] = {{0, 0}, {0, 0}};
 
 int sn_tap_gemm_plan_init(TapGemmPlan* plan, const sn_tap_gemm_desc* d) {
@@ -444,7 +480,8 @@ int sn_tap_gemm_plan_init(TapGemmPlan* plan, const sn_tap_gemm_desc* d) {
   SN_REQUIRE(d->a_fmt == d->b_fmt, "A and B of one tcgen05.mma must share a 16-bit format (a=%d b=%d)",
              d->a_fmt, d->b_fmt);
   int th, tw, nb;
-  pick_patch(d->m_h, d->m_w, 128, &th, &tw, &nb);
+  pick_patch_conv(d->m_n, d->m_h, d->m_w, &th, &tw, &nb);
+  p.a_rows = th * tw * nb;
   p.tw = tw; p.th = th; p.nb = nb;
   p.tiles_w = (d->m_w + tw - 1) / tw;
   p.tiles_h = (d->m_h + th - 1) / th;

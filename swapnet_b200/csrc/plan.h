@@ -17,6 +17,7 @@ struct alignas(64) TapGemmParams {
   int ntaps, chunks;
   int tiles_w, tiles_h, tiles_n;
   int tw, th, nb;
+  int a_rows;  // th * tw * nb <= 128 GEMM rows actually loaded / stored per tile
   int m_w, m_h, m_n;
   int block_n, n_valid;
   float* out;

@@ -226,8 +226,8 @@ class WarpEngine(Engine):
     def forward(self, body: torch.Tensor, cloth: torch.Tensor, training: bool = True, seed: int = 0) -> torch.Tensor:
         """body [B,cb,S,S], cloth [B,cc,S,S] fp32 NCHW on device -> fakes [B,S,S,cc] (NHWC storage)."""
         self.training, self.seed = training, seed
-        ops.pack_planes(body, self.in_body)
-        ops.pack_planes(cloth, self.in_cloth)
+        ops.pack_concat([(body, False)], self.in_body)
+        ops.pack_concat([(cloth, False)], self.in_cloth)
         for s in self._fwd_order:
             s.forward()
         return self.fakes

@@ -95,12 +95,9 @@ class TextureModel(BaseGAN):
         self.fakes = out.permute(0, 3, 1, 2)
 
     def pack_D_inputs(self, din_fake, din_real):
-        cc, ct = self.opt.cloth_channels, self.opt.texture_channels
-        ops.pack_planes(self.cloths, din_fake.slice(0, cc))
-        ops.pack_planes(self._eng_G.fakes, din_fake.slice(cc, ct), nhwc=True)
+        ops.pack_concat([(self.cloths, False), (self._eng_G.fakes, True)], din_fake)
         if din_real is not None:
-            ops.pack_planes(self.cloths, din_real.slice(0, cc))
-            ops.pack_planes(self.targets, din_real.slice(cc, ct))
+            ops.pack_concat([(self.cloths, False), (self.targets, False)], din_real)
 
     def backward_G(self):
         g = self._eng_G

@@ -86,12 +86,9 @@ class WarpModel(BaseGAN):
 
     def pack_D_inputs(self, din_fake, din_real):
         """conditioned = cat((bodys, cloth), 1): body first (warp_model.py:115,119,157)."""
-        cb, cc = self.body_channels, self.cloth_channels
-        ops.pack_planes(self.bodys, din_fake.slice(0, cb))
-        ops.pack_planes(self._eng_G.fakes, din_fake.slice(cb, cc), nhwc=True)
+        ops.pack_concat([(self.bodys, False), (self._eng_G.fakes, True)], din_fake)
         if din_real is not None:
-            ops.pack_planes(self.bodys, din_real.slice(0, cb))
-            ops.pack_planes(self.targets, din_real.slice(cb, cc))
+            ops.pack_concat([(self.bodys, False), (self.targets, False)], din_real)
 
     def backward_G(self):
         g = self._eng_G

@@ -235,6 +235,29 @@ def pack_planes(src: torch.Tensor, dst: Planes, *, nhwc: bool = False) -> None:
     assert (n, h, w) == (dst.n, dst.h, dst.w)
 
 
+def pack_concat(srcs, dst: Planes) -> None:
+    """srcs: 1-2 tuples (tensor, nhwc: bool); channels concatenated, zero-filled to dst.c, written to dst
+    and its twin in one pass.  Replaces cat((a, b), 1) + the channel padding of the operand."""
+    assert 1 <= len(srcs) <= 2 and dst.c % 8 == 0 and dst.c_off % 8 == 0
+    args = []
+    for t, nhwc in srcs:
+        assert t.dtype == torch.float32
+        if nhwc:
+            n, h, w, c = t.shape
+            args += [t.data_ptr(), LAYOUT_NHWC, _pitch(t), c]
+        else:
+            assert t.is_contiguous()
+            n, c, h, w = t.shape
+            args += [t.data_ptr(), LAYOUT_NCHW, 0, c]
+        assert (n, h, w) == (dst.n, dst.h, dst.w)
+    if len(srcs) == 1:
+        args += [None, 0, 0, 0]
+    tw = dst.twin
+    check(_lib.load().sn_pack_concat(*args, dst.n, dst.h, dst.w, dst.c, dst.hi.data_ptr(), dst.lo.data_ptr(),
+                                     None if tw is None else tw.hi.data_ptr(), None if tw is None else tw.lo.data_ptr(),
+                                     dst.pitch, dst.c_off, dst.fmt, FMT_BF16 if tw is None else tw.fmt, _stream()))
+
+
 def weight_scale(weight: torch.Tensor, scale: torch.Tensor) -> None:
     """scale <- (s, 1/s), s = 2^k with max|w| * s in [2^13, 2^14) (device side, no sync)."""
     check(_lib.load().sn_weight_scale(weight.data_ptr(), weight.numel(), scale.data_ptr(), _stream()))
