@@ -357,6 +357,51 @@ __global__ void bias_grad_kernel(const uint16_t* __restrict__ hi, const uint16_t
     atomic_add_f64(&acc[c], a);
   }
 }
+// 8 channels per thread (one 16-B load per plane); block (G = C/8 groups, 256/G pixel rows)
+__global__ void bias_grad_v8_kernel(const uint16_t* __restrict__ hi, const uint16_t* __restrict__ lo, int pitch,
+                                    int fmt, long long npix, int C, double* __restrict__ acc) {
+  __shared__ float red[256][8];
+  const int gch = blockIdx.x * blockDim.x + threadIdx.x;   // channel group
+  const int c = gch * 8;
+  const long long per = (npix + gridDim.y - 1) / gridDim.y;
+  const long long p0 = blockIdx.y * per;
+  const long long p1 = p0 + per < npix ? p0 + per : npix;
+  float s[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  double d[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (c < C) {
+    int cnt = 0;
+    for (long long p = p0 + threadIdx.y; p < p1; p += blockDim.y) {
+      const uint4 vh = *reinterpret_cast<const uint4*>(hi + p * pitch + c);
+      const uint4 vl = lo ? *reinterpret_cast<const uint4*>(lo + p * pitch + c) : make_uint4(0, 0, 0, 0);
+      const uint32_t wh[4] = {vh.x, vh.y, vh.z, vh.w}, wl[4] = {vl.x, vl.y, vl.z, vl.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        s[2 * j] += decode16((uint16_t)(wh[j] & 0xFFFF), fmt) + (lo ? decode16((uint16_t)(wl[j] & 0xFFFF), fmt) : 0.f);
+        s[2 * j + 1] += decode16((uint16_t)(wh[j] >> 16), fmt) + (lo ? decode16((uint16_t)(wl[j] >> 16), fmt) : 0.f);
+      }
+      if (++cnt == 64) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { d[j] += (double)s[j]; s[j] = 0.f; }
+        cnt = 0;
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) d[j] += (double)s[j];
+  }
+  const int slot = threadIdx.y * blockDim.x + threadIdx.x;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) red[slot][j] = (float)d[j];
+  __syncthreads();
+  if (threadIdx.y == 0 && c < C) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      if (c + j >= C) break;
+      double u = 0.0;
+      for (int r = 0; r < (int)blockDim.y; ++r) u += (double)red[r * blockDim.x + threadIdx.x][j];
+      atomic_add_f64(&acc[c + j], u);
+    }
+  }
+}
 __global__ void bias_grad_finalize_kernel(const double* acc, int C, float* db) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < C) db[i] = (float)acc[i];
@@ -598,21 +643,24 @@ __global__ void sum_grads_kernel(const GradSrcs g, int H, int W, int C, float* d
     }
 }
 
-__global__ void tanh_bwd_kernel(const GradSrcs g, const float* __restrict__ out, int out_pitch, int H,
+// flat (pixel, channel) index: consecutive threads walk consecutive channels then pixels, so the 19-channel
+// head rows (76 B) are read fully coalesced
+__global__ void tanh_bwd_kernel(const GradSrcs g, const float* __restrict__ out, int out_pitch, int N, int H,
                                 int W, int C, uint16_t* hi, uint16_t* lo, int dy_pitch,
                                 int dy_coff, int fmt) {
-  const int n = blockIdx.y;
   const int HW = H * W;
-  const int per = (HW + gridDim.x - 1) / gridDim.x;
-  const int p0 = blockIdx.x * per, p1 = min(HW, p0 + per);
-  for (int c = threadIdx.x; c < C; c += blockDim.x)
-    for (int p = p0 + threadIdx.y; p < p1; p += blockDim.y) {
-      const int h = p / W, w = p - h * W;
-      const long long pix = (long long)n * HW + p;
-      const float o = out[pix * out_pitch + c];
-      const float v = gather_grad(g, n, h, w, H, W, c) * (1.f - o * o);
-      store_split(hi, lo, pix * dy_pitch + dy_coff + c, v, fmt);
-    }
+  const long long total = (long long)N * HW * C;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long pix = i / C;
+    const int c = (int)(i - pix * C);
+    const int n = (int)(pix / HW);
+    const int p = (int)(pix - (long long)n * HW);
+    const int h = p / W, w = p - h * W;
+    const float o = out[pix * out_pitch + c];
+    const float v = gather_grad(g, n, h, w, H, W, c) * (1.f - o * o);
+    store_split(hi, lo, pix * dy_pitch + dy_coff + c, v, fmt);
+  }
 }
 
 __global__ void upsample_planes_kernel(const uint16_t* __restrict__ shi, const uint16_t* __restrict__ slo,
@@ -822,10 +870,11 @@ __global__ void __launch_bounds__(256, 4) norm_act_fwd_v4_kernel(const NormActFw
   const int HW = a.H * a.W, Q = a.C >> 2;
   const int per = (HW + gridDim.x - 1) / gridDim.x;
   const int p0 = blockIdx.x * per, p1 = min(HW, p0 + per);
-  const long long i1 = (long long)p1 * Q;
-  for (long long i = (long long)p0 * Q + threadIdx.x; i < i1; i += blockDim.x) {
-    const int p = (int)(i / Q);
-    const int c = ((int)(i - (long long)p * Q)) << 2;
+  const int i1 = (p1 - p0) * Q;   // slab-relative 32-bit index
+  for (int i = threadIdx.x; i < i1; i += blockDim.x) {
+    const int pl = i / Q;
+    const int p = p0 + pl;
+    const int c = (i - pl * Q) << 2;
     const long long pix = (long long)n * HW + p;
     const float4 yv = *reinterpret_cast<const float4*>(a.y + pix * a.y_pitch + c);
     float v[4] = {yv.x, yv.y, yv.z, yv.w};
@@ -946,10 +995,11 @@ __device__ __forceinline__ void grad_xhat4(const NormActBwdArgs& a, int n, int p
   }
 }
 
-// grid (ceil(Q/32), slabs, N), block (32, 8): thread = channel quad, strided over pixels
+// grid (ceil(Q/bx), slabs, N), block (bx, 256/bx) with bx = min(32, pow2 >= Q): thread = channel quad,
+// strided over pixels (C = 64 layers — the largest tensors — use bx = 16, 16 pixel rows)
 __global__ void __launch_bounds__(256, 4) norm_act_bwd_reduce_v4_kernel(const NormActBwdArgs a) {
-  __shared__ float red[8][32][8];
-  const int q = blockIdx.x * 32 + threadIdx.x;
+  __shared__ float red[256][8];
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
   const int c = q << 2;
   const int n = blockIdx.z;
   const int HW = a.H * a.W;
@@ -963,7 +1013,7 @@ __global__ void __launch_bounds__(256, 4) norm_act_bwd_reduce_v4_kernel(const No
       mean[j] = (float)a.stats[((long long)n * a.C + c + j) * 2];
       rstd[j] = (float)a.stats[((long long)n * a.C + c + j) * 2 + 1];
     }
-    for (int p = p0 + threadIdx.y; p < p1; p += 8) {
+    for (int p = p0 + threadIdx.y; p < p1; p += blockDim.y) {
       float g[4], xh[4];
       grad_xhat4(a, n, p, c, mean, rstd, g, xh);
 #pragma unroll
@@ -973,20 +1023,20 @@ __global__ void __launch_bounds__(256, 4) norm_act_bwd_reduce_v4_kernel(const No
       }
     }
   }
+  const int slot = threadIdx.y * blockDim.x + threadIdx.x;
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
-    red[threadIdx.y][threadIdx.x][j] = s1[j];
-    red[threadIdx.y][threadIdx.x][4 + j] = s2[j];
+    red[slot][j] = s1[j];
+    red[slot][4 + j] = s2[j];
   }
   __syncthreads();
   if (threadIdx.y == 0 && c < a.C) {
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       double u = 0.0, v = 0.0;
-#pragma unroll
-      for (int r = 0; r < 8; ++r) {
-        u += (double)red[r][threadIdx.x][j];
-        v += (double)red[r][threadIdx.x][4 + j];
+      for (int r = 0; r < (int)blockDim.y; ++r) {
+        u += (double)red[r * blockDim.x + threadIdx.x][j];
+        v += (double)red[r * blockDim.x + threadIdx.x][4 + j];
       }
       atomic_add_f64(&a.gstats[((long long)n * a.C + c + j) * 2 + 0], u);
       atomic_add_f64(&a.gstats[((long long)n * a.C + c + j) * 2 + 1], v);
@@ -1012,10 +1062,11 @@ __global__ void __launch_bounds__(256, 4) norm_act_bwd_apply_v4_kernel(const Nor
   const int HW = a.H * a.W, Q = a.C >> 2;
   const int per = (HW + gridDim.x - 1) / gridDim.x;
   const int p0 = blockIdx.x * per, p1 = min(HW, p0 + per);
-  const long long i1 = (long long)p1 * Q;
-  for (long long i = (long long)p0 * Q + threadIdx.x; i < i1; i += blockDim.x) {
-    const int p = (int)(i / Q);
-    const int c = ((int)(i - (long long)p * Q)) << 2;
+  const int i1 = (p1 - p0) * Q;   // slab-relative 32-bit index
+  for (int i = threadIdx.x; i < i1; i += blockDim.x) {
+    const int pl = i / Q;
+    const int p = p0 + pl;
+    const int c = (i - pl * Q) << 2;
     float g[4], xh[4];
     grad_xhat4(a, n, p, c, s_mean + c, s_rstd + c, g, xh);
     if (a.stats) {
@@ -1031,10 +1082,11 @@ __global__ void sum_grads_v4_kernel(const GradSrcs g, int H, int W, int C, float
   const int HW = H * W, Q = C >> 2;
   const int per = (HW + gridDim.x - 1) / gridDim.x;
   const int p0 = blockIdx.x * per, p1 = min(HW, p0 + per);
-  const long long i1 = (long long)p1 * Q;
-  for (long long i = (long long)p0 * Q + threadIdx.x; i < i1; i += blockDim.x) {
-    const int p = (int)(i / Q);
-    const int c = ((int)(i - (long long)p * Q)) << 2;
+  const int i1 = (p1 - p0) * Q;   // slab-relative 32-bit index
+  for (int i = threadIdx.x; i < i1; i += blockDim.x) {
+    const int pl = i / Q;
+    const int p = p0 + pl;
+    const int c = (i - pl * Q) << 2;
     const int h = p / W, w = p - h * W;
     *reinterpret_cast<float4*>(dst + ((long long)n * HW + p) * dst_pitch + c) = gather_grad4(g, n, h, w, H, W, c);
   }
@@ -1257,11 +1309,13 @@ int sn_norm_act_bwd(const sn_norm_act_bwd_desc* d, void* stream) {
     SN_REQUIRE(d->gstats, "InstanceNorm backward needs gstats scratch");
     SN_CHECK_CUDA(cudaMemsetAsync(d->gstats, 0, sizeof(double) * 2 * d->n * d->c, st));
     if (vec) {
-      const int qg = (d->c / 4 + 31) / 32;
+      int bx = 1;
+      while (bx < d->c / 4 && bx < 32) bx <<= 1;
+      const int qg = (d->c / 4 + bx - 1) / bx;
       int slabs = (148 * 6 + d->n * qg - 1) / (d->n * qg);
-      if (slabs > (hw + 63) / 64) slabs = (hw + 63) / 64;
+      if (slabs > (hw + 127) / 128) slabs = (hw + 127) / 128;
       if (slabs < 1) slabs = 1;
-      norm_act_bwd_reduce_v4_kernel<<<dim3(qg, slabs, d->n), dim3(32, 8), 0, st>>>(a);
+      norm_act_bwd_reduce_v4_kernel<<<dim3(qg, slabs, d->n), dim3(bx, 256 / bx), 0, st>>>(a);
     } else {
       const int cg = (d->c + 31) / 32;
       int slabs = (148 * 4 + d->n * cg - 1) / (d->n * cg);
@@ -1297,6 +1351,18 @@ int sn_bias_grad(const void* dy_hi, const void* dy_lo, int pitch, int coff, int 
   if (slabs < 1) slabs = 1;
   const uint16_t* hi = (const uint16_t*)dy_hi + coff;
   const uint16_t* lo = dy_lo ? (const uint16_t*)dy_lo + coff : nullptr;
+  const bool v8 = (pitch % 8 == 0) && (coff % 8 == 0) && (((uintptr_t)dy_hi | (uintptr_t)dy_lo) & 15) == 0 &&
+                  ((c + 7) / 8 * 8 + coff <= pitch);
+  if (v8) {
+    const int groups = (c + 7) / 8;
+    int bx = 1;
+    while (bx < groups && bx < 32) bx <<= 1;
+    const int gx = (groups + bx - 1) / bx;
+    long long sl = (148 * 6 + gx - 1) / gx;
+    if (sl > (npix + 255) / 256) sl = (npix + 255) / 256;
+    if (sl < 1) sl = 1;
+    bias_grad_v8_kernel<<<dim3(gx, (int)sl), dim3(bx, 256 / bx), 0, st>>>(hi, lo, pitch, fmt, npix, c, scratch);
+  } else
   bias_grad_kernel<<<dim3(cg, (int)slabs), dim3(32, 8), 0, st>>>(hi, lo, pitch, fmt, npix, c, scratch);
   LAUNCH_CHECK();
   bias_grad_finalize_kernel<<<(c + 255) / 256, 256, 0, st>>>(scratch, c, db);
@@ -1325,9 +1391,7 @@ int sn_tanh_bwd(const sn_grad_src* src, int nsrc, const float* out, int out_pitc
   GradSrcs g;
   int rc = fill_srcs(&g, src, nsrc);
   if (rc) return rc;
-  dim3 blk = cblock(c);
-  dim3 grid(slabs_for(h * w, n, blk.y), n);
-  tanh_bwd_kernel<<<grid, blk, 0, (cudaStream_t)stream>>>(g, out, out_pitch, h, w, c,
+  tanh_bwd_kernel<<<grid_for((long long)n * h * w * c), kEwThreads, 0, (cudaStream_t)stream>>>(g, out, out_pitch, n, h, w, c,
                                                           (uint16_t*)dy_hi, (uint16_t*)dy_lo,
                                                           dy_pitch, dy_coff, dy_fmt);
   LAUNCH_CHECK();

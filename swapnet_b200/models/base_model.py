@@ -51,6 +51,29 @@ class BaseModel(ABC):
         self.metric = 0
         self.training = True
 
+    # ---- late H2D copies: tensors that the step needs only after its first phase ----
+    def copy_late(self, t: torch.Tensor) -> torch.Tensor:
+        if t.is_cuda:
+            return t.to(device=self.device, dtype=torch.float32).contiguous()
+        if not hasattr(self, "_copy_stream"):
+            self._copy_stream = torch.cuda.Stream(device=self.device)
+            self._late_events = []
+        cur = torch.cuda.current_stream(self.device)
+        self._copy_stream.wait_stream(cur)   # the destination buffer may still be read by earlier work
+        with torch.cuda.stream(self._copy_stream):
+            out = t.to(device=self.device, dtype=torch.float32, non_blocking=True).contiguous()
+            ev = torch.cuda.Event()
+            ev.record(self._copy_stream)
+        out.record_stream(cur)
+        self._late_events.append(ev)
+        return out
+
+    def wait_late_copies(self) -> None:
+        for ev in getattr(self, "_late_events", []):
+            torch.cuda.current_stream(self.device).wait_event(ev)
+        if hasattr(self, "_late_events"):
+            self._late_events.clear()
+
     @staticmethod
     def modify_commandline_options(parser, is_train):
         return parser

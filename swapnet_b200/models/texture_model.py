@@ -81,7 +81,7 @@ class TextureModel(BaseGAN):
         self.textures = input["input_textures"].to(**f32).contiguous()
         self.rois = input["rois"].to(**f32).contiguous()
         self.cloths = input["cloths"].to(**f32).contiguous()
-        self.targets = input["target_textures"].to(**f32).contiguous()
+        self.targets = self.copy_late(input["target_textures"])
         self.image_paths = tuple(zip(input["cloth_paths"], input["texture_paths"]))
 
     def forward(self):
@@ -93,6 +93,7 @@ class TextureModel(BaseGAN):
         out = g.forward(self.textures, self.rois, self.cloths, training=self.training and self.is_train,
                         seed=self.step_seed())
         self.fakes = out.permute(0, 3, 1, 2)
+        self.wait_late_copies()
 
     def pack_D_inputs(self, din_fake, din_real):
         ops.pack_concat([(self.cloths, False), (self._eng_G.fakes, True)], din_fake)

@@ -72,7 +72,9 @@ class WarpModel(BaseGAN):
         f32 = dict(device=self.device, dtype=torch.float32, non_blocking=True)
         self.bodys = input["bodys"].to(**f32).contiguous()
         self.inputs = input["input_cloths"].to(**f32).contiguous()
-        self.targets = input["target_cloths"].to(**f32).contiguous()
+        # the targets are first needed by the D step, one generator forward later: their H2D copy runs on
+        # a side stream and overlaps that forward (pinned host tensors; no-op for device tensors)
+        self.targets = self.copy_late(input["target_cloths"])
         self.image_paths = tuple(zip(input["cloth_paths"], input["body_paths"]))
 
     def forward(self):
@@ -83,6 +85,7 @@ class WarpModel(BaseGAN):
         g.pack()
         out = g.forward(self.bodys, self.inputs, training=self.training and self.is_train, seed=self.step_seed())
         self.fakes = out.permute(0, 3, 1, 2)   # [B,19,S,S] view of the NHWC storage
+        self.wait_late_copies()
 
     def pack_D_inputs(self, din_fake, din_real):
         """conditioned = cat((bodys, cloth), 1): body first (warp_model.py:115,119,157)."""
