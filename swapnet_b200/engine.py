@@ -237,9 +237,26 @@ class WarpEngine(Engine):
         h16 = self.size // 16
         self._dres = [torch.zeros(self.batch, h16, h16, 1024, device=self.device) for _ in range(4)]
 
-    def backward(self, srcs: Sequence[GradSrc]) -> None:
-        """srcs: gradient(s) w.r.t. fakes (NHWC fp32).  Accumulates parameter grads into flat_grad."""
+    def grad_buckets(self):
+        """Contiguous [lo, hi) slices of flat_grad in the order backward() completes them."""
+        names = [n for n, _ in self.net.named_parameters()]
+        sizes = [p.numel() for _, p in self.net.named_parameters()]
+        offs = [0]
+        for s_ in sizes:
+            offs.append(offs[-1] + s_)
+
+        def span(prefixes):
+            idx = [i for i, n in enumerate(names) if n.startswith(prefixes)]
+            assert idx == list(range(idx[0], idx[-1] + 1)), "bucket is not contiguous in the flat buffer"
+            return offs[idx[0]], offs[idx[-1] + 1]
+
+        return [span(("dual_up", "upsample_and_pad")), span(("resblocks",)), span(("cloth_",)), span(("body_",))]
+
+    def backward(self, srcs: Sequence[GradSrc], on_bucket=None) -> None:
+        """srcs: gradient(s) w.r.t. fakes (NHWC fp32).  Accumulates parameter grads into flat_grad.
+        on_bucket(i): called when bucket i of grad_buckets() has all its gradient launches enqueued."""
         B, h16 = self.batch, self.size // 16
+        done = on_bucket or (lambda i: None)
         self.head.backward(srcs)
         g3 = self.head.dx                                     # d cat3 [.,192]
         self.d3.backward([GradSrc(g3, 0)])
@@ -248,12 +265,14 @@ class WarpEngine(Engine):
         g1 = self.d2.dx                                       # d cat1 [.,768]
         self.d1.backward([GradSrc(g1, 0)])
         gx = self.d1.dx                                       # d x4 [.,1024]
+        done(0)
         for k in (3, 2, 1, 0):
             r1, r2 = self.res[k]
             r2.backward([GradSrc(gx)])                        # IN(y2) branch; identity branch handled below
             r1.backward([GradSrc(r2.dx, 0, True)])
             ops.sum_grads([GradSrc(gx), GradSrc(r1.dx, 0, True)], B, h16, h16, 1024, self._dres[k])
             gx = self._dres[k]
+        done(1)
         self.u2.backward([GradSrc(gx, 512)])
         self.u1.backward([GradSrc(self.u2.dx)])
         self.c6.backward([GradSrc(self.u1.dx)])
@@ -262,10 +281,12 @@ class WarpEngine(Engine):
         self.c3.backward([GradSrc(self.c4.dx), GradSrc(g1, 512)])
         self.c2.backward([GradSrc(self.c3.dx), GradSrc(g2, 256)])
         self.c1.backward([GradSrc(self.c2.dx), GradSrc(g3, 128)])
+        done(2)
         self.b4.backward([GradSrc(gx, 0)])
         self.b3.backward([GradSrc(self.b4.dx), GradSrc(g1, 256)])
         self.b2.backward([GradSrc(self.b3.dx), GradSrc(g2, 128)])
         self.b1.backward([GradSrc(self.b2.dx), GradSrc(g3, 64)])
+        done(3)
 
 
 # =============================================================================================

@@ -104,8 +104,13 @@ class WarpModel(BaseGAN):
         if self.opt.warp_mode == "gan":
             dx = self.gan_backward_through_D()
             srcs.append(GradSrc(dx, self.body_channels))
-        g.backward(srcs)
-        self.allreduce_grads(g)
+        if self._world > 1:
+            from .. import parallel
+            avg = parallel.BucketedAverager(g.flat_grad, g.grad_buckets())
+            g.backward(srcs, on_bucket=avg.ready)
+            avg.finish()
+        else:
+            g.backward(srcs)
 
     def optimize_parameters(self):
         if self.opt.warp_mode == "gan":

@@ -30,6 +30,32 @@ def average_gradients(flat_grad: torch.Tensor) -> None:
         flat_grad.mul_(1.0 / w)
 
 
+class BucketedAverager:
+    """Overlaps the gradient all-reduce with the rest of the backward pass.
+
+    The flat gradient buffer is cut into contiguous buckets in the order the backward pass finishes them
+    (WarpEngine: decoder+head, resblocks, cloth branch, body branch).  `ready(i)` is called right after
+    the last weight-gradient launch of bucket i has been enqueued: the all-reduce of that slice starts on
+    NCCL's stream as soon as those kernels finish, while the remaining backward keeps the SMs busy.
+    `finish()` waits for all of them and applies the 1/world scale."""
+
+    def __init__(self, flat_grad: torch.Tensor, bounds):
+        self.flat, self.bounds, self.work = flat_grad, list(bounds), []
+
+    def ready(self, i: int) -> None:
+        if world_size() > 1:
+            lo, hi = self.bounds[i]
+            self.work.append(dist.all_reduce(self.flat[lo:hi], op=dist.ReduceOp.SUM, async_op=True))
+
+    def finish(self) -> None:
+        w = world_size()
+        if w > 1:
+            for wk in self.work:
+                wk.wait()
+            self.work.clear()
+            self.flat.mul_(1.0 / w)
+
+
 def broadcast_parameters(params: Iterable[torch.Tensor], src: int = 0) -> None:
     if world_size() > 1:
         for p in params:

@@ -40,7 +40,15 @@ def _worker(rank, world, port, q):
     labels = parallel.LabelDraws(1234)
     t = [torch.tensor([labels.draw()]), torch.tensor([labels.draw()])]
     flat = _d_grads(sdD, mine["bodys"], mine["input_cloths"], mine["target_cloths"], t)
+    flat2 = flat.clone()
     parallel.average_gradients(flat)
+    # the bucketed (overlapped) averager must give the same result as the single all-reduce
+    half = flat2.numel() // 2
+    avg = parallel.BucketedAverager(flat2, [(half, flat2.numel()), (0, half)])
+    avg.ready(0)
+    avg.ready(1)
+    avg.finish()
+    assert torch.allclose(flat, flat2, rtol=0, atol=0)
     if rank == 0:
         ref = _d_grads(sdD, body, inp, tgt, t)
         q.put((float((flat - ref).abs().max() / ref.abs().max()), [float(x) for x in t]))
