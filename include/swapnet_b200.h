@@ -66,6 +66,10 @@ typedef struct sn_tap_gemm_desc {
   int a_n, a_h, a_w, a_c, a_pitch;
   int a_parity;                          /* 1: address through the 2x2 parity view (stride-2) */
   int a_fmt;                             /* SN_FMT_* of the A planes */
+  int a_chunk;                           /* channels per TMA row: 64 (default when 0), 32 or 16.  Narrow
+                                            operands (3/19/22-channel images, 1/3/19-channel gradients)
+                                            are padded to 16/32 instead of 64: then k_per_tap == a_chunk,
+                                            64/a_chunk taps share one pipeline stage, ntaps %% (64/a_chunk) == 0 */
   const void* b_hi; const void* b_lo;   /* packed weights [b_rows][b_k] 16-bit, K contiguous */
   int b_rows; long long b_k;
   int b_fmt;                             /* SN_FMT_* of the packed weights */
@@ -73,7 +77,7 @@ typedef struct sn_tap_gemm_desc {
                                             sn_weight_scale: weights were packed as w*s, the
                                             epilogue multiplies the accumulator by 1/s */
   int m_n, m_h, m_w;                     /* GEMM row grid */
-  int ntaps; int k_per_tap;              /* k_per_tap % 64 == 0 */
+  int ntaps; int k_per_tap;              /* k_per_tap % 64 == 0 (or == a_chunk when narrow) */
   sn_tap taps[SN_MAX_TAPS];
   float* out;                            /* fp32, element strides below, channel stride 1 */
   long long out_sn, out_sh, out_sw;
@@ -98,7 +102,8 @@ typedef struct sn_wgrad_desc {
   long long tap_off[SN_MAX_TAPS];
   float* out; long long s_row, s_col;
   int rows_valid, cols_valid;
-  int block_n;                           /* 64 or 128 */
+  int block_n;                           /* 64 or 128; == y_chunk when Y is narrow */
+  int y_chunk;                           /* channels per TMA row of Y: 64 (default when 0), 32 or 16 */
   int ksplit;                            /* 0 = auto */
   int nsplit;
 } sn_wgrad_desc;
@@ -129,17 +134,18 @@ int sn_pack_concat(const float* src0, int layout0, int pitch0, int c0, const flo
 /* exact power-of-two scale that brings max|w| into [2^13, 2^14): scale2 <- (s, 1/s). */
 int sn_weight_scale(const float* w, long long count, float* scale2, void* stream);
 
-/* weights -> packed [rows][taps][k_pad] split planes.  Source element (row r, tap t, k) is read
- * at src[r*s_row + k*s_k + t] (taps contiguous, as in torch OIHW / IOHW).  k >= k_real is zero. */
-int sn_pack_weights(const float* src, long long s_row, long long s_k, int rows, int taps, int k_real,
-                    int k_pad, void* dst_hi, void* dst_lo, int fmt, const float* scale2, void* stream);
+/* weights -> packed [rows][taps_pitch][k_pad] split planes (taps_pitch >= taps: extra tap slots stay
+ * zero, see a_chunk).  Source element (row r, tap t, k) is read at src[r*s_row + k*s_k + t] (taps
+ * contiguous, as in torch OIHW / IOHW).  k >= k_real is zero. */
+int sn_pack_weights(const float* src, long long s_row, long long s_k, int rows, int taps, int taps_pitch,
+                    int k_real, int k_pad, void* dst_hi, void* dst_lo, int fmt, const float* scale2, void* stream);
 
 /* head conv (swapnet_modules.py:85-90): nearest x2 upsample + ZeroPad2d((1,0,1,0)) + Conv2d(k4,p1)
  * folded into 4 output-parity phases with 2/3 effective taps per dim (25 taps in total).
  *   fwd pack:  dst[phase][row=co (rows_pad)][teff][ci (k_pad)]   (rows >= cout are zero)
- *   dgrad pack: dst[row=ci][ (phase,teff) ][co (k_pad)]
+ *   dgrad pack: dst[row=ci][ (phase,teff) : taps_pitch >= 25 ][co (k_pad)]
  * src is torch OIHW [cout][cin][4][4]. */
-int sn_pack_head_weights(const float* src, int cout, int cin, int rows_pad, int k_pad, int dgrad,
+int sn_pack_head_weights(const float* src, int cout, int cin, int rows_pad, int k_pad, int dgrad, int taps_pitch,
                          void* dst_hi, void* dst_lo, int fmt, const float* scale2, void* stream);
 /* fold the 25 effective-tap gradients [cout][25][cin] back onto dW [cout][cin][4][4] (+=) */
 int sn_fold_head_wgrad(const float* geff, int cout, int cin, float* dw, void* stream);

@@ -26,7 +26,7 @@ class SnTapGemmDesc(C.Structure):
     _fields_ = [
         ("a_hi", C.c_void_p), ("a_lo", C.c_void_p),
         ("a_n", C.c_int), ("a_h", C.c_int), ("a_w", C.c_int), ("a_c", C.c_int), ("a_pitch", C.c_int),
-        ("a_parity", C.c_int), ("a_fmt", C.c_int),
+        ("a_parity", C.c_int), ("a_fmt", C.c_int), ("a_chunk", C.c_int),
         ("b_hi", C.c_void_p), ("b_lo", C.c_void_p),
         ("b_rows", C.c_int), ("b_k", C.c_longlong), ("b_fmt", C.c_int), ("b_scale", C.c_void_p),
         ("m_n", C.c_int), ("m_h", C.c_int), ("m_w", C.c_int),
@@ -54,7 +54,7 @@ class SnWgradDesc(C.Structure):
         ("tap_off", C.c_longlong * SN_MAX_TAPS),
         ("out", C.c_void_p), ("s_row", C.c_longlong), ("s_col", C.c_longlong),
         ("rows_valid", C.c_int), ("cols_valid", C.c_int),
-        ("block_n", C.c_int), ("ksplit", C.c_int), ("nsplit", C.c_int),
+        ("block_n", C.c_int), ("y_chunk", C.c_int), ("ksplit", C.c_int), ("nsplit", C.c_int),
     ]
 
 
@@ -105,8 +105,8 @@ SIGNATURES = {
     "sn_pack_planes": (_I, [_VP, _I, _I, _I, _I, _I, _I, _VP, _VP, _I, _I, _I, _VP]),
     "sn_pack_concat": (_I, [_VP, _I, _I, _I, _VP, _I, _I, _I, _I, _I, _I, _I, _VP, _VP, _VP, _VP, _I, _I, _I, _I, _VP]),
     "sn_weight_scale": (_I, [_VP, _LL, _VP, _VP]),
-    "sn_pack_weights": (_I, [_VP, _LL, _LL, _I, _I, _I, _I, _VP, _VP, _I, _VP, _VP]),
-    "sn_pack_head_weights": (_I, [_VP, _I, _I, _I, _I, _I, _VP, _VP, _I, _VP, _VP]),
+    "sn_pack_weights": (_I, [_VP, _LL, _LL, _I, _I, _I, _I, _I, _VP, _VP, _I, _VP, _VP]),
+    "sn_pack_head_weights": (_I, [_VP, _I, _I, _I, _I, _I, _I, _VP, _VP, _I, _VP, _VP]),
     "sn_fold_head_wgrad": (_I, [_VP, _I, _I, _VP, _VP]),
     "sn_plane_stats": (_I, [_VP, _I, _I, _I, _I, _F, _VP, _VP]),
     "sn_norm_act_fwd": (_I, [C.POINTER(SnNormActDesc), _VP]),

@@ -188,15 +188,20 @@ __device__ __forceinline__ void tmem_ld_wait() {
 // Shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout):
 //   [0,14) start>>4 | [16,30) LBO>>4 | [32,46) SBO>>4 | [46,48) version=1 |
 //   [49,52) base_offset=0 | [61,64) layout (2 = SWIZZLE_128B)
+//   layout codes (cute::UMMA::LayoutType): 2 = SWIZZLE_128B, 4 = SWIZZLE_64B, 6 = SWIZZLE_32B
 __device__ __forceinline__ uint64_t umma_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes,
-                                                   uint32_t sbo_bytes) {
+                                                   uint32_t sbo_bytes, uint32_t layout = 2) {
   uint64_t d = 0;
   d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
   d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
   d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
   d |= (uint64_t)1 << 46;
-  d |= (uint64_t)2 << 61;
+  d |= (uint64_t)(layout & 7u) << 61;
   return d;
+}
+// swizzle layout code of an operand whose rows are `chunk` 16-bit elements (64 / 32 / 16) wide
+__host__ __device__ __forceinline__ uint32_t umma_layout_of_chunk(int chunk) {
+  return chunk >= 64 ? 2u : (chunk == 32 ? 4u : 6u);
 }
 // Instruction descriptor (cute::UMMA::InstrDescriptor), kind::f16, bf16 x bf16 -> f32.
 //   c_format[4,6)=1(F32) a_format[7,10)=1(BF16) b_format[10,13)=1(BF16)

@@ -146,7 +146,7 @@ __global__ void __launch_bounds__(256) pack_concat_kernel(const PackConcatArgs a
 // pack_weights: dst[r][t][k] <- src[r*s_row + k*s_k + t]
 // ---------------------------------------------------------------------------------
 __global__ void pack_weights_kernel(const float* __restrict__ src, long long s_row, long long s_k,
-                                    int taps, int k_real, int k_pad, uint16_t* __restrict__ hi,
+                                    int taps, int taps_pitch, int k_real, int k_pad, uint16_t* __restrict__ hi,
                                     uint16_t* __restrict__ lo, int fmt, const float* __restrict__ scale2) {
   extern __shared__ float tile[];  // [32][taps + 1]
   const float sc = scale2 ? scale2[0] : 1.f;
@@ -163,7 +163,7 @@ __global__ void pack_weights_kernel(const float* __restrict__ src, long long s_r
   for (int i = threadIdx.x; i < 32 * taps; i += blockDim.x) {
     const int t = i / 32, kk = i % 32;
     if (k0 + kk < k_pad) {
-      const long long off = ((long long)r * taps + t) * k_pad + k0 + kk;
+      const long long off = ((long long)r * taps_pitch + t) * k_pad + k0 + kk;
       store_split(hi, lo, off, tile[kk * T1 + t] * sc, fmt);
     }
   }
@@ -194,7 +194,7 @@ __host__ __device__ __forceinline__ int head_taps_of(int par, int e, int ks[2]) 
   return 1;
 }
 __global__ void pack_head_weights_kernel(const float* __restrict__ w, int cout, int cin, int rows_pad,
-                                         int k_pad, int dgrad, uint16_t* __restrict__ hi,
+                                         int k_pad, int dgrad, int taps_pitch, uint16_t* __restrict__ hi,
                                          uint16_t* __restrict__ lo, int fmt,
                                          const float* __restrict__ scale2) {
   // one thread per (co, te, ci) with te the global effective tap 0..24
@@ -221,7 +221,7 @@ __global__ void pack_head_weights_kernel(const float* __restrict__ w, int cout, 
       off = (long long)rows_pad * k_pad * head_phase_off(p) +
             ((long long)co * (head_neff(py) * head_neff(px)) + local) * k_pad + ci;
     } else {
-      off = ((long long)ci * 25 + te) * k_pad + co;  // [ci][25][k_pad]
+      off = ((long long)ci * taps_pitch + te) * k_pad + co;  // [ci][taps_pitch >= 25][k_pad]
     }
     store_split(hi, lo, off, acc * sc, fmt);
   }
@@ -1180,24 +1180,25 @@ int sn_pack_concat(const float* src0, int layout0, int pitch0, int c0, const flo
   return SN_OK;
 }
 
-int sn_pack_weights(const float* src, long long s_row, long long s_k, int rows, int taps, int k_real,
-                    int k_pad, void* dst_hi, void* dst_lo, int fmt, const float* scale2, void* stream) {
+int sn_pack_weights(const float* src, long long s_row, long long s_k, int rows, int taps, int taps_pitch,
+                    int k_real, int k_pad, void* dst_hi, void* dst_lo, int fmt, const float* scale2, void* stream) {
   SN_REQUIRE(src && dst_hi, "null pointer");
-  SN_REQUIRE(taps >= 1 && taps <= 64 && k_pad >= k_real, "bad pack_weights shape");
+  SN_REQUIRE(taps >= 1 && taps <= 64 && k_pad >= k_real && taps_pitch >= taps, "bad pack_weights shape");
   dim3 grid((k_pad + 31) / 32, rows);
   size_t smem = (size_t)32 * (taps + 1) * sizeof(float);
   pack_weights_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(
-      src, s_row, s_k, taps, k_real, k_pad, (uint16_t*)dst_hi, (uint16_t*)dst_lo, fmt, scale2);
+      src, s_row, s_k, taps, taps_pitch, k_real, k_pad, (uint16_t*)dst_hi, (uint16_t*)dst_lo, fmt, scale2);
   LAUNCH_CHECK();
   return SN_OK;
 }
 
-int sn_pack_head_weights(const float* src, int cout, int cin, int rows_pad, int k_pad, int dgrad,
+int sn_pack_head_weights(const float* src, int cout, int cin, int rows_pad, int k_pad, int dgrad, int taps_pitch,
                          void* dst_hi, void* dst_lo, int fmt, const float* scale2, void* stream) {
   SN_REQUIRE(src && dst_hi, "null pointer");
+  SN_REQUIRE(taps_pitch >= 25, "head pack: taps_pitch must be >= 25");
   SN_REQUIRE(dgrad ? (k_pad >= cout) : (k_pad >= cin && rows_pad >= cout), "bad head pack shape");
   pack_head_weights_kernel<<<grid_for((long long)cout * 25 * cin), kEwThreads, 0, (cudaStream_t)stream>>>(
-      src, cout, cin, rows_pad, k_pad, dgrad, (uint16_t*)dst_hi, (uint16_t*)dst_lo, fmt, scale2);
+      src, cout, cin, rows_pad, k_pad, dgrad, taps_pitch, (uint16_t*)dst_hi, (uint16_t*)dst_lo, fmt, scale2);
   LAUNCH_CHECK();
   return SN_OK;
 }

@@ -73,7 +73,9 @@ tap_gemm_kernel(const __grid_constant__ TapGemmParams p) {
   const int tn_i = mt / (p.tiles_w * p.tiles_h);
   const int w0 = tw_i * p.tw, h0 = th_i * p.th, n0 = tn_i * p.nb;
   const int ncol0 = blockIdx.y * p.block_n;
-  const int k_iters = p.ntaps * p.chunks;
+  const int cw = p.a_chunk;                 // channels per A row: 64, 32 or 16
+  const int tps = 64 / cw;                  // taps sharing one 64-deep stage (1, 2 or 4)
+  const int k_iters = cw == 64 ? p.ntaps * p.chunks : p.ntaps / tps;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < C::kStages; ++s) {
@@ -104,16 +106,33 @@ tap_gemm_kernel(const __grid_constant__ TapGemmParams p) {
         const uint32_t ph = (it / C::kStages) & 1;
         mbar_wait(&empty_bar[s], ph ^ 1);
         mbar_expect_tx(&full_bar[s], stage_tx);
-        const int t = it / p.chunks;
-        const int ch = it - t * p.chunks;
-        const TapDesc tap = p.taps[t];
         uint8_t* st = smem + s * C::kStageBytes;
+        if (cw == 64) {
+          const int t = it / p.chunks;
+          const int ch = it - t * p.chunks;
+          const TapDesc tap = p.taps[t];
 #pragma unroll
-        for (int pl = 0; pl < C::kPlanes; ++pl) {
-          tma_load_5d(&p.tmA[pl], &full_bar[s], st + pl * kTileBytes, tap.c_off + ch * 64,
-                      w0 + tap.dw, tap.hp, h0 + tap.dh, n0);
-          tma_load_2d(&p.tmB[pl], &full_bar[s], st + (C::kPlanes + pl) * kTileBytes,
-                      tap.kb_off + ch * 64, ncol0);
+          for (int pl = 0; pl < C::kPlanes; ++pl) {
+            tma_load_5d(&p.tmA[pl], &full_bar[s], st + pl * kTileBytes, tap.c_off + ch * 64,
+                        w0 + tap.dw, tap.hp, h0 + tap.dh, n0);
+            tma_load_2d(&p.tmB[pl], &full_bar[s], st + (C::kPlanes + pl) * kTileBytes,
+                        tap.kb_off + ch * 64, ncol0);
+          }
+        } else {
+          // narrow operand: 64/cw taps, each a [128 rows][cw channels] sub-tile, fill one stage; the
+          // weights of consecutive taps are contiguous in K, so B is still one 64-deep box
+          const int sub = 128 * cw * 2;
+          for (int j = 0; j < tps; ++j) {
+            const TapDesc tap = p.taps[it * tps + j];
+#pragma unroll
+            for (int pl = 0; pl < C::kPlanes; ++pl)
+              tma_load_5d(&p.tmA[pl], &full_bar[s], st + pl * kTileBytes + j * sub, tap.c_off,
+                          w0 + tap.dw, tap.hp, h0 + tap.dh, n0);
+          }
+          const int kb = p.taps[it * tps].kb_off;
+#pragma unroll
+          for (int pl = 0; pl < C::kPlanes; ++pl)
+            tma_load_2d(&p.tmB[pl], &full_bar[s], st + (C::kPlanes + pl) * kTileBytes, kb, ncol0);
         }
       }
     }
@@ -128,19 +147,24 @@ tap_gemm_kernel(const __grid_constant__ TapGemmParams p) {
         mbar_wait(&full_bar[s], ph);
         tc_fence_after();
         const uint32_t st = smem_base + s * C::kStageBytes;
-        // K-major SWIZZLE_128B: SBO = 1024 B (8 rows x 128 B), LBO unused (1)
-        const uint64_t a_hi = umma_smem_desc(st, 16, 1024);
+        // K-major, rows of cw channels: SWIZZLE_128B/64B/32B, SBO = 8 rows, LBO unused (1)
+        const uint32_t a_layout = umma_layout_of_chunk(cw);
+        const uint32_t a_sbo = 8u * cw * 2u;
+        const uint64_t a_hi = umma_smem_desc(st, 16, a_sbo, a_layout);
         const uint64_t b_hi = umma_smem_desc(st + C::kPlanes * kTileBytes, 16, 1024);
-        const uint64_t a_lo = umma_smem_desc(st + kTileBytes, 16, 1024);
+        const uint64_t a_lo = umma_smem_desc(st + kTileBytes, 16, a_sbo, a_layout);
         const uint64_t b_lo = umma_smem_desc(st + (C::kPlanes + 1) * kTileBytes, 16, 1024);
+        const uint32_t sub16 = (uint32_t)(128 * cw * 2) >> 4;  // sub-tile stride in 16-B units
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {  // 4 x (UMMA_K = 16 bf16 = 32 B) per 128-B row
-          const uint64_t adv = (uint64_t)(k * 2);
-          umma_bf16(tmem_base, a_hi + adv, b_hi + adv, idesc, acc);
+        for (int k = 0; k < 4; ++k) {  // 4 x (UMMA_K = 16 elements = 32 B) per 64-deep stage
+          const uint64_t badv = (uint64_t)(k * 2);
+          // A: k-step k lives in sub-tile (16k / cw), at byte offset ((16k) % cw) * 2 of its rows
+          const uint64_t aadv = (uint64_t)(((k * 16) / cw) * sub16 + (((k * 16) % cw) >> 3));
+          umma_bf16(tmem_base, a_hi + aadv, b_hi + badv, idesc, acc);
           acc = 1;
           if (NSPLIT == 3) {
-            umma_bf16(tmem_base, a_lo + adv, b_hi + adv, idesc, 1);
-            umma_bf16(tmem_base, a_hi + adv, b_lo + adv, idesc, 1);
+            umma_bf16(tmem_base, a_lo + aadv, b_hi + badv, idesc, 1);
+            umma_bf16(tmem_base, a_hi + aadv, b_lo + badv, idesc, 1);
           }
         }
         umma_commit(&empty_bar[s]);  // frees the smem stage once these MMAs retire
@@ -231,7 +255,9 @@ wgrad_gemm_kernel(const __grid_constant__ WgradParams p) {
   const int kt0 = (int)(((long long)total * blockIdx.z) / gridDim.z);
   const int kt1 = (int)(((long long)total * (blockIdx.z + 1)) / gridDim.z);
   const int k_iters = kt1 - kt0;
-  const int y_blocks = p.block_n / 64;
+  const int ycw = p.y_chunk;                               // channels per Y row: 64, 32, 16
+  const int y_blocks = ycw == 64 ? p.block_n / 64 : 1;     // narrow Y: one atom, block_n == ycw
+  const int y_block_bytes = 64 * ycw * 2;                  // 64 pixels x ycw channels
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < C::kStages; ++s) {
@@ -258,7 +284,7 @@ wgrad_gemm_kernel(const __grid_constant__ WgradParams p) {
       if (lane == 0) {
         const TapDesc xt = p.xtaps[tap_i];
         const TapDesc yt = p.ytaps[tap_i];
-        const uint32_t stage_tx = C::kPlanes * (2 + y_blocks) * 8192;
+        const uint32_t stage_tx = C::kPlanes * (2 * 8192 + y_blocks * y_block_bytes);
         for (int it = 0; it < k_iters; ++it) {
           const int s = it % C::kStages;
           const uint32_t ph = (it / C::kStages) & 1;
@@ -277,7 +303,7 @@ wgrad_gemm_kernel(const __grid_constant__ WgradParams p) {
                           xt.c_off + m0 + b * 64, w0 + xt.dw, xt.hp, h0 + xt.dh, n0);
             for (int b = 0; b < y_blocks; ++b)
               tma_load_5d(&p.tmY[pl], &full_bar[s],
-                          st + (C::kPlanes + pl) * kTileBytes + b * 8192,
+                          st + (C::kPlanes + pl) * kTileBytes + b * y_block_bytes,
                           yt.c_off + ncol0 + b * 64, w0 + yt.dw, yt.hp, h0 + yt.dh, n0);
           }
         }
@@ -294,18 +320,21 @@ wgrad_gemm_kernel(const __grid_constant__ WgradParams p) {
           const uint32_t st = smem_base + s * C::kStageBytes;
           // MN-major SWIZZLE_128B: LBO = stride between 64-channel blocks (8192 B),
           // SBO = stride between 8-pixel groups (1024 B)
+          const uint32_t y_layout = umma_layout_of_chunk(ycw);
+          const uint32_t y_sbo = 8u * ycw * 2u;              // 8 pixel rows of the narrow / full atom
           const uint64_t x_hi = umma_smem_desc(st, 8192, 1024);
-          const uint64_t y_hi = umma_smem_desc(st + C::kPlanes * kTileBytes, 8192, 1024);
+          const uint64_t y_hi = umma_smem_desc(st + C::kPlanes * kTileBytes, 8192, y_sbo, y_layout);
           const uint64_t x_lo = umma_smem_desc(st + kTileBytes, 8192, 1024);
-          const uint64_t y_lo = umma_smem_desc(st + (C::kPlanes + 1) * kTileBytes, 8192, 1024);
+          const uint64_t y_lo = umma_smem_desc(st + (C::kPlanes + 1) * kTileBytes, 8192, y_sbo, y_layout);
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {  // 4 x 16 pixels; 16 pixel rows = 2048 B
-            const uint64_t adv = (uint64_t)(k * 128);
-            umma_bf16(tmem_base, x_hi + adv, y_hi + adv, idesc, acc);
+          for (int k = 0; k < 4; ++k) {  // 4 x 16 pixels; 16 pixel rows = 2048 B (X), 16 * ycw * 2 B (Y)
+            const uint64_t xadv = (uint64_t)(k * 128);
+            const uint64_t yadv = (uint64_t)((k * 16 * ycw * 2) >> 4);
+            umma_bf16(tmem_base, x_hi + xadv, y_hi + yadv, idesc, acc);
             acc = 1;
             if (NSPLIT == 3) {
-              umma_bf16(tmem_base, x_lo + adv, y_hi + adv, idesc, 1);
-              umma_bf16(tmem_base, x_hi + adv, y_lo + adv, idesc, 1);
+              umma_bf16(tmem_base, x_lo + xadv, y_hi + yadv, idesc, 1);
+              umma_bf16(tmem_base, x_hi + xadv, y_lo + yadv, idesc, 1);
             }
           }
           umma_commit(&empty_bar[s]);
@@ -364,7 +393,7 @@ static PFN_encodeTiled get_encode_fn() {
 
 // 5-D map over a split-bf16 NHWC plane.  dims (c', w, hp, h, n); see file header.
 int sn_make_act_map(CUtensorMap* tm, const void* base, int N, int H, int W, int C, int pitch,
-                    int parity, int box_w, int box_h, int box_n) {
+                    int parity, int box_w, int box_h, int box_n, int chunk = 64) {
   PFN_encodeTiled enc = get_encode_fn();
   SN_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled driver entry point unavailable");
   SN_REQUIRE(pitch % 8 == 0 && ((uintptr_t)base % 16) == 0,
@@ -388,10 +417,13 @@ int sn_make_act_map(CUtensorMap* tm, const void* base, int N, int H, int W, int 
     strides[2] = (cuuint64_t)2 * W * pitch * e;
     strides[3] = (cuuint64_t)H * W * pitch * e;
   }
-  cuuint32_t box[5] = {64, (cuuint32_t)box_w, 1, (cuuint32_t)box_h, (cuuint32_t)box_n};
+  SN_REQUIRE(chunk == 64 || chunk == 32 || chunk == 16, "row chunk must be 64, 32 or 16 channels (got %d)", chunk);
+  cuuint32_t box[5] = {(cuuint32_t)chunk, (cuuint32_t)box_w, 1, (cuuint32_t)box_h, (cuuint32_t)box_n};
   cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  const CUtensorMapSwizzle swz = chunk == 64 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                 : chunk == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
   CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(base), dims, strides,
-                   box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   SN_REQUIRE(r == CUDA_SUCCESS,
              "cuTensorMapEncodeTiled(act) failed: %d (N=%d H=%d W=%d C=%d pitch=%d parity=%d box=%dx%dx%d)",
@@ -472,7 +504,16 @@ int sn_tap_gemm_plan_init(TapGemmPlan* plan, const sn_tap_gemm_desc* d) {
   TapGemmParams& p = plan->p;
   SN_REQUIRE(d->nsplit == 1 || d->nsplit == 3, "nsplit must be 1 or 3");
   SN_REQUIRE(d->ntaps >= 1 && d->ntaps <= SN_MAX_TAPS, "ntaps out of range: %d", d->ntaps);
-  SN_REQUIRE(d->k_per_tap > 0 && d->k_per_tap % 64 == 0, "k_per_tap must be a multiple of 64");
+  const int a_chunk = d->a_chunk ? d->a_chunk : 64;
+  SN_REQUIRE(a_chunk == 64 || a_chunk == 32 || a_chunk == 16, "a_chunk must be 64, 32 or 16");
+  if (a_chunk == 64) {
+    SN_REQUIRE(d->k_per_tap > 0 && d->k_per_tap % 64 == 0, "k_per_tap must be a multiple of 64");
+  } else {
+    SN_REQUIRE(d->k_per_tap == a_chunk && d->ntaps % (64 / a_chunk) == 0,
+               "narrow operand: k_per_tap must equal a_chunk (%d) and ntaps (%d) be a multiple of %d", a_chunk,
+               d->ntaps, 64 / a_chunk);
+  }
+  p.a_chunk = a_chunk;
   SN_REQUIRE(d->block_n >= 16 && d->block_n <= 128 && d->block_n % 16 == 0,
              "block_n must be a multiple of 16 in [16,128]");
   SN_REQUIRE(d->a_hi && d->b_hi && d->out, "null operand");
@@ -488,7 +529,7 @@ int sn_tap_gemm_plan_init(TapGemmPlan* plan, const sn_tap_gemm_desc* d) {
   p.tiles_n = (d->m_n + nb - 1) / nb;
   p.m_w = d->m_w; p.m_h = d->m_h; p.m_n = d->m_n;
   p.ntaps = d->ntaps;
-  p.chunks = d->k_per_tap / 64;
+  p.chunks = a_chunk == 64 ? d->k_per_tap / 64 : 1;
   for (int t = 0; t < d->ntaps; ++t) {
     p.taps[t].c_off = d->taps[t].c_off;
     p.taps[t].kb_off = d->taps[t].kb_off;
@@ -513,7 +554,7 @@ int sn_tap_gemm_plan_init(TapGemmPlan* plan, const sn_tap_gemm_desc* d) {
   const void* b_pl[2] = {d->b_hi, d->b_lo};
   for (int pl = 0; pl < (d->nsplit == 3 ? 2 : 1); ++pl) {
     rc = sn_make_act_map(&p.tmA[pl], a_pl[pl], d->a_n, d->a_h, d->a_w, d->a_c, d->a_pitch,
-                         d->a_parity, tw, th, nb);
+                         d->a_parity, tw, th, nb, a_chunk);
     if (rc) return rc;
     rc = sn_make_weight_map(&p.tmB[pl], b_pl[pl], d->b_rows, d->b_k, d->block_n);
     if (rc) return rc;
@@ -549,7 +590,11 @@ int sn_wgrad_plan_init(WgradPlan* plan, const sn_wgrad_desc* d, int sm_count) {
   WgradParams& p = plan->p;
   SN_REQUIRE(d->nsplit == 1 || d->nsplit == 3, "nsplit must be 1 or 3");
   SN_REQUIRE(d->ntaps >= 1 && d->ntaps <= SN_MAX_TAPS, "ntaps out of range: %d", d->ntaps);
-  SN_REQUIRE(d->block_n == 64 || d->block_n == 128, "wgrad block_n must be 64 or 128");
+  const int y_chunk = d->y_chunk ? d->y_chunk : 64;
+  SN_REQUIRE(y_chunk == 64 || y_chunk == 32 || y_chunk == 16, "y_chunk must be 64, 32 or 16");
+  SN_REQUIRE(y_chunk == 64 ? (d->block_n == 64 || d->block_n == 128) : d->block_n == y_chunk,
+             "wgrad block_n must be 64 or 128 (or equal the narrow y_chunk)");
+  p.y_chunk = y_chunk;
   SN_REQUIRE(d->x_hi && d->y_hi && d->out, "null operand");
   SN_REQUIRE(d->nsplit == 1 || (d->x_lo && d->y_lo), "nsplit=3 needs lo planes");
   SN_REQUIRE(d->x_fmt == d->y_fmt, "X and Y of one tcgen05.mma must share a 16-bit format (x=%d y=%d)",
@@ -586,7 +631,7 @@ int sn_wgrad_plan_init(WgradPlan* plan, const sn_wgrad_desc* d, int sm_count) {
                          d->x_parity, tw, th, nb);
     if (rc) return rc;
     rc = sn_make_act_map(&p.tmY[pl], y_pl[pl], d->y_n, d->y_h, d->y_w, d->y_c, d->y_pitch,
-                         d->y_parity, tw, th, nb);
+                         d->y_parity, tw, th, nb, y_chunk);
     if (rc) return rc;
   }
   plan->nsplit = d->nsplit;

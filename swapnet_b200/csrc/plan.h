@@ -28,6 +28,7 @@ struct alignas(64) TapGemmParams {
   int act;
   int vec4;
   int a_fmt, b_fmt;
+  int a_chunk;  // 64 / 32 / 16 channels per A row
 };
 
 struct alignas(64) WgradParams {
@@ -44,6 +45,7 @@ struct alignas(64) WgradParams {
   float* out;
   long long s_row, s_col;
   int x_fmt, y_fmt;
+  int y_chunk;  // 64 / 32 / 16 channels per Y row
 };
 
 struct TapGemmPlan {

@@ -94,7 +94,7 @@ class Stage:
     def bind_backward(self, wgrad: bool = True) -> None:
         dev = self.eng.device
         ly = self.layer
-        self.dy = Planes(self.n, self.oh, self.ow, L.pad64(self.cout), dev, fmt=FMT_BF16)  # gradients: fp32 range
+        self.dy = Planes(self.n, self.oh, self.ow, L.padc(self.cout), dev, fmt=FMT_BF16)  # gradients: fp32 range
         if self.need_dx:
             ih, iw = (ly.in_h + 2, ly.in_w + 2) if self.kind == "conv3r" else (ly.in_h, ly.in_w)
             self.dx = torch.zeros(self.n, ih, iw, (ly.cin + 3) // 4 * 4, device=dev)[..., :ly.cin]
@@ -173,8 +173,8 @@ class WarpEngine(Engine):
         self.batch, self.size = B, S
         self.cb, self.cc = net.body_channels, net.cloth_channels
         dp = net.dropout
-        self.in_body = self.planes(B, S, S, 64)
-        self.in_cloth = self.planes(B, S, S, 64)
+        self.in_body = self.planes(B, S, S, L.padc(self.cb))      # 3 -> 16 channels (32-byte TMA rows)
+        self.in_cloth = self.planes(B, S, S, L.padc(self.cc))     # 19 -> 32
         cat3 = self.planes(B, S // 2, S // 2, 192)
         cat2 = self.planes(B, S // 4, S // 4, 384)
         cat1 = self.planes(B, S // 8, S // 8, 768)
@@ -300,7 +300,7 @@ class PatchGANEngine(Engine):
         super().__init__(net, device, nsplit, train)
         B, S, dev = batch, size, self.device
         self.batch, self.size = B, S
-        self.din = din if din is not None else self.planes(B, S, S, L.pad64(net.input_nc))
+        self.din = din if din is not None else self.planes(B, S, S, L.padc(net.input_nc))
         assert (self.din.n, self.din.h, self.din.w) == (B, S, S)
         convs = net.convs()
         use_norm = net.norm == "instance"
@@ -310,7 +310,7 @@ class PatchGANEngine(Engine):
         for i, conv in enumerate(convs[:-1]):
             kind = "conv4s2" if conv.stride[0] == 2 else "conv4s1"
             oh = h // 2 if kind == "conv4s2" else h - 1
-            out = self.planes(B, oh, oh, L.pad64(conv.out_channels))
+            out = self.planes(B, oh, oh, L.padc(conv.out_channels))
             st = Stage(self, f"model.{net.conv_index[i]}", kind, conv, x, out=out, norm=use_norm and i > 0,
                        act=ACT_LRELU, slope=0.2, need_dx=(i > 0) or input_grad)
             self.chain.append(st)
@@ -363,9 +363,9 @@ class TextureEngine(Engine):
         blocks = unet.blocks()
         assert len(blocks) == nd
         self.pool = 128
-        self.pooled = self.planes(B, self.pool, self.pool, L.pad64(ch))
-        self.enc = self.planes(B, self.pool // 2, self.pool // 2, L.pad64(ch))
-        self.in_unet = self.planes(B, S, S, L.pad64(ch + self.cc))
+        self.pooled = self.planes(B, self.pool, self.pool, L.padc(ch))
+        self.enc = self.planes(B, self.pool // 2, self.pool // 2, L.padc(ch))
+        self.in_unet = self.planes(B, S, S, L.padc(ch + self.cc))
         self.up_factor = S // (self.pool // 2)
         St = lambda *a, **k: Stage(self, *a, **k)  # noqa: E731
         self.encode = St("encode", "conv4s2", net.encode.model[0], self.pooled, out=self.enc, norm=True,
@@ -378,10 +378,10 @@ class TextureEngine(Engine):
             h = S >> (j + 1)
             last = j == nd - 1
             if last:
-                out = self.planes(B, h, h, L.pad64(chans[j]))
+                out = self.planes(B, h, h, L.padc(chans[j]))
                 st = St(f"unet.D{j}", "conv4s2", blocks[j].down, x, out=out, norm=False, act=ACT_RELU)
             else:
-                out = self.planes(B, h, h, L.pad64(chans[j]))
+                out = self.planes(B, h, h, L.padc(chans[j]))
                 st = St(f"unet.D{j}", "conv4s2", blocks[j].down, x, out=out, norm=(j >= 1), act=ACT_LRELU,
                         out_relu=self.cu[j].slice(0, chans[j]))
             self.down.append(st)

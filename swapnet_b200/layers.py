@@ -34,8 +34,8 @@ class ConvLayer:
         self.in_h, self.in_w = (x.h - 2, x.w - 2) if kind == "conv3r" else (x.h, x.w)
         self.out_h, self.out_w = L.out_hw(kind, self.in_h, self.in_w)
         self.n = x.n
-        self.k_pad = x.c                       # input channels as the planes carry them (multiple of 64)
-        assert self.k_pad % 64 == 0 and self.k_pad >= self.cin, (name, x.c, self.cin)
+        self.k_pad = x.c                       # input channels as the planes carry them (16, 32 or 64k)
+        assert (self.k_pad % 64 == 0 or self.k_pad in (16, 32)) and self.k_pad >= self.cin, (name, x.c, self.cin)
         self.block_n = L.pick_block_n(self.cout)
         self.t = L.ntaps(kind)
         self.wscale = torch.ones(2, dtype=torch.float32, device=dev)  # (s, 1/s), shared by fwd and dgrad packs
@@ -43,7 +43,8 @@ class ConvLayer:
             self.rows_pad = (self.cout + self.block_n - 1) // self.block_n * self.block_n
             self.wp = PackedWeights(self.rows_pad, 25 * self.k_pad, dev, self.wscale)
         else:
-            self.wp = PackedWeights(self.cout, self.t * self.k_pad, dev, self.wscale)
+            # narrow operands: the tap count is padded to a multiple of 64/k_pad with all-zero K columns
+            self.wp = PackedWeights(self.cout, self._tpad(self.t, self.k_pad) * self.k_pad, dev, self.wscale)
         self.fwd_plans: List[ops.Plan] = []
         self.y: Optional[torch.Tensor] = None
         # backward state
@@ -56,6 +57,11 @@ class ConvLayer:
         self.bgrad_out: Optional[torch.Tensor] = None
         self._geff: Optional[torch.Tensor] = None
         self._bscratch: Optional[torch.Tensor] = None
+
+    @staticmethod
+    def _tpad(t: int, k: int) -> int:
+        tps = max(1, 64 // k)
+        return (t + tps - 1) // tps * tps
 
     # ---- forward --------------------------------------------------------------------------
     def bind_forward(self, y: torch.Tensor, y_c_off: int = 0) -> None:
@@ -101,15 +107,15 @@ class ConvLayer:
         (must be zeroed by the caller once per step)."""
         dev = self.weight.device
         assert (dy.n, dy.h, dy.w) == (self.n, self.out_h, self.out_w), (self.name, dy.h, dy.w)
-        assert dy.c % 64 == 0 and dy.c >= self.cout
+        assert (dy.c % 64 == 0 or dy.c in (16, 32)) and dy.c >= self.cout
         self.dy = dy
         self.dx = dx
         self.dgrad_plans = []
         if dx is not None:
             if self.kind == "head":
-                self.wd = PackedWeights(self.cin, 25 * dy.c, dev, fmt=dy.fmt)
+                self.wd = PackedWeights(self.cin, self._tpad(25, dy.c) * dy.c, dev, fmt=dy.fmt)
             else:
-                self.wd = PackedWeights(self.cin, self.t * dy.c, dev, fmt=dy.fmt)
+                self.wd = PackedWeights(self.cin, self._tpad(self.t, dy.c) * dy.c, dev, fmt=dy.fmt)
             bn = L.pick_block_n(self.cin)
             for spec in L.dgrad_specs(self.kind, self.in_h, self.in_w):
                 d = ops.tap_gemm_desc(dy, spec, self.wd, dy.c, dx, self.cin, nsplit=self.nsplit, block_n=bn,
@@ -133,8 +139,12 @@ class ConvLayer:
                 out, tap_off = self._geff, [t * self.cin for t in ws.tap_ids]
             else:
                 out, tap_off = wgrad, list(ws.tap_ids)
-            # the 128-row M side should be the operand with more channels
-            swap = cy > cx
+            # the 128-row M side must carry >= 64 channels; otherwise it is the operand with more channels
+            if xs.c < 64 or ys.c < 64:
+                swap = xs.c < 64
+                assert (ys.c if swap else xs.c) >= 64, f"{self.name}: both wgrad operands are narrow"
+            else:
+                swap = cy > cx
             d = ops.wgrad_desc(xs, ys, ws, out, s_row, s_col, tap_off, cx, cy, swap=swap, nsplit=self.nsplit)
             self.wgrad_plan = ops.wgrad_plan(d, keep=(xs.hi, xs.lo, ys.hi, ys.lo, out))
             self.wgrad_plan.tag = ("wgrad", self.name)

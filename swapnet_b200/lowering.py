@@ -249,6 +249,16 @@ def pad64(c: int) -> int:
     return (c + 63) // 64 * 64
 
 
+def padc(c: int) -> int:
+    """Channel padding of an operand plane: 16 or 32 for narrow tensors (3/19/22-channel images,
+    1/3/19-channel gradients: TMA rows of 32 / 64 bytes, SWIZZLE_32B / 64B), else a multiple of 64."""
+    if c <= 16:
+        return 16
+    if c <= 32:
+        return 32
+    return pad64(c)
+
+
 def pick_block_n(n_valid: int) -> int:
     """N tile of the tap GEMM: largest of 128/64/32/16 that does not over-pad small outputs."""
     if n_valid >= 128:

@@ -135,8 +135,18 @@ def tap_gemm_desc(a: Planes, spec: L.GemmSpec, w: PackedWeights, k_per_tap: int,
     """out: fp32 NHWC tensor [n, OH, OW, pitch_out]; rows (h, w) land on pixel
     (h*mul_h + off_h, w*mul_w + off_w)."""
     assert (a.h, a.w) == tuple(spec.a_hw), f"operand is {a.h}x{a.w}, spec wants {spec.a_hw}"
-    assert k_per_tap % 64 == 0 and k_per_tap <= a.c and a.c_off % 8 == 0
+    assert a.c_off % 8 == 0 and k_per_tap <= a.c
+    narrow = k_per_tap < 64
+    assert (k_per_tap in (16, 32)) if narrow else (k_per_tap % 64 == 0)
+    taps = list(spec.taps)
+    if narrow:  # 64/k taps share a pipeline stage: pad with dummy taps whose packed weights are zero
+        tps = 64 // k_per_tap
+        kb_next = max(t.kb for t in taps) + 1
+        while len(taps) % tps:
+            taps.append(L.Tap(taps[0].pw, kb_next, taps[0].dw, taps[0].dh, taps[0].hp))
+            kb_next += 1
     d = SnTapGemmDesc()
+    d.a_chunk = k_per_tap if narrow else 64
     d.a_hi, d.a_lo = a.hi_ptr, a.lo_ptr
     d.a_n, d.a_h, d.a_w, d.a_c, d.a_pitch = a.n, a.h, a.w, a.c, a.pitch
     d.a_parity = 1 if spec.parity else 0
@@ -147,8 +157,8 @@ def tap_gemm_desc(a: Planes, spec: L.GemmSpec, w: PackedWeights, k_per_tap: int,
     d.b_rows = w.rows if w_rows is None else w_rows
     d.b_k = w.k_total if w_k is None else w_k
     d.m_n, d.m_h, d.m_w = a.n, spec.m_h, spec.m_w
-    d.ntaps, d.k_per_tap = len(spec.taps), k_per_tap
-    for i, t in enumerate(spec.taps):
+    d.ntaps, d.k_per_tap = len(taps), k_per_tap
+    for i, t in enumerate(taps):
         _fill_tap(d.taps[i], t, a.pitch, k_per_tap)
     assert out.dtype == torch.float32 and out.dim() == 4 and (out.shape[3] == 1 or out.stride(3) == 1)
     d.out = out.data_ptr() + 4 * out_c_off
@@ -200,7 +210,13 @@ def wgrad_desc(x: Planes, y: Planes, spec: L.WgradSpec, out: torch.Tensor, s_row
     d.out = out.data_ptr()
     d.s_row, d.s_col = s_row, s_col
     d.rows_valid, d.cols_valid = rows_valid, cols_valid
-    d.block_n = block_n or (128 if cols_valid > 64 else 64)
+    assert x.c >= 64, "the 128-row operand of a wgrad GEMM must carry >= 64 channels (swap the roles)"
+    if y.c < 64:   # narrow N-side operand: one 16/32-channel atom
+        assert y.c in (16, 32) and cols_valid <= y.c
+        d.y_chunk, d.block_n = y.c, y.c
+    else:
+        d.y_chunk = 64
+        d.block_n = block_n or (128 if cols_valid > 64 else 64)
     d.ksplit = ksplit
     d.nsplit = nsplit
     return d
@@ -271,8 +287,9 @@ def pack_weights(weight: torch.Tensor, kind: str, dgrad: bool, k_pad: int, dst: 
         cout, cin = weight.shape[0], weight.shape[1]
     s_row, s_k, rows, k_real = L.pack_strides(kind, cin, cout, dgrad)
     t = L.ntaps(kind)
-    assert dst.rows >= rows and dst.k_total == t * k_pad and k_pad >= k_real
-    check(_lib.load().sn_pack_weights(weight.data_ptr(), s_row, s_k, rows, t, k_real, k_pad, dst.hi.data_ptr(),
+    assert dst.rows >= rows and dst.k_total >= t * k_pad and k_pad >= k_real and dst.k_total % k_pad == 0
+    check(_lib.load().sn_pack_weights(weight.data_ptr(), s_row, s_k, rows, t, dst.k_total // k_pad, k_real, k_pad,
+                                      dst.hi.data_ptr(),
                                       dst.lo.data_ptr(), dst.fmt, None if dst.scale is None else dst.scale.data_ptr(),
                                       _stream()))
 
@@ -280,7 +297,8 @@ def pack_weights(weight: torch.Tensor, kind: str, dgrad: bool, k_pad: int, dst: 
 def pack_head_weights(weight: torch.Tensor, rows_pad: int, k_pad: int, dgrad: bool, dst: PackedWeights) -> None:
     cout, cin = weight.shape[:2]
     assert dst.hi.numel() >= (cin * 25 * k_pad if dgrad else rows_pad * 25 * k_pad)
-    check(_lib.load().sn_pack_head_weights(weight.data_ptr(), cout, cin, rows_pad, k_pad, int(dgrad),
+    taps_pitch = dst.k_total // k_pad if dgrad else 25
+    check(_lib.load().sn_pack_head_weights(weight.data_ptr(), cout, cin, rows_pad, k_pad, int(dgrad), taps_pitch,
                                            dst.hi.data_ptr(), dst.lo.data_ptr(), dst.fmt,
                                            None if dst.scale is None else dst.scale.data_ptr(), _stream()))
 

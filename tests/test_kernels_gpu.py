@@ -65,6 +65,9 @@ CONV_CASES = [
     ("conv4s1", 1, 64, 64, 8, 8),
     ("head", 2, 192, 19, 32, 32),
     ("head", 1, 64, 19, 16, 48),
+    ("conv4s2", 2, 19, 64, 32, 32),      # 19 -> 32-channel rows (SWIZZLE_64B)
+    ("conv4s1", 2, 16, 32, 16, 16),      # exactly 16 channels (SWIZZLE_32B), narrow dy too
+    ("convT4s2", 2, 32, 16, 8, 8),
 ]
 
 
@@ -78,7 +81,7 @@ def make_layer(kind, n, cin, cout, h, w, nsplit, with_bias=True):
     wshape = (cin, cout, k, k) if kind == "convT4s2" else (cout, cin, k, k)
     wt = torch.randn(*wshape, generator=g) * (1.0 / (cin * k * k) ** 0.5)
     bias = torch.randn(cout, generator=g) if with_bias else None
-    cp = L.pad64(cin)
+    cp = L.padc(cin)   # 3 -> 16, 22 -> 32 (narrow TMA rows), else multiples of 64
     if kind == "conv3r":
         xp = F.pad(x, (1, 1, 1, 1), mode="reflect")
         planes = ops.Planes(n, h + 2, w + 2, cp + 64, dev(), c=cp, c_off=64, dual=True)  # inside a wider buffer
@@ -147,7 +150,7 @@ def test_conv_backward(kind, n, cin, cout, h, w):
         gw, gb = torch.autograd.grad(yr, (wr, br), gy.double())
     else:
         gx, gw, gb = torch.autograd.grad(yr, (xr, wr, br), gy.double())
-    dy = ops.Planes(n, oh, ow, L.pad64(cout), dev(), fmt=ops.FMT_BF16)  # gradients travel as bf16-split
+    dy = ops.Planes(n, oh, ow, L.padc(cout), dev(), fmt=ops.FMT_BF16)  # gradients travel as bf16-split
     ops.pack_planes(gy.to(dev()), dy)
     ih, iw = (h + 2, w + 2) if kind == "conv3r" else (h, w)
     dx = torch.full((n, ih, iw, cin + 3), 5.0, device=dev())
