@@ -138,7 +138,8 @@ int sn_weight_scale(const float* w, long long count, float* scale2, void* stream
  * zero, see a_chunk).  Source element (row r, tap t, k) is read at src[r*s_row + k*s_k + t] (taps
  * contiguous, as in torch OIHW / IOHW).  k >= k_real is zero. */
 int sn_pack_weights(const float* src, long long s_row, long long s_k, int rows, int taps, int taps_pitch,
-                    int k_real, int k_pad, void* dst_hi, void* dst_lo, int fmt, const float* scale2, void* stream);
+                    const int* slot_of_tap /* HOST array [taps] or NULL = identity */, int k_real, int k_pad,
+                    void* dst_hi, void* dst_lo, int fmt, const float* scale2, void* stream);
 
 /* head conv (swapnet_modules.py:85-90): nearest x2 upsample + ZeroPad2d((1,0,1,0)) + Conv2d(k4,p1)
  * folded into 4 output-parity phases with 2/3 effective taps per dim (25 taps in total).

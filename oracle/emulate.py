@@ -82,7 +82,7 @@ def pack_weights_ref(weight: torch.Tensor, kind: str, dgrad: bool, k_pad: int) -
     k = torch.arange(k_real)[None, None, :]
     vals = flat[r * s_row + k * s_k + tt]
     out = weight.new_zeros(rows, t, k_pad)
-    out[:, :, :k_real] = vals
+    out[:, L.pack_slots(kind, dgrad), :k_real] = vals      # packed slot of each torch tap
     return out.reshape(rows, t * k_pad)
 
 

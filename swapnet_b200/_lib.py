@@ -105,7 +105,7 @@ SIGNATURES = {
     "sn_pack_planes": (_I, [_VP, _I, _I, _I, _I, _I, _I, _VP, _VP, _I, _I, _I, _VP]),
     "sn_pack_concat": (_I, [_VP, _I, _I, _I, _VP, _I, _I, _I, _I, _I, _I, _I, _VP, _VP, _VP, _VP, _I, _I, _I, _I, _VP]),
     "sn_weight_scale": (_I, [_VP, _LL, _VP, _VP]),
-    "sn_pack_weights": (_I, [_VP, _LL, _LL, _I, _I, _I, _I, _I, _VP, _VP, _I, _VP, _VP]),
+    "sn_pack_weights": (_I, [_VP, _LL, _LL, _I, _I, _I, C.POINTER(C.c_int), _I, _I, _VP, _VP, _I, _VP, _VP]),
     "sn_pack_head_weights": (_I, [_VP, _I, _I, _I, _I, _I, _I, _VP, _VP, _I, _VP, _VP]),
     "sn_fold_head_wgrad": (_I, [_VP, _I, _I, _VP, _VP]),
     "sn_plane_stats": (_I, [_VP, _I, _I, _I, _I, _F, _VP, _VP]),

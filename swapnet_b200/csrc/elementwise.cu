@@ -145,7 +145,8 @@ __global__ void __launch_bounds__(256) pack_concat_kernel(const PackConcatArgs a
 // ---------------------------------------------------------------------------------
 // pack_weights: dst[r][t][k] <- src[r*s_row + k*s_k + t]
 // ---------------------------------------------------------------------------------
-__global__ void pack_weights_kernel(const float* __restrict__ src, long long s_row, long long s_k,
+struct TapSlots { int slot[64]; };   // packed slot of each source tap
+__global__ void pack_weights_kernel(const TapSlots ts, const float* __restrict__ src, long long s_row, long long s_k,
                                     int taps, int taps_pitch, int k_real, int k_pad, uint16_t* __restrict__ hi,
                                     uint16_t* __restrict__ lo, int fmt, const float* __restrict__ scale2) {
   extern __shared__ float tile[];  // [32][taps + 1]
@@ -163,7 +164,7 @@ __global__ void pack_weights_kernel(const float* __restrict__ src, long long s_r
   for (int i = threadIdx.x; i < 32 * taps; i += blockDim.x) {
     const int t = i / 32, kk = i % 32;
     if (k0 + kk < k_pad) {
-      const long long off = ((long long)r * taps_pitch + t) * k_pad + k0 + kk;
+      const long long off = ((long long)r * taps_pitch + ts.slot[t]) * k_pad + k0 + kk;
       store_split(hi, lo, off, tile[kk * T1 + t] * sc, fmt);
     }
   }
@@ -1181,13 +1182,19 @@ int sn_pack_concat(const float* src0, int layout0, int pitch0, int c0, const flo
 }
 
 int sn_pack_weights(const float* src, long long s_row, long long s_k, int rows, int taps, int taps_pitch,
-                    int k_real, int k_pad, void* dst_hi, void* dst_lo, int fmt, const float* scale2, void* stream) {
+                    const int* slot_of_tap, int k_real, int k_pad, void* dst_hi, void* dst_lo, int fmt,
+                    const float* scale2, void* stream) {
   SN_REQUIRE(src && dst_hi, "null pointer");
+  TapSlots ts;
+  for (int t = 0; t < taps && t < 64; ++t) {
+    ts.slot[t] = slot_of_tap ? slot_of_tap[t] : t;
+    SN_REQUIRE(ts.slot[t] >= 0 && ts.slot[t] < taps_pitch, "pack_weights: slot_of_tap[%d] out of range", t);
+  }
   SN_REQUIRE(taps >= 1 && taps <= 64 && k_pad >= k_real && taps_pitch >= taps, "bad pack_weights shape");
   dim3 grid((k_pad + 31) / 32, rows);
   size_t smem = (size_t)32 * (taps + 1) * sizeof(float);
   pack_weights_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(
-      src, s_row, s_k, taps, taps_pitch, k_real, k_pad, (uint16_t*)dst_hi, (uint16_t*)dst_lo, fmt, scale2);
+      ts, src, s_row, s_k, taps, taps_pitch, k_real, k_pad, (uint16_t*)dst_hi, (uint16_t*)dst_lo, fmt, scale2);
   LAUNCH_CHECK();
   return SN_OK;
 }

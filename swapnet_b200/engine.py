@@ -94,7 +94,10 @@ class Stage:
     def bind_backward(self, wgrad: bool = True) -> None:
         dev = self.eng.device
         ly = self.layer
-        self.dy = Planes(self.n, self.oh, self.ow, L.padc(self.cout), dev, fmt=FMT_BF16)  # gradients: fp32 range
+        dyc = L.padc(self.cout)
+        if dyc < 64 and ly.x.c < 64:   # the weight-gradient GEMM needs one operand with >= 64 channels
+            dyc = 64
+        self.dy = Planes(self.n, self.oh, self.ow, dyc, dev, fmt=FMT_BF16)  # gradients: fp32 range
         if self.need_dx:
             ih, iw = (ly.in_h + 2, ly.in_w + 2) if self.kind == "conv3r" else (ly.in_h, ly.in_w)
             self.dx = torch.zeros(self.n, ih, iw, (ly.cin + 3) // 4 * 4, device=dev)[..., :ly.cin]

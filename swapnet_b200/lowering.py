@@ -62,6 +62,35 @@ class WgradSpec:
     tap_ids: List[int] = field(default_factory=list)
 
 
+def _phase_taps():
+    """The 4 output-parity phases of a stride-2 transposed structure (ConvTranspose2d forward, Conv2d
+    input-gradient): per phase the (kh, dh) x (kw, dw) pairs.  ho = 2*hi - 1 + kh."""
+    out = []
+    for py in range(2):
+        khs = [(1, 0), (3, -1)] if py == 0 else [(0, 1), (2, 0)]
+        for px in range(2):
+            kws = [(1, 0), (3, -1)] if px == 0 else [(0, 1), (2, 0)]
+            out.append(((py, px), [(kh, dh, kw, dw) for kh, dh in khs for kw, dw in kws]))
+    return out
+
+
+def phase_major_slots() -> List[int]:
+    """slot_of_tap[kh*4+kw] for the packed weights of the 4-phase structures: the 4 taps of a phase are
+    contiguous in K (needed when 64/k narrow taps share one weight box), phases in (py, px) order."""
+    slot = [0] * 16
+    for p, (_, taps) in enumerate(_phase_taps()):
+        for j, (kh, _, kw, _) in enumerate(taps):
+            slot[kh * 4 + kw] = p * 4 + j
+    return slot
+
+
+def pack_slots(kind: str, dgrad: bool) -> List[int]:
+    """slot_of_tap for sn_pack_weights (identity except for the 4-phase structures)."""
+    if (kind == "convT4s2" and not dgrad) or (kind == "conv4s2" and dgrad):
+        return phase_major_slots()
+    return list(range(ntaps(kind)))
+
+
 def _s2_tap(k: int) -> Tuple[int, int]:
     """stride-2, pad-1 gather: source index 2*o - 1 + k  ->  (delta on the half grid, parity)."""
     return ((k - 1) >> 1, (k - 1) & 1)
@@ -106,14 +135,9 @@ def forward_specs(kind: str, h: int, w: int) -> List[GemmSpec]:
                 taps.append(Tap(pw, kh * 4 + kw, dw, dh, hp))
         return [GemmSpec(True, h // 2, w // 2, taps, a_hw=(h, w))]
     if kind == "convT4s2":
-        specs = []
-        for py in range(2):
-            khs = [(1, 0), (3, -1)] if py == 0 else [(0, 1), (2, 0)]
-            for px in range(2):
-                kws = [(1, 0), (3, -1)] if px == 0 else [(0, 1), (2, 0)]
-                taps = [Tap(0, kh * 4 + kw, dw, dh) for kh, dh in khs for kw, dw in kws]
-                specs.append(GemmSpec(False, h, w, taps, (2, 2), (py, px), a_hw=(h, w)))
-        return specs
+        slot = phase_major_slots()
+        return [GemmSpec(False, h, w, [Tap(0, slot[kh * 4 + kw], dw, dh) for kh, dh, kw, dw in taps], (2, 2),
+                         (py, px), a_hw=(h, w)) for (py, px), taps in _phase_taps()]
     if kind == "conv3r":  # A = reflect-padded planes [h+2, w+2]
         taps = [Tap(0, kh * 3 + kw, kw, kh) for kh in range(3) for kw in range(3)]
         return [GemmSpec(False, h, w, taps, a_hw=(h + 2, w + 2))]
@@ -140,14 +164,9 @@ def dgrad_specs(kind: str, h: int, w: int) -> List[GemmSpec]:
     """h, w = spatial size of the layer INPUT (un-padded); dy has out_hw(kind, h, w)."""
     oh, ow = out_hw(kind, h, w)
     if kind == "conv4s2":  # transposed structure over the dy grid, 4 input-parity phases
-        specs = []
-        for py in range(2):
-            khs = [(1, 0), (3, -1)] if py == 0 else [(0, 1), (2, 0)]
-            for px in range(2):
-                kws = [(1, 0), (3, -1)] if px == 0 else [(0, 1), (2, 0)]
-                taps = [Tap(0, kh * 4 + kw, dw, dh) for kh, dh in khs for kw, dw in kws]
-                specs.append(GemmSpec(False, oh, ow, taps, (2, 2), (py, px), a_hw=(oh, ow)))
-        return specs
+        slot = phase_major_slots()
+        return [GemmSpec(False, oh, ow, [Tap(0, slot[kh * 4 + kw], dw, dh) for kh, dh, kw, dw in taps], (2, 2),
+                         (py, px), a_hw=(oh, ow)) for (py, px), taps in _phase_taps()]
     if kind == "convT4s2":  # strided conv of dy (dy is 2h x 2w)
         taps = []
         for kh in range(4):

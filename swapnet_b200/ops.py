@@ -288,8 +288,9 @@ def pack_weights(weight: torch.Tensor, kind: str, dgrad: bool, k_pad: int, dst: 
     s_row, s_k, rows, k_real = L.pack_strides(kind, cin, cout, dgrad)
     t = L.ntaps(kind)
     assert dst.rows >= rows and dst.k_total >= t * k_pad and k_pad >= k_real and dst.k_total % k_pad == 0
-    check(_lib.load().sn_pack_weights(weight.data_ptr(), s_row, s_k, rows, t, dst.k_total // k_pad, k_real, k_pad,
-                                      dst.hi.data_ptr(),
+    slots = (C.c_int * t)(*L.pack_slots(kind, dgrad))
+    check(_lib.load().sn_pack_weights(weight.data_ptr(), s_row, s_k, rows, t, dst.k_total // k_pad, slots, k_real,
+                                      k_pad, dst.hi.data_ptr(),
                                       dst.lo.data_ptr(), dst.fmt, None if dst.scale is None else dst.scale.data_ptr(),
                                       _stream()))
 

@@ -150,7 +150,8 @@ def test_conv_backward(kind, n, cin, cout, h, w):
         gw, gb = torch.autograd.grad(yr, (wr, br), gy.double())
     else:
         gx, gw, gb = torch.autograd.grad(yr, (xr, wr, br), gy.double())
-    dy = ops.Planes(n, oh, ow, L.padc(cout), dev(), fmt=ops.FMT_BF16)  # gradients travel as bf16-split
+    dyc = L.padc(cout) if layer.x.c >= 64 else L.pad64(cout)   # one wgrad operand must carry >= 64 channels
+    dy = ops.Planes(n, oh, ow, dyc, dev(), fmt=ops.FMT_BF16)  # gradients travel as bf16-split
     ops.pack_planes(gy.to(dev()), dy)
     ih, iw = (h + 2, w + 2) if kind == "conv3r" else (h, w)
     dx = torch.full((n, ih, iw, cin + 3), 5.0, device=dev())
