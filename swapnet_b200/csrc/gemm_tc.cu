@@ -51,7 +51,9 @@ __device__ __forceinline__ float apply_act(float v, int act) {
 // ============================================================================
 // conv mode
 // ============================================================================
-template <int NSPLIT>
+// CW = channels per A row (64 / 32 / 16): a template parameter so that the single MMA-issuing thread
+// carries no runtime index arithmetic (measured: runtime div/mod there costs 30 % of the kernel).
+template <int NSPLIT, int CW>
 __global__ void __launch_bounds__(kThreads, 1)
 tap_gemm_kernel(const __grid_constant__ TapGemmParams p) {
   using C = Cfg<NSPLIT>;
@@ -73,8 +75,8 @@ tap_gemm_kernel(const __grid_constant__ TapGemmParams p) {
   const int tn_i = mt / (p.tiles_w * p.tiles_h);
   const int w0 = tw_i * p.tw, h0 = th_i * p.th, n0 = tn_i * p.nb;
   const int ncol0 = blockIdx.y * p.block_n;
-  const int cw = p.a_chunk;                 // channels per A row: 64, 32 or 16
-  const int tps = 64 / cw;                  // taps sharing one 64-deep stage (1, 2 or 4)
+  constexpr int cw = CW;                    // channels per A row: 64, 32 or 16
+  constexpr int tps = 64 / cw;              // taps sharing one 64-deep stage (1, 2 or 4)
   const int k_iters = cw == 64 ? p.ntaps * p.chunks : p.ntaps / tps;
 
   if (threadIdx.x == 0) {
@@ -121,7 +123,8 @@ tap_gemm_kernel(const __grid_constant__ TapGemmParams p) {
         } else {
           // narrow operand: 64/cw taps, each a [128 rows][cw channels] sub-tile, fill one stage; the
           // weights of consecutive taps are contiguous in K, so B is still one 64-deep box
-          const int sub = 128 * cw * 2;
+          constexpr int sub = 128 * cw * 2;
+#pragma unroll
           for (int j = 0; j < tps; ++j) {
             const TapDesc tap = p.taps[it * tps + j];
 #pragma unroll
@@ -148,13 +151,13 @@ tap_gemm_kernel(const __grid_constant__ TapGemmParams p) {
         tc_fence_after();
         const uint32_t st = smem_base + s * C::kStageBytes;
         // K-major, rows of cw channels: SWIZZLE_128B/64B/32B, SBO = 8 rows, LBO unused (1)
-        const uint32_t a_layout = umma_layout_of_chunk(cw);
-        const uint32_t a_sbo = 8u * cw * 2u;
+        constexpr uint32_t a_layout = cw >= 64 ? 2u : (cw == 32 ? 4u : 6u);
+        constexpr uint32_t a_sbo = 8u * cw * 2u;
         const uint64_t a_hi = umma_smem_desc(st, 16, a_sbo, a_layout);
         const uint64_t b_hi = umma_smem_desc(st + C::kPlanes * kTileBytes, 16, 1024);
         const uint64_t a_lo = umma_smem_desc(st + kTileBytes, 16, a_sbo, a_layout);
         const uint64_t b_lo = umma_smem_desc(st + (C::kPlanes + 1) * kTileBytes, 16, 1024);
-        const uint32_t sub16 = (uint32_t)(128 * cw * 2) >> 4;  // sub-tile stride in 16-B units
+        constexpr uint32_t sub16 = (uint32_t)(128 * cw * 2) >> 4;  // sub-tile stride in 16-B units
 #pragma unroll
         for (int k = 0; k < 4; ++k) {  // 4 x (UMMA_K = 16 elements = 32 B) per 64-deep stage
           const uint64_t badv = (uint64_t)(k * 2);
@@ -564,25 +567,29 @@ int sn_tap_gemm_plan_init(TapGemmPlan* plan, const sn_tap_gemm_desc* d) {
   return SN_OK;
 }
 
-int sn_tap_gemm_plan_launch(const TapGemmPlan* plan, cudaStream_t stream) {
-  const int idx = plan->nsplit == 3 ? 1 : 0;
-  if (plan->nsplit == 3) {
-    if (!g_smem_attr_done[0][idx]) {
-      SN_CHECK_CUDA(cudaFuncSetAttribute(tap_gemm_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         Cfg<3>::kSmemBytes));
-      g_smem_attr_done[0][idx] = 1;
-    }
-    tap_gemm_kernel<3><<<plan->grid, kThreads, Cfg<3>::kSmemBytes, stream>>>(plan->p);
-  } else {
-    if (!g_smem_attr_done[0][idx]) {
-      SN_CHECK_CUDA(cudaFuncSetAttribute(tap_gemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         Cfg<1>::kSmemBytes));
-      g_smem_attr_done[0][idx] = 1;
-    }
-    tap_gemm_kernel<1><<<plan->grid, kThreads, Cfg<1>::kSmemBytes, stream>>>(plan->p);
+template <int NSPLIT, int CW>
+static int launch_tap(const TapGemmPlan* plan, cudaStream_t stream) {
+  static bool attr_done = false;
+  if (!attr_done) {
+    SN_CHECK_CUDA(cudaFuncSetAttribute(tap_gemm_kernel<NSPLIT, CW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       Cfg<NSPLIT>::kSmemBytes));
+    attr_done = true;
   }
+  tap_gemm_kernel<NSPLIT, CW><<<plan->grid, kThreads, Cfg<NSPLIT>::kSmemBytes, stream>>>(plan->p);
   SN_CHECK_CUDA(cudaGetLastError());
   return SN_OK;
+}
+
+int sn_tap_gemm_plan_launch(const TapGemmPlan* plan, cudaStream_t stream) {
+  const int cw = plan->p.a_chunk;
+  if (plan->nsplit == 3) {
+    if (cw == 64) return launch_tap<3, 64>(plan, stream);
+    if (cw == 32) return launch_tap<3, 32>(plan, stream);
+    return launch_tap<3, 16>(plan, stream);
+  }
+  if (cw == 64) return launch_tap<1, 64>(plan, stream);
+  if (cw == 32) return launch_tap<1, 32>(plan, stream);
+  return launch_tap<1, 16>(plan, stream);
 }
 
 int sn_wgrad_plan_init(WgradPlan* plan, const sn_wgrad_desc* d, int sm_count) {
