@@ -104,6 +104,10 @@ typedef struct sn_wgrad_desc {
   int rows_valid, cols_valid;
   int block_n;                           /* 64 or 128; == y_chunk when Y is narrow */
   int y_chunk;                           /* channels per TMA row of Y: 64 (default when 0), 32 or 16 */
+  /* narrow Y only: taps that share the same X tap are grouped, one CTA handles a group and reads X once:
+   * group g = taps [group_start[g], +group_size[g]), each tap one y_chunk-wide column block of the
+   * block_n = max_group * y_chunk accumulator.  ngroups == 0: every tap is its own launch slice. */
+  int ngroups; int group_start[SN_MAX_TAPS]; int group_size[SN_MAX_TAPS];
   int ksplit;                            /* 0 = auto */
   int nsplit;
 } sn_wgrad_desc;

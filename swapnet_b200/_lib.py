@@ -54,7 +54,9 @@ class SnWgradDesc(C.Structure):
         ("tap_off", C.c_longlong * SN_MAX_TAPS),
         ("out", C.c_void_p), ("s_row", C.c_longlong), ("s_col", C.c_longlong),
         ("rows_valid", C.c_int), ("cols_valid", C.c_int),
-        ("block_n", C.c_int), ("y_chunk", C.c_int), ("ksplit", C.c_int), ("nsplit", C.c_int),
+        ("block_n", C.c_int), ("y_chunk", C.c_int),
+        ("ngroups", C.c_int), ("group_start", C.c_int * SN_MAX_TAPS), ("group_size", C.c_int * SN_MAX_TAPS),
+        ("ksplit", C.c_int), ("nsplit", C.c_int),
     ]
 
 

@@ -251,7 +251,11 @@ wgrad_gemm_kernel(const __grid_constant__ WgradParams p) {
 
   const int m_tile = blockIdx.x / p.n_tiles;
   const int n_tile = blockIdx.x - m_tile * p.n_tiles;
-  const int tap_i = blockIdx.y;
+  // grid.y = tap (wide Y) or tap group (narrow Y: the group's taps are column blocks of one accumulator
+  // and share the X tile, which is then read once per pixel tile instead of once per tap)
+  const bool grouped = p.ngroups > 0;
+  const int tap_i = grouped ? p.gstart[blockIdx.y] : blockIdx.y;
+  const int gsize = grouped ? p.gsize[blockIdx.y] : 1;
   const int m0 = m_tile * kBlockM;
   const int ncol0 = n_tile * p.block_n;
   const int total = p.tiles_w * p.tiles_h * p.tiles_n;
@@ -259,7 +263,7 @@ wgrad_gemm_kernel(const __grid_constant__ WgradParams p) {
   const int kt1 = (int)(((long long)total * (blockIdx.z + 1)) / gridDim.z);
   const int k_iters = kt1 - kt0;
   const int ycw = p.y_chunk;                               // channels per Y row: 64, 32, 16
-  const int y_blocks = ycw == 64 ? p.block_n / 64 : 1;     // narrow Y: one atom, block_n == ycw
+  const int y_blocks = ycw == 64 ? p.block_n / 64 : gsize; // narrow Y: one ycw-wide atom per grouped tap
   const int y_block_bytes = 64 * ycw * 2;                  // 64 pixels x ycw channels
 
   if (threadIdx.x == 0) {
@@ -286,7 +290,6 @@ wgrad_gemm_kernel(const __grid_constant__ WgradParams p) {
     if (warp == 0) {
       if (lane == 0) {
         const TapDesc xt = p.xtaps[tap_i];
-        const TapDesc yt = p.ytaps[tap_i];
         const uint32_t stage_tx = C::kPlanes * (2 * 8192 + y_blocks * y_block_bytes);
         for (int it = 0; it < k_iters; ++it) {
           const int s = it % C::kStages;
@@ -304,10 +307,12 @@ wgrad_gemm_kernel(const __grid_constant__ WgradParams p) {
             for (int b = 0; b < 2; ++b)
               tma_load_5d(&p.tmX[pl], &full_bar[s], st + pl * kTileBytes + b * 8192,
                           xt.c_off + m0 + b * 64, w0 + xt.dw, xt.hp, h0 + xt.dh, n0);
-            for (int b = 0; b < y_blocks; ++b)
+            for (int b = 0; b < y_blocks; ++b) {
+              const TapDesc yt = p.ytaps[grouped ? tap_i + b : tap_i];
               tma_load_5d(&p.tmY[pl], &full_bar[s],
                           st + (C::kPlanes + pl) * kTileBytes + b * y_block_bytes,
-                          yt.c_off + ncol0 + b * 64, w0 + yt.dw, yt.hp, h0 + yt.dh, n0);
+                          yt.c_off + (grouped ? 0 : ncol0 + b * 64), w0 + yt.dw, yt.hp, h0 + yt.dh, n0);
+            }
           }
         }
       }
@@ -326,9 +331,10 @@ wgrad_gemm_kernel(const __grid_constant__ WgradParams p) {
           const uint32_t y_layout = umma_layout_of_chunk(ycw);
           const uint32_t y_sbo = 8u * ycw * 2u;              // 8 pixel rows of the narrow / full atom
           const uint64_t x_hi = umma_smem_desc(st, 8192, 1024);
-          const uint64_t y_hi = umma_smem_desc(st + C::kPlanes * kTileBytes, 8192, y_sbo, y_layout);
+          // LBO = stride between the N atoms (64-channel blocks, or the grouped taps' narrow blocks)
+          const uint64_t y_hi = umma_smem_desc(st + C::kPlanes * kTileBytes, y_block_bytes, y_sbo, y_layout);
           const uint64_t x_lo = umma_smem_desc(st + kTileBytes, 8192, 1024);
-          const uint64_t y_lo = umma_smem_desc(st + (C::kPlanes + 1) * kTileBytes, 8192, y_sbo, y_layout);
+          const uint64_t y_lo = umma_smem_desc(st + (C::kPlanes + 1) * kTileBytes, y_block_bytes, y_sbo, y_layout);
 #pragma unroll
           for (int k = 0; k < 4; ++k) {  // 4 x 16 pixels; 16 pixel rows = 2048 B (X), 16 * ycw * 2 B (Y)
             const uint64_t xadv = (uint64_t)(k * 128);
@@ -348,7 +354,7 @@ wgrad_gemm_kernel(const __grid_constant__ WgradParams p) {
       const int q = warp & 3;
       const int row = m0 + q * 32 + lane;
       const bool valid = row < p.rows_valid;
-      float* optr = p.out + (long long)row * p.s_row + p.tap_off[tap_i];
+      float* orow = p.out + (long long)row * p.s_row;
       mbar_wait(&accum_bar, 0);
       tc_fence_after();
       for (int c0 = 0; c0 < p.block_n; c0 += 16) {
@@ -356,11 +362,24 @@ wgrad_gemm_kernel(const __grid_constant__ WgradParams p) {
         tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
         tmem_ld_wait();
         if (valid) {
+          if (!grouped) {
+            float* optr = orow + p.tap_off[tap_i];
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const int col = ncol0 + c0 + j;
-            if (col < p.cols_valid)
-              atomicAdd(optr + (long long)col * p.s_col, __uint_as_float(r[j]));
+            for (int j = 0; j < 16; ++j) {
+              const int col = ncol0 + c0 + j;
+              if (col < p.cols_valid)
+                atomicAdd(optr + (long long)col * p.s_col, __uint_as_float(r[j]));
+            }
+          } else {
+            const int b = c0 / ycw;               // which grouped tap this 16-column chunk belongs to
+            if (b < gsize) {
+              float* optr = orow + p.tap_off[tap_i + b];
+              const int cbase = c0 - b * ycw;
+#pragma unroll
+              for (int j = 0; j < 16; ++j)
+                if (cbase + j < p.cols_valid)
+                  atomicAdd(optr + (long long)(cbase + j) * p.s_col, __uint_as_float(r[j]));
+            }
           }
         }
       }
@@ -599,9 +618,31 @@ int sn_wgrad_plan_init(WgradPlan* plan, const sn_wgrad_desc* d, int sm_count) {
   SN_REQUIRE(d->ntaps >= 1 && d->ntaps <= SN_MAX_TAPS, "ntaps out of range: %d", d->ntaps);
   const int y_chunk = d->y_chunk ? d->y_chunk : 64;
   SN_REQUIRE(y_chunk == 64 || y_chunk == 32 || y_chunk == 16, "y_chunk must be 64, 32 or 16");
-  SN_REQUIRE(y_chunk == 64 ? (d->block_n == 64 || d->block_n == 128) : d->block_n == y_chunk,
-             "wgrad block_n must be 64 or 128 (or equal the narrow y_chunk)");
   p.y_chunk = y_chunk;
+  p.ngroups = 0;
+  int grid_y = d->ntaps;
+  if (y_chunk == 64) {
+    SN_REQUIRE(d->block_n == 64 || d->block_n == 128, "wgrad block_n must be 64 or 128 for 64-channel Y rows");
+  } else {
+    SN_REQUIRE(d->cols_valid <= y_chunk, "narrow Y: cols_valid must fit one %d-channel block", y_chunk);
+    if (d->ngroups > 0) {
+      int maxg = 0, covered = 0;
+      for (int g = 0; g < d->ngroups; ++g) {
+        SN_REQUIRE(d->group_size[g] >= 1 && d->group_start[g] >= 0 &&
+                       d->group_start[g] + d->group_size[g] <= d->ntaps, "bad tap group %d", g);
+        if (d->group_size[g] > maxg) maxg = d->group_size[g];
+        covered += d->group_size[g];
+        p.gstart[g] = (short)d->group_start[g];
+        p.gsize[g] = (short)d->group_size[g];
+      }
+      SN_REQUIRE(covered == d->ntaps && maxg * y_chunk <= 128 && d->block_n == maxg * y_chunk,
+                 "tap groups must cover all taps and block_n == max group * y_chunk <= 128");
+      p.ngroups = d->ngroups;
+      grid_y = d->ngroups;
+    } else {
+      SN_REQUIRE(d->block_n == y_chunk, "narrow Y without groups: block_n must equal y_chunk");
+    }
+  }
   SN_REQUIRE(d->x_hi && d->y_hi && d->out, "null operand");
   SN_REQUIRE(d->nsplit == 1 || (d->x_lo && d->y_lo), "nsplit=3 needs lo planes");
   SN_REQUIRE(d->x_fmt == d->y_fmt, "X and Y of one tcgen05.mma must share a 16-bit format (x=%d y=%d)",
@@ -622,7 +663,7 @@ int sn_wgrad_plan_init(WgradPlan* plan, const sn_wgrad_desc* d, int sm_count) {
   }
   p.block_n = d->block_n;
   p.m_tiles = (d->rows_valid + kBlockM - 1) / kBlockM;
-  p.n_tiles = (d->cols_valid + d->block_n - 1) / d->block_n;
+  p.n_tiles = y_chunk == 64 ? (d->cols_valid + d->block_n - 1) / d->block_n : 1;
   p.rows_valid = d->rows_valid;
   p.cols_valid = d->cols_valid;
   p.out = d->out;
@@ -642,7 +683,7 @@ int sn_wgrad_plan_init(WgradPlan* plan, const sn_wgrad_desc* d, int sm_count) {
     if (rc) return rc;
   }
   plan->nsplit = d->nsplit;
-  const int base_ctas = p.m_tiles * p.n_tiles * d->ntaps;
+  const int base_ctas = p.m_tiles * p.n_tiles * grid_y;
   const int total = p.tiles_w * p.tiles_h * p.tiles_n;
   int ks = d->ksplit;
   if (ks <= 0) {  // aim for ~3 waves, at least 8 k-iterations per CTA
@@ -653,7 +694,7 @@ int sn_wgrad_plan_init(WgradPlan* plan, const sn_wgrad_desc* d, int sm_count) {
     if (ks < 1) ks = 1;
   }
   if (ks > total) ks = total;
-  plan->grid = dim3(p.m_tiles * p.n_tiles, d->ntaps, ks);
+  plan->grid = dim3(p.m_tiles * p.n_tiles, grid_y, ks);
   return SN_OK;
 }
 

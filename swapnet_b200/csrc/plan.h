@@ -46,6 +46,8 @@ struct alignas(64) WgradParams {
   long long s_row, s_col;
   int x_fmt, y_fmt;
   int y_chunk;  // 64 / 32 / 16 channels per Y row
+  int ngroups;  // > 0: narrow-Y tap groups (grid.y = group)
+  short gstart[SN_MAX_TAPS], gsize[SN_MAX_TAPS];
 };
 
 struct TapGemmPlan {

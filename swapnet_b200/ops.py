@@ -194,6 +194,23 @@ def wgrad_desc(x: Planes, y: Planes, spec: L.WgradSpec, out: torch.Tensor, s_row
         s_row, s_col = s_col, s_row
         rows_valid, cols_valid = cols_valid, rows_valid
     assert x.c_off % 8 == 0 and y.c_off % 8 == 0
+    order = list(range(len(xt)))
+    groups = []
+    if y.c < 64:
+        # narrow N side: taps with the same X tap become column blocks of one accumulator (X read once)
+        gmax = 128 // y.c
+        key = lambda i: (xt[i].pw, xt[i].dw, xt[i].dh, xt[i].hp)
+        order = sorted(order, key=key)           # stable: keeps the tap order inside a group
+        i = 0
+        while i < len(order):
+            j = i
+            while j < len(order) and j - i < gmax and key(order[j]) == key(order[i]):
+                j += 1
+            groups.append((i, j - i))
+            i = j
+        xt = [xt[i] for i in order]
+        yt = [yt[i] for i in order]
+        tap_off = [tap_off[i] for i in order]
     d = SnWgradDesc()
     d.x_hi, d.x_lo = x.hi_ptr, x.lo_ptr
     d.x_n, d.x_h, d.x_w, d.x_c, d.x_pitch, d.x_parity = x.n, x.h, x.w, x.c, x.pitch, int(xp)
@@ -213,7 +230,11 @@ def wgrad_desc(x: Planes, y: Planes, spec: L.WgradSpec, out: torch.Tensor, s_row
     assert x.c >= 64, "the 128-row operand of a wgrad GEMM must carry >= 64 channels (swap the roles)"
     if y.c < 64:   # narrow N-side operand: one 16/32-channel atom
         assert y.c in (16, 32) and cols_valid <= y.c
-        d.y_chunk, d.block_n = y.c, y.c
+        d.y_chunk = y.c
+        d.ngroups = len(groups)
+        for g, (st, sz) in enumerate(groups):
+            d.group_start[g], d.group_size[g] = st, sz
+        d.block_n = max(sz for _, sz in groups) * y.c
     else:
         d.y_chunk = 64
         d.block_n = block_n or (128 if cols_valid > 64 else 64)
