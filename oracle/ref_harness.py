@@ -1,6 +1,6 @@
 """TEST INFRASTRUCTURE ONLY — imports the UNMODIFIED reference from /root/reference (build container
 only; the GPU box has no /root/reference) so that the oracle restatement can be pinned against it and
-golden vectors generated (tools/make_golden.py).  Recipe: SURVEY.md App. C.
+golden vectors generated (tests/tools/make_golden.py).  Recipe: SURVEY.md App. C.
 """
 from __future__ import annotations
 

@@ -1,5 +1,5 @@
 """Pins the CPU oracle (oracle/) against the reference: golden vectors generated from the UNMODIFIED
-reference by tools/make_golden.py (committed under tests/golden/), and — when /root/reference is
+reference by tests/tools/make_golden.py (committed under tests/golden/), and — when /root/reference is
 mounted (build container) — the reference modules themselves, bit for bit."""
 import os
 

@@ -1,8 +1,9 @@
 """Stage-by-stage comparison of the engines against the CPU oracle (fp64): conv outputs y,
 dL/dy, dL/d(input) — prints relmax per stage.  Diagnostic; run on the GPU box."""
 import sys, os
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
 import torch
 import torch.nn.functional as F
 from oracle import nets as ON

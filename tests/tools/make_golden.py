@@ -1,6 +1,6 @@
 """Generate tests/golden/*.pt from the UNMODIFIED reference (/root/reference) — build container only.
 
-    python tools/make_golden.py
+    python tests/tools/make_golden.py
 
 Fixtures (all seeded; see tests/test_oracle_cpu.py for how they are consumed):
   warp_64.pt     reference WarpModule / define_D forward (eval) + one full reference
@@ -12,7 +12,7 @@ Fixtures (all seeded; see tests/test_oracle_cpu.py for how they are consumed):
 import os
 import sys
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 import numpy as np
