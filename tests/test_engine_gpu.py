@@ -113,16 +113,20 @@ def _opt(B, S, **over):
     return argparse.Namespace(**d)
 
 
-def test_warp_model_step_matches_oracle():
-    """One WarpModel.optimize_parameters() (eval-mode dropout): all six losses and every parameter
-    gradient of G and D against the oracle's autograd (fp64), then the AdamW-updated weights."""
+@pytest.mark.parametrize("mode", ["eval", "train_shared_masks"])
+def test_warp_model_step_matches_oracle(mode):
+    """One WarpModel.optimize_parameters(): all six losses and every parameter gradient of G and D
+    against the oracle's autograd (fp64).  eval: dropout off.  train_shared_masks: dropout(0.5) active in
+    body_down4, cloth_down5/6 and the four resblocks, the oracle applying the library's own masks."""
+    from swapnet_b200 import engine as E
     from swapnet_b200.models import create_model
 
     B, S = 2, 64
     torch.manual_seed(0)
     model = create_model(_opt(B, S))
     model.setup(model.opt)
-    model.eval()                      # dropout off; IN has no running stats
+    if mode == "eval":
+        model.eval()                  # dropout off; IN has no running stats
     model.is_train = True
     sdG = {k: v.detach().cpu().double().requires_grad_() for k, v in model.net_generator.state_dict().items()}
     sdD = {k: v.detach().cpu().double().requires_grad_() for k, v in model.net_discriminator.state_dict().items()}
@@ -158,7 +162,11 @@ def test_warp_model_step_matches_oracle():
         return gates_D[k][name]
 
     ON.gate_with(gate)
-    o = ON.warp_step_losses(sdG, sdD, body.double(), inp.double(), tgt.double(), draws)
+    drop = None
+    if mode != "eval":
+        eng = model._eng_G
+        drop = OD.make_drop({s.name: E._mix_seed(eng.seed, s.id) for s in eng.stages}, 0.5)
+    o = ON.warp_step_losses(sdG, sdD, body.double(), inp.double(), tgt.double(), draws, drop=drop)
     stats = dict(ON.GATE_STATS)
     ON.gate_with(None)
     flips = {k: v for k, v in stats.items() if k != "__total__" and v}
@@ -189,8 +197,8 @@ def test_warp_model_step_matches_oracle():
             continue
         worst["G." + k] = relmax(gG[k], r)
     bad = {k: v for k, v in worst.items() if v >= 1e-3}
-    record("warp_step_worst_grads", sorted(worst.items(), key=lambda kv: -kv[1])[:5])
-    record("warp_step_fakes", f"{err_f:.3e}")
+    record(f"warp_step_worst_grads[{mode}]", sorted(worst.items(), key=lambda kv: -kv[1])[:5])
+    record(f"warp_step_fakes[{mode}]", f"{err_f:.3e}")
     assert not bad, f"parameter gradients beyond 1e-3: {bad}"
 
 
@@ -371,3 +379,55 @@ def test_warp_forward_full_size_512():
     worst = sorted(per_layer.items(), key=lambda kv: -kv[1])[:4]
     record("warp_forward_512", f"fakes {err:.3e}; worst conv outputs {[(k, f'{v:.2e}') for k, v in worst]}")
     assert err < 1e-3, f"512x512 forward relmax {err:.3e}"
+
+
+@pytest.mark.parametrize("B,S", [(1, 192), (3, 128)])
+def test_warp_forward_other_shapes(B, S):
+    """Non-power-of-two planes (192 -> 96, 48, 24, 12, 6, 3) and odd batch sizes."""
+    from swapnet_b200 import engine as E
+
+    G, _ = make_nets()
+    body, inp, _ = synth_warp_batch(B, S) if S % 16 == 0 else (None, None, None)
+    sd = {k: v.clone().double() for k, v in G.state_dict().items()}
+    eng = E.WarpEngine(G.to(dev()), B, S, dev(), train=False)
+    eng.pack()
+    out = eng.forward(body.to(dev()), inp.to(dev()), training=False)
+    torch.cuda.synchronize()
+    with torch.no_grad():
+        ref = ON.warp_forward(sd, body.double(), inp.double())
+    err = relmax(out.permute(0, 3, 1, 2).cpu(), ref)
+    record(f"warp_forward_shape[{B},{S}]", f"{err:.3e}")
+    assert err < 1e-3
+
+
+def test_warp_model_ce_mode_and_checkpoint_roundtrip():
+    """--warp_mode ce (no discriminator, warp_model.py:69-74,175-183) and a save/load round trip through the
+    reference's checkpoint file names."""
+    import os
+
+    from swapnet_b200.models import create_model
+
+    B, S = 2, 64
+    torch.manual_seed(0)
+    opt = _opt(B, S, warp_mode="ce")
+    model = create_model(opt)
+    model.setup(opt)
+    assert not hasattr(model, "net_discriminator") and model.optimizer_names == ["G"]
+    body, inp, tgt = synth_warp_batch(B, S)
+    batch = dict(bodys=body, input_cloths=inp, target_cloths=tgt, cloth_paths=["c"] * B, body_paths=["b"] * B)
+    model.set_input(batch)
+    model.optimize_parameters()
+    l0 = float(model.loss_G)
+    for _ in range(3):
+        model.set_input(batch)
+        model.optimize_parameters()
+    assert float(model.loss_G) < l0, "cross-entropy did not decrease over 4 AdamW steps on a fixed batch"
+    model.save_checkpoint("latest")
+    assert os.path.exists(os.path.join(model.save_dir, "latest_net_generator.pth"))
+    assert os.path.exists(os.path.join(model.save_dir, "latest_optim_G.pth"))
+    w = model.net_generator.dual_up3.model[0].weight.detach().clone()
+    model.net_generator.dual_up3.model[0].weight.data.zero_()
+    model.load_checkpoint_dir("latest")
+    assert torch.equal(w, model.net_generator.dual_up3.model[0].weight)
+    model.set_input(batch)
+    model.optimize_parameters()     # engines keep working on the re-loaded storage
