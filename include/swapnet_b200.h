@@ -220,6 +220,11 @@ int sn_tanh_bwd(const sn_grad_src* src, int nsrc, const float* out, int out_pitc
 int sn_upsample_planes(const void* src_hi, const void* src_lo, int src_pitch, int src_coff, int n, int h, int w,
                        int c, int factor, void* dst_hi, void* dst_lo, int dst_pitch, int dst_coff, void* stream);
 
+/* fused AdamW step over flat fp32 buffers (torch.optim.AdamW semantics as optimizers/__init__.py:48-59
+ * builds it: decoupled weight decay, bias correction, eps outside the sqrt); step is 1-based. */
+int sn_adamw_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
+                  float eps, float weight_decay, int step, void* stream);
+
 /* deterministic dropout keep-mask shared by forward, backward and the test oracle:
  * keep(seed, idx) with idx the linear NHWC element index; returns 0/1 bytes. */
 int sn_dropout_mask(unsigned long long seed, float p, long long count, uint8_t* out, void* stream);

@@ -95,34 +95,38 @@ struct PackConcatArgs {
   uint16_t *hi, *lo, *hi2, *lo2; int pitch, coff, fmt, fmt2;
 };
 __global__ void __launch_bounds__(256) pack_concat_kernel(const PackConcatArgs a) {
-  extern __shared__ float tile[];  // [c_fill][33]
-  const int w0 = blockIdx.x * 32, h = blockIdx.y, n = blockIdx.z;
+  // one block = one (n, h, PW-pixel run), PW = 32 * (64 / c_fill) so that narrow outputs keep all
+  // 256 threads busy (c_fill = 16 -> 128 pixels); smem tile [c_fill][PW + 1]
+  extern __shared__ float tile[];
+  const int PW = 32 * (64 / (a.c_fill < 64 ? a.c_fill : 64));
+  const int TP = PW + 1;
+  const int w0 = blockIdx.x * PW, h = blockIdx.y, n = blockIdx.z;
   int cbase = 0;
   for (int si = 0; si < a.nsrc; ++si) {
     const PackSrc s = a.s[si];
     if (s.layout == SN_LAYOUT_NCHW) {
-      for (int i = threadIdx.x; i < s.c * 32; i += blockDim.x) {
-        const int c = i >> 5, w = i & 31;
-        tile[(cbase + c) * 33 + w] = (w0 + w < a.W) ? s.p[(((long long)n * s.c + c) * a.H + h) * a.W + w0 + w] : 0.f;
+      for (int i = threadIdx.x; i < s.c * PW; i += blockDim.x) {
+        const int c = i / PW, w = i - c * PW;
+        tile[(cbase + c) * TP + w] = (w0 + w < a.W) ? s.p[(((long long)n * s.c + c) * a.H + h) * a.W + w0 + w] : 0.f;
       }
     } else {
-      for (int i = threadIdx.x; i < s.c * 32; i += blockDim.x) {
+      for (int i = threadIdx.x; i < s.c * PW; i += blockDim.x) {
         const int w = i / s.c, c = i - w * s.c;
-        tile[(cbase + c) * 33 + w] = (w0 + w < a.W) ? s.p[(((long long)n * a.H + h) * a.W + w0 + w) * s.pitch + c] : 0.f;
+        tile[(cbase + c) * TP + w] = (w0 + w < a.W) ? s.p[(((long long)n * a.H + h) * a.W + w0 + w) * s.pitch + c] : 0.f;
       }
     }
     cbase += s.c;
   }
-  for (int i = threadIdx.x; i < (a.c_fill - cbase) * 32; i += blockDim.x) tile[(cbase + (i >> 5)) * 33 + (i & 31)] = 0.f;
+  for (int i = threadIdx.x; i < (a.c_fill - cbase) * PW; i += blockDim.x) tile[(cbase + i / PW) * TP + (i % PW)] = 0.f;
   __syncthreads();
   const int G = a.c_fill >> 3;
-  for (int i = threadIdx.x; i < 32 * G; i += blockDim.x) {
+  for (int i = threadIdx.x; i < PW * G; i += blockDim.x) {
     const int w = i / G, g = i - w * G;
     if (w0 + w >= a.W) continue;
     uint16_t h1[8], l1[8], h2[8], l2[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const float v = tile[(g * 8 + j) * 33 + w];
+      const float v = tile[(g * 8 + j) * TP + w];
       split16(v, a.fmt, h1[j], l1[j]);
       if (a.hi2) split16(v, a.fmt2, h2[j], l2[j]);
     }
@@ -679,6 +683,45 @@ __global__ void upsample_planes_kernel(const uint16_t* __restrict__ shi, const u
   }
 }
 
+// ---------------------------------------------------------------------------------
+// fused AdamW over flat fp32 buffers (torch.optim.AdamW semantics, optimizers/__init__.py:48-59):
+//   p *= 1 - lr*wd;  m += (g - m)(1 - b1);  v = v*b2 + (1 - b2) g*g;
+//   p -= (lr / (1 - b1^t)) * m / (sqrt(v) / sqrt(1 - b2^t) + eps)
+// ---------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ p, const float* __restrict__ g,
+                                                    float* __restrict__ m, float* __restrict__ v, long long n,
+                                                    float decay, float omb1, float b2, float omb2, float step_size,
+                                                    float inv_bc2_sqrt, float eps) {
+  const long long n4 = n >> 2;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4;
+       i += (long long)gridDim.x * blockDim.x) {
+    float4 P = reinterpret_cast<float4*>(p)[i];
+    const float4 G = reinterpret_cast<const float4*>(g)[i];
+    float4 M = reinterpret_cast<float4*>(m)[i];
+    float4 V = reinterpret_cast<float4*>(v)[i];
+    float* pp = &P.x; const float* gg = &G.x; float* mm = &M.x; float* vv = &V.x;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      pp[j] *= decay;
+      mm[j] = mm[j] + (gg[j] - mm[j]) * omb1;
+      vv[j] = vv[j] * b2 + omb2 * gg[j] * gg[j];
+      pp[j] -= step_size * (mm[j] / (sqrtf(vv[j]) * inv_bc2_sqrt + eps));
+    }
+    reinterpret_cast<float4*>(p)[i] = P;
+    reinterpret_cast<float4*>(m)[i] = M;
+    reinterpret_cast<float4*>(v)[i] = V;
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {   // tail
+    const long long i = (n4 << 2) + threadIdx.x;
+    float P = p[i] * decay;
+    const float G = g[i];
+    const float M = m[i] + (G - m[i]) * omb1;
+    const float V = v[i] * b2 + omb2 * G * G;
+    P -= step_size * (M / (sqrtf(V) * inv_bc2_sqrt + eps));
+    p[i] = P; m[i] = M; v[i] = V;
+  }
+}
+
 __global__ void dropout_mask_kernel(unsigned long long seed, uint32_t thresh, long long count,
                                     uint8_t* out) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < count;
@@ -1174,9 +1217,10 @@ int sn_pack_concat(const float* src0, int layout0, int pitch0, int c0, const flo
   a.N = n; a.H = h; a.W = w; a.c_fill = c_fill;
   a.hi = (uint16_t*)dst_hi; a.lo = (uint16_t*)dst_lo; a.hi2 = (uint16_t*)dst2_hi; a.lo2 = (uint16_t*)dst2_lo;
   a.pitch = dst_pitch; a.coff = dst_coff; a.fmt = fmt; a.fmt2 = fmt2;
-  const size_t smem = (size_t)c_fill * 33 * sizeof(float);
+  const int pw = 32 * (64 / (c_fill < 64 ? c_fill : 64));
+  const size_t smem = (size_t)c_fill * (pw + 1) * sizeof(float);
   SN_REQUIRE(smem <= 48 * 1024, "pack_concat: c_fill too large (%d)", c_fill);
-  pack_concat_kernel<<<dim3((w + 31) / 32, h, n), 256, smem, (cudaStream_t)stream>>>(a);
+  pack_concat_kernel<<<dim3((w + pw - 1) / pw, h, n), 256, smem, (cudaStream_t)stream>>>(a);
   LAUNCH_CHECK();
   return SN_OK;
 }
@@ -1413,6 +1457,19 @@ int sn_upsample_planes(const void* src_hi, const void* src_lo, int src_pitch, in
   upsample_planes_kernel<<<grid_for(total), kEwThreads, 0, (cudaStream_t)stream>>>(
       (const uint16_t*)src_hi + src_coff, src_lo ? (const uint16_t*)src_lo + src_coff : nullptr, src_pitch, h, w, c,
       factor, (uint16_t*)dst_hi + dst_coff, dst_lo ? (uint16_t*)dst_lo + dst_coff : nullptr, dst_pitch, total);
+  LAUNCH_CHECK();
+  return SN_OK;
+}
+
+int sn_adamw_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
+                  float eps, float weight_decay, int step, void* stream) {
+  SN_REQUIRE(p && g && m && v && n > 0 && step >= 1, "bad adamw arguments");
+  SN_REQUIRE((((uintptr_t)p | (uintptr_t)g | (uintptr_t)m | (uintptr_t)v) & 15) == 0, "adamw buffers must be 16-B aligned");
+  const double bc1 = 1.0 - pow((double)beta1, (double)step);
+  const double bc2 = 1.0 - pow((double)beta2, (double)step);
+  adamw_kernel<<<grid_for(n / 4 + 1), kEwThreads, 0, (cudaStream_t)stream>>>(
+      p, g, m, v, n, 1.f - lr * weight_decay, 1.f - beta1, beta2, 1.f - beta2, (float)((double)lr / bc1),
+      (float)(1.0 / sqrt(bc2)), eps);
   LAUNCH_CHECK();
   return SN_OK;
 }

@@ -40,8 +40,11 @@ def adam_modifier(parser: ArgumentParser, *_):
     return parser
 
 
-def define_optimizer(parameters, opt, net: str) -> torch.optim.Optimizer:
-    """optimizers/__init__.py:37-60 for the AdamW choice."""
+def define_optimizer(module, opt, net: str) -> torch.optim.Optimizer:
+    """optimizers/__init__.py:37-60 for the AdamW choice, as one fused kernel over flat buffers
+    (swapnet_b200/optim.py); same hyper-parameters, same state_dict layout."""
+    from ..optim import FusedAdamW, flatten_parameters
+
     if net not in ("D", "G"):
         raise ValueError(f"net arg must be 'D' or 'G', received {net}")
     choice = getattr(opt, "optimizer_" + net)
@@ -49,7 +52,9 @@ def define_optimizer(parameters, opt, net: str) -> torch.optim.Optimizer:
         raise NotImplementedError(f"optimizer {choice}: only AdamW is available on the B200 plugin")
     lr = opt.d_lr if net == "D" else opt.lr
     wd = opt.d_weight_decay if net == "D" else opt.weight_decay
-    return torch.optim.AdamW(parameters, lr=lr, weight_decay=wd, betas=(opt.b1, opt.b2))
+    params = list(module.parameters())
+    flat = flatten_parameters(params)
+    return FusedAdamW(params, flat, lr=lr, weight_decay=wd, betas=(opt.b1, opt.b2), eps=1e-8)
 
 
 class BaseGAN(BaseModel, ABC):
@@ -118,8 +123,8 @@ class BaseGAN(BaseModel, ABC):
             self.loss_names += ["G"]
             if opt.lambda_gan:
                 self.loss_names += ["G_gan"]
-            self.optimizer_G = define_optimizer(self.net_generator.parameters(), opt, "G")
-            self.optimizer_D = define_optimizer(self.net_discriminator.parameters(), opt, "D")
+            self.optimizer_G = define_optimizer(self.net_generator, opt, "G")
+            self.optimizer_D = define_optimizer(self.net_discriminator, opt, "D")
             self.optimizer_names = ("G", "D")
             self._acc = torch.zeros(8, dtype=torch.float64, device=self.device)  # device-side loss sums
             lam = float(opt.lambda_gan)
@@ -157,12 +162,14 @@ class BaseGAN(BaseModel, ABC):
         if self.is_train:
             self._eng_G.alloc_grads()
             self._eng_G.bind_backward()
+            self.optimizer_G.flat_grad = self._eng_G.flat_grad
         self._eng_Dd = self._eng_Dg = None
         if self.is_train and hasattr(self, "net_discriminator"):
             dn = self.net_discriminator
             self._eng_Dd = E.PatchGANEngine(dn, 2 * batch, size, self.device, self.nsplit)
             self._eng_Dd.alloc_grads()
             self._eng_Dd.bind_backward()
+            self.optimizer_D.flat_grad = self._eng_Dd.flat_grad
             self._eng_Dg = E.PatchGANEngine(dn, batch, size, self.device, self.nsplit,
                                             din=self._eng_Dd.din.batch_slice(0, batch), input_grad=True)
             self._eng_Dg.alloc_grads(share_with=self._eng_Dd)

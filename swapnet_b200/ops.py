@@ -461,6 +461,13 @@ def upsample_planes(src: Planes, dst: Planes, factor: int) -> None:
                                              d_.c_off, _stream()))
 
 
+def adamw_step(p: torch.Tensor, g: torch.Tensor, m: torch.Tensor, v: torch.Tensor, lr: float, b1: float, b2: float,
+               eps: float, wd: float, step: int) -> None:
+    assert p.is_contiguous() and g.is_contiguous() and p.numel() == g.numel() == m.numel() == v.numel()
+    check(_lib.load().sn_adamw_step(p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), p.numel(), lr, b1, b2, eps,
+                                    wd, step, _stream()))
+
+
 def dropout_mask(seed: int, p: float, count: int, device) -> torch.Tensor:
     out = torch.empty(count, dtype=torch.uint8, device=device)
     check(_lib.load().sn_dropout_mask(seed, p, count, out.data_ptr(), _stream()))

@@ -340,3 +340,43 @@ def test_roi_align_pack_bit_exact():
     got = out[..., :36].permute(0, 3, 1, 2).cpu().numpy()
     assert np.array_equal(got, ref), f"max abs diff {np.abs(got - ref).max()}"
     assert relmax(planes.dense().cpu()[..., :36], torch.from_numpy(ref).permute(0, 2, 3, 1)) < 1e-6
+
+
+def test_fused_adamw_matches_torch():
+    """FusedAdamW (one kernel over flat buffers) vs torch.optim.AdamW as the reference builds it
+    (optimizers/__init__.py:48-59), 5 steps, G-like (wd 0) and D-like (wd 0.01) settings; state_dict round trip."""
+    from swapnet_b200.optim import FusedAdamW, flatten_parameters
+
+    for lr, wd in ((1e-4, 0.0), (4e-4, 0.01)):
+        torch.manual_seed(1)
+        shapes = [(64, 3, 4, 4), (19,), (128, 64, 3, 3), (7,)]
+        ref_p = [torch.nn.Parameter(torch.randn(s, device=dev())) for s in shapes]
+        my_p = [torch.nn.Parameter(p.detach().clone()) for p in ref_p]
+        flat = flatten_parameters(my_p)
+        ref = torch.optim.AdamW(ref_p, lr=lr, weight_decay=wd, betas=(0.9, 0.999))
+        mine = FusedAdamW(my_p, flat, lr=lr, weight_decay=wd, betas=(0.9, 0.999))
+        mine.flat_grad = torch.zeros_like(flat)
+        off = 0
+        views = []
+        for p in my_p:
+            views.append(mine.flat_grad[off:off + p.numel()].view_as(p))
+            off += p.numel()
+        for step in range(5):
+            for rp, gv in zip(ref_p, views):
+                g = torch.randn(rp.shape, device=dev()) * (10.0 ** (-step))
+                rp.grad = g.clone()
+                gv.copy_(g)
+            ref.step()
+            mine.step()
+            if step == 2:   # state_dict round trip in torch's layout
+                sd = mine.state_dict()
+                assert set(sd["state"][0]) == {"step", "exp_avg", "exp_avg_sq"}
+                mine.load_state_dict(sd)
+        torch.cuda.synchronize()
+        for rp, mp in zip(ref_p, my_p):
+            assert relmax(mp.detach().cpu(), rp.detach().cpu()) < 2e-6, (lr, wd)
+        rs = ref.state_dict()["state"]
+        ms = mine.state_dict()["state"]
+        for i in range(len(shapes)):
+            assert relmax(ms[i]["exp_avg_sq"].cpu(), rs[i]["exp_avg_sq"].cpu()) < 1e-5
+            assert float(ms[i]["step"]) == float(rs[i]["step"]) == 5.0
