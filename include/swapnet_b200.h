@@ -222,8 +222,8 @@ int sn_upsample_planes(const void* src_hi, const void* src_lo, int src_pitch, in
 
 /* fused AdamW step over flat fp32 buffers (torch.optim.AdamW semantics as optimizers/__init__.py:48-59
  * builds it: decoupled weight decay, bias correction, eps outside the sqrt); step is 1-based. */
-int sn_adamw_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
-                  float eps, float weight_decay, int step, void* stream);
+int sn_adamw_step(float* p, const float* g, float* m, float* v, long long n, double lr, double beta1, double beta2,
+                  double eps, double weight_decay, int step, void* stream);
 
 /* deterministic dropout keep-mask shared by forward, backward and the test oracle:
  * keep(seed, idx) with idx the linear NHWC element index; returns 0/1 bytes. */

@@ -117,7 +117,7 @@ SIGNATURES = {
     "sn_sum_grads": (_I, [C.POINTER(SnGradSrc), _I, _I, _I, _I, _I, _VP, _I, _VP]),
     "sn_tanh_bwd": (_I, [C.POINTER(SnGradSrc), _I, _VP, _I, _I, _I, _I, _I, _VP, _VP, _I, _I, _I, _VP]),
     "sn_upsample_planes": (_I, [_VP, _VP, _I, _I, _I, _I, _I, _I, _I, _VP, _VP, _I, _I, _VP]),
-    "sn_adamw_step": (_I, [_VP, _VP, _VP, _VP, _LL, _F, _F, _F, _F, _F, _I, _VP]),
+    "sn_adamw_step": (_I, [_VP, _VP, _VP, _VP, _LL, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double, _I, _VP]),
     "sn_dropout_mask": (_I, [_ULL, _F, _LL, _VP, _VP]),
     "sn_ce_loss_fwd_bwd": (_I, [_VP, _I, _VP, _I, _I, _I, _I, _F, _VP, _VP, _I, _VP]),
     "sn_bce_logits_fwd_bwd": (_I, [_VP, _LL, _I, _F, _F, _F, _VP, _VP, _VP]),

@@ -1461,15 +1461,16 @@ int sn_upsample_planes(const void* src_hi, const void* src_lo, int src_pitch, in
   return SN_OK;
 }
 
-int sn_adamw_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
-                  float eps, float weight_decay, int step, void* stream) {
+int sn_adamw_step(float* p, const float* g, float* m, float* v, long long n, double lr, double beta1, double beta2,
+                  double eps, double weight_decay, int step, void* stream) {
   SN_REQUIRE(p && g && m && v && n > 0 && step >= 1, "bad adamw arguments");
   SN_REQUIRE((((uintptr_t)p | (uintptr_t)g | (uintptr_t)m | (uintptr_t)v) & 15) == 0, "adamw buffers must be 16-B aligned");
-  const double bc1 = 1.0 - pow((double)beta1, (double)step);
-  const double bc2 = 1.0 - pow((double)beta2, (double)step);
+  // scalars are formed in double and rounded once, as torch does with its Python-float hyper-parameters
+  const double bc1 = 1.0 - pow(beta1, (double)step);
+  const double bc2 = 1.0 - pow(beta2, (double)step);
   adamw_kernel<<<grid_for(n / 4 + 1), kEwThreads, 0, (cudaStream_t)stream>>>(
-      p, g, m, v, n, 1.f - lr * weight_decay, 1.f - beta1, beta2, 1.f - beta2, (float)((double)lr / bc1),
-      (float)(1.0 / sqrt(bc2)), eps);
+      p, g, m, v, n, (float)(1.0 - lr * weight_decay), (float)(1.0 - beta1), (float)beta2, (float)(1.0 - beta2),
+      (float)(lr / bc1), (float)(1.0 / sqrt(bc2)), (float)eps);
   LAUNCH_CHECK();
   return SN_OK;
 }
