@@ -87,6 +87,10 @@ typedef struct sn_tap_gemm_desc {
   const float* bias;                     /* optional [n_valid] */
   int act;                               /* SN_ACT_NONE | SN_ACT_TANH */
   int nsplit;                            /* 3 = fp32-faithful split product, 1 = bf16 fast mode */
+  int nphase;                            /* 0/1: one contraction.  4: the taps are 4 equal groups, one per
+                                            output parity phase (py, px) = (z >> 1, z & 1) of a stride-2 transposed
+                                            structure; phase z writes pixel (h*mul_h + off_h + py, w*mul_w + off_w + px)
+                                            — ONE launch (grid.z = 4) instead of four under-filled ones */
 } sn_tap_gemm_desc;
 
 /* G[i*s_row + j*s_col + tap_off[t]] += sum_{(n,h,w)} X[n, h+dh_t, w+dw_t, xc_t + i] * Y[n, h+dh'_t, w+dw'_t, yc_t + j]

@@ -36,7 +36,7 @@ class SnTapGemmDesc(C.Structure):
         ("out_sn", C.c_longlong), ("out_sh", C.c_longlong), ("out_sw", C.c_longlong),
         ("out_mul_h", C.c_int), ("out_off_h", C.c_int), ("out_mul_w", C.c_int), ("out_off_w", C.c_int),
         ("n_valid", C.c_int), ("block_n", C.c_int),
-        ("bias", C.c_void_p), ("act", C.c_int), ("nsplit", C.c_int),
+        ("bias", C.c_void_p), ("act", C.c_int), ("nsplit", C.c_int), ("nphase", C.c_int),
     ]
 
 

@@ -77,7 +77,10 @@ tap_gemm_kernel(const __grid_constant__ TapGemmParams p) {
   const int ncol0 = blockIdx.y * p.block_n;
   constexpr int cw = CW;                    // channels per A row: 64, 32 or 16
   constexpr int tps = 64 / cw;              // taps sharing one 64-deep stage (1, 2 or 4)
-  const int k_iters = cw == 64 ? p.ntaps * p.chunks : p.ntaps / tps;
+  // grid.z = output parity phase (merged 4-phase launches): phase z owns taps [z*tpp, (z+1)*tpp)
+  const int tpp = p.ntaps / p.nphase;
+  const int tap0 = blockIdx.z * tpp;
+  const int k_iters = cw == 64 ? tpp * p.chunks : tpp / tps;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < C::kStages; ++s) {
@@ -112,7 +115,7 @@ tap_gemm_kernel(const __grid_constant__ TapGemmParams p) {
         if (cw == 64) {
           const int t = it / p.chunks;
           const int ch = it - t * p.chunks;
-          const TapDesc tap = p.taps[t];
+          const TapDesc tap = p.taps[tap0 + t];
 #pragma unroll
           for (int pl = 0; pl < C::kPlanes; ++pl) {
             tma_load_5d(&p.tmA[pl], &full_bar[s], st + pl * kTileBytes, tap.c_off + ch * 64,
@@ -126,13 +129,13 @@ tap_gemm_kernel(const __grid_constant__ TapGemmParams p) {
           constexpr int sub = 128 * cw * 2;
 #pragma unroll
           for (int j = 0; j < tps; ++j) {
-            const TapDesc tap = p.taps[it * tps + j];
+            const TapDesc tap = p.taps[tap0 + it * tps + j];
 #pragma unroll
             for (int pl = 0; pl < C::kPlanes; ++pl)
               tma_load_5d(&p.tmA[pl], &full_bar[s], st + pl * kTileBytes + j * sub, tap.c_off,
                           w0 + tap.dw, tap.hp, h0 + tap.dh, n0);
           }
-          const int kb = p.taps[it * tps].kb_off;
+          const int kb = p.taps[tap0 + it * tps].kb_off;
 #pragma unroll
           for (int pl = 0; pl < C::kPlanes; ++pl)
             tma_load_2d(&p.tmB[pl], &full_bar[s], st + (C::kPlanes + pl) * kTileBytes, kb, ncol0);
@@ -183,8 +186,9 @@ tap_gemm_kernel(const __grid_constant__ TapGemmParams p) {
     const int n_i = row / (p.tw * p.th);
     const int gw = w0 + w_i, gh = h0 + h_i, gn = n0 + n_i;
     const bool valid = (row < p.a_rows) && (gw < p.m_w) && (gh < p.m_h) && (gn < p.m_n);
-    float* optr = p.out + (long long)gn * p.out_sn + (long long)(gh * p.omh + p.ooh) * p.out_sh +
-                  (long long)(gw * p.omw + p.oow) * p.out_sw + ncol0;
+    const int ph_h = p.nphase == 4 ? (int)(blockIdx.z >> 1) : 0, ph_w = p.nphase == 4 ? (int)(blockIdx.z & 1) : 0;
+    float* optr = p.out + (long long)gn * p.out_sn + (long long)(gh * p.omh + p.ooh + ph_h) * p.out_sh +
+                  (long long)(gw * p.omw + p.oow + ph_w) * p.out_sw + ncol0;
     const float oscale = p.b_scale ? p.b_scale[1] : 1.f;  // undo the power-of-two weight scale (exact)
     mbar_wait(&accum_bar, 0);
     tc_fence_after();
@@ -564,6 +568,13 @@ int sn_tap_gemm_plan_init(TapGemmPlan* plan, const sn_tap_gemm_desc* d) {
   p.out = d->out;
   p.out_sn = d->out_sn; p.out_sh = d->out_sh; p.out_sw = d->out_sw;
   p.omh = d->out_mul_h; p.ooh = d->out_off_h; p.omw = d->out_mul_w; p.oow = d->out_off_w;
+  p.nphase = d->nphase == 4 ? 4 : 1;
+  SN_REQUIRE(d->nphase == 0 || d->nphase == 1 || d->nphase == 4, "nphase must be 1 or 4");
+  if (p.nphase == 4) {
+    SN_REQUIRE(d->ntaps % 4 == 0, "4-phase launch: ntaps must split into 4 equal groups");
+    const int tpp = d->ntaps / 4;
+    SN_REQUIRE(a_chunk == 64 || tpp % (64 / a_chunk) == 0, "4-phase launch: taps per phase must fill whole stages");
+  }
   p.bias = d->bias;
   p.b_scale = d->b_scale;
   p.a_fmt = d->a_fmt;
@@ -582,7 +593,7 @@ int sn_tap_gemm_plan_init(TapGemmPlan* plan, const sn_tap_gemm_desc* d) {
     if (rc) return rc;
   }
   plan->nsplit = d->nsplit;
-  plan->grid = dim3(p.tiles_w * p.tiles_h * p.tiles_n, (d->n_valid + d->block_n - 1) / d->block_n, 1);
+  plan->grid = dim3(p.tiles_w * p.tiles_h * p.tiles_n, (d->n_valid + d->block_n - 1) / d->block_n, p.nphase);
   return SN_OK;
 }
 

@@ -29,6 +29,7 @@ struct alignas(64) TapGemmParams {
   int vec4;
   int a_fmt, b_fmt;
   int a_chunk;  // 64 / 32 / 16 channels per A row
+  int nphase;   // 1 or 4 (grid.z = output parity phase; taps split in nphase equal groups)
 };
 
 struct alignas(64) WgradParams {

@@ -70,7 +70,15 @@ class ConvLayer:
         assert y.shape[:3] == (self.n, self.out_h, self.out_w), (self.name, y.shape, self.out_h, self.out_w)
         self.y = y
         self.fwd_plans = []
-        for spec in L.forward_specs(self.kind, self.in_h, self.in_w):
+        specs = L.forward_specs(self.kind, self.in_h, self.in_w)
+        merged = ops.merge_phase_specs(specs)
+        if merged is not None and (self.k_pad >= 64 or (len(merged.taps) // 4) % (64 // self.k_pad) == 0):
+            d = ops.tap_gemm_desc(self.x, merged, self.wp, self.k_pad, y, self.cout, bias=self.bias, act=self.act,
+                                  nsplit=self.nsplit, block_n=self.block_n, out_c_off=y_c_off, nphase=4)
+            self.fwd_plans.append(ops.tap_gemm_plan(d, keep=(self.x.hi, self.x.lo, self.wp.hi, self.wp.lo, y)))
+            self.fwd_plans[-1].tag = ("fwd", self.name)
+            specs = []
+        for spec in specs:
             kw = {}
             if self.kind == "head":
                 p = spec.w_phase
@@ -117,7 +125,15 @@ class ConvLayer:
             else:
                 self.wd = PackedWeights(self.cin, self._tpad(self.t, dy.c) * dy.c, dev, fmt=dy.fmt)
             bn = L.pick_block_n(self.cin)
-            for spec in L.dgrad_specs(self.kind, self.in_h, self.in_w):
+            dspecs = L.dgrad_specs(self.kind, self.in_h, self.in_w)
+            merged = ops.merge_phase_specs(dspecs)
+            if merged is not None and (dy.c >= 64 or (len(merged.taps) // 4) % (64 // dy.c) == 0):
+                d = ops.tap_gemm_desc(dy, merged, self.wd, dy.c, dx, self.cin, nsplit=self.nsplit, block_n=bn,
+                                      out_c_off=dx_c_off, nphase=4)
+                self.dgrad_plans.append(ops.tap_gemm_plan(d, keep=(dy.hi, dy.lo, self.wd.hi, self.wd.lo, dx)))
+                self.dgrad_plans[-1].tag = ("dgrad", self.name)
+                dspecs = []
+            for spec in dspecs:
                 d = ops.tap_gemm_desc(dy, spec, self.wd, dy.c, dx, self.cin, nsplit=self.nsplit, block_n=bn,
                                       out_c_off=dx_c_off)
                 self.dgrad_plans.append(ops.tap_gemm_plan(d, keep=(dy.hi, dy.lo, self.wd.hi, self.wd.lo, dx)))

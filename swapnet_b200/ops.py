@@ -131,7 +131,7 @@ def tap_gemm_desc(a: Planes, spec: L.GemmSpec, w: PackedWeights, k_per_tap: int,
                   n_valid: int, *, w_row_off: int = 0, w_rows: Optional[int] = None,
                   w_k: Optional[int] = None, w_elem_off: int = 0, bias: Optional[torch.Tensor] = None,
                   act: int = ACT_NONE, nsplit: int = 3, block_n: Optional[int] = None,
-                  out_c_off: int = 0) -> SnTapGemmDesc:
+                  out_c_off: int = 0, nphase: int = 1) -> SnTapGemmDesc:
     """out: fp32 NHWC tensor [n, OH, OW, pitch_out]; rows (h, w) land on pixel
     (h*mul_h + off_h, w*mul_w + off_w)."""
     assert (a.h, a.w) == tuple(spec.a_hw), f"operand is {a.h}x{a.w}, spec wants {spec.a_hw}"
@@ -139,7 +139,9 @@ def tap_gemm_desc(a: Planes, spec: L.GemmSpec, w: PackedWeights, k_per_tap: int,
     narrow = k_per_tap < 64
     assert (k_per_tap in (16, 32)) if narrow else (k_per_tap % 64 == 0)
     taps = list(spec.taps)
-    if narrow:  # 64/k taps share a pipeline stage: pad with dummy taps whose packed weights are zero
+    if narrow and nphase == 4:
+        assert (len(taps) // 4) % (64 // k_per_tap) == 0, "4-phase narrow launch: taps per phase must fill whole stages"
+    elif narrow:  # 64/k taps share a pipeline stage: pad with dummy taps whose packed weights are zero
         tps = 64 // k_per_tap
         kb_next = max(t.kb for t in taps) + 1
         while len(taps) % tps:
@@ -170,7 +172,24 @@ def tap_gemm_desc(a: Planes, spec: L.GemmSpec, w: PackedWeights, k_per_tap: int,
     d.bias = _ptr(bias)
     d.act = act
     d.nsplit = nsplit
+    d.nphase = nphase
     return d
+
+
+def merge_phase_specs(specs) -> Optional[L.GemmSpec]:
+    """Four GemmSpecs that differ only by their taps and by the output offset (py, px) — the parity phases
+    of a ConvTranspose2d forward / Conv2d input-gradient — become ONE spec whose taps are the 4 groups
+    concatenated (phase z = 2*py + px), launched with grid.z = 4."""
+    if len(specs) != 4:
+        return None
+    s0 = specs[0]
+    n = len(s0.taps)
+    for z, s in enumerate(specs):
+        if (s.parity, s.m_h, s.m_w, s.out_mul, s.a_hw, len(s.taps)) != (s0.parity, s0.m_h, s0.m_w, s0.out_mul, s0.a_hw, n):
+            return None
+        if s.out_off != (z >> 1, z & 1) or s.w_phase != 0:
+            return None
+    return L.GemmSpec(s0.parity, s0.m_h, s0.m_w, [t for s in specs for t in s.taps], s0.out_mul, (0, 0), 0, s0.a_hw)
 
 
 def tap_gemm_plan(desc: SnTapGemmDesc, keep: Sequence = ()) -> Plan:
