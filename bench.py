@@ -54,6 +54,25 @@ def synth_batch(B, S, seed):
                 body_paths=["synthetic"] * B)
 
 
+def synth_texture_batch(B, S, seed):
+    """normalised-RGB-like textures, one-hot cloth, rois = notebook fixture (256 px
+    space, incl. degenerate rows) scaled to S and rotated per sample."""
+    g = torch.Generator().manual_seed(seed)
+    tex = torch.rand(B, 3, S, S, generator=g) * 4.5 - 2.0
+    tgt = torch.rand(B, 3, S, S, generator=g) * 4.5 - 2.0
+    lab = torch.randint(0, 19, (B, S // 16, S // 16), generator=g).repeat_interleave(16, 1).repeat_interleave(16, 2)
+    cloth = torch.zeros(B, 19, S, S)
+    for c in range(1, 19):
+        cloth[:, c] = (lab == c).float()
+    base = torch.tensor([[159, 0, 193, 14], [144, 15, 206, 89], [255, 0, 255, 0], [196, 20, 215, 94],
+                         [144, 151, 180, 229], [179, 151, 216, 226], [156, 1, 188, 24], [141, 83, 215, 155],
+                         [128, 20, 160, 82], [206, 92, 226, 158], [145, 220, 168, 255], [174, 217, 203, 255]],
+                        dtype=torch.float32) * (S / 256.0)
+    rois = torch.stack([torch.roll(base, b, 0) for b in range(B)])
+    return dict(input_textures=tex, rois=rois, cloths=cloth, target_textures=tgt, cloth_paths=["synthetic"] * B,
+                texture_paths=["synthetic"] * B)
+
+
 def warp_opt(B, S, precision):
     return argparse.Namespace(
         model="warp", gpu_id=int(os.environ.get("LOCAL_RANK", 0)), is_train=True,
@@ -98,6 +117,15 @@ class ClockSampler(threading.Thread):
         reasons = [n for i, n in enumerate(names) if any(r[3 + i].lower().startswith("active") for r in self.rows)]
         return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.rows[0][1]), "reasons": reasons,
                 "samples": len(self.rows)}
+
+
+def ncu_traffic():
+    """dram__bytes_read + dram__bytes_write per launch of the dominant kernel, from the committed
+    `ncu --set full` capture (profiles/r01_ncu_traffic.json); null if absent."""
+    p = os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")
+    if os.path.exists(p):
+        return json.load(open(p))
+    return None
 
 
 def measured_peaks():
@@ -174,6 +202,8 @@ def main():
     ap.add_argument("--precision", default="fp32x3", choices=("fp32x3", "bf16"))
     ap.add_argument("--cpu-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--model", default="warp", choices=("warp", "texture"),
+                    help="warp = the BASELINE.json metric (default); texture = configs[2] (informational)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
@@ -210,15 +240,23 @@ def main():
     import contextlib
 
     with contextlib.redirect_stdout(sys.stderr):   # stdout carries exactly one JSON line
-        model = create_model(warp_opt(B, S, args.precision))
+        o = warp_opt(B, S, args.precision)
+        if args.model == "texture":
+            o.model, o.name, o.netG, o.lambda_l1, o.lambda_content, o.lambda_style = "texture", "texture", "swapnet", 10, 0, 0
+        model = create_model(o)
         model.setup(model.opt)
-    host = synth_batch(B, S, 1234 + rank)
-    for k in ("bodys", "input_cloths", "target_cloths"):
+    if args.model == "texture":
+        host = synth_texture_batch(B, S, 1234 + rank)
+        tkeys = ("input_textures", "rois", "cloths", "target_textures")
+    else:
+        host = synth_batch(B, S, 1234 + rank)
+        tkeys = ("bodys", "input_cloths", "target_cloths")
+    for k in tkeys:
         host[k] = host[k].pin_memory()
     dev_batch = dict(host)
-    for k in ("bodys", "input_cloths", "target_cloths"):
+    for k in tkeys:
         dev_batch[k] = host[k].cuda(non_blocking=True)
-    h2d = sum(host[k].numel() * 4 for k in ("bodys", "input_cloths", "target_cloths"))
+    h2d = sum(host[k].numel() * 4 for k in tkeys)
 
     def barrier():
         if world > 1:
@@ -287,7 +325,7 @@ def main():
                 "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "pipe_frac": 3 * ach / peak, "peak_source": how,
                 "launches_per_step": gemm_n, "avg_launch_ms": gemm_ms / max(gemm_n, 1),
                 "algorithmic_gflop_per_launch": gemm_fl / max(gemm_n, 1) / 1e9,
-                "share_of_step": gemm_ms / step_ms, "traffic": None,
+                "share_of_step": gemm_ms / step_ms, "traffic": ncu_traffic(),
                 "wgrad_kernel": {"achieved": (tot["wgrad"][0] / (tot["wgrad"][1] * 1e-3) / 1e12) if tot["wgrad"][1] else 0.0,
                                  "share_of_step": tot["wgrad"][1] / step_ms, "launches_per_step": tot["wgrad"][2]}}
 
@@ -295,14 +333,19 @@ def main():
         torch.distributed.destroy_process_group()
         return
     cpu = None
-    if not args.no_cpu_baseline and args.gpus == 1:
+    if args.model == "texture":
+        workload = (f"texture_model {S}x{S} synthetic, 12-ROI, batch {B}/GPU, full GAN step "
+                    "(L1 + GAN; perceptual terms off)")
+    if not args.no_cpu_baseline and args.gpus == 1 and args.model == "warp":
         v, med = cpu_reference_run(S, 1, args.cpu_steps, 1)
         cpu = {"value": v, "unit": "images/s", "cores": cores, "kind": "port",
                "sample": f"{args.cpu_steps} timed full training steps at {S}x{S}, batch 1, torch CPU ({cores} threads)"}
     step_ms = ms / args.steps
     total_imgs = B * world
     out = {
-        "metric": "images/sec (G+D fwd+bwd) warp-stage 512x512", "value": total_imgs / (step_ms * 1e-3),
+        "metric": "images/sec (G+D fwd+bwd) warp-stage 512x512" if args.model == "warp"
+        else "images/sec (G+D fwd+bwd) texture-stage 512x512",
+        "value": total_imgs / (step_ms * 1e-3),
         "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "fp16/bf16-split x3 tensor-core products, fp32 accumulate (fp32-faithful)" if args.precision == "fp32x3"
@@ -310,7 +353,8 @@ def main():
         "data": "synthetic",
         "config": {"workload": workload, "global_batch": total_imgs, "parallelism": f"dp{world}",
                    "l2": "inputs+activations per step (>2 GB) exceed the 126 MB L2; no explicit flush",
-                   "algorithmic_tflop_per_step": FULL_STEP_GFLOP_PER_IMG_512 * (S / 512) ** 2 * total_imgs / 1e3},
+                   "algorithmic_tflop_per_step": (FULL_STEP_GFLOP_PER_IMG_512 if args.model == "warp" else 415.0)
+                   * (S / 512) ** 2 * total_imgs / 1e3},
         "e2e": {"value": total_imgs / (ms_e2e / args.steps * 1e-3), "unit": "images/s",
                 "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 6 * 8},
         "gpu_launches": launches, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,

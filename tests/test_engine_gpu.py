@@ -431,3 +431,22 @@ def test_warp_model_ce_mode_and_checkpoint_roundtrip():
     assert torch.equal(w, model.net_generator.dual_up3.model[0].weight)
     model.set_input(batch)
     model.optimize_parameters()     # engines keep working on the re-loaded storage
+
+
+def test_texture_forward_full_size_512():
+    """BASELINE config 3 size (512x512, num_downs = 9, ROI pooling at 128x128 -> x8 nearest up-sampling)."""
+    from swapnet_b200 import engine as E
+
+    B, S = 1, 512
+    T = make_texture_net(S)
+    tex, rois, cloth, _ = synth_texture_batch(B, S)
+    sd = {k: v.clone().double() for k, v in T.state_dict().items()}
+    eng = E.TextureEngine(T.to(dev()), B, S, dev(), train=False)
+    eng.pack()
+    out = eng.forward(tex.to(dev()), rois.to(dev()), cloth.to(dev()), training=False)
+    torch.cuda.synchronize()
+    with torch.no_grad():
+        ref = ON.texture_forward(sd, tex.double(), rois.double(), cloth.double())
+    err = relmax(out.permute(0, 3, 1, 2).cpu(), ref)
+    record("texture_forward_512", f"{err:.3e}")
+    assert err < 1e-3
