@@ -202,6 +202,8 @@ def main():
     ap.add_argument("--precision", default="fp32x3", choices=("fp32x3", "bf16"))
     ap.add_argument("--cpu-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--perceptual", action="store_true",
+                    help="--model texture: add the VGG16 content + Gram style terms (lambda 20 / 1e-8)")
     ap.add_argument("--model", default="warp", choices=("warp", "texture"),
                     help="warp = the BASELINE.json metric (default); texture = configs[2] (informational)")
     args = ap.parse_args()
@@ -243,6 +245,8 @@ def main():
         o = warp_opt(B, S, args.precision)
         if args.model == "texture":
             o.model, o.name, o.netG, o.lambda_l1, o.lambda_content, o.lambda_style = "texture", "texture", "swapnet", 10, 0, 0
+            if args.perceptual:   # the reference's default texture losses; seeded-random VGG16 (no weight file offline)
+                o.lambda_content, o.lambda_style, o.b200_vgg = 20.0, 1e-8, "random"
         model = create_model(o)
         model.setup(model.opt)
     if args.model == "texture":
@@ -335,7 +339,8 @@ def main():
     cpu = None
     if args.model == "texture":
         workload = (f"texture_model {S}x{S} synthetic, 12-ROI, batch {B}/GPU, full GAN step "
-                    "(L1 + GAN; perceptual terms off)")
+                    + ("(L1 + GAN + VGG16 content + Gram style, seeded-random VGG weights)" if args.perceptual
+                       else "(L1 + GAN; perceptual terms off)"))
     if not args.no_cpu_baseline and args.gpus == 1 and args.model == "warp":
         v, med = cpu_reference_run(S, 1, args.cpu_steps, 1)
         cpu = {"value": v, "unit": "images/s", "cores": cores, "kind": "port",
@@ -353,7 +358,7 @@ def main():
         "data": "synthetic",
         "config": {"workload": workload, "global_batch": total_imgs, "parallelism": f"dp{world}",
                    "l2": "inputs+activations per step (>2 GB) exceed the 126 MB L2; no explicit flush",
-                   "algorithmic_tflop_per_step": (FULL_STEP_GFLOP_PER_IMG_512 if args.model == "warp" else 415.0)
+                   "algorithmic_tflop_per_step": (FULL_STEP_GFLOP_PER_IMG_512 if args.model == "warp" else (896.0 if args.perceptual else 415.0))
                    * (S / 512) ** 2 * total_imgs / 1e3},
         "e2e": {"value": total_imgs / (ms_e2e / args.steps * 1e-3), "unit": "images/s",
                 "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 6 * 8},

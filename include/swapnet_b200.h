@@ -250,6 +250,38 @@ int sn_l1_loss_fwd_bwd(const float* a, int pitch, const float* b_nchw, int n, in
                        float weight, double* loss_acc, float* grad, int grad_pitch, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * VGG16 perceptual loss (modules/losses/perceptual.py:6-79, used by texture_model.py:68-69,171-176).
+ * The 13 conv3x3(+bias) layers run as tap-GEMM plans; these are the element-wise pieces.
+ * ---------------------------------------------------------------------------------------- */
+/* planes[n,h,w,0:16] = split(mul * src + add), channels >= c zero  (get_features' x <- 2x - 1, :70). c <= 16. */
+int sn_affine_pack(const float* src, int src_layout, int src_pitch, int n, int c, int h, int w, float mul, float add,
+                   void* dst_hi, void* dst_lo, int dst_pitch, int dst_coff, int fmt, void* stream);
+/* nn.ReLU + nn.MaxPool2d(2) of vgg16.features (indices 3-4, 8-9, 15-16, 22-23): y fp32 [n,h,w,c] ->
+ * split planes [n,h/2,w/2,c]. */
+int sn_relu_pool_fwd(const float* y, int y_pitch, int n, int h, int w, int c, void* out_hi, void* out_lo,
+                     int out_pitch, int out_coff, int fmt, void* stream);
+/* its adjoint: dy = (g_direct + [first max of the 2x2 window] g_pool) * (y > 0) as split planes.
+ * g_pool [n,h/2,w/2,c] and g_direct [n,h,w,c] fp32, either may be NULL. */
+int sn_relu_pool_bwd(const float* y, int y_pitch, const float* g_pool, int gp_pitch, const float* g_direct,
+                     int gd_pitch, int n, int h, int w, int c, void* dy_hi, void* dy_lo, int dy_pitch, int dy_coff,
+                     int dy_fmt, void* stream);
+/* one tap of the content loss (perceptual.py:53-57,72-78): x = relu(y), f = x / (|x|_2 over c + 1e-8),
+ * *loss_acc += weight * sum (f_out - f_tgt)^2  (weight = lambda / numel), dx = gscale * d(loss)/d(x_out)
+ * (gradient w.r.t. the post-ReLU feature; gscale carries the 2 of x <- 2x - 1). c in {64..512}, c % 4 == 0. */
+int sn_feat_loss_fwd_bwd(const float* y_out, int po, const float* y_tgt, int pt, long long npix, int c, double weight,
+                         double gscale, double* loss_acc, float* dx, int pdx, void* stream);
+/* gram_matrix (perceptual.py:6-10) of the rows r = (b, ch): X_r[p] = src[b*s_n + ch*s_c + p*s_p];
+ * gram: double [n*c][n*c] (zeroed here).  n*c <= 96. */
+int sn_gram(const float* src, long long s_n, long long s_c, long long s_p, int n, int c, long long npix, double* gram,
+            void* stream);
+/* *loss_acc += weight * MSELoss(gram_out, gram_tgt);  m[r][j] = d(that)/d(gram_out) + transpose (fp32). */
+int sn_gram_mse(const double* gram_out, const double* gram_tgt, int rows, double weight, double* loss_acc, float* m,
+                void* stream);
+/* dx[b, p, ch] (+)= sum_j m[b*c + ch][j] X_j[p]  — the style-loss gradient w.r.t. the raw image; dx NHWC fp32. */
+int sn_gram_bwd(const float* m, const float* src, long long s_n, long long s_c, long long s_p, int n, int c,
+                long long npix, float* dx, int dx_pitch, int accumulate, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * ROIAlign + channel repack (swapnet_modules.py:209-240, torchvision roi_align aligned=False,
  * spatial_scale=1, sampling_ratio=1, output 128x128): tex NCHW [b,3,h,w], rois [b,nroi,4]
  * (x1,y1,x2,y2) -> fp32 NHWC [b,pool,pool,3*nroi] and/or split planes.

@@ -122,6 +122,13 @@ SIGNATURES = {
     "sn_ce_loss_fwd_bwd": (_I, [_VP, _I, _VP, _I, _I, _I, _I, _F, _VP, _VP, _I, _VP]),
     "sn_bce_logits_fwd_bwd": (_I, [_VP, _LL, _I, _F, _F, _F, _VP, _VP, _VP]),
     "sn_l1_loss_fwd_bwd": (_I, [_VP, _I, _VP, _I, _I, _I, _I, _F, _VP, _VP, _I, _VP]),
+    "sn_affine_pack": (_I, [_VP, _I, _I, _I, _I, _I, _I, _F, _F, _VP, _VP, _I, _I, _I, _VP]),
+    "sn_relu_pool_fwd": (_I, [_VP, _I, _I, _I, _I, _I, _VP, _VP, _I, _I, _I, _VP]),
+    "sn_relu_pool_bwd": (_I, [_VP, _I, _VP, _I, _VP, _I, _I, _I, _I, _I, _VP, _VP, _I, _I, _I, _VP]),
+    "sn_feat_loss_fwd_bwd": (_I, [_VP, _I, _VP, _I, _LL, _I, C.c_double, C.c_double, _VP, _VP, _I, _VP]),
+    "sn_gram": (_I, [_VP, _LL, _LL, _LL, _I, _I, _LL, _VP, _VP]),
+    "sn_gram_mse": (_I, [_VP, _VP, _I, C.c_double, _VP, _VP, _VP]),
+    "sn_gram_bwd": (_I, [_VP, _VP, _LL, _LL, _LL, _I, _I, _LL, _VP, _I, _I, _VP]),
     "sn_roi_align_pack_fwd": (_I, [_VP, _I, _I, _I, _I, _VP, _I, _I, _VP, _I, _VP, _VP, _I, _I, _I, _VP]),
     "sn_tap_gemm_simt": (_I, [C.POINTER(SnTapGemmDesc), _VP]),
 }

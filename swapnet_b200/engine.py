@@ -71,7 +71,7 @@ class Stage:
         Conv2d out_elems*Cin*k*k, ConvTranspose2d in_elems*Cout*k*k; zero taps of padding and
         up-sampling counted)."""
         ly = self.layer
-        k2 = 9 if self.kind == "conv3r" else 16
+        k2 = 9 if self.kind in ("conv3r", "conv3z") else 16
         if self.kind == "convT4s2":
             return self.n * ly.in_h * ly.in_w * ly.cin * ly.cout * k2
         return self.n * self.oh * self.ow * ly.cout * ly.cin * k2
@@ -432,3 +432,122 @@ class TextureEngine(Engine):
             # L_{j+1} feeds D_{j+1} (as leaky_relu) and the skip slot of cu[j] (as relu)
             self.down[j].backward([GradSrc(self.down[j + 1].dx), GradSrc(gcu[j], 0, act=ACT_RELU)])
         self.encode.backward([GradSrc(self.down[0].dx, 0, up=self.up_factor)])
+
+
+# =============================================================================================
+# VGG16 perceptual loss (modules/losses/perceptual.py:13-79; texture_model.py:68-69,171-176)
+# =============================================================================================
+class VGGStage(Stage):
+    """conv3x3(pad 1)+bias -> ReLU [-> MaxPool2d(2)] of vgg16.features; frozen weights (no wgrad)."""
+
+    def __init__(self, eng: "Engine", name: str, conv: nn.Module, x: Planes, out: Optional[Planes], pool: bool,
+                 need_dx: bool):
+        super().__init__(eng, name, "conv3z", conv, x, out=out, act=ACT_RELU, need_dx=need_dx)
+        self.pool = pool
+
+    def forward(self) -> None:
+        self.layer.forward()
+        if self.pool:
+            ops.relu_pool_fwd(self.y, self.cout, self.out)
+        elif self.out is not None:
+            ops.norm_act_fwd(self.y, self.cout, None, ACT_RELU, 0.0, 0.0, 0, out=self.out)
+
+    def backward_vgg(self, g_next: Optional[torch.Tensor], g_feat: Optional[torch.Tensor]) -> None:
+        """g_next: gradient w.r.t. this stage's output planes (the next conv's dx; pooled size if `pool`);
+        g_feat: gradient w.r.t. the un-pooled ReLU output from the feature loss (tap stages)."""
+        if self.pool:
+            ops.relu_pool_bwd(self.y, self.cout, g_next, g_feat, self.dy)
+        else:
+            srcs = [GradSrc(g) for g in (g_next, g_feat) if g is not None]
+            ops.norm_act_bwd(srcs, self.y, self.cout, None, ACT_RELU, self.dy, None, 0.0, 0.0, 0)
+        self.layer.backward(dgrad=self.need_dx, wgrad=False)
+
+
+class VGGEngine(Engine):
+    """vgg16.features[0:30] on a [B,S,S,3] image (already mapped to [-1,1]); keeps every conv output `y`."""
+
+    def __init__(self, net: M.VGG16Features, batch: int, size: int, device, nsplit: int = 3, backward: bool = False):
+        super().__init__(net, device, nsplit, train=False)     # frozen weights: no bf16 twins, no wgrad
+        assert size % 16 == 0, "VGG16 perceptual loss: H = W = 16k"
+        B, S = batch, size
+        self.batch, self.size = B, S
+        self.x_in = self.planes(B, S, S, 16)
+        x, h = self.x_in, S
+        self.chain: List[VGGStage] = []
+        self.taps: List[VGGStage] = []
+        for idx in M.VGG16_CONVS:
+            conv = net[idx]
+            pool = idx in M.VGG16_POOLED_CONVS
+            last = idx == M.VGG16_CONVS[-1]
+            oh = h // 2 if pool else h
+            out = None if last else self.planes(B, oh, oh, L.padc(conv.out_channels))
+            st = VGGStage(self, str(idx), conv, x, out, pool, need_dx=backward)
+            self.chain.append(st)
+            if idx in M.VGG16_TAP_CONVS:
+                self.taps.append(st)
+            x, h = out, oh
+        if backward:
+            self.bind_backward(wgrad=False)
+        self.pack()                                            # frozen: packed once
+
+    def forward(self) -> None:
+        for s in self.chain:
+            s.forward()
+
+
+class PerceptualEngine:
+    """PerceptualLoss(output=fakes, target) value and d/d(fakes) on the device.
+
+    content = sum over 5 taps of MSE(f_out, f_tgt), f = L2-normalised ReLU features of `2x - 1`;
+    style   = 5 * MSE(gram(out), gram(tgt)) of the raw images viewed as [B*3, H*W] (perceptual.py:58-63).
+    """
+
+    def __init__(self, net: Optional[M.VGG16Features], batch: int, size: int, device, nsplit: int = 3,
+                 content: bool = True):
+        dev = torch.device(device)
+        self.batch, self.size = batch, size
+        self.out = self.tgt = None
+        self.gfeat: List[torch.Tensor] = []
+        if content:
+            self.out = VGGEngine(net, batch, size, device, nsplit, backward=True)
+            self.tgt = VGGEngine(net, batch, size, device, nsplit, backward=False)
+            self.gfeat = [torch.zeros_like(s.y) for s in self.out.taps]
+        r = 3 * batch
+        self.gram_o = torch.zeros(r, r, dtype=torch.float64, device=dev)
+        self.gram_t = torch.zeros(r, r, dtype=torch.float64, device=dev)
+        self.gram_m = torch.zeros(r, r, dtype=torch.float32, device=dev)
+
+    def nominal_macs(self) -> int:
+        if self.out is None:
+            return 0
+        f = sum(s.nominal_macs() for s in self.out.chain)
+        return 3 * f            # VGG(fakes) + VGG(targets) + input-gradient of VGG(fakes)
+
+    def content(self, fakes: torch.Tensor, targets: torch.Tensor, lam: float, acc: torch.Tensor) -> torch.Tensor:
+        """fakes NHWC [B,S,S,3], targets NCHW [B,3,S,S] (fp32, device).  acc (float64[1]) += lam * content loss.
+        Returns d(lam * content)/d(fakes) as an fp32 NHWC [B,S,S,3] view."""
+        o, t = self.out, self.tgt
+        ops.affine_pack(targets, False, 2.0, -1.0, t.x_in)     # x = 2.0 * x - 1.0 (perceptual.py:70)
+        t.forward()
+        ops.affine_pack(fakes, True, 2.0, -1.0, o.x_in)
+        o.forward()
+        for so, st, g in zip(o.taps, t.taps, self.gfeat):
+            numel = so.n * so.oh * so.ow * so.cout             # MSELoss: mean over all elements
+            ops.feat_loss_fwd_bwd(so.y, st.y, so.cout, lam / numel, 2.0, acc, g)   # gscale 2 = d(2x-1)/dx
+        g = None
+        ti = len(o.taps) - 1
+        for s in reversed(o.chain):
+            gf = None
+            if ti >= 0 and s is o.taps[ti]:
+                gf, ti = self.gfeat[ti], ti - 1
+            s.backward_vgg(g, gf)
+            g = s.dx
+        return g
+
+    def style(self, fakes: torch.Tensor, targets: torch.Tensor, lam: float, acc: torch.Tensor,
+              grad_accum: torch.Tensor) -> None:
+        """acc += lam * 5 * MSE(gram(fakes), gram(targets)); grad_accum [B,S,S,3] += its gradient."""
+        ops.gram(fakes, True, self.gram_o)
+        ops.gram(targets, False, self.gram_t)
+        ops.gram_mse(self.gram_o, self.gram_t, 5.0 * lam, acc, self.gram_m)
+        ops.gram_bwd(self.gram_m, fakes, True, grad_accum, accumulate=True)

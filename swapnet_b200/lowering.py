@@ -10,6 +10,7 @@ Layer kinds (reference call sites):
   convT4s2  ConvTranspose2d(k4, s2, p1)     layers.py:31, pix2pix_modules.py:226-247
   conv3r    ReflectionPad2d(1)+Conv2d(k3)   layers.py:130-138
   conv4s1   Conv2d(k4, s1, p1)              discriminators.py:124-131
+  conv3z    Conv2d(k3, s1, p1) zero padding  torchvision vgg16.features (modules/losses/perceptual.py:26-42)
   head      Upsample(2)+ZeroPad2d((1,0,1,0))+Conv2d(k4,p1)   swapnet_modules.py:85-90
 
 Each kind provides forward, dgrad (gradient w.r.t. the conv input) and wgrad specs.  A spec is
@@ -21,7 +22,7 @@ from __future__ import annotations
 from dataclasses import dataclass, field
 from typing import List, Tuple
 
-KINDS = ("conv4s2", "convT4s2", "conv3r", "conv4s1", "head")
+KINDS = ("conv4s2", "convT4s2", "conv3r", "conv4s1", "head", "conv3z")
 
 # (c_off_is_pw, kb_off, dw, dh, hp): c_off is given as (pw, cbase) and resolved against the
 # operand pitch when the descriptor is bound.
@@ -101,7 +102,7 @@ def out_hw(kind: str, h: int, w: int) -> Tuple[int, int]:
         return h // 2, w // 2
     if kind == "convT4s2":
         return 2 * h, 2 * w
-    if kind == "conv3r":
+    if kind in ("conv3r", "conv3z"):
         return h, w
     if kind == "conv4s1":
         return h - 1, w - 1
@@ -111,7 +112,7 @@ def out_hw(kind: str, h: int, w: int) -> Tuple[int, int]:
 
 
 def ntaps(kind: str) -> int:
-    return {"conv4s2": 16, "convT4s2": 16, "conv3r": 9, "conv4s1": 16, "head": 25}[kind]
+    return {"conv4s2": 16, "convT4s2": 16, "conv3r": 9, "conv4s1": 16, "head": 25, "conv3z": 9}[kind]
 
 
 HEAD_PHASE_OFF = (0, 4, 10, 16)
@@ -144,6 +145,9 @@ def forward_specs(kind: str, h: int, w: int) -> List[GemmSpec]:
     if kind == "conv4s1":
         taps = [Tap(0, kh * 4 + kw, kw - 1, kh - 1) for kh in range(4) for kw in range(4)]
         return [GemmSpec(False, h - 1, w - 1, taps, a_hw=(h, w))]
+    if kind == "conv3z":  # zero padding = TMA out-of-bounds fill
+        taps = [Tap(0, kh * 3 + kw, kw - 1, kh - 1) for kh in range(3) for kw in range(3)]
+        return [GemmSpec(False, h, w, taps, a_hw=(h, w))]
     if kind == "head":
         specs = []
         for py in range(2):
@@ -180,6 +184,9 @@ def dgrad_specs(kind: str, h: int, w: int) -> List[GemmSpec]:
         return [GemmSpec(False, h + 2, w + 2, taps, a_hw=(oh, ow))]
     if kind == "conv4s1":
         taps = [Tap(0, kh * 4 + kw, 1 - kw, 1 - kh) for kh in range(4) for kw in range(4)]
+        return [GemmSpec(False, h, w, taps, a_hw=(oh, ow))]
+    if kind == "conv3z":
+        taps = [Tap(0, kh * 3 + kw, 1 - kw, 1 - kh) for kh in range(3) for kw in range(3)]
         return [GemmSpec(False, h, w, taps, a_hw=(oh, ow))]
     if kind == "head":  # dy is 2h x 2w, read through the parity view
         taps = []
@@ -223,6 +230,9 @@ def wgrad_specs(kind: str, h: int, w: int) -> List[WgradSpec]:
     if kind == "conv4s1":
         yt = [Tap(0, 0, kw - 1, kh - 1) for kh in range(4) for kw in range(4)]
         return [WgradSpec(oh, ow, False, False, [zero] * 16, yt, "dy", list(range(16)))]
+    if kind == "conv3z":
+        yt = [Tap(0, 0, kw - 1, kh - 1) for kh in range(3) for kw in range(3)]
+        return [WgradSpec(oh, ow, False, False, [zero] * 9, yt, "dy", list(range(9)))]
     if kind == "head":  # pixels = source grid; dy via parity view (x), in with eff-tap offsets (y)
         xt, yt, ids = [], [], []
         for py in range(2):

@@ -4,9 +4,10 @@ Options, attributes and step semantics of /root/reference/models/texture_model.p
 `--netG swapnet` generator (TextureModule): conditional PatchGAN on cat(cloths, texture) (cloth
 FIRST, :138,142,164), loss_G = lambda_gan * GAN + lambda_l1 * L1 (+ perceptual terms).
 
-The VGG16 perceptual terms (texture_model.py:171-178; weights `vgg16(pretrained=True)` are not
-obtainable offline) are not on the CUDA path yet: lambda_content / lambda_style must be 0
-— anything else raises instead of silently falling back.
+The VGG16 perceptual terms (texture_model.py:68-69,171-178 -> modules/losses/perceptual.py) run on
+engine.PerceptualEngine.  `vgg16(pretrained=True)` needs the torchvision weight file: `--b200_vgg`
+selects `pretrained` (default, like the reference; raises when the file cannot be obtained), a path to a
+saved state_dict, or `random[:seed]` (seeded torchvision init — what the offline tests and bench use).
 """
 from __future__ import annotations
 
@@ -32,6 +33,8 @@ class TextureModel(BaseGAN):
             parser.add_argument("--lambda_l1", type=float, default=10, help="weight for L1 loss in final term")
             parser.add_argument("--lambda_content", type=float, default=20, help="weight for content loss in final term")
             parser.add_argument("--lambda_style", type=float, default=1e-8, help="weight for style loss in final term")
+            parser.add_argument("--b200_vgg", default="pretrained",
+                                help="VGG16 weights of the perceptual loss: pretrained | random[:seed] | <state_dict path>")
             parser.set_defaults(display_ncols=5)
         return parser
 
@@ -42,15 +45,20 @@ class TextureModel(BaseGAN):
         self.visual_names = ["textures_unnormalized", "cloths_decoded", "fakes", "fakes_scaled"]
         if self.is_train:
             self.visual_names.append("targets_unnormalized")
-            if float(getattr(opt, "lambda_content", 0)) != 0 or float(getattr(opt, "lambda_style", 0)) != 0:
-                raise NotImplementedError(
-                    "VGG16 perceptual loss (lambda_content / lambda_style != 0) is not on the B200 path yet; "
-                    "run with --lambda_content 0 --lambda_style 0")
+            self.lam_content = float(getattr(opt, "lambda_content", 0))
+            self.lam_style = float(getattr(opt, "lambda_style", 0))
+            self.net_vgg = None
+            self._eng_P = None
+            if self.lam_content != 0:
+                # the reference builds PerceptualLoss unconditionally (texture_model.py:68); the frozen VGG is
+                # only needed when the content term is on (the style term uses the raw images)
+                self.net_vgg = M.load_vgg16_features(getattr(opt, "b200_vgg", "pretrained")).to(self.device)
             lam = float(opt.lambda_gan)
             self.loss_G_l1 = LazyLoss(lambda: self._acc[3].item())
-            self.loss_G_content = 0.0
-            self.loss_G_style = 0.0
-            self.loss_G = LazyLoss(lambda: lam * self._acc[2].item() + self._acc[3].item())
+            self.loss_G_content = LazyLoss(lambda: self._acc[4].item()) if self.lam_content != 0 else 0.0
+            self.loss_G_style = LazyLoss(lambda: self._acc[5].item()) if self.lam_style != 0 else 0.0
+            self.loss_G = LazyLoss(lambda: lam * self._acc[2].item() + self._acc[3].item() + self._acc[4].item()
+                                   + self._acc[5].item())
             for loss in ("l1", "content", "style"):
                 if getattr(opt, "lambda_" + loss, 0) != 0:
                     self.loss_names.append("G_" + loss)
@@ -75,6 +83,14 @@ class TextureModel(BaseGAN):
 
     def build_generator_engine(self, batch, size):
         return E.TextureEngine(self.net_generator, batch, size, self.device, self.nsplit, train=self.is_train)
+
+    def ensure_engines(self, batch, size):
+        key = (batch, size)
+        fresh = self._eng_key != key
+        super().ensure_engines(batch, size)
+        if fresh and self.is_train and (self.lam_content != 0 or self.lam_style != 0):
+            self._eng_P = E.PerceptualEngine(self.net_vgg, batch, size, self.device, self.nsplit,
+                                             content=self.lam_content != 0)
 
     def set_input(self, input):
         f32 = dict(device=self.device, dtype=torch.float32, non_blocking=True)
@@ -107,6 +123,12 @@ class TextureModel(BaseGAN):
         if not hasattr(self, "_dl1") or self._dl1.shape[0] != B or self._dl1.shape[1] != S:
             self._dl1 = torch.zeros(B, S, S, ct, device=self.device)
         ops.l1_loss_fwd_bwd(g.fakes, ct, self.targets, float(self.opt.lambda_l1), self._acc[3:4], self._dl1)
+        srcs = [GradSrc(self._dl1)]
+        if self.lam_style != 0:      # 5 x MSE of the raw-image Gram matrices (perceptual.py:58-63): adds into _dl1
+            self._eng_P.style(g.fakes, self.targets, self.lam_style, self._acc[5:6], self._dl1)
+        if self.lam_content != 0:
+            srcs.append(GradSrc(self._eng_P.content(g.fakes, self.targets, self.lam_content, self._acc[4:5])))
         dx = self.gan_backward_through_D()
-        g.backward([GradSrc(self._dl1), GradSrc(dx, self.opt.cloth_channels)])
+        srcs.append(GradSrc(dx, self.opt.cloth_channels))
+        g.backward(srcs)
         self.allreduce_grads(g)

@@ -206,3 +206,64 @@ def init_weights(net: nn.Module, init_type: str = "normal", init_gain: float = 0
 
     print("initialize network with %s" % init_type)
     net.apply(fn)
+
+
+# ---------------------------------------------------------------------------------------------
+# frozen VGG16 feature extractor of the perceptual loss (modules/losses/perceptual.py:26-46)
+# ---------------------------------------------------------------------------------------------
+VGG16_CFG = (64, 64, "M", 128, 128, "M", 256, 256, 256, "M", 512, 512, 512, "M", 512, 512, 512)
+VGG16_CONVS = (0, 2, 5, 7, 10, 12, 14, 17, 19, 21, 24, 26, 28)     # indices inside vgg16().features
+VGG16_TAP_CONVS = (2, 7, 14, 21, 28)     # convs whose ReLU output ends a slice [0:4],[4:9],[9:16],[16:23],[23:30]
+VGG16_POOLED_CONVS = (2, 7, 14, 21)      # convs followed by ReLU + MaxPool2d(2)
+
+
+class VGG16Features(nn.Sequential):
+    """Parameter container for torchvision `vgg16().features[0:30]`; state_dict keys '0.weight', '0.bias',
+    '2.weight', ... as in torchvision.  No eager forward: swapnet_b200.engine.PerceptualEngine runs it."""
+
+    def __init__(self):
+        layers, cin = [], 3
+        for v in VGG16_CFG:
+            if v == "M":
+                layers.append(nn.Identity())            # MaxPool2d(2, 2): no parameters
+            else:
+                layers += [nn.Conv2d(cin, v, 3, padding=1), nn.Identity()]   # conv, ReLU
+                cin = v
+        super().__init__(*layers)
+        assert len(self) == 30 and all(isinstance(self[i], nn.Conv2d) for i in VGG16_CONVS)
+        for p in self.parameters():
+            p.requires_grad = False                     # perceptual.py:44-45
+
+    def forward(self, *a, **k):  # pragma: no cover
+        raise RuntimeError("VGG16Features is a parameter container; there is no eager fallback")
+
+
+def load_vgg16_features(spec: str = "pretrained") -> VGG16Features:
+    """spec: 'pretrained' — torchvision's ImageNet weights exactly as perceptual.py:26 requests them
+             (needs the torch hub cache or network; raises otherwise — there is no silent substitute);
+             'random' / 'random:<seed>' — torchvision's own constructor init under a fixed seed (default 1234):
+             the stand-in used by the tests and bench.py, where the weights cannot be downloaded;
+             any other string — path of a torch-saved vgg16 (or vgg16.features) state_dict."""
+    import torchvision
+
+    net = VGG16Features()
+    if spec == "pretrained":
+        try:
+            tv = torchvision.models.vgg16(weights=torchvision.models.VGG16_Weights.IMAGENET1K_V1)
+        except Exception as e:  # offline: URLError etc.
+            raise RuntimeError(
+                "vgg16(pretrained=True) (modules/losses/perceptual.py:26) could not be loaded: "
+                f"{type(e).__name__}: {e}.  Put vgg16-397923af.pth in the torch hub cache, pass "
+                "--b200_vgg /path/to/vgg16.pth, or --b200_vgg random for seeded random weights") from e
+        sd = tv.features.state_dict()
+    elif spec.startswith("random"):
+        seed = int(spec.split(":", 1)[1]) if ":" in spec else 1234
+        with torch.random.fork_rng():
+            torch.manual_seed(seed)
+            sd = torchvision.models.vgg16(weights=None).features.state_dict()
+    else:
+        sd = torch.load(spec, map_location="cpu")
+        if any(k.startswith("features.") for k in sd):
+            sd = {k[len("features."):]: v for k, v in sd.items() if k.startswith("features.")}
+    net.load_state_dict({k: v for k, v in sd.items() if int(k.split(".")[0]) < 30})
+    return net

@@ -534,3 +534,80 @@ def roi_align_pack(tex_nchw: torch.Tensor, rois: torch.Tensor, pool: int, out_f3
 
 def launch_count() -> int:
     return int(_lib.load().sn_launch_count())
+
+
+# ---------------------------------------------------------------------------------------------
+# VGG16 perceptual loss pieces (modules/losses/perceptual.py:6-79)
+# ---------------------------------------------------------------------------------------------
+def affine_pack(src: torch.Tensor, nhwc: bool, mul: float, add: float, dst: Planes) -> None:
+    """dst[..., :16] = split(mul * src + add) (channels beyond src's are zero): `x = 2.0 * x - 1.0`."""
+    assert src.dtype == torch.float32 and dst.c == 16
+    if nhwc:
+        n, h, w, c = src.shape
+        pitch = _pitch(src)
+    else:
+        assert src.is_contiguous()
+        n, c, h, w = src.shape
+        pitch = 0
+    assert (n, h, w) == (dst.n, dst.h, dst.w)
+    check(_lib.load().sn_affine_pack(src.data_ptr(), LAYOUT_NHWC if nhwc else LAYOUT_NCHW, pitch, n, c, h, w, mul, add,
+                                     dst.hi.data_ptr(), dst.lo.data_ptr(), dst.pitch, dst.c_off, dst.fmt, _stream()))
+
+
+def relu_pool_fwd(y: torch.Tensor, c: int, out: Planes) -> None:
+    n, h, w, _ = y.shape
+    assert (out.n, out.h, out.w) == (n, h // 2, w // 2) and out.c >= c
+    check(_lib.load().sn_relu_pool_fwd(y.data_ptr(), _pitch(y), n, h, w, c, out.hi.data_ptr(), out.lo.data_ptr(),
+                                       out.pitch, out.c_off, out.fmt, _stream()))
+
+
+def relu_pool_bwd(y: torch.Tensor, c: int, g_pool: Optional[torch.Tensor], g_direct: Optional[torch.Tensor],
+                  dy: Planes) -> None:
+    n, h, w, _ = y.shape
+    assert (dy.n, dy.h, dy.w) == (n, h, w) and dy.c >= c
+    assert g_pool is None or g_pool.shape[:3] == (n, h // 2, w // 2)
+    assert g_direct is None or g_direct.shape[:3] == (n, h, w)
+    check(_lib.load().sn_relu_pool_bwd(y.data_ptr(), _pitch(y), _ptr(g_pool), 0 if g_pool is None else _pitch(g_pool),
+                                       _ptr(g_direct), 0 if g_direct is None else _pitch(g_direct), n, h, w, c,
+                                       dy.hi.data_ptr(), dy.lo.data_ptr(), dy.pitch, dy.c_off, dy.fmt, _stream()))
+
+
+def feat_loss_fwd_bwd(y_out: torch.Tensor, y_tgt: torch.Tensor, c: int, weight: float, gscale: float,
+                      loss_acc: torch.Tensor, dx: torch.Tensor) -> None:
+    """loss_acc += weight * sum((f_out - f_tgt)^2), f = relu(y) / (|relu(y)|_2 + 1e-8); dx = gscale * dloss/d relu(y_out)."""
+    n, h, w, _ = y_out.shape
+    assert y_tgt.shape[:3] == (n, h, w) and dx.shape[:3] == (n, h, w) and loss_acc.dtype == torch.float64
+    check(_lib.load().sn_feat_loss_fwd_bwd(y_out.data_ptr(), _pitch(y_out), y_tgt.data_ptr(), _pitch(y_tgt), n * h * w, c,
+                                           weight, gscale, loss_acc.data_ptr(), dx.data_ptr(), _pitch(dx), _stream()))
+
+
+def _gram_strides(x: torch.Tensor, nhwc: bool):
+    if nhwc:
+        n, h, w, c = x.shape
+        assert x.is_contiguous()
+        return n, c, h * w, h * w * c, 1, c
+    n, c, h, w = x.shape
+    assert x.is_contiguous()
+    return n, c, h * w, c * h * w, h * w, 1
+
+
+def gram(x: torch.Tensor, nhwc: bool, out: torch.Tensor) -> None:
+    """out [n*c, n*c] (float64) = gram_matrix(x) of perceptual.py:6-10 (rows = (sample, channel))."""
+    n, c, npix, sn, sc, sp = _gram_strides(x, nhwc)
+    assert out.dtype == torch.float64 and out.numel() == (n * c) ** 2
+    check(_lib.load().sn_gram(x.data_ptr(), sn, sc, sp, n, c, npix, out.data_ptr(), _stream()))
+
+
+def gram_mse(g_out: torch.Tensor, g_tgt: torch.Tensor, weight: float, loss_acc: torch.Tensor, m: torch.Tensor) -> None:
+    rows = g_out.shape[0]
+    assert m.dtype == torch.float32 and m.numel() == rows * rows
+    check(_lib.load().sn_gram_mse(g_out.data_ptr(), g_tgt.data_ptr(), rows, weight, loss_acc.data_ptr(), m.data_ptr(),
+                                  _stream()))
+
+
+def gram_bwd(m: torch.Tensor, x: torch.Tensor, nhwc: bool, dx: torch.Tensor, accumulate: bool) -> None:
+    """dx (NHWC fp32 [n,h,w,>=c]) (+)= m @ X."""
+    n, c, npix, sn, sc, sp = _gram_strides(x, nhwc)
+    assert dx.shape[0] == n and dx.shape[1] * dx.shape[2] == npix
+    check(_lib.load().sn_gram_bwd(m.data_ptr(), x.data_ptr(), sn, sc, sp, n, c, npix, dx.data_ptr(), _pitch(dx),
+                                  1 if accumulate else 0, _stream()))

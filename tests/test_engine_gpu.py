@@ -274,12 +274,17 @@ def test_texture_engine_forward(S):
     assert err < 1e-3, f"texture forward relmax {err:.3e}"
 
 
-def test_texture_model_step_matches_oracle():
+@pytest.mark.parametrize("perceptual", [False, True])
+def test_texture_model_step_matches_oracle(perceptual):
+    """perceptual=True: the reference's DEFAULT texture losses (lambda_content 20, lambda_style 1e-8,
+    texture_model.py:39-48) with seeded-random VGG16 weights (the pretrained file is not obtainable offline)."""
     from swapnet_b200.models import create_model
 
     B, S = 2, 128
     torch.manual_seed(0)
-    opt = _opt(B, S, model="texture", name="texture", netG="swapnet", lambda_l1=10, lambda_content=0, lambda_style=0)
+    lc, ls = (20.0, 1e-8) if perceptual else (0.0, 0.0)
+    opt = _opt(B, S, model="texture", name="texture", netG="swapnet", lambda_l1=10, lambda_content=lc, lambda_style=ls,
+               b200_vgg="random")
     model = create_model(opt)
     model.setup(opt)
     model.eval()
@@ -312,9 +317,17 @@ def test_texture_model_step_matches_oracle():
     gates_D = [stage_gates(model._eng_Dd, 0, B), stage_gates(model._eng_Dd, B, 2 * B), stage_gates(model._eng_Dg)]
     calls = {}
 
+    gates_P, vgg_sd = {}, None
+    if perceptual:
+        gates_P = {"vgg_o." + k: v for k, v in stage_gates(model._eng_P.out).items()}
+        gates_P.update({"vgg_t." + k: v for k, v in stage_gates(model._eng_P.tgt).items()})
+        vgg_sd = {k: v.detach().cpu().double() for k, v in model.net_vgg.state_dict().items()}
+
     def gate(name, x):
         if name in gates_G:
             return gates_G[name]
+        if name in gates_P:
+            return gates_P[name]
         k = calls.get(name, 0)
         calls[name] = k + 1
         return gates_D[k][name]
@@ -323,18 +336,20 @@ def test_texture_model_step_matches_oracle():
     d = model.fakes.detach() - tgt.to(dev())                     # same fp32 subtraction as the L1 kernel
     l1_sign = torch.sign(d).cpu().double()
     o = ON.texture_step_losses(sdG, sdD, tex.double(), rois.double(), cloth.double(), tgt.double(), draws,
-                               l1_sign=l1_sign)
+                               l1_sign=l1_sign, vgg=vgg_sd, lambda_content=lc, lambda_style=ls)
     ref_sign = torch.sign(o["fakes"].detach() - tgt.double())
     record("texture_step_l1_sign_flips", f"{int((ref_sign != l1_sign).sum())} of {l1_sign.numel()}")
     stats = dict(ON.GATE_STATS)
     ON.gate_with(None)
     flips = {k: v for k, v in stats.items() if k != "__total__" and v}
-    record("texture_step_gate_flips", f"{sum(flips.values())} of {stats.get('__total__', 1)}: {flips}")
+    record(f"texture_step_gate_flips[perceptual={perceptual}]", f"{sum(flips.values())} of {stats.get('__total__', 1)}: {flips}")
     refD = torch.autograd.grad(o["D"], list(sdD.values()), retain_graph=True)
     refG = torch.autograd.grad(o["G"], list(sdG.values()), allow_unused=True)
-    for k in ("D", "D_real", "D_fake", "G", "G_gan", "G_l1"):
+    for k in ("D", "D_real", "D_fake", "G", "G_gan", "G_l1") + (("G_content", "G_style") if perceptual else ()):
         ref = o[k].item()
         assert abs(losses[k] - ref) <= 1e-3 * abs(ref), f"loss_{k}: {losses[k]} vs {ref}"
+        if perceptual:
+            record(f"texture_step_perceptual_loss_{k}", f"{losses[k]:.9g} vs {ref:.9g}")
     err_f = relmax(model.fakes.cpu(), o["fakes"].detach())
     assert err_f < 1e-3, f"fakes relmax {err_f:.3e}"
     worst = {}
@@ -347,7 +362,7 @@ def test_texture_model_step_matches_oracle():
                 assert got[k].abs().max().item() < 1e-4 * mx, k
                 continue
             worst[name + k] = relmax(got[k], r)
-    record("texture_step_worst_grads", sorted(worst.items(), key=lambda kv: -kv[1])[:5])
+    record(f"texture_step_worst_grads[perceptual={perceptual}]", sorted(worst.items(), key=lambda kv: -kv[1])[:5])
     record("texture_step_fakes", f"{err_f:.3e}")
     bad = {k: v for k, v in worst.items() if v >= 1e-3}
     assert not bad, f"parameter gradients beyond 1e-3: {bad}"
@@ -450,3 +465,46 @@ def test_texture_forward_full_size_512():
     err = relmax(out.permute(0, 3, 1, 2).cpu(), ref)
     record("texture_forward_512", f"{err:.3e}")
     assert err < 1e-3
+
+
+@pytest.mark.parametrize("B,S", [(2, 64), (1, 128)])
+def test_perceptual_engine_matches_oracle(B, S):
+    """PerceptualLoss(fakes, targets) * (lambda_content, lambda_style) and its gradient w.r.t. fakes
+    (modules/losses/perceptual.py:49-79) — seeded-random VGG16, gates imposed from the device."""
+    from swapnet_b200 import engine as E
+    from swapnet_b200 import modules as M
+
+    vgg = M.load_vgg16_features("random").to(dev())
+    g = torch.Generator().manual_seed(B * 100 + S)
+    fakes = torch.rand(B, 3, S, S, generator=g) * 2 - 1            # tanh range
+    tgt = torch.rand(B, 3, S, S, generator=g) * 4.5 - 2.0          # normalised-RGB range
+    lc, ls = 20.0, 1e-8
+    P = E.PerceptualEngine(vgg, B, S, dev())
+    acc = torch.zeros(2, dtype=torch.float64, device=dev())
+    fk = fakes.permute(0, 2, 3, 1).contiguous().to(dev())
+    td = tgt.to(dev())
+    dstyle = torch.zeros(B, S, S, 3, device=dev())
+    P.style(fk, td, ls, acc[1:2], dstyle)
+    dcontent = P.content(fk, td, lc, acc[0:1])
+    torch.cuda.synchronize()
+    gates = {"vgg_o." + k: v for k, v in stage_gates(P.out).items()}
+    gates.update({"vgg_t." + k: v for k, v in stage_gates(P.tgt).items()})
+    ON.gate_with(lambda name, x: gates.get(name))
+    sd = {k: v.detach().cpu().double() for k, v in vgg.state_dict().items()}
+    f64 = fakes.double().requires_grad_()
+    c, st = ON.perceptual_loss(sd, f64, tgt.double(), True)
+    stats = dict(ON.GATE_STATS)
+    ON.gate_with(None)
+    (gc,) = torch.autograd.grad(c * lc, f64, retain_graph=True)
+    (gs,) = torch.autograd.grad(st * ls, f64)
+    flips = sum(v for k, v in stats.items() if k != "__total__")
+    record(f"perceptual_engine[{B},{S}]",
+           f"content {acc[0].item():.9g} vs {(c * lc).item():.9g}; style {acc[1].item():.9g} vs {(st * ls).item():.9g}; "
+           f"gate flips {flips} of {stats.get('__total__', 0)}")
+    assert abs(acc[0].item() - (c * lc).item()) <= 1e-3 * abs((c * lc).item())
+    assert abs(acc[1].item() - (st * ls).item()) <= 1e-3 * abs((st * ls).item())
+    ec = relmax(dcontent.cpu(), gc.permute(0, 2, 3, 1))
+    es = relmax(dstyle.cpu(), gs.permute(0, 2, 3, 1))
+    record(f"perceptual_engine_grads[{B},{S}]", f"content {ec:.3e} style {es:.3e}")
+    assert ec < 1e-3 and es < 1e-3
+    assert flips <= 2e-5 * stats.get("__total__", 1)

@@ -36,7 +36,7 @@ def ref_forward(kind, x, w, b=None):
         return F.conv_transpose2d(x, w, b, 2, 1)
     if kind == "conv3r":
         return F.conv2d(F.pad(x, (1, 1, 1, 1), mode="reflect"), w, b)
-    if kind == "conv4s1":
+    if kind in ("conv4s1", "conv3z"):
         return F.conv2d(x, w, b, 1, 1)
     if kind == "head":
         return F.conv2d(F.pad(F.interpolate(x, scale_factor=2), (1, 0, 1, 0)), w, b, 1, 1)
@@ -68,6 +68,10 @@ CONV_CASES = [
     ("conv4s2", 2, 19, 64, 32, 32),      # 19 -> 32-channel rows (SWIZZLE_64B)
     ("conv4s1", 2, 16, 32, 16, 16),      # exactly 16 channels (SWIZZLE_32B), narrow dy too
     ("convT4s2", 2, 32, 16, 8, 8),
+    ("conv3z", 2, 3, 64, 32, 32),        # vgg16.features.0 (3 -> 16-channel rows, 9 taps padded to 12)
+    ("conv3z", 2, 64, 64, 32, 48),
+    ("conv3z", 1, 128, 256, 16, 16),
+    ("conv3z", 3, 512, 512, 4, 4),
 ]
 
 
@@ -77,7 +81,7 @@ def make_layer(kind, n, cin, cout, h, w, nsplit, with_bias=True):
 
     g = torch.Generator().manual_seed(1234 + n * 7 + cin + cout + h)
     x = torch.randn(n, cin, h, w, generator=g)
-    k = 3 if kind == "conv3r" else 4
+    k = 3 if kind in ("conv3r", "conv3z") else 4
     wshape = (cin, cout, k, k) if kind == "convT4s2" else (cout, cin, k, k)
     wt = torch.randn(*wshape, generator=g) * (1.0 / (cin * k * k) ** 0.5)
     bias = torch.randn(cout, generator=g) if with_bias else None
@@ -380,3 +384,109 @@ def test_fused_adamw_matches_torch():
         for i in range(len(shapes)):
             assert relmax(ms[i]["exp_avg_sq"].cpu(), rs[i]["exp_avg_sq"].cpu()) < 1e-5
             assert float(ms[i]["step"]) == float(rs[i]["step"]) == 5.0
+
+
+# ---------------------------------------------------------------------------------------------
+# VGG16 perceptual-loss pieces (modules/losses/perceptual.py)
+# ---------------------------------------------------------------------------------------------
+def planes_to_float(p):
+    return p.dense()
+
+
+def test_affine_pack():
+    from swapnet_b200 import ops
+
+    g = torch.Generator().manual_seed(3)
+    a = torch.rand(2, 3, 16, 24, generator=g)
+    for nhwc_src in (False, True):
+        src = (a.permute(0, 2, 3, 1).contiguous() if nhwc_src else a).to(dev())
+        dst = ops.Planes(2, 16, 24, 16, dev())
+        dst.hi.fill_(1.0)                                    # stale data must be overwritten
+        ops.affine_pack(src, nhwc_src, 2.0, -1.0, dst)
+        got = planes_to_float(dst).cpu()
+        assert relmax(got[..., :3], nhwc(2.0 * a - 1.0)) < 1e-6
+        assert torch.all(got[..., 3:] == 0)
+
+
+@pytest.mark.parametrize("c,h,w", [(64, 16, 24), (128, 8, 8), (512, 4, 6)])
+def test_relu_pool_fwd_bwd(c, h, w):
+    from swapnet_b200 import ops
+
+    g = torch.Generator().manual_seed(c + h)
+    n = 2
+    y = torch.randn(n, c, h, w, generator=g)
+    y[0, :, :2, :2] = -1.0                                   # an all-negative window: zero output, zero gradient
+    y[1, :, 2:4, 2:4] = 0.75                                 # a tied window: gradient goes to the first element
+    gp = torch.randn(n, c, h // 2, w // 2, generator=g)
+    gd = torch.randn(n, c, h, w, generator=g)
+    yd = nhwc(y).to(dev())
+    out = ops.Planes(n, h // 2, w // 2, c, dev())
+    ops.relu_pool_fwd(yd, c, out)
+    yr = y.double().requires_grad_()
+    a = F.relu(yr)
+    pooled = F.max_pool2d(a, 2, 2)
+    assert relmax(planes_to_float(out).cpu(), nhwc(pooled.detach())) < 1e-6
+    (gx,) = torch.autograd.grad([pooled, a], [yr], [gp.double(), gd.double()])
+    dy = ops.Planes(n, h, w, c, dev(), fmt=ops.FMT_BF16)
+    ops.relu_pool_bwd(yd, c, nhwc(gp).to(dev()), nhwc(gd).to(dev()), dy)
+    assert relmax(planes_to_float(dy).cpu(), nhwc(gx)) < 2e-5          # bf16-split: 16 bits
+    ops.relu_pool_bwd(yd, c, nhwc(gp).to(dev()), None, dy)
+    (gx2,) = torch.autograd.grad([F.max_pool2d(F.relu(yr), 2, 2)], [yr], [gp.double()])
+    assert relmax(planes_to_float(dy).cpu(), nhwc(gx2)) < 2e-5
+
+
+@pytest.mark.parametrize("c", [64, 128, 256, 512])
+def test_feat_loss(c):
+    """one tap of PerceptualLoss: MSE of L2-normalised ReLU features, value + gradient (perceptual.py:53-57,72-78)"""
+    from swapnet_b200 import ops
+
+    g = torch.Generator().manual_seed(c)
+    n, h, w = 2, 6, 5
+    yo = torch.randn(n, c, h, w, generator=g)
+    yt = torch.randn(n, c, h, w, generator=g)
+    lam = 20.0
+    xo = F.relu(yo.double()).requires_grad_()
+    xt = F.relu(yt.double())
+    fo = xo / (torch.sqrt(torch.pow(xo, 2).sum(1, keepdim=True)) + 1e-8)
+    ft = xt / (torch.sqrt(torch.pow(xt, 2).sum(1, keepdim=True)) + 1e-8)
+    loss = F.mse_loss(fo, ft) * lam
+    (gx,) = torch.autograd.grad(loss, xo)
+    acc = torch.zeros(1, dtype=torch.float64, device=dev())
+    dx = torch.zeros(n, h, w, c, device=dev())
+    ops.feat_loss_fwd_bwd(nhwc(yo).to(dev()), nhwc(yt).to(dev()), c, lam / yo.numel(), 2.0, acc, dx)
+    assert abs(acc.item() - loss.item()) < 1e-5 * abs(loss.item())
+    assert relmax(dx.cpu(), 2.0 * nhwc(gx)) < 1e-5
+
+
+@pytest.mark.parametrize("n,s", [(2, 32), (16, 64), (1, 48)])
+def test_gram_style_loss(n, s):
+    """5 x MSE(gram(out), gram(tgt)) on raw images viewed as [B*3, H*W] (perceptual.py:6-10,58-63)"""
+    from swapnet_b200 import ops
+
+    g = torch.Generator().manual_seed(n + s)
+    out = torch.rand(n, 3, s, s, generator=g) * 2 - 1
+    tgt = torch.rand(n, 3, s, s, generator=g) * 4.5 - 2
+    lam = 1e-8
+    o = out.double().requires_grad_()
+
+    def gram(t):
+        t = t.reshape(n * 3, s * s)
+        return t @ t.t()
+
+    loss = 5 * F.mse_loss(gram(o), gram(tgt.double())) * lam
+    (gx,) = torch.autograd.grad(loss, o)
+    r = 3 * n
+    go = torch.zeros(r, r, dtype=torch.float64, device=dev())
+    gt = torch.zeros_like(go)
+    m = torch.zeros(r, r, device=dev())
+    fk = nhwc(out).to(dev())
+    ops.gram(fk, True, go)
+    ops.gram(tgt.to(dev()), False, gt)
+    assert relmax(go.cpu(), gram(out.double())) < 1e-5 and relmax(gt.cpu(), gram(tgt.double())) < 1e-5
+    acc = torch.zeros(1, dtype=torch.float64, device=dev())
+    ops.gram_mse(go, gt, 5 * lam, acc, m)
+    assert abs(acc.item() - loss.item()) < 1e-4 * abs(loss.item())
+    base = torch.randn(n, s, s, 3, generator=g)
+    dx = base.clone().to(dev())
+    ops.gram_bwd(m, fk, True, dx, accumulate=True)
+    assert relmax(dx.cpu() - base, nhwc(gx)) < 1e-4

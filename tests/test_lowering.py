@@ -20,6 +20,8 @@ def ref_forward(kind, x, w, b=None):
         return F.conv2d(F.pad(x, (1, 1, 1, 1), mode="reflect"), w, b)
     if kind == "conv4s1":
         return F.conv2d(x, w, b, 1, 1)
+    if kind == "conv3z":   # torchvision vgg16.features conv (perceptual.py:26)
+        return F.conv2d(x, w, b, 1, 1)
     if kind == "head":
         u = F.interpolate(x, scale_factor=2)  # nn.Upsample default = nearest
         u = F.pad(u, (1, 0, 1, 0))            # ZeroPad2d((1,0,1,0))
@@ -33,6 +35,7 @@ CASES = [
     ("conv3r", 4, 5, 6, 6), ("conv3r", 3, 3, 8, 10),
     ("conv4s1", 4, 3, 7, 9), ("conv4s1", 5, 1, 8, 8),
     ("head", 6, 5, 4, 4), ("head", 4, 3, 6, 8),
+    ("conv3z", 4, 5, 6, 6), ("conv3z", 3, 2, 8, 10),
 ]
 
 
@@ -57,7 +60,7 @@ def test_forward_dgrad_wgrad(kind, cin, cout, h, w):
     x = torch.randn(N, cin, h, w, dtype=torch.float64, requires_grad=True)
     wshape = (cin, cout, 4, 4) if kind == "convT4s2" else (cout, cin, 3 if kind == "conv3r" else 4,) * 1
     if kind != "convT4s2":
-        k = 3 if kind == "conv3r" else 4
+        k = 3 if kind in ("conv3r", "conv3z") else 4
         wshape = (cout, cin, k, k)
     wt = torch.randn(*wshape, dtype=torch.float64, requires_grad=True)
     bias = torch.randn(cout, dtype=torch.float64)

@@ -130,3 +130,45 @@ def test_oracle_is_bit_identical_to_reference_modules():
     b = M.WarpModule(); M.init_weights(b, "kaiming")
     assert list(a.state_dict()) == list(b.state_dict())
     assert all(torch.equal(a.state_dict()[k], b.state_dict()[k]) for k in a.state_dict())
+
+
+def seeded_vgg_features_sd(seed=1234):
+    """The stand-in for the unobtainable `vgg16(pretrained=True)`: torchvision's own constructor
+    (kaiming_normal fan_out convs, zero bias) under a fixed seed."""
+    import torchvision
+
+    with torch.random.fork_rng():
+        torch.manual_seed(seed)
+        net = torchvision.models.vgg16(weights=None)
+    return {k: v.detach().clone() for k, v in net.features.state_dict().items()}
+
+
+@pytest.mark.skipif(not RH.available(), reason="/root/reference not mounted (GPU box)")
+def test_perceptual_oracle_is_bit_identical_to_reference():
+    import torchvision
+
+    RH.import_reference()
+    import modules.losses.perceptual as P
+
+    def seeded(pretrained=False, **kw):
+        with torch.random.fork_rng():
+            torch.manual_seed(1234)
+            return torchvision.models.vgg16(weights=None)
+
+    orig = P.vgg16
+    P.vgg16 = seeded          # perceptual.py:26 calls vgg16(pretrained=True): a download, impossible offline
+    try:
+        crit = P.PerceptualLoss(use_style=True)
+    finally:
+        P.vgg16 = orig
+    sd = seeded_vgg_features_sd()
+    g = torch.Generator().manual_seed(5)
+    out = torch.rand(2, 3, 64, 64, generator=g).requires_grad_()
+    tgt = torch.rand(2, 3, 64, 64, generator=g)
+    c_ref, s_ref = crit(out, tgt)
+    (c_ref * 20 + s_ref * 1e-8).backward()
+    g_ref = out.grad.clone()
+    out.grad = None
+    c, s_ = ON.perceptual_loss(sd, out, tgt, True)
+    (c * 20 + s_ * 1e-8).backward()
+    assert torch.equal(c, c_ref) and torch.equal(s_, s_ref) and torch.equal(out.grad, g_ref)
