@@ -46,6 +46,19 @@ def stage_gates(eng, n0=0, n1=None):
     return out
 
 
+def vgg_pool_winners(eng, tag):
+    """name -> flat winner index [B,C,h/2,w/2] of every ReLU+MaxPool2d(2) the device evaluated (first maximum in
+    row-major window order of relu(y), as csrc/perceptual.cu and torch both define it)."""
+    import torch.nn.functional as F
+
+    out = {}
+    for st in eng.chain:
+        if st.pool:
+            a = F.relu(st.y.permute(0, 3, 1, 2)).cpu()
+            out[f"{tag}.{int(st.name) + 2}"] = F.max_pool2d(a, 2, 2, return_indices=True)[1]
+    return out
+
+
 def synth_warp_batch(B, S, seed=1234):
     """normalised-RGB-like body, 16x16-block one-hot cloth labels (label 0 = all-zero)."""
     g = torch.Generator().manual_seed(seed)
@@ -333,6 +346,9 @@ def test_texture_model_step_matches_oracle(perceptual):
         return gates_D[k][name]
 
     ON.gate_with(gate)
+    if perceptual:
+        winners = vgg_pool_winners(model._eng_P.out, "vgg_o")
+        ON.pool_with(lambda name, x: winners.get(name))
     d = model.fakes.detach() - tgt.to(dev())                     # same fp32 subtraction as the L1 kernel
     l1_sign = torch.sign(d).cpu().double()
     o = ON.texture_step_losses(sdG, sdD, tex.double(), rois.double(), cloth.double(), tgt.double(), draws,
@@ -341,6 +357,10 @@ def test_texture_model_step_matches_oracle(perceptual):
     record("texture_step_l1_sign_flips", f"{int((ref_sign != l1_sign).sum())} of {l1_sign.numel()}")
     stats = dict(ON.GATE_STATS)
     ON.gate_with(None)
+    ON.pool_with(None)
+    pool_flips = {k: stats.pop(k) for k in list(stats) if k.startswith("pool:")}
+    if perceptual:
+        record("texture_step_pool_winner_flips", pool_flips)
     flips = {k: v for k, v in stats.items() if k != "__total__" and v}
     record(f"texture_step_gate_flips[perceptual={perceptual}]", f"{sum(flips.values())} of {stats.get('__total__', 1)}: {flips}")
     refD = torch.autograd.grad(o["D"], list(sdD.values()), retain_graph=True)
@@ -489,12 +509,17 @@ def test_perceptual_engine_matches_oracle(B, S):
     torch.cuda.synchronize()
     gates = {"vgg_o." + k: v for k, v in stage_gates(P.out).items()}
     gates.update({"vgg_t." + k: v for k, v in stage_gates(P.tgt).items()})
+    winners = vgg_pool_winners(P.out, "vgg_o")
     ON.gate_with(lambda name, x: gates.get(name))
+    ON.pool_with(lambda name, x: winners.get(name))
     sd = {k: v.detach().cpu().double() for k, v in vgg.state_dict().items()}
     f64 = fakes.double().requires_grad_()
     c, st = ON.perceptual_loss(sd, f64, tgt.double(), True)
     stats = dict(ON.GATE_STATS)
     ON.gate_with(None)
+    ON.pool_with(None)
+    pool_flips = {k: stats.pop(k) for k in list(stats) if k.startswith("pool:")}
+    record(f"perceptual_engine_pool_winner_flips[{B},{S}]", pool_flips)
     (gc,) = torch.autograd.grad(c * lc, f64, retain_graph=True)
     (gs,) = torch.autograd.grad(st * ls, f64)
     flips = sum(v for k, v in stats.items() if k != "__total__")

@@ -71,7 +71,7 @@ CONV_CASES = [
     ("conv3z", 2, 3, 64, 32, 32),        # vgg16.features.0 (3 -> 16-channel rows, 9 taps padded to 12)
     ("conv3z", 2, 64, 64, 32, 48),
     ("conv3z", 1, 128, 256, 16, 16),
-    ("conv3z", 3, 512, 512, 4, 4),
+    ("conv3z", 3, 256, 512, 4, 4),
 ]
 
 
