@@ -304,7 +304,11 @@ def main():
     trace, ops.Plan.trace = ops.Plan.trace, None
     if rank == 0:
         info = {}
-        for eng in (model._eng_G, model._eng_Dd, model._eng_Dg):
+        engs = [model._eng_G, model._eng_Dd, model._eng_Dg]
+        pe = getattr(model, "_eng_P", None)
+        if pe is not None and pe.out is not None:
+            engs += [pe.out, pe.tgt]
+        for eng in engs:
             for st in eng.stages:
                 fl, ly = 2.0 * st.nominal_macs(), st.layer
                 for p in ly.fwd_plans:
