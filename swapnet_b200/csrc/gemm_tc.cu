@@ -26,6 +26,8 @@
 //
 // Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM owner + MMA
 // issuer, warps 2..5 = epilogue (TMEM -> registers -> global).
+#include <cstdlib>
+
 #include "common.cuh"
 #include "plan.h"
 
@@ -55,12 +57,17 @@ __device__ __forceinline__ float apply_act(float v, int act) {
 // carries no runtime index arithmetic (measured: runtime div/mod there costs 30 % of the kernel).
 template <int NSPLIT, int CW>
 __global__ void __launch_bounds__(kThreads, 1)
-tap_gemm_kernel(const __grid_constant__ TapGemmParams p) {
+tap_gemm_kernel(const __grid_constant__ TapGemmParams p, const int m_tiles, const int n_tiles, const int total_tiles) {
+  // Persistent: one CTA per SM walks tiles blockIdx.x, blockIdx.x + gridDim.x, ... (M tile fastest, then N tile,
+  // then output-parity phase).  The smem ring keeps running across tiles and the accumulator is double
+  // buffered in TMEM (2 x 128 columns), so the epilogue of tile i overlaps the main loop of tile i + 1 and
+  // the pipeline prologue is paid once per CTA instead of once per tile.
   using C = Cfg<NSPLIT>;
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[C::kStages];
   __shared__ __align__(8) uint64_t empty_bar[C::kStages];
-  __shared__ __align__(8) uint64_t accum_bar;
+  __shared__ __align__(8) uint64_t tfull_bar[2];    // MMA -> epilogue: accumulator b complete
+  __shared__ __align__(8) uint64_t tempty_bar[2];   // epilogue -> MMA: accumulator b drained (4 warps)
   __shared__ uint32_t tmem_base_smem;
 
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -68,18 +75,10 @@ tap_gemm_kernel(const __grid_constant__ TapGemmParams p) {
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
-  // ---- tile coordinates ------------------------------------------------------
-  const int mt = blockIdx.x;
-  const int tw_i = mt % p.tiles_w;
-  const int th_i = (mt / p.tiles_w) % p.tiles_h;
-  const int tn_i = mt / (p.tiles_w * p.tiles_h);
-  const int w0 = tw_i * p.tw, h0 = th_i * p.th, n0 = tn_i * p.nb;
-  const int ncol0 = blockIdx.y * p.block_n;
   constexpr int cw = CW;                    // channels per A row: 64, 32 or 16
   constexpr int tps = 64 / cw;              // taps sharing one 64-deep stage (1, 2 or 4)
-  // grid.z = output parity phase (merged 4-phase launches): phase z owns taps [z*tpp, (z+1)*tpp)
+  // output parity phase z (merged 4-phase launches) owns taps [z*tpp, (z+1)*tpp)
   const int tpp = p.ntaps / p.nphase;
-  const int tap0 = blockIdx.z * tpp;
   const int k_iters = cw == 64 ? tpp * p.chunks : tpp / tps;
 
   if (threadIdx.x == 0) {
@@ -87,7 +86,10 @@ tap_gemm_kernel(const __grid_constant__ TapGemmParams p) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
-    mbar_init(&accum_bar, 1);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&tfull_bar[b], 1);
+      mbar_init(&tempty_bar[b], 4);
+    }
     mbar_fence_init();
   }
   if (warp == 0 && lane == 0) {
@@ -96,7 +98,7 @@ tap_gemm_kernel(const __grid_constant__ TapGemmParams p) {
       tma_prefetch_desc(&p.tmB[pl]);
     }
   }
-  if (warp == 1) tmem_alloc(&tmem_base_smem, 128);
+  if (warp == 1) tmem_alloc(&tmem_base_smem, 256);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -106,39 +108,49 @@ tap_gemm_kernel(const __grid_constant__ TapGemmParams p) {
     // ===================== TMA producer =====================
     if (lane == 0) {
       const uint32_t stage_tx = C::kPlanes * (p.a_rows * 128 + p.block_n * 128);
-      for (int it = 0; it < k_iters; ++it) {
-        const int s = it % C::kStages;
-        const uint32_t ph = (it / C::kStages) & 1;
-        mbar_wait(&empty_bar[s], ph ^ 1);
-        mbar_expect_tx(&full_bar[s], stage_tx);
-        uint8_t* st = smem + s * C::kStageBytes;
-        if (cw == 64) {
-          const int t = it / p.chunks;
-          const int ch = it - t * p.chunks;
-          const TapDesc tap = p.taps[tap0 + t];
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int mt = tile % m_tiles;
+        const int rest = tile / m_tiles;
+        const int ncol0 = (rest % n_tiles) * p.block_n;
+        const int tap0 = (rest / n_tiles) * tpp;
+        const int w0 = (mt % p.tiles_w) * p.tw;
+        const int h0 = ((mt / p.tiles_w) % p.tiles_h) * p.th;
+        const int n0 = (mt / (p.tiles_w * p.tiles_h)) * p.nb;
+        for (int k = 0; k < k_iters; ++k, ++it) {
+          const uint32_t s = it % C::kStages;
+          const uint32_t ph = (it / C::kStages) & 1;
+          mbar_wait(&empty_bar[s], ph ^ 1);
+          mbar_expect_tx(&full_bar[s], stage_tx);
+          uint8_t* st = smem + s * C::kStageBytes;
+          if (cw == 64) {
+            const int t = k / p.chunks;
+            const int ch = k - t * p.chunks;
+            const TapDesc tap = p.taps[tap0 + t];
 #pragma unroll
-          for (int pl = 0; pl < C::kPlanes; ++pl) {
-            tma_load_5d(&p.tmA[pl], &full_bar[s], st + pl * kTileBytes, tap.c_off + ch * 64,
-                        w0 + tap.dw, tap.hp, h0 + tap.dh, n0);
-            tma_load_2d(&p.tmB[pl], &full_bar[s], st + (C::kPlanes + pl) * kTileBytes,
-                        tap.kb_off + ch * 64, ncol0);
-          }
-        } else {
-          // narrow operand: 64/cw taps, each a [128 rows][cw channels] sub-tile, fill one stage; the
-          // weights of consecutive taps are contiguous in K, so B is still one 64-deep box
-          constexpr int sub = 128 * cw * 2;
+            for (int pl = 0; pl < C::kPlanes; ++pl) {
+              tma_load_5d(&p.tmA[pl], &full_bar[s], st + pl * kTileBytes, tap.c_off + ch * 64,
+                          w0 + tap.dw, tap.hp, h0 + tap.dh, n0);
+              tma_load_2d(&p.tmB[pl], &full_bar[s], st + (C::kPlanes + pl) * kTileBytes,
+                          tap.kb_off + ch * 64, ncol0);
+            }
+          } else {
+            // narrow operand: 64/cw taps, each a [128 rows][cw channels] sub-tile, fill one stage; the
+            // weights of consecutive taps are contiguous in K, so B is still one 64-deep box
+            constexpr int sub = 128 * cw * 2;
 #pragma unroll
-          for (int j = 0; j < tps; ++j) {
-            const TapDesc tap = p.taps[tap0 + it * tps + j];
+            for (int j = 0; j < tps; ++j) {
+              const TapDesc tap = p.taps[tap0 + k * tps + j];
+#pragma unroll
+              for (int pl = 0; pl < C::kPlanes; ++pl)
+                tma_load_5d(&p.tmA[pl], &full_bar[s], st + pl * kTileBytes + j * sub, tap.c_off,
+                            w0 + tap.dw, tap.hp, h0 + tap.dh, n0);
+            }
+            const int kb = p.taps[tap0 + k * tps].kb_off;
 #pragma unroll
             for (int pl = 0; pl < C::kPlanes; ++pl)
-              tma_load_5d(&p.tmA[pl], &full_bar[s], st + pl * kTileBytes + j * sub, tap.c_off,
-                          w0 + tap.dw, tap.hp, h0 + tap.dh, n0);
+              tma_load_2d(&p.tmB[pl], &full_bar[s], st + (C::kPlanes + pl) * kTileBytes, kb, ncol0);
           }
-          const int kb = p.taps[tap0 + it * tps].kb_off;
-#pragma unroll
-          for (int pl = 0; pl < C::kPlanes; ++pl)
-            tma_load_2d(&p.tmB[pl], &full_bar[s], st + (C::kPlanes + pl) * kTileBytes, kb, ncol0);
         }
       }
     }
@@ -146,36 +158,43 @@ tap_gemm_kernel(const __grid_constant__ TapGemmParams p) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
       const uint32_t idesc = umma_idesc_16(kBlockM, p.block_n, p.a_fmt, p.b_fmt, 0, 0);
-      uint32_t acc = 0;
-      for (int it = 0; it < k_iters; ++it) {
-        const int s = it % C::kStages;
-        const uint32_t ph = (it / C::kStages) & 1;
-        mbar_wait(&full_bar[s], ph);
+      uint32_t it = 0, tcount = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
+        const uint32_t b = tcount & 1;
+        mbar_wait(&tempty_bar[b], ((tcount >> 1) & 1) ^ 1);   // the epilogue has drained accumulator b
         tc_fence_after();
-        const uint32_t st = smem_base + s * C::kStageBytes;
-        // K-major, rows of cw channels: SWIZZLE_128B/64B/32B, SBO = 8 rows, LBO unused (1)
-        constexpr uint32_t a_layout = cw >= 64 ? 2u : (cw == 32 ? 4u : 6u);
-        constexpr uint32_t a_sbo = 8u * cw * 2u;
-        const uint64_t a_hi = umma_smem_desc(st, 16, a_sbo, a_layout);
-        const uint64_t b_hi = umma_smem_desc(st + C::kPlanes * kTileBytes, 16, 1024);
-        const uint64_t a_lo = umma_smem_desc(st + kTileBytes, 16, a_sbo, a_layout);
-        const uint64_t b_lo = umma_smem_desc(st + (C::kPlanes + 1) * kTileBytes, 16, 1024);
-        constexpr uint32_t sub16 = (uint32_t)(128 * cw * 2) >> 4;  // sub-tile stride in 16-B units
+        const uint32_t tmem_d = tmem_base + b * 128;
+        uint32_t acc = 0;
+        for (int k = 0; k < k_iters; ++k, ++it) {
+          const uint32_t s = it % C::kStages;
+          const uint32_t ph = (it / C::kStages) & 1;
+          mbar_wait(&full_bar[s], ph);
+          tc_fence_after();
+          const uint32_t st = smem_base + s * C::kStageBytes;
+          // K-major, rows of cw channels: SWIZZLE_128B/64B/32B, SBO = 8 rows, LBO unused (1)
+          constexpr uint32_t a_layout = cw >= 64 ? 2u : (cw == 32 ? 4u : 6u);
+          constexpr uint32_t a_sbo = 8u * cw * 2u;
+          const uint64_t a_hi = umma_smem_desc(st, 16, a_sbo, a_layout);
+          const uint64_t b_hi = umma_smem_desc(st + C::kPlanes * kTileBytes, 16, 1024);
+          const uint64_t a_lo = umma_smem_desc(st + kTileBytes, 16, a_sbo, a_layout);
+          const uint64_t b_lo = umma_smem_desc(st + (C::kPlanes + 1) * kTileBytes, 16, 1024);
+          constexpr uint32_t sub16 = (uint32_t)(128 * cw * 2) >> 4;  // sub-tile stride in 16-B units
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {  // 4 x (UMMA_K = 16 elements = 32 B) per 64-deep stage
-          const uint64_t badv = (uint64_t)(k * 2);
-          // A: k-step k lives in sub-tile (16k / cw), at byte offset ((16k) % cw) * 2 of its rows
-          const uint64_t aadv = (uint64_t)(((k * 16) / cw) * sub16 + (((k * 16) % cw) >> 3));
-          umma_bf16(tmem_base, a_hi + aadv, b_hi + badv, idesc, acc);
-          acc = 1;
-          if (NSPLIT == 3) {
-            umma_bf16(tmem_base, a_lo + aadv, b_hi + badv, idesc, 1);
-            umma_bf16(tmem_base, a_hi + aadv, b_lo + badv, idesc, 1);
+          for (int kk = 0; kk < 4; ++kk) {  // 4 x (UMMA_K = 16 elements = 32 B) per 64-deep stage
+            const uint64_t badv = (uint64_t)(kk * 2);
+            // A: k-step kk lives in sub-tile (16kk / cw), at byte offset ((16kk) % cw) * 2 of its rows
+            const uint64_t aadv = (uint64_t)(((kk * 16) / cw) * sub16 + (((kk * 16) % cw) >> 3));
+            umma_bf16(tmem_d, a_hi + aadv, b_hi + badv, idesc, acc);
+            acc = 1;
+            if (NSPLIT == 3) {
+              umma_bf16(tmem_d, a_lo + aadv, b_hi + badv, idesc, 1);
+              umma_bf16(tmem_d, a_hi + aadv, b_lo + badv, idesc, 1);
+            }
           }
+          umma_commit(&empty_bar[s]);  // frees the smem stage once these MMAs retire
         }
-        umma_commit(&empty_bar[s]);  // frees the smem stage once these MMAs retire
+        umma_commit(&tfull_bar[b]);
       }
-      umma_commit(&accum_bar);
     }
   } else {
     // ===================== epilogue =====================
@@ -184,45 +203,61 @@ tap_gemm_kernel(const __grid_constant__ TapGemmParams p) {
     const int w_i = row % p.tw;
     const int h_i = (row / p.tw) % p.th;
     const int n_i = row / (p.tw * p.th);
-    const int gw = w0 + w_i, gh = h0 + h_i, gn = n0 + n_i;
-    const bool valid = (row < p.a_rows) && (gw < p.m_w) && (gh < p.m_h) && (gn < p.m_n);
-    const int ph_h = p.nphase == 4 ? (int)(blockIdx.z >> 1) : 0, ph_w = p.nphase == 4 ? (int)(blockIdx.z & 1) : 0;
-    float* optr = p.out + (long long)gn * p.out_sn + (long long)(gh * p.omh + p.ooh + ph_h) * p.out_sh +
-                  (long long)(gw * p.omw + p.oow + ph_w) * p.out_sw + ncol0;
     const float oscale = p.b_scale ? p.b_scale[1] : 1.f;  // undo the power-of-two weight scale (exact)
-    mbar_wait(&accum_bar, 0);
-    tc_fence_after();
-    for (int c0 = 0; c0 < p.block_n; c0 += 16) {
-      uint32_t r[16];
-      tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
-      tmem_ld_wait();
-      if (valid) {
-        if (p.vec4 && ncol0 + c0 + 16 <= p.n_valid) {
+    uint32_t tcount = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
+      const int mt = tile % m_tiles;
+      const int rest = tile / m_tiles;
+      const int ncol0 = (rest % n_tiles) * p.block_n;
+      const int z = rest / n_tiles;
+      const int gw = (mt % p.tiles_w) * p.tw + w_i;
+      const int gh = ((mt / p.tiles_w) % p.tiles_h) * p.th + h_i;
+      const int gn = (mt / (p.tiles_w * p.tiles_h)) * p.nb + n_i;
+      const bool valid = (row < p.a_rows) && (gw < p.m_w) && (gh < p.m_h) && (gn < p.m_n);
+      const int ph_h = p.nphase == 4 ? (z >> 1) : 0, ph_w = p.nphase == 4 ? (z & 1) : 0;
+      float* optr = p.out + (long long)gn * p.out_sn + (long long)(gh * p.omh + p.ooh + ph_h) * p.out_sh +
+                    (long long)(gw * p.omw + p.oow + ph_w) * p.out_sw + ncol0;
+      const uint32_t b = tcount & 1;
+      mbar_wait(&tfull_bar[b], (tcount >> 1) & 1);
+      tc_fence_after();
+      const uint32_t tmem_d = tmem_base + b * 128 + ((uint32_t)(q * 32) << 16);
+      for (int c0 = 0; c0 < p.block_n; c0 += 16) {
+        uint32_t r[16];
+        tmem_ld16(tmem_d + (uint32_t)c0, r);
+        tmem_ld_wait();
+        if (c0 + 16 >= p.block_n) {   // last read of this accumulator: hand it back before the stores
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tempty_bar[b]);
+        }
+        if (valid) {
+          if (p.vec4 && ncol0 + c0 + 16 <= p.n_valid) {
 #pragma unroll
-          for (int j = 0; j < 16; j += 4) {
-            float4 v;
-            v.x = __uint_as_float(r[j + 0]) * oscale;
-            v.y = __uint_as_float(r[j + 1]) * oscale;
-            v.z = __uint_as_float(r[j + 2]) * oscale;
-            v.w = __uint_as_float(r[j + 3]) * oscale;
-            if (p.bias) {
-              const float4 b = *reinterpret_cast<const float4*>(p.bias + ncol0 + c0 + j);
-              v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+            for (int j = 0; j < 16; j += 4) {
+              float4 v;
+              v.x = __uint_as_float(r[j + 0]) * oscale;
+              v.y = __uint_as_float(r[j + 1]) * oscale;
+              v.z = __uint_as_float(r[j + 2]) * oscale;
+              v.w = __uint_as_float(r[j + 3]) * oscale;
+              if (p.bias) {
+                const float4 bb = *reinterpret_cast<const float4*>(p.bias + ncol0 + c0 + j);
+                v.x += bb.x; v.y += bb.y; v.z += bb.z; v.w += bb.w;
+              }
+              if (p.act) {
+                v.x = apply_act(v.x, p.act); v.y = apply_act(v.y, p.act);
+                v.z = apply_act(v.z, p.act); v.w = apply_act(v.w, p.act);
+              }
+              *reinterpret_cast<float4*>(optr + c0 + j) = v;
             }
-            if (p.act) {
-              v.x = apply_act(v.x, p.act); v.y = apply_act(v.y, p.act);
-              v.z = apply_act(v.z, p.act); v.w = apply_act(v.w, p.act);
-            }
-            *reinterpret_cast<float4*>(optr + c0 + j) = v;
-          }
-        } else {
+          } else {
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const int col = ncol0 + c0 + j;
-            if (col < p.n_valid) {
-              float v = __uint_as_float(r[j]) * oscale;
-              if (p.bias) v += p.bias[col];
-              optr[c0 + j] = apply_act(v, p.act);
+            for (int j = 0; j < 16; ++j) {
+              const int col = ncol0 + c0 + j;
+              if (col < p.n_valid) {
+                float v = __uint_as_float(r[j]) * oscale;
+                if (p.bias) v += p.bias[col];
+                optr[c0 + j] = apply_act(v, p.act);
+              }
             }
           }
         }
@@ -232,7 +267,7 @@ tap_gemm_kernel(const __grid_constant__ TapGemmParams p) {
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, 128);
+  if (warp == 1) tmem_dealloc(tmem_base, 256);
 }
 
 // ============================================================================
@@ -605,7 +640,20 @@ static int launch_tap(const TapGemmPlan* plan, cudaStream_t stream) {
                                        Cfg<NSPLIT>::kSmemBytes));
     attr_done = true;
   }
-  tap_gemm_kernel<NSPLIT, CW><<<plan->grid, kThreads, Cfg<NSPLIT>::kSmemBytes, stream>>>(plan->p);
+  // persistent launch: at most one CTA per SM; plan->grid = (M tiles, N tiles, phases)
+  static int sms = 0;
+  static int one_tile_per_cta = -1;
+  if (sms == 0) {
+    int dev = 0;
+    SN_CHECK_CUDA(cudaGetDevice(&dev));
+    SN_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const char* e = getenv("SN_TAP_ONE_TILE_PER_CTA");   // A/B switch: the non-persistent schedule
+    one_tile_per_cta = (e && e[0] == '1') ? 1 : 0;
+  }
+  const int m_tiles = (int)plan->grid.x, n_tiles = (int)plan->grid.y;
+  const int total = m_tiles * n_tiles * (int)plan->grid.z;
+  const int ctas = one_tile_per_cta ? total : (total < sms ? total : sms);
+  tap_gemm_kernel<NSPLIT, CW><<<ctas, kThreads, Cfg<NSPLIT>::kSmemBytes, stream>>>(plan->p, m_tiles, n_tiles, total);
   SN_CHECK_CUDA(cudaGetLastError());
   return SN_OK;
 }
