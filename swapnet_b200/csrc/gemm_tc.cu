@@ -275,16 +275,12 @@ tap_gemm_kernel(const __grid_constant__ TapGemmParams p, const int m_tiles, cons
 // ============================================================================
 template <int NSPLIT>
 __global__ void __launch_bounds__(kThreads, 1)
-wgrad_gemm_kernel(const __grid_constant__ WgradParams p, const int gx, const int gy, const int gz) {
-  // Persistent like tap_gemm_kernel: work item = (M/N tile [gx], tap or tap group [gy], pixel slice [gz]),
-  // item index x fastest; the accumulator is double buffered in TMEM so that the atomic epilogue of item i
-  // overlaps the main loop of item i + 1.
+wgrad_gemm_kernel(const __grid_constant__ WgradParams p) {
   using C = Cfg<NSPLIT>;
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[C::kStages];
   __shared__ __align__(8) uint64_t empty_bar[C::kStages];
-  __shared__ __align__(8) uint64_t tfull_bar[2];
-  __shared__ __align__(8) uint64_t tempty_bar[2];
+  __shared__ __align__(8) uint64_t accum_bar;
   __shared__ uint32_t tmem_base_smem;
 
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -292,12 +288,21 @@ wgrad_gemm_kernel(const __grid_constant__ WgradParams p, const int gx, const int
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
+  const int m_tile = blockIdx.x / p.n_tiles;
+  const int n_tile = blockIdx.x - m_tile * p.n_tiles;
   // grid.y = tap (wide Y) or tap group (narrow Y: the group's taps are column blocks of one accumulator
   // and share the X tile, which is then read once per pixel tile instead of once per tap)
   const bool grouped = p.ngroups > 0;
+  const int tap_i = grouped ? p.gstart[blockIdx.y] : blockIdx.y;
+  const int gsize = grouped ? p.gsize[blockIdx.y] : 1;
+  const int m0 = m_tile * kBlockM;
+  const int ncol0 = n_tile * p.block_n;
   const int total = p.tiles_w * p.tiles_h * p.tiles_n;
-  const int items = gx * gy * gz;
+  const int kt0 = (int)(((long long)total * blockIdx.z) / gridDim.z);
+  const int kt1 = (int)(((long long)total * (blockIdx.z + 1)) / gridDim.z);
+  const int k_iters = kt1 - kt0;
   const int ycw = p.y_chunk;                               // channels per Y row: 64, 32, 16
+  const int y_blocks = ycw == 64 ? p.block_n / 64 : gsize; // narrow Y: one ycw-wide atom per grouped tap
   const int y_block_bytes = 64 * ycw * 2;                  // 64 pixels x ycw channels
 
   if (threadIdx.x == 0) {
@@ -305,10 +310,7 @@ wgrad_gemm_kernel(const __grid_constant__ WgradParams p, const int gx, const int
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
-    for (int b = 0; b < 2; ++b) {
-      mbar_init(&tfull_bar[b], 1);
-      mbar_init(&tempty_bar[b], 4);
-    }
+    mbar_init(&accum_bar, 1);
     mbar_fence_init();
   }
   if (warp == 0 && lane == 0) {
@@ -317,41 +319,23 @@ wgrad_gemm_kernel(const __grid_constant__ WgradParams p, const int gx, const int
       tma_prefetch_desc(&p.tmY[pl]);
     }
   }
-  if (warp == 1) tmem_alloc(&tmem_base_smem, 256);
+  if (warp == 1) tmem_alloc(&tmem_base_smem, 128);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_smem;
 
-  // item -> (mn tile, tap index, group size, first pixel tile, pixel tiles)
-#define SN_WG_ITEM(item)                                                              \
-  const int ix = (item) % gx;                                                         \
-  const int iy = ((item) / gx) % gy;                                                  \
-  const int iz = (item) / (gx * gy);                                                  \
-  const int m_tile = ix / p.n_tiles;                                                  \
-  const int n_tile = ix - m_tile * p.n_tiles;                                         \
-  const int tap_i = grouped ? p.gstart[iy] : iy;                                      \
-  const int gsize = grouped ? p.gsize[iy] : 1;                                        \
-  const int m0 = m_tile * kBlockM;                                                    \
-  const int ncol0 = n_tile * p.block_n;                                               \
-  const int kt0 = (int)(((long long)total * iz) / gz);                                \
-  const int k_iters = (int)(((long long)total * (iz + 1)) / gz) - kt0;                \
-  (void)gsize; (void)m0; (void)ncol0; (void)tap_i
-
-  if (warp == 0) {
-    if (lane == 0) {
-      uint32_t it = 0;
-      for (int item = blockIdx.x; item < items; item += gridDim.x) {
-        SN_WG_ITEM(item);
-        const int y_blocks = ycw == 64 ? p.block_n / 64 : gsize; // narrow Y: one ycw-wide atom per grouped tap
+  if (k_iters > 0) {
+    if (warp == 0) {
+      if (lane == 0) {
         const TapDesc xt = p.xtaps[tap_i];
         const uint32_t stage_tx = C::kPlanes * (2 * 8192 + y_blocks * y_block_bytes);
-        for (int k = 0; k < k_iters; ++k, ++it) {
-          const uint32_t s = it % C::kStages;
+        for (int it = 0; it < k_iters; ++it) {
+          const int s = it % C::kStages;
           const uint32_t ph = (it / C::kStages) & 1;
           mbar_wait(&empty_bar[s], ph ^ 1);
           mbar_expect_tx(&full_bar[s], stage_tx);
-          const int kt = kt0 + k;
+          const int kt = kt0 + it;
           const int tw_i = kt % p.tiles_w;
           const int th_i = (kt / p.tiles_w) % p.tiles_h;
           const int tn_i = kt / (p.tiles_w * p.tiles_h);
@@ -371,21 +355,12 @@ wgrad_gemm_kernel(const __grid_constant__ WgradParams p, const int gx, const int
           }
         }
       }
-    }
-  } else if (warp == 1) {
-    if (lane == 0) {
-      const uint32_t idesc = umma_idesc_16(kBlockM, p.block_n, p.x_fmt, p.y_fmt, 1, 1);
-      uint32_t it = 0, tcount = 0;
-      for (int item = blockIdx.x; item < items; item += gridDim.x) {
-        SN_WG_ITEM(item);
-        if (k_iters <= 0) continue;
-        const uint32_t b = tcount & 1;
-        mbar_wait(&tempty_bar[b], ((tcount >> 1) & 1) ^ 1);
-        tc_fence_after();
-        const uint32_t tmem_d = tmem_base + b * 128;
+    } else if (warp == 1) {
+      if (lane == 0) {
+        const uint32_t idesc = umma_idesc_16(kBlockM, p.block_n, p.x_fmt, p.y_fmt, 1, 1);
         uint32_t acc = 0;
-        for (int k = 0; k < k_iters; ++k, ++it) {
-          const uint32_t s = it % C::kStages;
+        for (int it = 0; it < k_iters; ++it) {
+          const int s = it % C::kStages;
           const uint32_t ph = (it / C::kStages) & 1;
           mbar_wait(&full_bar[s], ph);
           tc_fence_after();
@@ -400,44 +375,31 @@ wgrad_gemm_kernel(const __grid_constant__ WgradParams p, const int gx, const int
           const uint64_t x_lo = umma_smem_desc(st + kTileBytes, 8192, 1024);
           const uint64_t y_lo = umma_smem_desc(st + (C::kPlanes + 1) * kTileBytes, y_block_bytes, y_sbo, y_layout);
 #pragma unroll
-          for (int kk = 0; kk < 4; ++kk) {  // 4 x 16 pixels; 16 pixel rows = 2048 B (X), 16 * ycw * 2 B (Y)
-            const uint64_t xadv = (uint64_t)(kk * 128);
-            const uint64_t yadv = (uint64_t)((kk * 16 * ycw * 2) >> 4);
-            umma_bf16(tmem_d, x_hi + xadv, y_hi + yadv, idesc, acc);
+          for (int k = 0; k < 4; ++k) {  // 4 x 16 pixels; 16 pixel rows = 2048 B (X), 16 * ycw * 2 B (Y)
+            const uint64_t xadv = (uint64_t)(k * 128);
+            const uint64_t yadv = (uint64_t)((k * 16 * ycw * 2) >> 4);
+            umma_bf16(tmem_base, x_hi + xadv, y_hi + yadv, idesc, acc);
             acc = 1;
             if (NSPLIT == 3) {
-              umma_bf16(tmem_d, x_lo + xadv, y_hi + yadv, idesc, 1);
-              umma_bf16(tmem_d, x_hi + xadv, y_lo + yadv, idesc, 1);
+              umma_bf16(tmem_base, x_lo + xadv, y_hi + yadv, idesc, 1);
+              umma_bf16(tmem_base, x_hi + xadv, y_lo + yadv, idesc, 1);
             }
           }
           umma_commit(&empty_bar[s]);
         }
-        umma_commit(&tfull_bar[b]);
-        ++tcount;
+        umma_commit(&accum_bar);
       }
-    }
-  } else {
-    const int q = warp & 3;
-    uint32_t tcount = 0;
-    for (int item = blockIdx.x; item < items; item += gridDim.x) {
-      SN_WG_ITEM(item);
-      if (k_iters <= 0) continue;
+    } else {
+      const int q = warp & 3;
       const int row = m0 + q * 32 + lane;
       const bool valid = row < p.rows_valid;
       float* orow = p.out + (long long)row * p.s_row;
-      const uint32_t b = tcount & 1;
-      mbar_wait(&tfull_bar[b], (tcount >> 1) & 1);
+      mbar_wait(&accum_bar, 0);
       tc_fence_after();
-      const uint32_t tmem_d = tmem_base + b * 128 + ((uint32_t)(q * 32) << 16);
       for (int c0 = 0; c0 < p.block_n; c0 += 16) {
         uint32_t r[16];
-        tmem_ld16(tmem_d + (uint32_t)c0, r);
+        tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
         tmem_ld_wait();
-        if (c0 + 16 >= p.block_n) {   // accumulator fully read: hand it back before the atomics
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&tempty_bar[b]);
-        }
         if (valid) {
           if (!grouped) {
             float* optr = orow + p.tap_off[tap_i];
@@ -448,10 +410,10 @@ wgrad_gemm_kernel(const __grid_constant__ WgradParams p, const int gx, const int
                 atomicAdd(optr + (long long)col * p.s_col, __uint_as_float(r[j]));
             }
           } else {
-            const int bt = c0 / ycw;               // which grouped tap this 16-column chunk belongs to
-            if (bt < gsize) {
-              float* optr = orow + p.tap_off[tap_i + bt];
-              const int cbase = c0 - bt * ycw;
+            const int b = c0 / ycw;               // which grouped tap this 16-column chunk belongs to
+            if (b < gsize) {
+              float* optr = orow + p.tap_off[tap_i + b];
+              const int cbase = c0 - b * ycw;
 #pragma unroll
               for (int j = 0; j < 16; ++j)
                 if (cbase + j < p.cols_valid)
@@ -460,14 +422,12 @@ wgrad_gemm_kernel(const __grid_constant__ WgradParams p, const int gx, const int
           }
         }
       }
-      ++tcount;
     }
   }
-#undef SN_WG_ITEM
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, 256);
+  if (warp == 1) tmem_dealloc(tmem_base, 128);
 }
 
 }  // namespace
@@ -799,32 +759,20 @@ int sn_wgrad_plan_init(WgradPlan* plan, const sn_wgrad_desc* d, int sm_count) {
 
 int sn_wgrad_plan_launch(const WgradPlan* plan, cudaStream_t stream) {
   const int idx = plan->nsplit == 3 ? 1 : 0;
-  static int sms = 0;
-  static int one_item_per_cta = 0;
-  if (sms == 0) {
-    int dev = 0;
-    SN_CHECK_CUDA(cudaGetDevice(&dev));
-    SN_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    const char* e = getenv("SN_WGRAD_ONE_ITEM_PER_CTA");   // A/B switch: the non-persistent schedule
-    one_item_per_cta = (e && e[0] == '1') ? 1 : 0;
-  }
-  const int gx = (int)plan->grid.x, gy = (int)plan->grid.y, gz = (int)plan->grid.z;
-  const int items = gx * gy * gz;
-  const int ctas = one_item_per_cta ? items : (items < sms ? items : sms);
   if (plan->nsplit == 3) {
     if (!g_smem_attr_done[1][idx]) {
       SN_CHECK_CUDA(cudaFuncSetAttribute(wgrad_gemm_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          Cfg<3>::kSmemBytes));
       g_smem_attr_done[1][idx] = 1;
     }
-    wgrad_gemm_kernel<3><<<ctas, kThreads, Cfg<3>::kSmemBytes, stream>>>(plan->p, gx, gy, gz);
+    wgrad_gemm_kernel<3><<<plan->grid, kThreads, Cfg<3>::kSmemBytes, stream>>>(plan->p);
   } else {
     if (!g_smem_attr_done[1][idx]) {
       SN_CHECK_CUDA(cudaFuncSetAttribute(wgrad_gemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          Cfg<1>::kSmemBytes));
       g_smem_attr_done[1][idx] = 1;
     }
-    wgrad_gemm_kernel<1><<<ctas, kThreads, Cfg<1>::kSmemBytes, stream>>>(plan->p, gx, gy, gz);
+    wgrad_gemm_kernel<1><<<plan->grid, kThreads, Cfg<1>::kSmemBytes, stream>>>(plan->p);
   }
   SN_CHECK_CUDA(cudaGetLastError());
   return SN_OK;
