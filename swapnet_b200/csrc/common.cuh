@@ -120,6 +120,14 @@ __device__ __forceinline__ void tma_load_2d(const void* desc, uint64_t* bar, voi
         "r"(c1)
       : "memory");
 }
+__device__ __forceinline__ void tma_load_3d(const void* desc, uint64_t* bar, void* dst, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5}], [%2];"
+      :
+      : "r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(desc)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
 __device__ __forceinline__ void tma_load_5d(const void* desc, uint64_t* bar, void* dst, int c0,
                                             int c1, int c2, int c3, int c4) {
   asm volatile(

@@ -127,12 +127,21 @@ tap_gemm_kernel(const __grid_constant__ TapGemmParams p, const int m_tiles, cons
             const int t = k / p.chunks;
             const int ch = k - t * p.chunks;
             const TapDesc tap = p.taps[tap0 + t];
+            if (p.a_merged) {   // dims (c, w, h, n, plane): hi tile, then lo tile
+              tma_load_5d(&p.tmA[0], &full_bar[s], st, tap.c_off + ch * 64, w0 + tap.dw, h0 + tap.dh, n0, 0);
+            } else {
 #pragma unroll
-            for (int pl = 0; pl < C::kPlanes; ++pl) {
-              tma_load_5d(&p.tmA[pl], &full_bar[s], st + pl * kTileBytes, tap.c_off + ch * 64,
-                          w0 + tap.dw, tap.hp, h0 + tap.dh, n0);
-              tma_load_2d(&p.tmB[pl], &full_bar[s], st + (C::kPlanes + pl) * kTileBytes,
-                          tap.kb_off + ch * 64, ncol0);
+              for (int pl = 0; pl < C::kPlanes; ++pl)
+                tma_load_5d(&p.tmA[pl], &full_bar[s], st + pl * kTileBytes, tap.c_off + ch * 64,
+                            w0 + tap.dw, tap.hp, h0 + tap.dh, n0);
+            }
+            if (p.b_merged) {   // dims (k, row, plane)
+              tma_load_3d(&p.tmB[0], &full_bar[s], st + C::kPlanes * kTileBytes, tap.kb_off + ch * 64, ncol0, 0);
+            } else {
+#pragma unroll
+              for (int pl = 0; pl < C::kPlanes; ++pl)
+                tma_load_2d(&p.tmB[pl], &full_bar[s], st + (C::kPlanes + pl) * kTileBytes,
+                            tap.kb_off + ch * 64, ncol0);
             }
           } else {
             // narrow operand: 64/cw taps, each a [128 rows][cw channels] sub-tile, fill one stage; the
@@ -147,9 +156,13 @@ tap_gemm_kernel(const __grid_constant__ TapGemmParams p, const int m_tiles, cons
                             w0 + tap.dw, tap.hp, h0 + tap.dh, n0);
             }
             const int kb = p.taps[tap0 + k * tps].kb_off;
+            if (p.b_merged) {
+              tma_load_3d(&p.tmB[0], &full_bar[s], st + C::kPlanes * kTileBytes, kb, ncol0, 0);
+            } else {
 #pragma unroll
-            for (int pl = 0; pl < C::kPlanes; ++pl)
-              tma_load_2d(&p.tmB[pl], &full_bar[s], st + (C::kPlanes + pl) * kTileBytes, kb, ncol0);
+              for (int pl = 0; pl < C::kPlanes; ++pl)
+                tma_load_2d(&p.tmB[pl], &full_bar[s], st + (C::kPlanes + pl) * kTileBytes, kb, ncol0);
+            }
           }
         }
       }
@@ -176,8 +189,8 @@ tap_gemm_kernel(const __grid_constant__ TapGemmParams p, const int m_tiles, cons
           constexpr uint32_t a_sbo = 8u * cw * 2u;
           const uint64_t a_hi = umma_smem_desc(st, 16, a_sbo, a_layout);
           const uint64_t b_hi = umma_smem_desc(st + C::kPlanes * kTileBytes, 16, 1024);
-          const uint64_t a_lo = umma_smem_desc(st + kTileBytes, 16, a_sbo, a_layout);
-          const uint64_t b_lo = umma_smem_desc(st + (C::kPlanes + 1) * kTileBytes, 16, 1024);
+          const uint64_t a_lo = umma_smem_desc(st + p.a_lo_off, 16, a_sbo, a_layout);
+          const uint64_t b_lo = umma_smem_desc(st + C::kPlanes * kTileBytes + p.b_lo_off, 16, 1024);
           constexpr uint32_t sub16 = (uint32_t)(128 * cw * 2) >> 4;  // sub-tile stride in 16-B units
 #pragma unroll
           for (int kk = 0; kk < 4; ++kk) {  // 4 x (UMMA_K = 16 elements = 32 B) per 64-deep stage
@@ -330,28 +343,50 @@ wgrad_gemm_kernel(const __grid_constant__ WgradParams p) {
       if (lane == 0) {
         const TapDesc xt = p.xtaps[tap_i];
         const uint32_t stage_tx = C::kPlanes * (2 * 8192 + y_blocks * y_block_bytes);
+        // rot_mode 0: every CTA walks the pixel tiles in the same order (a narrow wavefront shared through L2);
+        // 1: staggered per tap (blockIdx.y); 2: staggered per CTA
+        int rot = 0;
+        if (p.rot_mode == 1) rot = (int)(((long long)k_iters * blockIdx.y) / gridDim.y);
+        else if (p.rot_mode == 2)
+          rot = (int)(((long long)k_iters * ((blockIdx.x + blockIdx.y * gridDim.x) % 148)) / 148);
         for (int it = 0; it < k_iters; ++it) {
           const int s = it % C::kStages;
           const uint32_t ph = (it / C::kStages) & 1;
           mbar_wait(&empty_bar[s], ph ^ 1);
           mbar_expect_tx(&full_bar[s], stage_tx);
-          const int kt = kt0 + it;
+          int kr = it + rot;                       // per-CTA rotation of the pixel-tile order (see p.rot_mode)
+          if (kr >= k_iters) kr -= k_iters;
+          const int kt = kt0 + kr;
           const int tw_i = kt % p.tiles_w;
           const int th_i = (kt / p.tiles_w) % p.tiles_h;
           const int tn_i = kt / (p.tiles_w * p.tiles_h);
           const int w0 = tw_i * p.tw, h0 = th_i * p.th, n0 = tn_i * p.nb;
           uint8_t* st = smem + s * C::kStageBytes;
-#pragma unroll
-          for (int pl = 0; pl < C::kPlanes; ++pl) {
+          if (p.x_merged) {   // one box per 64-channel block: [hi 8 KB][lo 8 KB]
             for (int b = 0; b < 2; ++b)
-              tma_load_5d(&p.tmX[pl], &full_bar[s], st + pl * kTileBytes + b * 8192,
-                          xt.c_off + m0 + b * 64, w0 + xt.dw, xt.hp, h0 + xt.dh, n0);
-            for (int b = 0; b < y_blocks; ++b) {
-              const TapDesc yt = p.ytaps[grouped ? tap_i + b : tap_i];
-              tma_load_5d(&p.tmY[pl], &full_bar[s],
-                          st + (C::kPlanes + pl) * kTileBytes + b * y_block_bytes,
-                          yt.c_off + (grouped ? 0 : ncol0 + b * 64), w0 + yt.dw, yt.hp, h0 + yt.dh, n0);
-            }
+              tma_load_5d(&p.tmX[0], &full_bar[s], st + b * 16384, xt.c_off + m0 + b * 64, w0 + xt.dw, h0 + xt.dh,
+                          n0, 0);
+          } else {
+#pragma unroll
+            for (int pl = 0; pl < C::kPlanes; ++pl)
+              for (int b = 0; b < 2; ++b)
+                tma_load_5d(&p.tmX[pl], &full_bar[s], st + pl * kTileBytes + b * 8192,
+                            xt.c_off + m0 + b * 64, w0 + xt.dw, xt.hp, h0 + xt.dh, n0);
+          }
+          if (p.y_merged) {
+            const TapDesc yt = p.ytaps[tap_i];
+            for (int b = 0; b < y_blocks; ++b)
+              tma_load_5d(&p.tmY[0], &full_bar[s], st + C::kPlanes * kTileBytes + b * 16384,
+                          yt.c_off + ncol0 + b * 64, w0 + yt.dw, h0 + yt.dh, n0, 0);
+          } else {
+#pragma unroll
+            for (int pl = 0; pl < C::kPlanes; ++pl)
+              for (int b = 0; b < y_blocks; ++b) {
+                const TapDesc yt = p.ytaps[grouped ? tap_i + b : tap_i];
+                tma_load_5d(&p.tmY[pl], &full_bar[s],
+                            st + (C::kPlanes + pl) * kTileBytes + b * y_block_bytes,
+                            yt.c_off + (grouped ? 0 : ncol0 + b * 64), w0 + yt.dw, yt.hp, h0 + yt.dh, n0);
+              }
           }
         }
       }
@@ -369,11 +404,16 @@ wgrad_gemm_kernel(const __grid_constant__ WgradParams p) {
           // SBO = stride between 8-pixel groups (1024 B)
           const uint32_t y_layout = umma_layout_of_chunk(ycw);
           const uint32_t y_sbo = 8u * ycw * 2u;              // 8 pixel rows of the narrow / full atom
-          const uint64_t x_hi = umma_smem_desc(st, 8192, 1024);
+          // merged planes: the 64-channel blocks are [hi 8 KB][lo 8 KB] pairs, 16 KB apart
+          const uint32_t x_lbo = p.x_merged ? 16384u : 8192u;
+          const uint32_t x_lo_off = p.x_merged ? 8192u : (uint32_t)kTileBytes;
+          const uint32_t y_lbo = p.y_merged ? 16384u : (uint32_t)y_block_bytes;
+          const uint32_t y_lo_off = p.y_merged ? 8192u : (uint32_t)kTileBytes;
+          const uint64_t x_hi = umma_smem_desc(st, x_lbo, 1024);
           // LBO = stride between the N atoms (64-channel blocks, or the grouped taps' narrow blocks)
-          const uint64_t y_hi = umma_smem_desc(st + C::kPlanes * kTileBytes, y_block_bytes, y_sbo, y_layout);
-          const uint64_t x_lo = umma_smem_desc(st + kTileBytes, 8192, 1024);
-          const uint64_t y_lo = umma_smem_desc(st + (C::kPlanes + 1) * kTileBytes, y_block_bytes, y_sbo, y_layout);
+          const uint64_t y_hi = umma_smem_desc(st + C::kPlanes * kTileBytes, y_lbo, y_sbo, y_layout);
+          const uint64_t x_lo = umma_smem_desc(st + x_lo_off, x_lbo, 1024);
+          const uint64_t y_lo = umma_smem_desc(st + C::kPlanes * kTileBytes + y_lo_off, y_lbo, y_sbo, y_layout);
 #pragma unroll
           for (int k = 0; k < 4; ++k) {  // 4 x 16 pixels; 16 pixel rows = 2048 B (X), 16 * ycw * 2 B (Y)
             const uint64_t xadv = (uint64_t)(k * 128);
@@ -453,8 +493,10 @@ static PFN_encodeTiled get_encode_fn() {
 }
 
 // 5-D map over a split-bf16 NHWC plane.  dims (c', w, hp, h, n); see file header.
+// plane_stride > 0 (non-parity only): one extra outermost dimension of 2 planes (hi, lo) `plane_stride`
+// bytes apart -> dims (c, w, h, n, plane); otherwise dims (c', w, h parity, h, n).
 int sn_make_act_map(CUtensorMap* tm, const void* base, int N, int H, int W, int C, int pitch,
-                    int parity, int box_w, int box_h, int box_n, int chunk = 64) {
+                    int parity, int box_w, int box_h, int box_n, int chunk = 64, long long plane_stride = 0) {
   PFN_encodeTiled enc = get_encode_fn();
   SN_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled driver entry point unavailable");
   SN_REQUIRE(pitch % 8 == 0 && ((uintptr_t)base % 16) == 0,
@@ -464,7 +506,16 @@ int sn_make_act_map(CUtensorMap* tm, const void* base, int N, int H, int W, int 
   cuuint64_t dims[5];
   cuuint64_t strides[4];
   const cuuint64_t e = 2;  // bytes per bf16
-  if (!parity) {
+  cuuint32_t box[5] = {(cuuint32_t)chunk, (cuuint32_t)box_w, 1, (cuuint32_t)box_h, (cuuint32_t)box_n};
+  if (plane_stride > 0) {
+    SN_REQUIRE(!parity && plane_stride % 16 == 0, "merged planes: non-parity operand, 16-B aligned plane stride");
+    dims[0] = C; dims[1] = W; dims[2] = H; dims[3] = N; dims[4] = 2;
+    strides[0] = (cuuint64_t)pitch * e;
+    strides[1] = (cuuint64_t)W * pitch * e;
+    strides[2] = (cuuint64_t)H * W * pitch * e;
+    strides[3] = (cuuint64_t)plane_stride;
+    box[2] = (cuuint32_t)box_h; box[3] = (cuuint32_t)box_n; box[4] = 2;
+  } else if (!parity) {
     dims[0] = C; dims[1] = W; dims[2] = 1; dims[3] = H; dims[4] = N;
     strides[0] = (cuuint64_t)pitch * e;
     strides[1] = (cuuint64_t)W * pitch * e;
@@ -479,7 +530,6 @@ int sn_make_act_map(CUtensorMap* tm, const void* base, int N, int H, int W, int 
     strides[3] = (cuuint64_t)H * W * pitch * e;
   }
   SN_REQUIRE(chunk == 64 || chunk == 32 || chunk == 16, "row chunk must be 64, 32 or 16 channels (got %d)", chunk);
-  cuuint32_t box[5] = {(cuuint32_t)chunk, (cuuint32_t)box_w, 1, (cuuint32_t)box_h, (cuuint32_t)box_n};
   cuuint32_t estr[5] = {1, 1, 1, 1, 1};
   const CUtensorMapSwizzle swz = chunk == 64 ? CU_TENSOR_MAP_SWIZZLE_128B
                                  : chunk == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
@@ -493,15 +543,16 @@ int sn_make_act_map(CUtensorMap* tm, const void* base, int N, int H, int W, int 
 }
 
 // 2-D map over packed weights [rows][k_total] bf16, K contiguous.
-int sn_make_weight_map(CUtensorMap* tm, const void* base, int rows, long long k_total, int box_rows) {
+int sn_make_weight_map(CUtensorMap* tm, const void* base, int rows, long long k_total, int box_rows,
+                       long long plane_stride = 0) {
   PFN_encodeTiled enc = get_encode_fn();
   SN_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled driver entry point unavailable");
   SN_REQUIRE(k_total % 64 == 0 && ((uintptr_t)base % 16) == 0, "packed weights need K %% 64 == 0");
-  cuuint64_t dims[2] = {(cuuint64_t)k_total, (cuuint64_t)rows};
-  cuuint64_t strides[1] = {(cuuint64_t)k_total * 2};
-  cuuint32_t box[2] = {64, (cuuint32_t)box_rows};
-  cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides,
+  cuuint64_t dims[3] = {(cuuint64_t)k_total, (cuuint64_t)rows, 2};
+  cuuint64_t strides[2] = {(cuuint64_t)k_total * 2, (cuuint64_t)plane_stride};
+  cuuint32_t box[3] = {64, (cuuint32_t)box_rows, 2};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, plane_stride > 0 ? 3 : 2, const_cast<void*>(base), dims, strides,
                    box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   SN_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(weights) failed: %d (rows=%d K=%lld box_rows=%d)",
@@ -620,13 +671,31 @@ int sn_tap_gemm_plan_init(TapGemmPlan* plan, const sn_tap_gemm_desc* d) {
   int rc;
   const void* a_pl[2] = {d->a_hi, d->a_lo};
   const void* b_pl[2] = {d->b_hi, d->b_lo};
-  for (int pl = 0; pl < (d->nsplit == 3 ? 2 : 1); ++pl) {
-    rc = sn_make_act_map(&p.tmA[pl], a_pl[pl], d->a_n, d->a_h, d->a_w, d->a_c, d->a_pitch,
-                         d->a_parity, tw, th, nb, a_chunk);
-    if (rc) return rc;
-    rc = sn_make_weight_map(&p.tmB[pl], b_pl[pl], d->b_rows, d->b_k, d->block_n);
-    if (rc) return rc;
+  static int merge_ok = -1;
+  if (merge_ok < 0) {
+    const char* e = getenv("SN_NO_MERGED_PLANES");   // A/B switch
+    merge_ok = (e && e[0] == '1') ? 0 : 1;
   }
+  const long long a_ps = d->nsplit == 3 ? (const char*)d->a_lo - (const char*)d->a_hi : 0;
+  const long long b_ps = d->nsplit == 3 ? (const char*)d->b_lo - (const char*)d->b_hi : 0;
+  // the lo tile must start on a swizzle-atom boundary (8 rows x 128 B)
+  p.a_merged = merge_ok && a_chunk == 64 && !d->a_parity && a_ps > 0 && a_ps % 16 == 0 && p.a_rows % 8 == 0;
+  p.b_merged = merge_ok && b_ps > 0 && b_ps % 16 == 0 && d->block_n % 8 == 0;
+  p.a_lo_off = p.a_merged ? p.a_rows * 128 : kTileBytes;
+  p.b_lo_off = p.b_merged ? d->block_n * 128 : kTileBytes;
+  for (int pl = 0; pl < (d->nsplit == 3 ? 2 : 1); ++pl) {
+    if (!(p.a_merged && pl == 1)) {
+      rc = sn_make_act_map(&p.tmA[pl], a_pl[pl], d->a_n, d->a_h, d->a_w, d->a_c, d->a_pitch,
+                           d->a_parity, tw, th, nb, a_chunk, p.a_merged ? a_ps : 0);
+      if (rc) return rc;
+    }
+    if (!(p.b_merged && pl == 1)) {
+      rc = sn_make_weight_map(&p.tmB[pl], b_pl[pl], d->b_rows, d->b_k, d->block_n, p.b_merged ? b_ps : 0);
+      if (rc) return rc;
+    }
+  }
+  if (p.a_merged) p.tmA[1] = p.tmA[0];
+  if (p.b_merged) p.tmB[1] = p.tmB[0];
   plan->nsplit = d->nsplit;
   plan->grid = dim3(p.tiles_w * p.tiles_h * p.tiles_n, (d->n_valid + d->block_n - 1) / d->block_n, p.nphase);
   return SN_OK;
@@ -733,18 +802,38 @@ int sn_wgrad_plan_init(WgradPlan* plan, const sn_wgrad_desc* d, int sm_count) {
   int rc;
   const void* x_pl[2] = {d->x_hi, d->x_lo};
   const void* y_pl[2] = {d->y_hi, d->y_lo};
-  for (int pl = 0; pl < (d->nsplit == 3 ? 2 : 1); ++pl) {
-    rc = sn_make_act_map(&p.tmX[pl], x_pl[pl], d->x_n, d->x_h, d->x_w, d->x_c, d->x_pitch,
-                         d->x_parity, tw, th, nb);
-    if (rc) return rc;
-    rc = sn_make_act_map(&p.tmY[pl], y_pl[pl], d->y_n, d->y_h, d->y_w, d->y_c, d->y_pitch,
-                         d->y_parity, tw, th, nb, y_chunk);
-    if (rc) return rc;
+  {
+    const char* e = getenv("SN_NO_MERGED_PLANES");
+    const bool merge_ok = !(e && e[0] == '1');
+    const long long x_ps = d->nsplit == 3 ? (const char*)d->x_lo - (const char*)d->x_hi : 0;
+    const long long y_ps = d->nsplit == 3 ? (const char*)d->y_lo - (const char*)d->y_hi : 0;
+    p.x_merged = merge_ok && !d->x_parity && x_ps > 0 && x_ps % 16 == 0 && tw * th * nb == 64;
+    p.y_merged = merge_ok && !d->y_parity && y_ps > 0 && y_ps % 16 == 0 && tw * th * nb == 64 && y_chunk == 64 &&
+                 d->ngroups == 0;
+    for (int pl = 0; pl < (d->nsplit == 3 ? 2 : 1); ++pl) {
+      if (!(p.x_merged && pl == 1)) {
+        rc = sn_make_act_map(&p.tmX[pl], x_pl[pl], d->x_n, d->x_h, d->x_w, d->x_c, d->x_pitch,
+                             d->x_parity, tw, th, nb, 64, p.x_merged ? x_ps : 0);
+        if (rc) return rc;
+      }
+      if (!(p.y_merged && pl == 1)) {
+        rc = sn_make_act_map(&p.tmY[pl], y_pl[pl], d->y_n, d->y_h, d->y_w, d->y_c, d->y_pitch,
+                             d->y_parity, tw, th, nb, y_chunk, p.y_merged ? y_ps : 0);
+        if (rc) return rc;
+      }
+    }
+    if (p.x_merged) p.tmX[1] = p.tmX[0];
+    if (p.y_merged) p.tmY[1] = p.tmY[0];
   }
   plan->nsplit = d->nsplit;
   const int base_ctas = p.m_tiles * p.n_tiles * grid_y;
   const int total = p.tiles_w * p.tiles_h * p.tiles_n;
+  p.rot_mode = 0;
+  if (const char* e = getenv("SN_WGRAD_ROT")) p.rot_mode = atoi(e);
   int ks = d->ksplit;
+  if (const char* e = getenv("SN_WGRAD_KSPLIT")) {   // experiment override
+    if (atoi(e) > 0) ks = atoi(e);
+  }
   if (ks <= 0) {  // aim for ~3 waves, at least 8 k-iterations per CTA
     ks = (3 * sm_count + base_ctas - 1) / base_ctas;
     int max_ks = total / 8;

@@ -30,6 +30,10 @@ struct alignas(64) TapGemmParams {
   int a_fmt, b_fmt;
   int a_chunk;  // 64 / 32 / 16 channels per A row
   int nphase;   // 1 or 4 (grid.z = output parity phase; taps split in nphase equal groups)
+  // merged planes: hi and lo of an operand live `plane stride` apart in one buffer and come in ONE TMA box
+  // (an extra outermost box dimension of 2) — the TMA unit is bound by the number of box operations, not bytes
+  int a_merged, b_merged;
+  int a_lo_off, b_lo_off;   // byte offset of the lo tile behind the hi tile inside a stage
 };
 
 struct alignas(64) WgradParams {
@@ -48,6 +52,8 @@ struct alignas(64) WgradParams {
   int x_fmt, y_fmt;
   int y_chunk;  // 64 / 32 / 16 channels per Y row
   int ngroups;  // > 0: narrow-Y tap groups (grid.y = group)
+  int x_merged, y_merged;   // hi+lo of a 64-channel block in one TMA box (see TapGemmParams)
+  int rot_mode; // pixel-tile order stagger (0 none, 1 per tap, 2 per CTA)
   short gstart[SN_MAX_TAPS], gsize[SN_MAX_TAPS];
 };
 

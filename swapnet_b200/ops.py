@@ -50,8 +50,13 @@ class Planes:
         self.n, self.h, self.w, self.pitch = n, h, w, pitch
         self.c = pitch if c is None else c
         self.c_off = c_off
-        self.hi = hi if hi is not None else torch.zeros(n, h, w, pitch, dtype=torch.bfloat16, device=device)
-        self.lo = lo if lo is not None else torch.zeros(n, h, w, pitch, dtype=torch.bfloat16, device=device)
+        if hi is None:
+            # hi and lo live in ONE buffer, a fixed plane stride apart: the GEMM kernels then fetch both planes of
+            # a tile with a single TMA box (extra box dimension of 2) — views (slice / batch_slice) keep the stride
+            assert lo is None
+            buf = torch.zeros(2, n, h, w, pitch, dtype=torch.bfloat16, device=device)
+            hi, lo = buf[0], buf[1]
+        self.hi, self.lo = hi, lo
 
     def slice(self, c_off: int, c: int) -> "Planes":
         assert c_off + c <= self.pitch
@@ -87,8 +92,8 @@ class PackedWeights:
         self.fmt = fmt
         # bf16-split packs (backward GEMMs) are unscaled; fp16-split packs carry the per-tensor 2^k
         self.scale = scale if (scale is not None and fmt == FMT_F16) else None
-        self.hi = torch.zeros(rows, k_total, dtype=torch.bfloat16, device=device)
-        self.lo = torch.zeros(rows, k_total, dtype=torch.bfloat16, device=device)
+        buf = torch.zeros(2, rows, k_total, dtype=torch.bfloat16, device=device)   # one buffer: see Planes
+        self.hi, self.lo = buf[0], buf[1]
 
 
 class Plan:
