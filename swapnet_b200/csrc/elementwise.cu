@@ -683,6 +683,22 @@ __global__ void upsample_planes_kernel(const uint16_t* __restrict__ shi, const u
   }
 }
 
+// 4 channels (8 bytes) per thread: c, pitches and channel offsets multiples of 4
+__global__ void upsample_planes_v4_kernel(const uint16_t* __restrict__ shi, const uint16_t* __restrict__ slo,
+                                          int spitch, int H, int W, int C4, int f, uint16_t* __restrict__ dhi,
+                                          uint16_t* __restrict__ dlo, int dpitch, long long total) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C4) * 4;
+    const long long pix = i / C4;
+    const int w = (int)(pix % W), h = (int)((pix / W) % H);
+    const long long n = pix / ((long long)W * H);
+    const long long sp = (n * (H / f) + h / f) * (W / f) + w / f;
+    *reinterpret_cast<uint2*>(dhi + pix * dpitch + c) = *reinterpret_cast<const uint2*>(shi + sp * spitch + c);
+    if (dlo) *reinterpret_cast<uint2*>(dlo + pix * dpitch + c) = *reinterpret_cast<const uint2*>(slo + sp * spitch + c);
+  }
+}
+
 // ---------------------------------------------------------------------------------
 // fused AdamW over flat fp32 buffers (torch.optim.AdamW semantics, optimizers/__init__.py:48-59):
 //   p *= 1 - lr*wd;  m += (g - m)(1 - b1);  v = v*b2 + (1 - b2) g*g;
@@ -1454,6 +1470,16 @@ int sn_upsample_planes(const void* src_hi, const void* src_lo, int src_pitch, in
                        int c, int factor, void* dst_hi, void* dst_lo, int dst_pitch, int dst_coff, void* stream) {
   SN_REQUIRE(src_hi && dst_hi && factor >= 1 && h % factor == 0 && w % factor == 0, "bad upsample arguments");
   const long long total = (long long)n * h * w * c;
+  if (c % 4 == 0 && src_pitch % 4 == 0 && dst_pitch % 4 == 0 && src_coff % 4 == 0 && dst_coff % 4 == 0 &&
+      ((uintptr_t)src_hi % 8) == 0 && ((uintptr_t)dst_hi % 8) == 0 && (!src_lo || ((uintptr_t)src_lo % 8) == 0) &&
+      (!dst_lo || ((uintptr_t)dst_lo % 8) == 0)) {
+    upsample_planes_v4_kernel<<<grid_for(total / 4), kEwThreads, 0, (cudaStream_t)stream>>>(
+        (const uint16_t*)src_hi + src_coff, src_lo ? (const uint16_t*)src_lo + src_coff : nullptr, src_pitch, h, w,
+        c / 4, factor, (uint16_t*)dst_hi + dst_coff, dst_lo ? (uint16_t*)dst_lo + dst_coff : nullptr, dst_pitch,
+        total / 4);
+    LAUNCH_CHECK();
+    return SN_OK;
+  }
   upsample_planes_kernel<<<grid_for(total), kEwThreads, 0, (cudaStream_t)stream>>>(
       (const uint16_t*)src_hi + src_coff, src_lo ? (const uint16_t*)src_lo + src_coff : nullptr, src_pitch, h, w, c,
       factor, (uint16_t*)dst_hi + dst_coff, dst_lo ? (uint16_t*)dst_lo + dst_coff : nullptr, dst_pitch, total);

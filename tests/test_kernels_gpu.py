@@ -493,3 +493,22 @@ def test_gram_style_loss(n, s):
     dx = base.clone().to(dev())
     ops.gram_bwd(m, fk, True, dx, accumulate=True)
     assert relmax(dx.cpu(), base.double() + nhwc(gx)) < 1e-4
+
+
+@pytest.mark.parametrize("c,f", [(36, 8), (6, 2), (64, 4)])
+def test_upsample_planes(c, f):
+    """F.interpolate(scale_factor=f) (nearest) of the encoded textures (swapnet_modules.py:244-247) on split planes."""
+    from swapnet_b200 import ops
+
+    g = torch.Generator().manual_seed(c)
+    n, h, w = 2, 4, 6
+    x = torch.randn(n, c, h, w, generator=g)
+    src = ops.Planes(n, h, w, 64, dev(), c=L.padc(c) if c > 8 else 8)
+    ops.pack_planes(x.to(dev()), src.slice(0, c))
+    dst = ops.Planes(n, h * f, w * f, 128, dev(), c=64, c_off=8)
+    ops.upsample_planes(src.slice(0, c), dst.slice(0, c), f)
+    torch.cuda.synchronize()
+    ref = nhwc(F.interpolate(x, scale_factor=f))
+    got = dst.dense().cpu()
+    assert relmax(got[..., :c], ref) < 1e-6
+    assert torch.all(got[..., c:] == 0)
