@@ -508,10 +508,19 @@ int sn_make_act_map(CUtensorMap* tm, const void* base, int N, int H, int W, int 
   const cuuint64_t e = 2;  // bytes per bf16
   cuuint32_t box[5] = {(cuuint32_t)chunk, (cuuint32_t)box_w, 1, (cuuint32_t)box_h, (cuuint32_t)box_n};
   if (plane_stride > 0) {
-    SN_REQUIRE(!parity && plane_stride % 16 == 0, "merged planes: non-parity operand, 16-B aligned plane stride");
-    dims[0] = C; dims[1] = W; dims[2] = H; dims[3] = N; dims[4] = 2;
-    strides[0] = (cuuint64_t)pitch * e;
-    strides[1] = (cuuint64_t)W * pitch * e;
+    SN_REQUIRE(plane_stride % 16 == 0, "merged planes: 16-B aligned plane stride");
+    if (!parity) {
+      dims[0] = C; dims[1] = W; dims[2] = H; dims[3] = N; dims[4] = 2;
+      strides[0] = (cuuint64_t)pitch * e;
+      strides[1] = (cuuint64_t)W * pitch * e;
+    } else {
+      // parity view with BOTH parities folded into the channel coordinate: c' = hp*W*pitch + pw*pitch + c
+      // (overlapping dimensions are fine for loads), dims (c', w/2, h/2, n, plane)
+      SN_REQUIRE(H % 2 == 0 && W % 2 == 0, "parity view needs even H, W (got %d x %d)", H, W);
+      dims[0] = (cuuint64_t)(W + 1) * pitch + C; dims[1] = W / 2; dims[2] = H / 2; dims[3] = N; dims[4] = 2;
+      strides[0] = (cuuint64_t)2 * pitch * e;
+      strides[1] = (cuuint64_t)2 * W * pitch * e;
+    }
     strides[2] = (cuuint64_t)H * W * pitch * e;
     strides[3] = (cuuint64_t)plane_stride;
     box[2] = (cuuint32_t)box_h; box[3] = (cuuint32_t)box_n; box[4] = 2;
@@ -679,7 +688,9 @@ int sn_tap_gemm_plan_init(TapGemmPlan* plan, const sn_tap_gemm_desc* d) {
   const long long a_ps = d->nsplit == 3 ? (const char*)d->a_lo - (const char*)d->a_hi : 0;
   const long long b_ps = d->nsplit == 3 ? (const char*)d->b_lo - (const char*)d->b_hi : 0;
   // the lo tile must start on a swizzle-atom boundary (8 rows x 128 B)
-  p.a_merged = merge_ok && a_chunk == 64 && !d->a_parity && a_ps > 0 && a_ps % 16 == 0 && p.a_rows % 8 == 0;
+  p.a_merged = merge_ok && a_chunk == 64 && a_ps > 0 && a_ps % 16 == 0 && p.a_rows % 8 == 0;
+  if (p.a_merged && d->a_parity)   // h parity moves into the channel coordinate of the merged parity map
+    for (int t = 0; t < d->ntaps; ++t) p.taps[t].c_off += p.taps[t].hp * d->a_w * d->a_pitch;
   p.b_merged = merge_ok && b_ps > 0 && b_ps % 16 == 0 && d->block_n % 8 == 0;
   p.a_lo_off = p.a_merged ? p.a_rows * 128 : kTileBytes;
   p.b_lo_off = p.b_merged ? d->block_n * 128 : kTileBytes;
@@ -807,9 +818,12 @@ int sn_wgrad_plan_init(WgradPlan* plan, const sn_wgrad_desc* d, int sm_count) {
     const bool merge_ok = !(e && e[0] == '1');
     const long long x_ps = d->nsplit == 3 ? (const char*)d->x_lo - (const char*)d->x_hi : 0;
     const long long y_ps = d->nsplit == 3 ? (const char*)d->y_lo - (const char*)d->y_hi : 0;
-    p.x_merged = merge_ok && !d->x_parity && x_ps > 0 && x_ps % 16 == 0 && tw * th * nb == 64;
-    p.y_merged = merge_ok && !d->y_parity && y_ps > 0 && y_ps % 16 == 0 && tw * th * nb == 64 && y_chunk == 64 &&
-                 d->ngroups == 0;
+    p.x_merged = merge_ok && x_ps > 0 && x_ps % 16 == 0 && tw * th * nb == 64;
+    p.y_merged = merge_ok && y_ps > 0 && y_ps % 16 == 0 && tw * th * nb == 64 && y_chunk == 64 && d->ngroups == 0;
+    for (int t = 0; t < d->ntaps; ++t) {   // h parity -> channel coordinate of the merged parity maps
+      if (p.x_merged && d->x_parity) p.xtaps[t].c_off += p.xtaps[t].hp * d->x_w * d->x_pitch;
+      if (p.y_merged && d->y_parity) p.ytaps[t].c_off += p.ytaps[t].hp * d->y_w * d->y_pitch;
+    }
     for (int pl = 0; pl < (d->nsplit == 3 ? 2 : 1); ++pl) {
       if (!(p.x_merged && pl == 1)) {
         rc = sn_make_act_map(&p.tmX[pl], x_pl[pl], d->x_n, d->x_h, d->x_w, d->x_c, d->x_pitch,
