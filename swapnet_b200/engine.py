@@ -226,12 +226,21 @@ class WarpEngine(Engine):
                            self.u1, self.u2] + [s for pair in self.res for s in pair] + [self.d1, self.d2, self.d3, self.head]
         self._dres: List[torch.Tensor] = []
 
-    def forward(self, body: torch.Tensor, cloth: torch.Tensor, training: bool = True, seed: int = 0) -> torch.Tensor:
-        """body [B,cb,S,S], cloth [B,cc,S,S] fp32 NCHW on device -> fakes [B,S,S,cc] (NHWC storage)."""
+    def forward(self, body: torch.Tensor, cloth: torch.Tensor, training: bool = True, seed: int = 0,
+                before_cloth=None) -> torch.Tensor:
+        """body [B,cb,S,S], cloth [B,cc,S,S] fp32 NCHW on device -> fakes [B,S,S,cc] (NHWC storage).
+        before_cloth(): called after the body branch (body_down1..4, which does not read the cloth) has been
+        enqueued and before the cloth is first read — the plugin waits there for the cloth's H2D copy."""
         self.training, self.seed = training, seed
         ops.pack_concat([(body, False)], self.in_body)
+        nbody = 4
+        assert self._fwd_order[nbody - 1] is self.b4
+        for s in self._fwd_order[:nbody]:
+            s.forward()
+        if before_cloth is not None:
+            before_cloth()
         ops.pack_concat([(cloth, False)], self.in_cloth)
-        for s in self._fwd_order:
+        for s in self._fwd_order[nbody:]:
             s.forward()
         return self.fakes
 
@@ -400,7 +409,7 @@ class TextureEngine(Engine):
         self.up[0] = St("unet.U0", "convT4s2", blocks[0].up, self.cu[0], plain=True, epi_act=ACT_TANH, y=self.fakes)
 
     def forward(self, tex: torch.Tensor, rois: torch.Tensor, cloth: torch.Tensor, training: bool = True,
-                seed: int = 0) -> torch.Tensor:
+                seed: int = 0, before_cloth=None) -> torch.Tensor:
         """tex [B,3,S,S], rois [B,12,4], cloth [B,19,S,S] (fp32, device) -> fakes [B,S,S,3] NHWC."""
         self.training, self.seed = training, seed
         ops.roi_align_pack(tex, rois, self.pool, None, self.pooled.slice(0, self.ch))
@@ -408,6 +417,8 @@ class TextureEngine(Engine):
             ops.roi_align_pack(tex, rois, self.pool, None, self.pooled.twin.slice(0, self.ch))
         self.encode.forward()
         ops.upsample_planes(self.enc.slice(0, self.ch), self.in_unet.slice(0, self.ch), self.up_factor)
+        if before_cloth is not None:       # the plugin waits here for the cloth's H2D copy
+            before_cloth()
         ops.pack_planes(cloth, self.in_unet.slice(self.ch, self.cc))
         for st in self.down:
             st.forward()

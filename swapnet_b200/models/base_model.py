@@ -52,12 +52,16 @@ class BaseModel(ABC):
         self.training = True
 
     # ---- late H2D copies: tensors that the step needs only after its first phase ----
-    def copy_late(self, t: torch.Tensor) -> torch.Tensor:
+    def copy_late(self, t: torch.Tensor, key: str = None) -> torch.Tensor:
+        """H2D copy on a side stream (pinned host tensors; plain conversion for device tensors).  The step
+        waits for it where the tensor is first needed: `wait_copy(key)` or, for everything still pending,
+        `wait_late_copies()`.  Copies run in issue order, so the tensors a step needs first go first."""
         if t.is_cuda:
             return t.to(device=self.device, dtype=torch.float32).contiguous()
         if not hasattr(self, "_copy_stream"):
             self._copy_stream = torch.cuda.Stream(device=self.device)
             self._late_events = []
+            self._copy_events = {}
         cur = torch.cuda.current_stream(self.device)
         self._copy_stream.wait_stream(cur)   # the destination buffer may still be read by earlier work
         with torch.cuda.stream(self._copy_stream):
@@ -66,13 +70,23 @@ class BaseModel(ABC):
             ev.record(self._copy_stream)
         out.record_stream(cur)
         self._late_events.append(ev)
+        if key is not None:
+            self._copy_events[key] = ev
         return out
+
+    def wait_copy(self, key: str) -> None:
+        ev = getattr(self, "_copy_events", {}).pop(key, None)
+        if ev is not None:
+            torch.cuda.current_stream(self.device).wait_event(ev)
+            if ev in self._late_events:
+                self._late_events.remove(ev)
 
     def wait_late_copies(self) -> None:
         for ev in getattr(self, "_late_events", []):
             torch.cuda.current_stream(self.device).wait_event(ev)
         if hasattr(self, "_late_events"):
             self._late_events.clear()
+            self._copy_events.clear()
 
     @staticmethod
     def modify_commandline_options(parser, is_train):

@@ -93,11 +93,11 @@ class TextureModel(BaseGAN):
                                              content=self.lam_content != 0)
 
     def set_input(self, input):
-        f32 = dict(device=self.device, dtype=torch.float32, non_blocking=True)
-        self.textures = input["input_textures"].to(**f32).contiguous()
-        self.rois = input["rois"].to(**f32).contiguous()
-        self.cloths = input["cloths"].to(**f32).contiguous()
-        self.targets = self.copy_late(input["target_textures"])
+        # side-stream H2D copies in the order the step needs them (see WarpModel.set_input)
+        self.textures = self.copy_late(input["input_textures"], "textures")
+        self.rois = self.copy_late(input["rois"], "rois")
+        self.cloths = self.copy_late(input["cloths"], "cloths")
+        self.targets = self.copy_late(input["target_textures"], "targets")
         self.image_paths = tuple(zip(input["cloth_paths"], input["texture_paths"]))
 
     def forward(self):
@@ -105,9 +105,11 @@ class TextureModel(BaseGAN):
         assert S == S2, "square inputs expected"
         self.ensure_engines(B, S)
         g = self._eng_G
-        g.pack()
+        g.pack()                      # needs the weights only: overlaps the input copies
+        self.wait_copy("textures")
+        self.wait_copy("rois")
         out = g.forward(self.textures, self.rois, self.cloths, training=self.training and self.is_train,
-                        seed=self.step_seed())
+                        seed=self.step_seed(), before_cloth=lambda: self.wait_copy("cloths"))
         self.fakes = out.permute(0, 3, 1, 2)
         self.wait_late_copies()
 

@@ -69,12 +69,12 @@ class WarpModel(BaseGAN):
         return E.WarpEngine(self.net_generator, batch, size, self.device, self.nsplit, train=self.is_train)
 
     def set_input(self, input):
-        f32 = dict(device=self.device, dtype=torch.float32, non_blocking=True)
-        self.bodys = input["bodys"].to(**f32).contiguous()
-        self.inputs = input["input_cloths"].to(**f32).contiguous()
-        # the targets are first needed by the D step, one generator forward later: their H2D copy runs on
-        # a side stream and overlaps that forward (pinned host tensors; no-op for device tensors)
-        self.targets = self.copy_late(input["target_cloths"])
+        # all H2D copies run on a side stream in the order the step needs them: the body (3 ch) first — the
+        # body branch and the weight packing run while the 19-channel cloth is still in flight —, the targets
+        # last (first needed by the D step, one generator forward later).  No-op for device tensors.
+        self.bodys = self.copy_late(input["bodys"], "bodys")
+        self.inputs = self.copy_late(input["input_cloths"], "inputs")
+        self.targets = self.copy_late(input["target_cloths"], "targets")
         self.image_paths = tuple(zip(input["cloth_paths"], input["body_paths"]))
 
     def forward(self):
@@ -82,8 +82,10 @@ class WarpModel(BaseGAN):
         assert S == S2, "square inputs expected"
         self.ensure_engines(B, S)
         g = self._eng_G
-        g.pack()
-        out = g.forward(self.bodys, self.inputs, training=self.training and self.is_train, seed=self.step_seed())
+        g.pack()                      # needs the weights only: overlaps the input copies
+        self.wait_copy("bodys")
+        out = g.forward(self.bodys, self.inputs, training=self.training and self.is_train, seed=self.step_seed(),
+                        before_cloth=lambda: self.wait_copy("inputs"))
         self.fakes = out.permute(0, 3, 1, 2)   # [B,19,S,S] view of the NHWC storage
         self.wait_late_copies()
 
