@@ -172,3 +172,21 @@ def test_perceptual_oracle_is_bit_identical_to_reference():
     c, s_ = ON.perceptual_loss(sd, out, tgt, True)
     (c * 20 + s_ * 1e-8).backward()
     assert torch.equal(c, c_ref) and torch.equal(s_, s_ref) and torch.equal(out.grad, g_ref)
+
+
+def test_perceptual_oracle_matches_golden():
+    """tests/golden/perceptual_64.pt: the reference PerceptualLoss(use_style=True) with seeded-random VGG16
+    (generated by tests/tools/make_golden_perceptual.py) — pins the oracle where /root/reference is absent."""
+    g = torch.load(os.path.join(GOLD, "perceptual_64.pt"))
+    sd = seeded_vgg_features_sd()
+    close_checksums({k: (float(v.double().sum()), float(v.double().abs().sum())) for k, v in sd.items()},
+                    g["vgg_checksums"], 1e-12)
+    gen = torch.Generator().manual_seed(5)
+    out = (torch.rand(2, 3, 64, 64, generator=gen) * 2 - 1).requires_grad_()
+    tgt = torch.rand(2, 3, 64, 64, generator=gen) * 4.5 - 2.0
+    c, s = ON.perceptual_loss(sd, out, tgt, True)
+    (c * 20 + s * 1e-8).backward()
+    assert abs(float(c) - g["content"]) <= 1e-6 * abs(g["content"])
+    assert abs(float(s) - g["style"]) <= 1e-6 * abs(g["style"])
+    assert relmax(out.grad[:, :, ::4, ::4], g["grad_sub"]) < 1e-5
+    assert abs(float(out.grad.double().abs().sum()) - g["grad_abs"]) <= 1e-5 * g["grad_abs"]
