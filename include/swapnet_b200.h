@@ -250,6 +250,17 @@ int sn_l1_loss_fwd_bwd(const float* a, int pitch, const float* b_nchw, int n, in
                        float weight, double* loss_acc, float* grad, int grad_pitch, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * one-output-channel conv (PatchGAN logits, discriminators.py:131) as 1-tap GEMMs over a per-tap
+ * product image P[n,h,w,t] = sum_c x[n,h,w,c] W[0,c,t] (the input is read once instead of once per tap):
+ *   y[n,oh,ow] = bias + sum_{kh,kw} P[n, oh+kh-pad, ow+kw-pad, kh*k+kw]
+ *   dP[n,h,w,kh*k+kw] = dy[n, h-kh+pad, w-kw+pad]   (split planes; dy = split planes, channel 0)
+ * ---------------------------------------------------------------------------------------- */
+int sn_tap_sum_fwd(const float* p, int p_pitch, int n, int h, int w, int k, int pad, const float* bias, float* y,
+                   int y_pitch, void* stream);
+int sn_tap_shift_pack(const void* dy_hi, const void* dy_lo, int dy_pitch, int dy_fmt, int n, int h, int w, int k,
+                      int pad, void* dst_hi, void* dst_lo, int dst_pitch, int dst_coff, int fmt, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * VGG16 perceptual loss (modules/losses/perceptual.py:6-79, used by texture_model.py:68-69,171-176).
  * The 13 conv3x3(+bias) layers run as tap-GEMM plans; these are the element-wise pieces.
  * ---------------------------------------------------------------------------------------- */

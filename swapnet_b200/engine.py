@@ -28,8 +28,13 @@ from torch import nn
 from . import lowering as L
 from . import modules as M
 from . import ops
-from .layers import ConvLayer
+import os
+
+from .layers import ConvLayer, ToOneConvLayer
 from .ops import ACT_LRELU, ACT_NONE, ACT_RELU, ACT_TANH, FMT_BF16, GradSrc, Planes
+
+
+TO_ONE = os.environ.get("SN_NO_TO_ONE", "0") != "1"    # A/B switch for layers.ToOneConvLayer
 
 
 def _mix_seed(step_seed: int, stage_id: int) -> int:
@@ -50,8 +55,11 @@ class Stage:
         self.id = len(eng.stages)
         eng.stages.append(self)
         dev = eng.device
-        self.layer = ConvLayer(kind, conv.weight.data, None if conv.bias is None else conv.bias.data, x,
-                               nsplit=eng.nsplit, act=epi_act, name=name)
+        # a stride-1 conv with ONE output channel (the PatchGAN logits) runs as 1-tap GEMMs (layers.ToOneConvLayer)
+        to_one = kind == "conv4s1" and conv.out_channels == 1 and epi_act == ACT_NONE and x.c % 64 == 0 and TO_ONE
+        self.layer = (ToOneConvLayer if to_one else ConvLayer)(
+            kind, conv.weight.data, None if conv.bias is None else conv.bias.data, x, nsplit=eng.nsplit, act=epi_act,
+            name=name)
         self.conv = conv
         ly = self.layer
         self.n, self.oh, self.ow, self.cout = ly.n, ly.out_h, ly.out_w, ly.cout

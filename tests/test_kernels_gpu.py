@@ -512,3 +512,39 @@ def test_upsample_planes(c, f):
     got = dst.dense().cpu()
     assert relmax(got[..., :c], ref) < 1e-6
     assert torch.all(got[..., c:] == 0)
+
+
+@pytest.mark.parametrize("n,cin,h,w", [(2, 512, 15, 15), (3, 64, 9, 12), (2, 128, 63, 63)])
+def test_to_one_conv_layer(n, cin, h, w):
+    """Conv2d(cin, 1, 4, 1, 1) (PatchGAN logits, discriminators.py:131) through layers.ToOneConvLayer:
+    forward, input gradient, weight and bias gradients vs torch (fp64)."""
+    from swapnet_b200 import ops
+    from swapnet_b200.layers import ToOneConvLayer
+
+    g = torch.Generator().manual_seed(n * 1000 + cin + h)
+    x = torch.randn(n, cin, h, w, generator=g)
+    wt = torch.randn(1, cin, 4, 4, generator=g) * (1.0 / (cin * 16) ** 0.5)
+    bias = torch.randn(1, generator=g)
+    planes = ops.Planes(n, h, w, L.pad64(cin), dev(), dual=True)
+    ops.pack_planes(x.to(dev()), planes)
+    layer = ToOneConvLayer("conv4s1", wt.to(dev()).contiguous(), bias.to(dev()), planes, nsplit=3, name="logits")
+    y = torch.zeros(n, h - 1, w - 1, 1, device=dev())
+    layer.bind_forward(y)
+    xr, wr, br = x.double().requires_grad_(), wt.double().requires_grad_(), bias.double().requires_grad_()
+    yr = F.conv2d(xr, wr, br, 1, 1)
+    gy = torch.randn(yr.shape, generator=g)
+    gx, gw, gb = torch.autograd.grad(yr, (xr, wr, br), gy.double())
+    dy = ops.Planes(n, h - 1, w - 1, 16, dev(), fmt=ops.FMT_BF16)
+    ops.pack_planes(gy.to(dev()), dy)
+    dx = torch.zeros(n, h, w, cin, device=dev())
+    wg = torch.zeros_like(layer.weight)
+    bg = torch.zeros(1, device=dev())
+    layer.bind_backward(dy, dx, wg, bg)
+    layer.pack()
+    layer.forward()
+    layer.backward()
+    torch.cuda.synchronize()
+    e_y = relmax(y.cpu(), nhwc(yr.detach()))
+    e_dx, e_w, e_b = relmax(dx.cpu(), nhwc(gx)), relmax(wg.cpu(), gw), relmax(bg.cpu(), gb)
+    record(f"to_one_conv[{n},{cin},{h}x{w}]", f"y {e_y:.3e} dx {e_dx:.3e} w {e_w:.3e} b {e_b:.3e}")
+    assert e_y < 1.5e-5 and e_dx < 1e-4 and e_w < 1e-4 and e_b < 1e-4
