@@ -514,7 +514,7 @@ def test_upsample_planes(c, f):
     assert torch.all(got[..., c:] == 0)
 
 
-@pytest.mark.parametrize("n,cin,h,w", [(2, 512, 15, 15), (3, 64, 9, 12), (2, 128, 63, 63)])
+@pytest.mark.parametrize("n,cin,h,w", [(2, 256, 15, 15), (3, 64, 9, 12), (2, 128, 63, 63)])
 def test_to_one_conv_layer(n, cin, h, w):
     """Conv2d(cin, 1, 4, 1, 1) (PatchGAN logits, discriminators.py:131) through layers.ToOneConvLayer:
     forward, input gradient, weight and bias gradients vs torch (fp64)."""
