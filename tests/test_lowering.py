@@ -123,3 +123,55 @@ def test_forward_dgrad_wgrad(kind, cin, cout, h, w):
     else:
         got = flat.reshape(wt.shape)
     torch.testing.assert_close(got, gw, rtol=1e-9, atol=1e-9)
+
+
+def test_to_one_factorisation():
+    """layers.ToOneConvLayer: Conv2d(cin, 1, 4, 1, 1) = per-tap product image P (a 1-tap GEMM) + shifted sums, and
+    its adjoint (dP = shifted dy; dW, dx = 1-tap contractions with dP) — fp64 proof against torch."""
+    N, cin, h, w = 2, 5, 7, 9
+    x = torch.randn(N, cin, h, w, dtype=torch.float64, requires_grad=True)
+    wt = torch.randn(1, cin, 4, 4, dtype=torch.float64, requires_grad=True)
+    b = torch.randn(1, dtype=torch.float64)
+    y = F.conv2d(x, wt, b, 1, 1)
+    gy = torch.randn_like(y)
+    gx, gw = torch.autograd.grad(y, (x, wt), gy)
+    X = nhwc(x.detach())                                           # [N,h,w,cin]
+    Wt = wt.detach().reshape(cin, 16)                              # [c][t]
+    P = X @ Wt                                                     # [N,h,w,16]: one 1-tap GEMM
+    out = torch.zeros(N, h - 1, w - 1, dtype=torch.float64)
+    dP = torch.zeros(N, h, w, 16, dtype=torch.float64)
+    GY = gy[:, 0]
+    for kh in range(4):
+        for kw in range(4):
+            t = kh * 4 + kw
+            for oh in range(h - 1):
+                ih = oh + kh - 1
+                if not 0 <= ih < h:
+                    continue
+                for ow in range(w - 1):
+                    iw = ow + kw - 1
+                    if 0 <= iw < w:
+                        out[:, oh, ow] += P[:, ih, iw, t]          # sn_tap_sum_fwd
+                        dP[:, ih, iw, t] = GY[:, oh, ow]           # sn_tap_shift_pack
+    torch.testing.assert_close(out + b, y.detach()[:, 0], rtol=1e-12, atol=1e-12)
+    dW = torch.einsum("nhwc,nhwt->ct", X, dP).reshape(1, cin, 4, 4)
+    dX = dP @ Wt.t()
+    torch.testing.assert_close(dW, gw, rtol=1e-12, atol=1e-12)
+    torch.testing.assert_close(dX, nhwc(gx), rtol=1e-12, atol=1e-12)
+
+
+def test_merged_parity_view_addresses():
+    """gemm_tc.cu sn_make_act_map(parity, plane_stride): the stride-2 'parity view' with BOTH parities folded into
+    the channel coordinate, c' = hp*W*pitch + pw*pitch + c over dims (c', w/2, h/2, n), must address element
+    (n, 2*h2 + hp, 2*w2 + pw, c) of the NHWC tensor."""
+    import itertools
+
+    N, H, W, pitch = 2, 6, 8, 16
+    e = 1                                             # element units
+    s_w2, s_h2, s_n = 2 * pitch * e, 2 * W * pitch * e, H * W * pitch * e
+    for n, h2, w2, hp, pw, c in itertools.product(range(N), range(H // 2), range(W // 2), range(2), range(2), (0, 5, 15)):
+        cprime = hp * W * pitch + pw * pitch + c
+        assert cprime < (W + 1) * pitch + pitch       # inside dims[0] of the map
+        addr = cprime + w2 * s_w2 + h2 * s_h2 + n * s_n
+        want = ((n * H + 2 * h2 + hp) * W + 2 * w2 + pw) * pitch + c
+        assert addr == want

@@ -190,3 +190,20 @@ def test_perceptual_oracle_matches_golden():
     assert abs(float(s) - g["style"]) <= 1e-6 * abs(g["style"])
     assert relmax(out.grad[:, :, ::4, ::4], g["grad_sub"]) < 1e-5
     assert abs(float(out.grad.double().abs().sum()) - g["grad_abs"]) <= 1e-5 * g["grad_abs"]
+
+
+def test_vgg16_container_and_loader():
+    """swapnet_b200.modules.VGG16Features: torchvision key names, frozen, seeded 'random' init reproducible;
+    'pretrained' must raise (no silent substitute) when the weight file cannot be obtained."""
+    a = M.load_vgg16_features("random")
+    b = M.load_vgg16_features("random:1234")
+    c = M.load_vgg16_features("random:7")
+    ref = seeded_vgg_features_sd(1234)
+    assert list(a.state_dict()) == list(ref) and all(torch.equal(a.state_dict()[k], ref[k]) for k in ref)
+    assert all(torch.equal(a.state_dict()[k], b.state_dict()[k]) for k in ref)
+    assert not torch.equal(a.state_dict()["0.weight"], c.state_dict()["0.weight"])
+    assert not any(p.requires_grad for p in a.parameters())
+    hub = os.path.join(torch.hub.get_dir(), "checkpoints", "vgg16-397923af.pth")
+    if not os.path.exists(hub):
+        with pytest.raises(RuntimeError, match="b200_vgg"):
+            M.load_vgg16_features("pretrained")
