@@ -140,13 +140,38 @@ def measured_peaks():
 # CPU arm: the reference training step restated in oracle/nets.py (bit-identical to the reference
 # modules), with torch.optim.AdamW as optimizers/__init__.py builds it
 # ------------------------------------------------------------------------------------------------
+def host_cores() -> int:
+    """CPUs this process may actually use: the scheduler affinity capped by the cgroup CPU quota (the GPU boxes
+    expose 128 logical CPUs under a 16-CPU quota — 128 torch threads there are 8x oversubscribed)."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    quota = None
+    try:
+        q, p = open("/sys/fs/cgroup/cpu.max").read().split()[:2]          # cgroup v2
+        if q != "max":
+            quota = int(q) / int(p)
+    except (OSError, ValueError):
+        try:
+            q = int(open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read())      # cgroup v1
+            p = int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+            if q > 0:
+                quota = q / p
+        except (OSError, ValueError):
+            pass
+    if quota is not None:
+        n = min(n, max(1, int(quota + 0.999)))
+    return max(1, n)
+
+
 def cpu_reference_run(S, B, steps, warmup):
     from oracle import nets as ON
     from swapnet_b200 import modules as M
 
     import contextlib
 
-    torch.set_num_threads(os.cpu_count() or 1)
+    torch.set_num_threads(host_cores())
     torch.manual_seed(0)
     with contextlib.redirect_stdout(sys.stderr):
         G = M.WarpModule()
@@ -200,7 +225,8 @@ def main():
     ap.add_argument("--size", type=int, default=512)
     ap.add_argument("--batch", type=int, default=16, help="images per GPU")
     ap.add_argument("--precision", default="fp32x3", choices=("fp32x3", "bf16"))
-    ap.add_argument("--cpu-steps", type=int, default=3)
+    ap.add_argument("--cpu-steps", type=int, default=3,
+                    help="timed CPU-oracle steps of the cpu_baseline leg (one step = ~5 s on the usable host cores)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--perceptual", action="store_true",
                     help="--model texture: add the VGG16 content + Gram style terms (lambda 20 / 1e-8)")
@@ -210,20 +236,23 @@ def main():
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
     S, B = args.size, args.batch
-    cores = os.cpu_count() or 1
+    cores = host_cores()
     workload = f"warp_model {S}x{S} synthetic, batch {B}/GPU, full GAN step (G fwd, D step, G step, AdamW x2)"
 
     if args.impl == "reference":
         if rank != 0:
             return
-        steps = max(1, min(args.steps, 5))
-        v, med = cpu_reference_run(S, 1, steps, min(args.warmup, 1))
+        # one CPU step at 512x512, batch 1, takes ~5 s on the 16 usable cores of a GPU box: K and W are clamped so
+        # that the run ends within a few minutes (the line reports the steps actually timed)
+        steps = max(1, min(args.steps, 10))
+        v, med = cpu_reference_run(S, 1, steps, min(args.warmup, 2))
         print(json.dumps({
             "impl": "reference", "metric": "images/sec (G+D fwd+bwd) warp-stage 512x512", "value": v,
-            "unit": "images/s", "n_gpus": args.gpus, "steps": steps, "warmup": min(args.warmup, 1),
+            "unit": "images/s", "n_gpus": args.gpus, "steps": steps, "warmup": min(args.warmup, 2),
             "ms_per_step": med * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": workload, "note": "CPU arm runs batch 1 per step (bounded sample of the same workload)"},
+            "config": {"workload": workload, "note": "CPU arm runs batch 1 per step (bounded sample of the same workload)",
+                       "steps_requested": args.steps, "warmup_requested": args.warmup},
             "cpu_baseline": {"value": v, "unit": "images/s", "cores": cores, "kind": "port",
                              "sample": f"{steps} timed full training steps at {S}x{S}, batch 1, torch CPU ({cores} threads)"},
             "e2e": {"value": v, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
@@ -348,7 +377,8 @@ def main():
     if not args.no_cpu_baseline and args.gpus == 1 and args.model == "warp":
         v, med = cpu_reference_run(S, 1, args.cpu_steps, 1)
         cpu = {"value": v, "unit": "images/s", "cores": cores, "kind": "port",
-               "sample": f"{args.cpu_steps} timed full training steps at {S}x{S}, batch 1, torch CPU ({cores} threads)"}
+               "sample": f"{args.cpu_steps} timed full training step(s) at {S}x{S}, batch 1, after 1 warm-up step, "
+                         f"torch CPU ({cores} threads = usable cores under the cgroup quota)"}
     step_ms = ms / args.steps
     total_imgs = B * world
     out = {
