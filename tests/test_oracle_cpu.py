@@ -207,3 +207,42 @@ def test_vgg16_container_and_loader():
     if not os.path.exists(hub):
         with pytest.raises(RuntimeError, match="b200_vgg"):
             M.load_vgg16_features("pretrained")
+
+
+def test_texture_full_step_with_default_losses_matches_golden():
+    """tests/golden/texture_step_64.pt: one full reference TextureModel.optimize_parameters() with the DEFAULT loss
+    set (L1 10 + GAN 1 + VGG16 content 20 + Gram style 1e-8; seeded-random VGG16) — the oracle's
+    texture_step_losses / perceptual_loss + AdamW must reproduce the eight losses and every updated parameter."""
+    g = torch.load(os.path.join(GOLD, "texture_step_64.pt"))
+    B, S = 2, 64
+    torch.manual_seed(0)
+    T = M.TextureModule(3, 19, 12, "instance", 0.5, S); M.init_weights(T, "kaiming")
+    D = M.NLayerDiscriminator(22, 64, 3, "instance"); M.init_weights(D, "kaiming")
+    close_checksums(checksums(T.state_dict()), g["init_checksums_G"], 0.0)
+    close_checksums(checksums(D.state_dict()), g["init_checksums_D"], 0.0)
+    vgg = seeded_vgg_features_sd()
+    tex, rois, cloth, tgt = synth_texture_batch(B, S)
+    sdG = {k: v.detach().clone().requires_grad_() for k, v in T.state_dict().items()}
+    sdD = {k: v.detach().clone().requires_grad_() for k, v in D.state_dict().items()}
+    optG = torch.optim.AdamW(list(sdG.values()), lr=1e-4, weight_decay=0, betas=(0.9, 0.999))
+    optD = torch.optim.AdamW(list(sdD.values()), lr=4e-4, weight_decay=0.01, betas=(0.9, 0.999))
+    torch.manual_seed(123)
+    fk = ON.texture_forward(sdG, tex, rois, cloth)
+    t_fake, t_real = ON.smooth_label(torch.rand(1)), ON.smooth_label(torch.rand(1))
+    lf = ON.gan_loss(ON.patchgan_forward(sdD, torch.cat((cloth, fk), 1).detach()), t_fake)
+    lr = ON.gan_loss(ON.patchgan_forward(sdD, torch.cat((cloth, tgt), 1)), t_real)
+    lD = 0.5 * (lf + lr)
+    lD.backward()
+    optD.step()
+    gan = ON.gan_loss(ON.patchgan_forward(sdD, torch.cat((cloth, fk), 1)), ON.smooth_label(torch.rand(1)))
+    l1 = torch.nn.functional.l1_loss(fk, tgt) * 10
+    c, s_ = ON.perceptual_loss(vgg, fk, tgt, True)
+    lG = gan + l1 + c * 20 + s_ * 1e-8
+    lG.backward()
+    optG.step()
+    got = dict(D=lD.item(), D_real=lr.item(), D_fake=lf.item(), G=lG.item(), G_gan=gan.item(), G_l1=l1.item(),
+               G_content=(c * 20).item(), G_style=(s_ * 1e-8).item())
+    for k, v in g["step_losses"].items():
+        assert abs(got[k] - v) <= 2e-5 * abs(v), (k, got[k], v)
+    close_checksums(checksums({k: v.detach() for k, v in sdG.items()}), g["step_checksums_G"], 5e-6)
+    close_checksums(checksums({k: v.detach() for k, v in sdD.items()}), g["step_checksums_D"], 5e-6)
