@@ -1,0 +1,61 @@
+"""CPU tests of host-side invariants the CUDA kernels rely on (no GPU, no library calls)."""
+import builtins
+import io
+
+import torch
+
+import bench
+from swapnet_b200 import lowering as L
+from swapnet_b200 import ops
+
+
+def test_planes_views_keep_the_plane_stride():
+    """The GEMM kernels fetch the hi and lo planes of a tile with ONE TMA box whose outermost dimension is the
+    plane (csrc/gemm_tc.cu sn_make_act_map(plane_stride)): hi and lo must live a fixed stride apart, also for
+    channel slices and batch slices of a buffer."""
+    p = ops.Planes(4, 6, 8, 64, "cpu", dual=True)
+    stride = p.lo.data_ptr() - p.hi.data_ptr()
+    assert stride == 2 * 4 * 6 * 8 * 64 and stride % 16 == 0
+    for v in (p.slice(16, 32), p.batch_slice(1, 2), p.slice(8, 8).batch_slice(2, 2), p.twin, p.twin.batch_slice(3, 1)):
+        assert v.lo_ptr - v.hi_ptr == stride
+        assert v.lo.data_ptr() - v.hi.data_ptr() == stride
+    w = ops.PackedWeights(48, 128, "cpu")
+    assert w.lo.data_ptr() - w.hi.data_ptr() == 2 * 48 * 128
+
+
+def test_phase_merge_only_for_the_four_parity_phases():
+    specs = L.forward_specs("convT4s2", 8, 8)
+    m = ops.merge_phase_specs(specs)
+    assert m is not None and len(m.taps) == 16 and m.out_mul == (2, 2)
+    assert [t.kb for t in m.taps] == list(range(16))          # phase-major packed slots: phase z owns taps 4z..4z+3
+    assert ops.merge_phase_specs(L.forward_specs("head", 8, 8)) is None      # unequal tap counts / per-phase weights
+    assert ops.merge_phase_specs(L.forward_specs("conv3r", 8, 8)) is None
+
+
+def test_block_n_and_channel_padding_rules():
+    assert [L.padc(c) for c in (1, 3, 16, 19, 22, 36, 64, 65)] == [16, 16, 16, 32, 32, 64, 64, 128]
+    assert [L.pick_block_n(n) for n in (1, 16, 19, 36, 64, 100, 128, 1024)] == [16, 16, 32, 64, 64, 128, 128, 128]
+
+
+def test_host_cores_respects_the_cgroup_quota(monkeypatch):
+    """bench.host_cores(): the GPU boxes show 128 logical CPUs under a 16-CPU cgroup quota."""
+    real_open = builtins.open
+
+    def fake_open(path, *a, **k):
+        if path == "/sys/fs/cgroup/cpu.max":
+            return io.StringIO("1600000 100000\n")
+        return real_open(path, *a, **k)
+
+    monkeypatch.setattr(bench.os, "sched_getaffinity", lambda pid: set(range(128)), raising=False)
+    monkeypatch.setattr(builtins, "open", fake_open)
+    assert bench.host_cores() == 16
+
+    def fake_open_max(path, *a, **k):
+        if path == "/sys/fs/cgroup/cpu.max":
+            return io.StringIO("max 100000\n")
+        if path.startswith("/sys/fs/cgroup/cpu/"):
+            raise OSError(path)
+        return real_open(path, *a, **k)
+
+    monkeypatch.setattr(builtins, "open", fake_open_max)
+    assert bench.host_cores() == 128
