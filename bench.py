@@ -19,7 +19,10 @@ Prints ONE JSON line (rank 0).  Field notes:
             (fp16/bf16-split fp32-faithful product), so frac <= 1/3 by construction; `pipe_frac`
             is the tensor-pipe view (3x).
   cpu_baseline  the CPU oracle port (oracle/nets.py, pinned bit-exactly to the reference modules)
-            running the same training step at 512x512, batch 1, all host cores, a few steps.
+            running the same training step at 512x512, batch 1, on the host cores the cgroup CPU quota
+            allows (host_cores()), a few steps; `--impl reference` times the same port as the reference arm
+            (K <= 10, W <= 2 so that the run stays within a few minutes).
+  --model texture [--perceptual]   informational: the texture stage (BASELINE configs[2]), not the headline.
 """
 from __future__ import annotations
 
