@@ -14,7 +14,7 @@ import torch
 
 from . import lowering as L
 from . import ops
-from .ops import ACT_NONE, ACT_TANH, FMT_BF16, FMT_F16, PackedWeights, Planes
+from .ops import ACT_NONE, PackedWeights, Planes
 
 
 class ConvLayer:
