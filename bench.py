@@ -365,7 +365,9 @@ def main():
                 "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "pipe_frac": 3 * ach / peak, "peak_source": how,
                 "launches_per_step": gemm_n, "avg_launch_ms": gemm_ms / max(gemm_n, 1),
                 "algorithmic_gflop_per_launch": gemm_fl / max(gemm_n, 1) / 1e9,
-                "share_of_step": gemm_ms / step_ms, "traffic": ncu_traffic(),
+                "share_of_step": gemm_ms / step_ms,
+                # DRAM bytes of one launch of the dominant shape from the committed `ncu --set full` capture
+                "traffic": (ncu_traffic() or {}).get("dram_bytes_per_launch"), "traffic_detail": ncu_traffic(),
                 "wgrad_kernel": {"achieved": (tot["wgrad"][0] / (tot["wgrad"][1] * 1e-3) / 1e12) if tot["wgrad"][1] else 0.0,
                                  "share_of_step": tot["wgrad"][1] / step_ms, "launches_per_step": tot["wgrad"][2]}}
 
