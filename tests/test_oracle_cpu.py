@@ -25,11 +25,16 @@ def checksums(sd):
     return {k: (float(v.double().sum()), float(v.double().abs().sum())) for k, v in sd.items()}
 
 
-def close_checksums(a, b, tol):
+def close_checksums(a, b, tol, numel=None, lr=0.0):
+    """flips / lr: checksums of parameters AFTER the first AdamW step.  That update is lr * g / (|g| + eps) ~ lr * sign(g),
+    so an element whose gradient is within CPU-kernel rounding of zero (oneDNN picks different kernels on different
+    hosts) moves by up to 2 * lr the other way; allow max(8, 2e-5 * numel) such elements per tensor on top of the
+    relative bound (measured across two hosts: 9 of 8.4 M; a wrong gradient flips a large fraction)."""
     assert a.keys() == b.keys()
     for k in a:
         for x, y in zip(a[k], b[k]):
-            assert abs(x - y) <= tol * max(1.0, abs(y)), (k, x, y)
+            flips = 0 if numel is None else max(8, 2e-5 * numel[k])
+            assert abs(x - y) <= tol * max(1.0, abs(y)) + 2 * lr * flips, (k, x, y)
 
 
 def test_warp_forward_and_step_match_golden():
@@ -65,8 +70,8 @@ def test_warp_forward_and_step_match_golden():
     got = dict(D=lD.item(), D_real=lr.item(), D_fake=lf.item(), G=(ce + gan).item(), G_gan=gan.item(), G_ce=ce.item())
     for k, v in g["step_losses"].items():
         assert abs(got[k] - v) <= 1e-5 * abs(v), (k, got[k], v)
-    close_checksums(checksums({k: v.detach() for k, v in sdG.items()}), g["step_checksums_G"], 2e-6)
-    close_checksums(checksums({k: v.detach() for k, v in sdD.items()}), g["step_checksums_D"], 2e-6)
+    close_checksums(checksums({k: v.detach() for k, v in sdG.items()}), g["step_checksums_G"], 2e-6, numel={k: v.numel() for k, v in sdG.items()}, lr=1e-4)
+    close_checksums(checksums({k: v.detach() for k, v in sdD.items()}), g["step_checksums_D"], 2e-6, numel={k: v.numel() for k, v in sdD.items()}, lr=4e-4)
 
 
 def test_texture_forward_matches_golden():
@@ -244,5 +249,5 @@ def test_texture_full_step_with_default_losses_matches_golden():
                G_content=(c * 20).item(), G_style=(s_ * 1e-8).item())
     for k, v in g["step_losses"].items():
         assert abs(got[k] - v) <= 2e-5 * abs(v), (k, got[k], v)
-    close_checksums(checksums({k: v.detach() for k, v in sdG.items()}), g["step_checksums_G"], 5e-6)
-    close_checksums(checksums({k: v.detach() for k, v in sdD.items()}), g["step_checksums_D"], 5e-6)
+    close_checksums(checksums({k: v.detach() for k, v in sdG.items()}), g["step_checksums_G"], 5e-6, numel={k: v.numel() for k, v in sdG.items()}, lr=1e-4)
+    close_checksums(checksums({k: v.detach() for k, v in sdD.items()}), g["step_checksums_D"], 5e-6, numel={k: v.numel() for k, v in sdD.items()}, lr=4e-4)
