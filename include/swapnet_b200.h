@@ -173,6 +173,12 @@ typedef struct sn_norm_act_desc {
   const double* stats;                   /* (mean, rstd) [n][c][2] or NULL (no InstanceNorm) */
   int act; float slope;                  /* SN_ACT_NONE / LRELU / RELU */
   float drop_p; unsigned long long drop_seed; /* drop_p == 0: no dropout */
+  unsigned long long drop_offset;        /* added to the NHWC element index of the keep-mask: global sample index *
+                                            h*w*c of the first local sample (data-parallel shards draw the masks of
+                                            the samples they hold, SURVEY 8e ii) */
+  const unsigned long long* drop_step_seed_dev; unsigned int drop_stage_id; /* non-NULL: the seed is
+                                            mix(*drop_step_seed_dev, drop_stage_id) read on the device (CUDA-graph replay
+                                            with a fresh step seed); drop_seed is ignored */
   const float* residual; int res_pitch;  /* optional: out = residual + xhat (ResidualBlock tail) */
   void* out_hi; void* out_lo; int out_pitch, out_coff; /* optional split planes */
   int out_fmt;
@@ -201,6 +207,7 @@ typedef struct sn_norm_act_bwd_desc {
   const double* stats;
   int act; float slope;
   float drop_p; unsigned long long drop_seed;
+  unsigned long long drop_offset; const unsigned long long* drop_step_seed_dev; unsigned int drop_stage_id;
   double* gstats;                        /* scratch [n][c][2] (needed when stats != NULL) */
   void* dy_hi; void* dy_lo; int dy_pitch, dy_coff; /* split planes of dL/dy */
   int dy_fmt;

@@ -67,6 +67,7 @@ class SnNormActDesc(C.Structure):
         ("stats", C.c_void_p),
         ("act", C.c_int), ("slope", C.c_float),
         ("drop_p", C.c_float), ("drop_seed", C.c_ulonglong),
+        ("drop_offset", C.c_ulonglong), ("drop_step_seed_dev", C.c_void_p), ("drop_stage_id", C.c_uint),
         ("residual", C.c_void_p), ("res_pitch", C.c_int),
         ("out_hi", C.c_void_p), ("out_lo", C.c_void_p), ("out_pitch", C.c_int), ("out_coff", C.c_int),
         ("out_fmt", C.c_int), ("out2_hi", C.c_void_p), ("out2_lo", C.c_void_p), ("out2_fmt", C.c_int),
@@ -88,6 +89,7 @@ class SnNormActBwdDesc(C.Structure):
         ("stats", C.c_void_p),
         ("act", C.c_int), ("slope", C.c_float),
         ("drop_p", C.c_float), ("drop_seed", C.c_ulonglong),
+        ("drop_offset", C.c_ulonglong), ("drop_step_seed_dev", C.c_void_p), ("drop_stage_id", C.c_uint),
         ("gstats", C.c_void_p),
         ("dy_hi", C.c_void_p), ("dy_lo", C.c_void_p), ("dy_pitch", C.c_int), ("dy_coff", C.c_int),
         ("dy_fmt", C.c_int),

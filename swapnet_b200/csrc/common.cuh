@@ -240,7 +240,9 @@ __host__ __device__ __forceinline__ uint32_t umma_idesc_16(uint32_t m, uint32_t 
 //                the ReLU / LeakyReLU gates identical to the reference's.
 __device__ __forceinline__ void split16(float v, int fmt, uint16_t& hi, uint16_t& lo) {
   if (fmt == SN_FMT_F16) {
-    v = fminf(fmaxf(v, -65504.f), 65504.f);
+    // finite values saturate at the fp16 range (un-normalised layers); NaN / Inf pass through so that a diverged
+    // run surfaces as it would in the fp32 reference instead of being masked by fminf / fmaxf
+    if (fabsf(v) <= 3.402823466e38f) v = fminf(fmaxf(v, -65504.f), 65504.f);
     const __half h = __float2half_rn(v);
     const __half l = __float2half_rn(v - __half2float(h));
     hi = __half_as_ushort(h);

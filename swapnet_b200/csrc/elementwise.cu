@@ -40,6 +40,16 @@ __host__ __device__ __forceinline__ uint32_t drop_thresh(float p) {
   return (uint32_t)t;
 }
 
+// per-stage dropout seed from the step seed (host twin: engine._mix_seed).  With `seed_dev` the step seed lives in
+// device memory (updated once per step), so that a captured CUDA graph of the step replays with fresh masks.
+__host__ __device__ __forceinline__ unsigned long long sn_mix_seed(unsigned long long step_seed, unsigned int stage_id) {
+  return (step_seed * 0x9E3779B1ull + (unsigned long long)stage_id * 0x85EBCA77ull + 0x165667B1ull) & 0xFFFFFFFFFFFFull;
+}
+template <class Args>
+__device__ __forceinline__ unsigned long long drop_seed_of(const Args& a) {
+  return a.seed_dev ? sn_mix_seed(*a.seed_dev, a.stage_id) : a.seed;
+}
+
 __device__ __forceinline__ void store_split(uint16_t* hi, uint16_t* lo, long long off, float v, int fmt) {
   uint16_t h, l;
   split16(v, fmt, h, l);
@@ -422,6 +432,7 @@ struct NormActFwdArgs {
   const double* stats;
   int act; float slope;
   uint32_t drop_thresh; float drop_scale; unsigned long long seed;
+  unsigned long long drop_off; const unsigned long long* seed_dev; unsigned int stage_id;
   const float* residual; int res_pitch;
   uint16_t* hi; uint16_t* lo; int out_pitch, out_coff, reflect, fmt;
   uint16_t* hi2; uint16_t* lo2; int fmt2;
@@ -440,6 +451,7 @@ __device__ __forceinline__ float act_grad(float xhat, int act, float slope) {
 }
 
 __global__ void norm_act_fwd_kernel(const NormActFwdArgs a) {
+  const unsigned long long seed = a.drop_thresh ? drop_seed_of(a) : 0ull;
   const int n = blockIdx.y;
   const int HW = a.H * a.W;
   const int per = (HW + gridDim.x - 1) / gridDim.x;
@@ -456,7 +468,7 @@ __global__ void norm_act_fwd_kernel(const NormActFwdArgs a) {
       v = (v - mean) * rstd;
       v = act_fwd(v, a.act, a.slope);
       if (a.drop_thresh) {
-        const bool keep = sn_keep(a.seed, (unsigned long long)pix * a.C + c, a.drop_thresh);
+        const bool keep = sn_keep(seed, a.drop_off + (unsigned long long)pix * a.C + c, a.drop_thresh);
         v = keep ? v * a.drop_scale : 0.f;
       }
       if (a.residual) v += a.residual[pix * a.res_pitch + c];
@@ -552,13 +564,14 @@ struct NormActBwdArgs {
   const double* stats;
   int act; float slope;
   uint32_t drop_thresh; float drop_scale; unsigned long long seed;
+  unsigned long long drop_off; const unsigned long long* seed_dev; unsigned int stage_id;
   double* gstats;
   uint16_t* hi; uint16_t* lo; int dy_pitch, dy_coff, fmt;
 };
 
 // gradient w.r.t. xhat (before the InstanceNorm backward), and xhat itself
-__device__ __forceinline__ float grad_xhat(const NormActBwdArgs& a, int n, int p, int c, float mean,
-                                           float rstd, float* xhat_out) {
+__device__ __forceinline__ float grad_xhat(const NormActBwdArgs& a, unsigned long long seed, int n, int p, int c,
+                                           float mean, float rstd, float* xhat_out) {
   const int HW = a.H * a.W;
   const long long pix = (long long)n * HW + p;
   const int h = p / a.W, w = p - h * a.W;
@@ -571,7 +584,7 @@ __device__ __forceinline__ float grad_xhat(const NormActBwdArgs& a, int n, int p
     g += gather_one(s, n, h, w, a.H, a.W, c) * act_grad(xhat, s.act >= 0 ? s.act : a.act, a.slope);
   }
   if (a.drop_thresh) {
-    const bool keep = sn_keep(a.seed, (unsigned long long)pix * a.C + c, a.drop_thresh);
+    const bool keep = sn_keep(seed, a.drop_off + (unsigned long long)pix * a.C + c, a.drop_thresh);
     g = keep ? g * a.drop_scale : 0.f;
   }
   *xhat_out = xhat;
@@ -581,6 +594,7 @@ __device__ __forceinline__ float grad_xhat(const NormActBwdArgs& a, int n, int p
 // grid (ceil(C/32), slabs, N), block (32, 8): sums of g and g*xhat per (n, c)
 __global__ void norm_act_bwd_reduce_kernel(const NormActBwdArgs a) {
   __shared__ float s1s[8][33], s2s[8][33];
+  const unsigned long long seed = a.drop_thresh ? drop_seed_of(a) : 0ull;
   const int c = blockIdx.x * 32 + threadIdx.x;
   const int n = blockIdx.z;
   const int HW = a.H * a.W;
@@ -592,7 +606,7 @@ __global__ void norm_act_bwd_reduce_kernel(const NormActBwdArgs a) {
     const float rstd = (float)a.stats[((long long)n * a.C + c) * 2 + 1];
     for (int p = p0 + threadIdx.y; p < p1; p += 8) {
       float xhat;
-      const float g = grad_xhat(a, n, p, c, mean, rstd, &xhat);
+      const float g = grad_xhat(a, seed, n, p, c, mean, rstd, &xhat);
       s1 += g;
       s2 += g * xhat;
     }
@@ -614,6 +628,7 @@ __global__ void norm_act_bwd_reduce_kernel(const NormActBwdArgs a) {
 
 // grid (slabs, N); block (cx, py)
 __global__ void norm_act_bwd_apply_kernel(const NormActBwdArgs a) {
+  const unsigned long long seed = a.drop_thresh ? drop_seed_of(a) : 0ull;
   const int n = blockIdx.y;
   const int HW = a.H * a.W;
   const int per = (HW + gridDim.x - 1) / gridDim.x;
@@ -628,7 +643,7 @@ __global__ void norm_act_bwd_apply_kernel(const NormActBwdArgs a) {
     }
     for (int p = p0 + threadIdx.y; p < p1; p += blockDim.y) {
       float xhat;
-      float g = grad_xhat(a, n, p, c, mean, rstd, &xhat);
+      float g = grad_xhat(a, seed, n, p, c, mean, rstd, &xhat);
       if (a.stats) g = rstd * (g - m1 - xhat * m2);
       const long long off = ((long long)n * HW + p) * a.dy_pitch + a.dy_coff + c;
       store_split(a.hi, a.lo, off, g, a.fmt);
@@ -921,6 +936,7 @@ __global__ void __launch_bounds__(256, 4) norm_act_fwd_v4_kernel(const NormActFw
   extern __shared__ float sm[];  // mean[C], rstd[C]
   float* s_mean = sm;
   float* s_rstd = sm + a.C;
+  const unsigned long long seed = a.drop_thresh ? drop_seed_of(a) : 0ull;
   const int n = blockIdx.y;
   for (int c = threadIdx.x; c < a.C; c += blockDim.x) {
     s_mean[c] = a.stats ? (float)a.stats[((long long)n * a.C + c) * 2] : 0.f;
@@ -943,7 +959,7 @@ __global__ void __launch_bounds__(256, 4) norm_act_fwd_v4_kernel(const NormActFw
       float t = (v[j] - s_mean[c + j]) * s_rstd[c + j];
       t = act_fwd(t, a.act, a.slope);
       if (a.drop_thresh) {
-        const bool keep = sn_keep(a.seed, (unsigned long long)pix * a.C + c + j, a.drop_thresh);
+        const bool keep = sn_keep(seed, a.drop_off + (unsigned long long)pix * a.C + c + j, a.drop_thresh);
         t = keep ? t * a.drop_scale : 0.f;
       }
       v[j] = t;
@@ -1024,8 +1040,8 @@ __device__ __forceinline__ float4 gather_grad4(const GradSrcs& g, int n, int h, 
 }
 
 // g (w.r.t. xhat) and xhat for a channel quad
-__device__ __forceinline__ void grad_xhat4(const NormActBwdArgs& a, int n, int p, int c, const float* mean,
-                                           const float* rstd, float g[4], float xh[4]) {
+__device__ __forceinline__ void grad_xhat4(const NormActBwdArgs& a, unsigned long long seed, int n, int p, int c,
+                                           const float* mean, const float* rstd, float g[4], float xh[4]) {
   const int HW = a.H * a.W;
   const long long pix = (long long)n * HW + p;
   const int h = p / a.W, w = p - h * a.W;
@@ -1049,7 +1065,7 @@ __device__ __forceinline__ void grad_xhat4(const NormActBwdArgs& a, int n, int p
   if (a.drop_thresh) {
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const bool keep = sn_keep(a.seed, (unsigned long long)pix * a.C + c + j, a.drop_thresh);
+      const bool keep = sn_keep(seed, a.drop_off + (unsigned long long)pix * a.C + c + j, a.drop_thresh);
       g[j] = keep ? g[j] * a.drop_scale : 0.f;
     }
   }
@@ -1059,6 +1075,7 @@ __device__ __forceinline__ void grad_xhat4(const NormActBwdArgs& a, int n, int p
 // strided over pixels (C = 64 layers — the largest tensors — use bx = 16, 16 pixel rows)
 __global__ void __launch_bounds__(256, 4) norm_act_bwd_reduce_v4_kernel(const NormActBwdArgs a) {
   __shared__ float red[256][8];
+  const unsigned long long seed = a.drop_thresh ? drop_seed_of(a) : 0ull;
   const int q = blockIdx.x * blockDim.x + threadIdx.x;
   const int c = q << 2;
   const int n = blockIdx.z;
@@ -1075,7 +1092,7 @@ __global__ void __launch_bounds__(256, 4) norm_act_bwd_reduce_v4_kernel(const No
     }
     for (int p = p0 + threadIdx.y; p < p1; p += blockDim.y) {
       float g[4], xh[4];
-      grad_xhat4(a, n, p, c, mean, rstd, g, xh);
+      grad_xhat4(a, seed, n, p, c, mean, rstd, g, xh);
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         s1[j] += g[j];
@@ -1110,6 +1127,7 @@ __global__ void __launch_bounds__(256, 4) norm_act_bwd_apply_v4_kernel(const Nor
   float* s_rstd = sm + a.C;
   float* s_m1 = sm + 2 * a.C;
   float* s_m2 = sm + 3 * a.C;
+  const unsigned long long seed = a.drop_thresh ? drop_seed_of(a) : 0ull;
   const int n = blockIdx.y;
   for (int c = threadIdx.x; c < a.C; c += blockDim.x) {
     const long long k = ((long long)n * a.C + c) * 2;
@@ -1128,7 +1146,7 @@ __global__ void __launch_bounds__(256, 4) norm_act_bwd_apply_v4_kernel(const Nor
     const int p = p0 + pl;
     const int c = (i - pl * Q) << 2;
     float g[4], xh[4];
-    grad_xhat4(a, n, p, c, s_mean + c, s_rstd + c, g, xh);
+    grad_xhat4(a, seed, n, p, c, s_mean + c, s_rstd + c, g, xh);
     if (a.stats) {
 #pragma unroll
       for (int j = 0; j < 4; ++j) g[j] = s_rstd[c + j] * (g[j] - s_m1[c + j] - xh[j] * s_m2[c + j]);
@@ -1317,6 +1335,7 @@ int sn_norm_act_fwd(const sn_norm_act_desc* d, void* stream) {
   a.drop_thresh = d->drop_p > 0.f ? drop_thresh(d->drop_p) : 0u;
   a.drop_scale = d->drop_p > 0.f ? 1.f / (1.f - d->drop_p) : 1.f;
   a.seed = d->drop_seed;
+  a.drop_off = d->drop_offset; a.seed_dev = d->drop_step_seed_dev; a.stage_id = d->drop_stage_id;
   a.residual = d->residual; a.res_pitch = d->res_pitch;
   a.hi = (uint16_t*)d->out_hi; a.lo = (uint16_t*)d->out_lo;
   a.out_pitch = d->out_pitch; a.out_coff = d->out_coff; a.reflect = d->out_reflect_pad;
@@ -1366,6 +1385,7 @@ int sn_norm_act_bwd(const sn_norm_act_bwd_desc* d, void* stream) {
   a.drop_thresh = d->drop_p > 0.f ? drop_thresh(d->drop_p) : 0u;
   a.drop_scale = d->drop_p > 0.f ? 1.f / (1.f - d->drop_p) : 1.f;
   a.seed = d->drop_seed;
+  a.drop_off = d->drop_offset; a.seed_dev = d->drop_step_seed_dev; a.stage_id = d->drop_stage_id;
   a.gstats = d->gstats;
   a.hi = (uint16_t*)d->dy_hi; a.lo = (uint16_t*)d->dy_lo;
   a.dy_pitch = d->dy_pitch; a.dy_coff = d->dy_coff; a.fmt = d->dy_fmt;

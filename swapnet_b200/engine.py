@@ -74,6 +74,12 @@ class Stage:
         self.dx: Optional[torch.Tensor] = None
         self.gstats = None
 
+    def drop_offset(self) -> int:
+        """Keep-mask index of this stage's first element: the masks are indexed by GLOBAL sample (Engine.sample_base =
+        global index of local sample 0), so a data-parallel shard, or a batch-1 run of sample i, draws the masks the
+        full batch would (SURVEY §8e ii)."""
+        return self.eng.sample_base * self.oh * self.ow * self.cout
+
     def nominal_macs(self) -> int:
         """Dense multiply-accumulates of the reference op for this stage's batch (SURVEY §8d:
         Conv2d out_elems*Cin*k*k, ConvTranspose2d in_elems*Cout*k*k; zero taps of padding and
@@ -94,7 +100,8 @@ class Stage:
         p = self.drop_p if self.eng.training else 0.0
         ops.norm_act_fwd(self.y, self.cout, self.stats, self.act, self.slope, p,
                          _mix_seed(self.eng.seed, self.id), residual=self.residual, out=self.out,
-                         reflect_pad=self.reflect_out, out_f32=self.out_f32)
+                         reflect_pad=self.reflect_out, out_f32=self.out_f32, drop_offset=self.drop_offset(),
+                         seed_dev=self.eng.seed_dev, stage_id=self.id)
         if self.out_relu is not None:
             ops.norm_act_fwd(self.y, self.cout, self.stats, ACT_RELU, 0.0, 0.0, 0, out=self.out_relu)
 
@@ -122,7 +129,8 @@ class Stage:
             p = 0.0 if self.plain else (self.drop_p if self.eng.training else 0.0)
             ops.norm_act_bwd(srcs, self.y, self.cout, None if self.plain else self.stats,
                              ACT_NONE if self.plain else self.act, self.dy, self.gstats, self.slope, p,
-                             _mix_seed(self.eng.seed, self.id))
+                             _mix_seed(self.eng.seed, self.id), drop_offset=self.drop_offset(),
+                             seed_dev=self.eng.seed_dev, stage_id=self.id)
         self.layer.backward(dgrad=self.need_dx, wgrad=wgrad)
 
 
@@ -135,6 +143,8 @@ class Engine:
         self.stages: List[Stage] = []
         self.training = True
         self.seed = 0
+        self.seed_dev: Optional[torch.Tensor] = None   # device copy of the step seed (CUDA-graph replay), else host seeds
+        self.sample_base = 0        # global index of local sample 0 (dropout masks follow the global sample)
         self.flat_grad: Optional[torch.Tensor] = None
 
     def planes(self, n: int, h: int, w: int, c: int) -> Planes:
@@ -532,6 +542,9 @@ class PerceptualEngine:
             self.tgt = VGGEngine(net, batch, size, device, nsplit, backward=False)
             self.gfeat = [torch.zeros_like(s.y) for s in self.out.taps]
         r = 3 * batch
+        if r > 96:   # csrc/perceptual.cu kGramMaxR: the Gram matrix of the style term is held in registers / smem
+            raise NotImplementedError(f"style loss: the Gram matrix couples 3 x batch = {r} rows, at most 96 are "
+                                      "supported per GPU (batch <= 32); use --lambda_style 0 or a smaller per-GPU batch")
         self.gram_o = torch.zeros(r, r, dtype=torch.float64, device=dev)
         self.gram_t = torch.zeros(r, r, dtype=torch.float64, device=dev)
         self.gram_m = torch.zeros(r, r, dtype=torch.float32, device=dev)

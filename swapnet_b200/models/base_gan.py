@@ -153,30 +153,56 @@ class BaseGAN(BaseModel, ABC):
         ...
 
     # ---- engines ----
+    ENGINE_CACHE = 2   # plans kept alive: the full batch and the short last batch of an epoch (DataLoader without
+                       # drop_last, datasets/__init__.py:69) alternate without re-planning / re-allocating
+
     def ensure_engines(self, batch: int, size: int) -> None:
+        """Engines (buffers + TMA plans) of the current (batch, size); built once per shape and cached (LRU)."""
         key = (batch, size)
         if self._eng_key == key:
             return
+        cache = self.__dict__.setdefault("_eng_cache", {})
+        if key not in cache:
+            while len(cache) >= self.ENGINE_CACHE:           # evict the least recently used shape
+                old = next(iter(cache))
+                for eng in cache.pop(old).values():
+                    if hasattr(eng, "stages"):
+                        for st in eng.stages:                # break the Stage <-> Engine cycle: buffers free now
+                            st.eng = None
+                        eng.stages.clear()
+            cache[key] = self._build_engines(batch, size)
+        else:
+            cache[key] = cache.pop(key)                      # most recently used last
         self._eng_key = key
-        self._eng_G = self.build_generator_engine(batch, size)
+        e = cache[key]
+        self._eng_G, self._eng_Dd, self._eng_Dg = e["G"], e.get("Dd"), e.get("Dg")
+        self._dpred_d, self._dpred_g = e.get("dpred_d"), e.get("dpred_g")
+        self._eng_extra = e
         if self.is_train:
-            self._eng_G.alloc_grads()
-            self._eng_G.bind_backward()
             self.optimizer_G.flat_grad = self._eng_G.flat_grad
-        self._eng_Dd = self._eng_Dg = None
+            if self._eng_Dd is not None:
+                self.optimizer_D.flat_grad = self._eng_Dd.flat_grad
+
+    def _build_engines(self, batch: int, size: int) -> dict:
+        e = {}
+        g = e["G"] = self.build_generator_engine(batch, size)
+        # dropout masks follow the GLOBAL sample index: rank r holds samples [r*batch, (r+1)*batch)  (SURVEY §8e ii)
+        g.sample_base = int(getattr(self.opt, "b200_sample_base", parallel.rank() * batch))
+        if self.is_train:
+            g.alloc_grads()
+            g.bind_backward()
         if self.is_train and hasattr(self, "net_discriminator"):
             dn = self.net_discriminator
-            self._eng_Dd = E.PatchGANEngine(dn, 2 * batch, size, self.device, self.nsplit)
-            self._eng_Dd.alloc_grads()
-            self._eng_Dd.bind_backward()
-            self.optimizer_D.flat_grad = self._eng_Dd.flat_grad
-            self._eng_Dg = E.PatchGANEngine(dn, batch, size, self.device, self.nsplit,
-                                            din=self._eng_Dd.din.batch_slice(0, batch), input_grad=True)
-            self._eng_Dg.alloc_grads(share_with=self._eng_Dd)
-            self._eng_Dg.bind_backward(wgrad=False)
-            p = self._eng_Dd.pred
-            self._dpred_d = torch.zeros_like(p)
-            self._dpred_g = torch.zeros_like(self._eng_Dg.pred)
+            dd = e["Dd"] = E.PatchGANEngine(dn, 2 * batch, size, self.device, self.nsplit)
+            dd.alloc_grads()
+            dd.bind_backward()
+            dg = e["Dg"] = E.PatchGANEngine(dn, batch, size, self.device, self.nsplit,
+                                            din=dd.din.batch_slice(0, batch), input_grad=True)
+            dg.alloc_grads(share_with=dd)
+            dg.bind_backward(wgrad=False)
+            e["dpred_d"] = torch.zeros_like(dd.pred)
+            e["dpred_g"] = torch.zeros_like(dg.pred)
+        return e
 
     def step_seed(self) -> int:
         return (self._seed_base * 1000003 + self._step) & 0xFFFFFFFF

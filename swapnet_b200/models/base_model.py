@@ -42,7 +42,12 @@ class BaseModel(ABC):
         torch.cuda.set_device(self.device)
         self.save_dir = os.path.join(opt.checkpoints_dir, opt.name)
         if self.is_train:
-            os.makedirs(self.save_dir, exist_ok=True)
+            try:        # base_model.py:43-44: ask before re-using a non-empty experiment directory (--no_confirm skips)
+                from util.util import PromptOnce
+            except ImportError:                # standalone use (bench, tests): no reference tree on the path
+                os.makedirs(self.save_dir, exist_ok=True)
+            else:
+                PromptOnce.makedirs(self.save_dir, not getattr(opt, "no_confirm", True))
         self.loss_names = []
         self.model_names = []
         self.visual_names = []
@@ -63,7 +68,9 @@ class BaseModel(ABC):
             self._late_events = []
             self._copy_events = {}
         cur = torch.cuda.current_stream(self.device)
-        self._copy_stream.wait_stream(cur)   # the destination buffer may still be read by earlier work
+        # no wait on `cur`: the destination is a fresh allocation of the copy stream's pool (the caching allocator
+        # only recycles a block once the streams recorded on it — record_stream below — have passed its last use),
+        # so the copy of step N+1's inputs overlaps the compute of step N
         with torch.cuda.stream(self._copy_stream):
             out = t.to(device=self.device, dtype=torch.float32, non_blocking=True).contiguous()
             ev = torch.cuda.Event()

@@ -27,9 +27,8 @@ class TextureModel(BaseGAN):
     @staticmethod
     def modify_commandline_options(parser: ArgumentParser, is_train):
         parser = super(TextureModel, TextureModel).modify_commandline_options(parser, is_train)
-        parser.set_defaults(input_transforms=["hflip", "vflip", "affine", "perspective"])
-        parser.add_argument("--netG", default="swapnet", choices=["swapnet", "unet_128"])
         if is_train:
+            parser.add_argument("--netG", default="swapnet", choices=["swapnet", "unet_128"])
             parser.add_argument("--lambda_l1", type=float, default=10, help="weight for L1 loss in final term")
             parser.add_argument("--lambda_content", type=float, default=20, help="weight for content loss in final term")
             parser.add_argument("--lambda_style", type=float, default=1e-8, help="weight for style loss in final term")
@@ -68,6 +67,12 @@ class TextureModel(BaseGAN):
         from util.decode_labels import decode_cloth_labels
 
         self.textures_unnormalized = unnormalize(self.textures, *self.opt.texture_norm_stats)
+        try:                                   # texture_model.py:79-81 (needs seaborn through util/draw_rois.py)
+            from util.draw_rois import draw_rois_on_texture
+        except ImportError:
+            draw_rois_on_texture = None
+        if draw_rois_on_texture is not None:
+            self.textures_unnormalized = draw_rois_on_texture(self.rois, self.textures_unnormalized)
         self.cloths_decoded = decode_cloth_labels(self.cloths)
         self.fakes_scaled = scale_tensor(self.fakes, scale_each=True)
         if self.is_train:
@@ -84,13 +89,16 @@ class TextureModel(BaseGAN):
     def build_generator_engine(self, batch, size):
         return E.TextureEngine(self.net_generator, batch, size, self.device, self.nsplit, train=self.is_train)
 
+    def _build_engines(self, batch, size):
+        e = super()._build_engines(batch, size)
+        if self.is_train and (self.lam_content != 0 or self.lam_style != 0):
+            e["P"] = E.PerceptualEngine(self.net_vgg, batch, size, self.device, self.nsplit,
+                                        content=self.lam_content != 0)
+        return e
+
     def ensure_engines(self, batch, size):
-        key = (batch, size)
-        fresh = self._eng_key != key
         super().ensure_engines(batch, size)
-        if fresh and self.is_train and (self.lam_content != 0 or self.lam_style != 0):
-            self._eng_P = E.PerceptualEngine(self.net_vgg, batch, size, self.device, self.nsplit,
-                                             content=self.lam_content != 0)
+        self._eng_P = self._eng_extra.get("P")
 
     def set_input(self, input):
         # side-stream H2D copies in the order the step needs them (see WarpModel.set_input)

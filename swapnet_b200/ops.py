@@ -384,7 +384,11 @@ def plane_stats(y: torch.Tensor, c: int, stats: torch.Tensor, eps: float = IN_EP
 def norm_act_fwd(y: torch.Tensor, c: int, stats: Optional[torch.Tensor], act: int, slope: float = 0.2,
                  drop_p: float = 0.0, drop_seed: int = 0, residual: Optional[torch.Tensor] = None,
                  out: Optional[Planes] = None, reflect_pad: bool = False,
-                 out_f32: Optional[torch.Tensor] = None) -> None:
+                 out_f32: Optional[torch.Tensor] = None, drop_offset: int = 0,
+                 seed_dev: Optional[torch.Tensor] = None, stage_id: int = 0) -> None:
+    """drop_offset: element offset of the keep-mask index (global sample index of the first local sample * h*w*c);
+    seed_dev (uint64/int64[1] on the device) + stage_id: the per-stage seed is derived on the device from the
+    step seed stored there (CUDA-graph replay), drop_seed is then ignored."""
     n, h, w, _ = y.shape
     pitch = _pitch(y)
     d = SnNormActDesc()
@@ -393,6 +397,7 @@ def norm_act_fwd(y: torch.Tensor, c: int, stats: Optional[torch.Tensor], act: in
     d.stats = _ptr(stats)
     d.act, d.slope = act, slope
     d.drop_p, d.drop_seed = drop_p, drop_seed
+    d.drop_offset, d.drop_step_seed_dev, d.drop_stage_id = drop_offset, _ptr(seed_dev), stage_id
     if residual is not None:
         d.residual, d.res_pitch = residual.data_ptr(), _pitch(residual)
     if out is not None:
@@ -434,7 +439,8 @@ def _fill_srcs(arr, srcs: Sequence[GradSrc]) -> None:
 
 def norm_act_bwd(srcs: Sequence[GradSrc], y: torch.Tensor, c: int, stats: Optional[torch.Tensor], act: int,
                  dy: Planes, gstats: Optional[torch.Tensor] = None, slope: float = 0.2, drop_p: float = 0.0,
-                 drop_seed: int = 0) -> None:
+                 drop_seed: int = 0, drop_offset: int = 0, seed_dev: Optional[torch.Tensor] = None,
+                 stage_id: int = 0) -> None:
     n, h, w, _ = y.shape
     pitch = _pitch(y)
     d = SnNormActBwdDesc()
@@ -445,6 +451,7 @@ def norm_act_bwd(srcs: Sequence[GradSrc], y: torch.Tensor, c: int, stats: Option
     d.stats = _ptr(stats)
     d.act, d.slope = act, slope
     d.drop_p, d.drop_seed = drop_p, drop_seed
+    d.drop_offset, d.drop_step_seed_dev, d.drop_stage_id = drop_offset, _ptr(seed_dev), stage_id
     d.gstats = _ptr(gstats)
     assert (dy.n, dy.h, dy.w) == (n, h, w) and dy.c >= c
     d.dy_hi, d.dy_lo, d.dy_pitch, d.dy_coff = dy.hi.data_ptr(), dy.lo.data_ptr(), dy.pitch, dy.c_off
