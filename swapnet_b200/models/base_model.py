@@ -38,6 +38,13 @@ class BaseModel(ABC):
             raise RuntimeError(
                 "swapnet_b200 models run on a CUDA device only (--gpu_id >= 0 on a B200); there is no "
                 "CPU / eager fallback of the hot path")
+        # data parallel without touching train.py: under `torchrun ... train.py` (WORLD_SIZE > 1 in the environment)
+        # every rank drives the GPU of its LOCAL_RANK (train.py's --gpu_id default of 0 would put all ranks on one
+        # device) and the NCCL process group is created here, before the parameters are broadcast (base_gan.py)
+        from .. import parallel
+
+        if parallel.launched_distributed():
+            self.gpu_id = parallel.init_from_env()
         self.device = torch.device(f"cuda:{self.gpu_id}")
         torch.cuda.set_device(self.device)
         self.save_dir = os.path.join(opt.checkpoints_dir, opt.name)
@@ -153,6 +160,10 @@ class BaseModel(ABC):
 
     # ---- checkpoints: same file names and state_dict keys as the reference ----
     def save_checkpoint(self, epoch):
+        from .. import parallel
+
+        if parallel.rank() != 0:      # replicas are identical: one writer (all ranks share checkpoints_dir/name)
+            return
         for name in self.model_names:
             net = getattr(self, f"net_{name}")
             # parameters stay where they are (the engines hold their addresses); save a CPU copy

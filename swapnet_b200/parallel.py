@@ -14,6 +14,25 @@ import torch
 import torch.distributed as dist
 
 
+def launched_distributed() -> bool:
+    """True under torchrun / torch.distributed.run with more than one rank (WORLD_SIZE in the environment)."""
+    import os
+
+    return int(os.environ.get("WORLD_SIZE", "1")) > 1
+
+
+def init_from_env() -> int:
+    """Create the NCCL process group from torchrun's environment (idempotent) and return this rank's GPU index
+    (LOCAL_RANK).  Called by BaseModel.__init__, so the reference's train.py needs no distributed code."""
+    import os
+
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if dist.is_available() and not dist.is_initialized():
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+    return local
+
+
 def world_size() -> int:
     return dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
 

@@ -131,12 +131,24 @@ def test_warp_model_step_matches_oracle(mode):
     """One WarpModel.optimize_parameters(): all six losses and every parameter gradient of G and D
     against the oracle's autograd (fp64).  eval: dropout off.  train_shared_masks: dropout(0.5) active in
     body_down4, cloth_down5/6 and the four resblocks, the oracle applying the library's own masks."""
+    _warp_step_vs_oracle(2, 64, mode)
+
+
+@pytest.mark.parametrize("mode", ["eval", "train_shared_masks"])
+def test_warp_model_step_matches_oracle_512(mode):
+    """The same gradient-level check at the BENCHMARKED resolution (BASELINE configs[1]: 512x512; one image so
+    that the fp64 CPU oracle finishes in ~20 s): K = 9216 / 16384 contractions forward, weight gradients reduced
+    over up to 65536 pixels with split-K atomics, input gradients with K up to 16384."""
+    _warp_step_vs_oracle(1, 512, mode, tag="_512")
+
+
+def _warp_step_vs_oracle(B, S, mode, tag=""):
     from swapnet_b200 import engine as E
     from swapnet_b200.models import create_model
 
-    B, S = 2, 64
     torch.manual_seed(0)
-    model = create_model(_opt(B, S))
+    # the 512 case runs as if the image were global sample 5 of a larger batch (dropout masks follow the global index)
+    model = create_model(_opt(B, S, b200_sample_base=5 if tag else 0))
     model.setup(model.opt)
     if mode == "eval":
         model.eval()                  # dropout off; IN has no running stats
@@ -178,13 +190,13 @@ def test_warp_model_step_matches_oracle(mode):
     drop = None
     if mode != "eval":
         eng = model._eng_G
-        drop = OD.make_drop({s.name: E._mix_seed(eng.seed, s.id) for s in eng.stages}, 0.5)
+        drop = OD.make_drop({s.name: E._mix_seed(eng.seed, s.id) for s in eng.stages}, 0.5, sample_base=eng.sample_base)
     o = ON.warp_step_losses(sdG, sdD, body.double(), inp.double(), tgt.double(), draws, drop=drop)
     stats = dict(ON.GATE_STATS)
     ON.gate_with(None)
     flips = {k: v for k, v in stats.items() if k != "__total__" and v}
     total = stats.get("__total__", 1)
-    record("warp_step_gate_flips", f"{sum(flips.values())} of {total} gates differ from the fp64 oracle: {flips}")
+    record(f"warp_step_gate_flips{tag}[{mode}]", f"{sum(flips.values())} of {total} gates differ from the fp64 oracle: {flips}")
     assert sum(flips.values()) <= 2e-5 * total, f"too many activation gates differ: {flips}"
     refD = torch.autograd.grad(o["D"], list(sdD.values()), retain_graph=True)
     refG = torch.autograd.grad(o["G"], list(sdG.values()), allow_unused=True)
@@ -210,8 +222,8 @@ def test_warp_model_step_matches_oracle(mode):
             continue
         worst["G." + k] = relmax(gG[k], r)
     bad = {k: v for k, v in worst.items() if v >= 1e-3}
-    record(f"warp_step_worst_grads[{mode}]", sorted(worst.items(), key=lambda kv: -kv[1])[:5])
-    record(f"warp_step_fakes[{mode}]", f"{err_f:.3e}")
+    record(f"warp_step_worst_grads{tag}[{mode}]", sorted(worst.items(), key=lambda kv: -kv[1])[:5])
+    record(f"warp_step_fakes{tag}[{mode}]", f"{err_f:.3e}")
     assert not bad, f"parameter gradients beyond 1e-3: {bad}"
 
 
@@ -291,9 +303,18 @@ def test_texture_engine_forward(S):
 def test_texture_model_step_matches_oracle(perceptual):
     """perceptual=True: the reference's DEFAULT texture losses (lambda_content 20, lambda_style 1e-8,
     texture_model.py:39-48) with seeded-random VGG16 weights (the pretrained file is not obtainable offline)."""
+    _texture_step_vs_oracle(2, 128, perceptual)
+
+
+def test_texture_model_step_matches_oracle_512():
+    """BASELINE configs[2] resolution (512x512, num_downs = 9, 12 ROIs) with the reference's default loss set
+    (L1 + GAN + VGG16 content + Gram style), one image, against the fp64 oracle."""
+    _texture_step_vs_oracle(1, 512, True, tag="_512")
+
+
+def _texture_step_vs_oracle(B, S, perceptual, tag=""):
     from swapnet_b200.models import create_model
 
-    B, S = 2, 128
     torch.manual_seed(0)
     lc, ls = (20.0, 1e-8) if perceptual else (0.0, 0.0)
     opt = _opt(B, S, model="texture", name="texture", netG="swapnet", lambda_l1=10, lambda_content=lc, lambda_style=ls,
@@ -354,22 +375,22 @@ def test_texture_model_step_matches_oracle(perceptual):
     o = ON.texture_step_losses(sdG, sdD, tex.double(), rois.double(), cloth.double(), tgt.double(), draws,
                                l1_sign=l1_sign, vgg=vgg_sd, lambda_content=lc, lambda_style=ls)
     ref_sign = torch.sign(o["fakes"].detach() - tgt.double())
-    record("texture_step_l1_sign_flips", f"{int((ref_sign != l1_sign).sum())} of {l1_sign.numel()}")
+    record(f"texture_step_l1_sign_flips{tag}", f"{int((ref_sign != l1_sign).sum())} of {l1_sign.numel()}")
     stats = dict(ON.GATE_STATS)
     ON.gate_with(None)
     ON.pool_with(None)
     pool_flips = {k: stats.pop(k) for k in list(stats) if k.startswith("pool:")}
     if perceptual:
-        record("texture_step_pool_winner_flips", pool_flips)
+        record(f"texture_step_pool_winner_flips{tag}", pool_flips)
     flips = {k: v for k, v in stats.items() if k != "__total__" and v}
-    record(f"texture_step_gate_flips[perceptual={perceptual}]", f"{sum(flips.values())} of {stats.get('__total__', 1)}: {flips}")
+    record(f"texture_step_gate_flips{tag}[perceptual={perceptual}]", f"{sum(flips.values())} of {stats.get('__total__', 1)}: {flips}")
     refD = torch.autograd.grad(o["D"], list(sdD.values()), retain_graph=True)
     refG = torch.autograd.grad(o["G"], list(sdG.values()), allow_unused=True)
     for k in ("D", "D_real", "D_fake", "G", "G_gan", "G_l1") + (("G_content", "G_style") if perceptual else ()):
         ref = o[k].item()
         assert abs(losses[k] - ref) <= 1e-3 * abs(ref), f"loss_{k}: {losses[k]} vs {ref}"
         if perceptual:
-            record(f"texture_step_perceptual_loss_{k}", f"{losses[k]:.9g} vs {ref:.9g}")
+            record(f"texture_step_perceptual_loss{tag}_{k}", f"{losses[k]:.9g} vs {ref:.9g}")
     err_f = relmax(model.fakes.cpu(), o["fakes"].detach())
     assert err_f < 1e-3, f"fakes relmax {err_f:.3e}"
     worst = {}
@@ -382,8 +403,8 @@ def test_texture_model_step_matches_oracle(perceptual):
                 assert got[k].abs().max().item() < 1e-4 * mx, k
                 continue
             worst[name + k] = relmax(got[k], r)
-    record(f"texture_step_worst_grads[perceptual={perceptual}]", sorted(worst.items(), key=lambda kv: -kv[1])[:5])
-    record("texture_step_fakes", f"{err_f:.3e}")
+    record(f"texture_step_worst_grads{tag}[perceptual={perceptual}]", sorted(worst.items(), key=lambda kv: -kv[1])[:5])
+    record(f"texture_step_fakes{tag}", f"{err_f:.3e}")
     bad = {k: v for k, v in worst.items() if v >= 1e-3}
     assert not bad, f"parameter gradients beyond 1e-3: {bad}"
     assert sum(flips.values()) <= 2e-5 * stats.get("__total__", 1), f"too many activation gates differ: {flips}"
@@ -533,3 +554,112 @@ def test_perceptual_engine_matches_oracle(B, S):
     record(f"perceptual_engine_grads[{B},{S}]", f"content {ec:.3e} style {es:.3e}")
     assert ec < 1e-3 and es < 1e-3
     assert flips <= 2e-5 * stats.get("__total__", 1)
+
+
+def _run_phases(model, batch, seed):
+    """forward, D phase, G phase by hand (no optimizer step) -> (losses, flat D grads, flat G grads) on the CPU."""
+    torch.manual_seed(seed)            # the smooth-label draws come from the CPU default generator
+    model.set_input(batch)
+    model._acc.zero_()
+    model.forward()
+    model._eng_Dd.zero_grad()
+    model.backward_D()
+    gD = model._eng_Dd.flat_grad.detach().cpu().clone()
+    model._eng_G.zero_grad()
+    model.backward_G()
+    torch.cuda.synchronize()
+    gG = model._eng_G.flat_grad.detach().cpu().clone()
+    return dict(model.get_current_losses()), gD, gG
+
+
+@pytest.mark.parametrize("mode", ["eval", "train"])
+def test_warp_batch16_equals_mean_of_16_single_image_steps_512(mode):
+    """Self-consistency at the BENCHMARKED configuration (BASELINE configs[1]: 512x512, batch 16): every op on the
+    path is per-sample and every loss a batch mean, so the batch-16 gradients must equal the mean of the
+    16 single-image gradients (same weights, same label draws, dropout masks of global sample i).  Ties the
+    batch-16 training step that bench.py times to the single-image step pinned against the fp64 oracle above."""
+    from swapnet_b200.models import create_model
+
+    B, S = 16, 512
+    torch.manual_seed(0)
+    model = create_model(_opt(B, S))
+    model.setup(model.opt)
+    if mode == "eval":
+        model.eval()
+    model.is_train = True
+    body, inp, tgt = synth_warp_batch(B, S)
+    full = dict(bodys=body, input_cloths=inp, target_cloths=tgt, cloth_paths=["c"] * B, body_paths=["b"] * B)
+    l16, gD16, gG16 = _run_phases(model, full, 777)
+    sums = None
+    lsum = {k: 0.0 for k in l16}
+    for i in range(B):
+        one = dict(bodys=body[i:i + 1], input_cloths=inp[i:i + 1], target_cloths=tgt[i:i + 1], cloth_paths=["c"],
+                   body_paths=["b"])
+        model.ensure_engines(1, S)
+        model._eng_G.sample_base = i
+        l1, gD1, gG1 = _run_phases(model, one, 777)
+        sums = [gD1.double(), gG1.double()] if sums is None else [sums[0] + gD1, sums[1] + gG1]
+        for k in lsum:
+            lsum[k] += l1[k] / B
+    eD = relmax(gD16, sums[0] / B)
+    eG = relmax(gG16, sums[1] / B)
+    el = max(abs(l16[k] - lsum[k]) / abs(lsum[k]) for k in l16)
+    record(f"warp_b16_vs_16xb1_512[{mode}]", f"flat grad D {eD:.3e} G {eG:.3e}; losses {el:.3e}")
+    assert eD < 1e-4 and eG < 1e-4 and el < 1e-5, (eD, eG, el)
+
+
+def test_train_loop_protocol():
+    """The calls train.py:31-116 makes, in its order, on a two-epoch run whose last batch of each epoch is short (the
+    reference's DataLoader has no drop_last, datasets/__init__.py:69): set_input / optimize_parameters /
+    get_current_losses per iteration, save_checkpoint('latest') + save_checkpoint(epoch) per epoch, then a
+    --continue_train reload.  Checks the loss keys (loss_names), the checkpoint file names (base_model.py:161-173) and
+    that the state_dict keys are the reference's (golden list generated from the reference modules)."""
+    import os
+
+    from swapnet_b200.models import create_model
+
+    S = 64
+    torch.manual_seed(0)
+    opt = _opt(2, S)
+    model = create_model(opt)
+    model.setup(opt)
+    body, inp, tgt = synth_warp_batch(3, S)
+
+    def batch(i0, i1):
+        n = i1 - i0
+        return dict(bodys=body[i0:i1], input_cloths=inp[i0:i1], target_cloths=tgt[i0:i1], cloth_paths=["c"] * n,
+                    body_paths=["b"] * n)
+
+    loader = [batch(0, 2), batch(2, 3)]              # 3 samples, batch_size 2 -> a short last batch
+    engines = set()
+    for epoch in (1, 2):
+        for data in loader:
+            model.set_input(data)
+            model.optimize_parameters()
+            engines.add(id(model._eng_G))
+            losses = model.get_current_losses()
+            assert list(losses) == ["D", "D_real", "D_fake", "G", "G_gan", "G_ce"]
+            assert all(isinstance(v, float) and v == v for v in losses.values())
+        model.save_checkpoint("latest")
+        model.save_checkpoint(epoch)
+    assert len(engines) == 2, "the (batch, size) engine cache re-planned inside the run"
+    files = sorted(os.listdir(model.save_dir))
+    for prefix in ("latest", "1", "2"):
+        for f in (f"{prefix}_net_generator.pth", f"{prefix}_net_discriminator.pth", f"{prefix}_optim_G.pth",
+                  f"{prefix}_optim_D.pth"):
+            assert f in files, (f, files)
+    sd = torch.load(os.path.join(model.save_dir, "latest_net_generator.pth"))
+    g = torch.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "warp_64.pt"))
+    assert list(sd.keys()) == list(g["init_checksums_G"].keys())          # the reference WarpModule's state_dict keys
+    sdd = torch.load(os.path.join(model.save_dir, "latest_net_discriminator.pth"))
+    assert list(sdd.keys()) == list(g["init_checksums_D"].keys())
+    # --continue_train: a fresh model picks the files up (base_model.py:56-59,193-212) and keeps training
+    opt2 = _opt(2, S, continue_train=True, checkpoints_dir=opt.checkpoints_dir)
+    m2 = create_model(opt2)
+    m2.setup(opt2)
+    for k, v in m2.net_generator.state_dict().items():
+        assert torch.equal(v.cpu(), sd[k]), k
+    assert m2.optimizer_G._step == 4
+    m2.set_input(loader[0])
+    m2.optimize_parameters()
+    assert all(v == v for v in m2.get_current_losses().values())

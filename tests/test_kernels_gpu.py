@@ -175,6 +175,63 @@ def test_conv_backward(kind, n, cin, cout, h, w):
     assert torch.all(dx[..., 0] == 5.0) and torch.all(dx[..., 1 + cin:] == 5.0)
 
 
+# BASELINE configs[1] layer shapes (512x512, batch 16 per GPU; App. A of SURVEY.md): the resblock conv (K = 9216 forward,
+# 16384-pixel weight-gradient reduction), the PatchGAN stride-1 conv on the 2B batch of the D step (63x63 planes), the
+# up-sample+pad head (256x256 -> 512x512, 19 outputs) and the widest decoder ConvTranspose2d.  The checker is torch's
+# own fp64 convolution ON THE GPU (cuDNN / native fp64 — test infrastructure only; the same sizes on 16 CPU cores would
+# take minutes).
+BASELINE_CASES = [
+    ("conv3r", 16, 1024, 1024, 32, 32),
+    ("conv4s1", 32, 256, 512, 64, 64),
+    ("head", 16, 192, 19, 256, 256),
+    ("convT4s2", 16, 768, 128, 64, 64),
+]
+
+
+@pytest.mark.parametrize("kind,n,cin,cout,h,w", BASELINE_CASES)
+def test_conv_baseline_shapes_fwd_bwd(kind, n, cin, cout, h, w):
+    from swapnet_b200 import ops
+
+    layer, x, wt, bias = make_layer(kind, n, cin, cout, h, w, 3)
+    oh, ow = L.out_hw(kind, h, w)
+    d = dev()
+    xr = x.to(d).double().requires_grad_()
+    wr = wt.to(d).double().requires_grad_()
+    br = bias.to(d).double().requires_grad_()
+    y = torch.zeros(n, oh, ow, cout, device=d)
+    layer.bind_forward(y)
+    layer.pack()
+    layer.forward()
+    torch.cuda.synchronize()
+    with torch.backends.cudnn.flags(enabled=True, deterministic=True, allow_tf32=False):
+        yr = ref_forward(kind, xr, wr, br)
+        e_f = relmax(y, nhwc(yr.detach()))
+        gy = torch.randn(yr.shape, generator=torch.Generator().manual_seed(99)).to(d)
+        if kind == "conv3r":   # gradient w.r.t. the PADDED input (what the engine consumes)
+            xp = F.pad(x.to(d).double(), (1, 1, 1, 1), mode="reflect").requires_grad_()
+            gx = torch.autograd.grad(F.conv2d(xp, wt.to(d).double()), xp, gy.double())[0]
+            gw, gb = torch.autograd.grad(yr, (wr, br), gy.double())
+        else:
+            gx, gw, gb = torch.autograd.grad(yr, (xr, wr, br), gy.double())
+    dyc = L.padc(cout) if layer.x.c >= 64 else L.pad64(cout)
+    dy = ops.Planes(n, oh, ow, dyc, d, fmt=ops.FMT_BF16)
+    ops.pack_planes(gy, dy)
+    ih, iw = (h + 2, w + 2) if kind == "conv3r" else (h, w)
+    dx = torch.zeros(n, ih, iw, cin, device=d)
+    wg = torch.zeros_like(layer.weight)
+    bg = torch.zeros(cout, device=d)
+    layer.bind_backward(dy, dx, wg, bg)
+    layer.pack()
+    layer.backward()
+    torch.cuda.synchronize()
+    e_dx, e_w, e_b = relmax(dx, nhwc(gx)), relmax(wg, gw), relmax(bg, gb)
+    record(f"conv_baseline_shape[{kind},{n},{cin},{cout},{h}x{w}]",
+           f"fwd {e_f:.3e} dx {e_dx:.3e} w {e_w:.3e} b {e_b:.3e}")
+    # forward: fp16-split x3 operands; the floor is the tensor core's truncating fp32 accumulator (grows with K)
+    assert e_f < 3e-5, f"{kind} fwd relmax {e_f:.3e}"
+    assert e_dx < 1e-4 and e_w < 1e-4 and e_b < 1e-4, (e_dx, e_w, e_b)
+
+
 def test_pack_planes_roundtrip():
     from swapnet_b200 import ops
 
