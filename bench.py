@@ -43,12 +43,29 @@ sys.path.insert(0, ROOT)
 FULL_STEP_GFLOP_PER_IMG_512 = 1029.0   # full reference warp training step, nominal
 
 
-def synth_batch(B, S, seed):
+def step_gflop_per_img(args) -> float:
+    """Nominal conv GFLOP of one training step per 512x512 image."""
+    tex = 896.0 if args.perceptual else 415.0
+    return {"warp": FULL_STEP_GFLOP_PER_IMG_512, "texture": tex, "joint": FULL_STEP_GFLOP_PER_IMG_512 + tex}[args.model]
+
+
+def metric_name(args) -> str:
+    return {"warp": "images/sec (G+D fwd+bwd) warp-stage 512x512",
+            "texture": "images/sec (G+D fwd+bwd) texture-stage 512x512",
+            "joint": "images/sec (G+D fwd+bwd) joint warp+texture 512x512"}[args.model]
+
+
+def synth_batch(B, S, seed, labels=False):
     """normalised-RGB-like body, 16x16-block one-hot cloth (label 0 = all-zero),
-    input cloth = target rolled by (8, 8)."""
+    input cloth = target rolled by (8, 8).  labels=True: the two cloth tensors in compact form — uint8 label maps
+    [B,S,S], the wire format the plugin expands on the device (ops.SegMap) — instead of fp32 one-hot [B,19,S,S]."""
     g = torch.Generator().manual_seed(seed)
     body = torch.rand(B, 3, S, S, generator=g) * 4.8 - 0.31
     lab = torch.randint(0, 19, (B, S // 16, S // 16), generator=g).repeat_interleave(16, 1).repeat_interleave(16, 2)
+    if labels:
+        lab = lab.to(torch.uint8)
+        return dict(bodys=body, input_cloths=torch.roll(lab, (8, 8), (1, 2)).contiguous(), target_cloths=lab.contiguous(),
+                    cloth_paths=["synthetic"] * B, body_paths=["synthetic"] * B)
     tgt = torch.zeros(B, 19, S, S)
     for c in range(1, 19):
         tgt[:, c] = (lab == c).float()
@@ -168,44 +185,84 @@ def host_cores() -> int:
     return max(1, n)
 
 
-def cpu_reference_run(S, B, steps, warmup):
+def cpu_reference_run(S, B, steps, warmup, model="warp", perceptual=False):
+    """K timed steps (after W warm-up steps) of the reference training step on the host cores -> (images/s, median s).
+    model: warp | texture | joint (one warp step + one texture step per iteration, BASELINE configs[4])."""
     from oracle import nets as ON
     from swapnet_b200 import modules as M
 
     import contextlib
 
     torch.set_num_threads(host_cores())
-    torch.manual_seed(0)
-    with contextlib.redirect_stdout(sys.stderr):
-        G = M.WarpModule()
-        M.init_weights(G, "kaiming")
-        D = M.NLayerDiscriminator(22, 64, 3, "instance")
-        M.init_weights(D, "kaiming")
-    sdG = {k: v.detach().clone().requires_grad_() for k, v in G.state_dict().items()}
-    sdD = {k: v.detach().clone().requires_grad_() for k, v in D.state_dict().items()}
-    optG = torch.optim.AdamW(list(sdG.values()), lr=1e-4, weight_decay=0, betas=(0.9, 0.999))
-    optD = torch.optim.AdamW(list(sdD.values()), lr=4e-4, weight_decay=0.01, betas=(0.9, 0.999))
-    b = synth_batch(B, S, 1234)
-    body, inp, tgt = b["bodys"], b["input_cloths"], b["target_cloths"]
     g = torch.Generator().manual_seed(7)
 
     def drop(name, x):  # training-mode dropout(0.5) as in the reference (cost parity; masks irrelevant)
         return torch.nn.functional.dropout(x, 0.5, True)
 
+    def leaf(net):
+        return {k: v.detach().clone().requires_grad_() for k, v in net.state_dict().items()}
+
+    def adamw(sd, lr, wd):
+        return torch.optim.AdamW(list(sd.values()), lr=lr, weight_decay=wd, betas=(0.9, 0.999))
+
+    steps_fns = []
+    torch.manual_seed(0)
+    if model in ("warp", "joint"):
+        with contextlib.redirect_stdout(sys.stderr):
+            G = M.WarpModule()
+            M.init_weights(G, "kaiming")
+            D = M.NLayerDiscriminator(22, 64, 3, "instance")
+            M.init_weights(D, "kaiming")
+        sdG, sdD = leaf(G), leaf(D)
+        optG, optD = adamw(sdG, 1e-4, 0), adamw(sdD, 4e-4, 0.01)
+        b = synth_batch(B, S, 1234)
+        body, inp, tgt = b["bodys"], b["input_cloths"], b["target_cloths"]
+
+        def warp_step():
+            fakes = ON.warp_forward(sdG, body, inp, drop)
+            optD.zero_grad()
+            t = [ON.smooth_label(torch.rand(1, generator=g)) for _ in range(3)]
+            lf = ON.gan_loss(ON.patchgan_forward(sdD, torch.cat((body, fakes), 1).detach()), t[0])
+            lr = ON.gan_loss(ON.patchgan_forward(sdD, torch.cat((body, tgt), 1)), t[1])
+            (0.5 * (lf + lr)).backward()
+            optD.step()
+            optG.zero_grad()
+            ce = torch.nn.functional.cross_entropy(fakes, torch.argmax(tgt, 1)) * 100
+            gan = ON.gan_loss(ON.patchgan_forward(sdD, torch.cat((body, fakes), 1)), t[2])
+            (ce + gan).backward()
+            optG.step()
+
+        steps_fns.append(warp_step)
+    if model in ("texture", "joint"):
+        with contextlib.redirect_stdout(sys.stderr):
+            T = M.TextureModule(3, 19, 12, "instance", 0.5, S)
+            M.init_weights(T, "kaiming")
+            DT = M.NLayerDiscriminator(22, 64, 3, "instance")
+            M.init_weights(DT, "kaiming")
+            vgg = None
+            if perceptual:
+                vgg = {k: v.detach() for k, v in M.load_vgg16_features("random").state_dict().items()}
+        sdT, sdDT = leaf(T), leaf(DT)
+        optT, optDT = adamw(sdT, 1e-4, 0), adamw(sdDT, 4e-4, 0.01)
+        tb = synth_texture_batch(B, S, 1234)
+        lc, ls = (20.0, 1e-8) if perceptual else (0.0, 0.0)
+
+        def texture_step():
+            draws = [torch.rand(1, generator=g) for _ in range(3)]
+            o = ON.texture_step_losses(sdT, sdDT, tb["input_textures"], tb["rois"], tb["cloths"], tb["target_textures"],
+                                       draws, drop=drop, vgg=vgg, lambda_content=lc, lambda_style=ls)
+            optDT.zero_grad()
+            o["D"].backward(retain_graph=True)
+            optDT.step()
+            optT.zero_grad()
+            o["G"].backward()        # (evaluates D once for both phases: slightly LESS work than the reference)
+            optT.step()
+
+        steps_fns.append(texture_step)
+
     def step():
-        fakes = ON.warp_forward(sdG, body, inp, drop)
-        optD.zero_grad()
-        t = [ON.smooth_label(torch.rand(1, generator=g)) for _ in range(3)]
-        lf = ON.gan_loss(ON.patchgan_forward(sdD, torch.cat((body, fakes), 1).detach()), t[0])
-        lr = ON.gan_loss(ON.patchgan_forward(sdD, torch.cat((body, tgt), 1)), t[1])
-        (0.5 * (lf + lr)).backward()
-        optD.step()
-        optG.zero_grad()
-        ce = torch.nn.functional.cross_entropy(fakes, torch.argmax(tgt, 1)) * 100
-        gan = ON.gan_loss(ON.patchgan_forward(sdD, torch.cat((body, fakes), 1)), t[2])
-        (ce + gan).backward()
-        optG.step()
-        return float((ce + gan).detach())
+        for f in steps_fns:
+            f()
 
     for _ in range(warmup):
         step()
@@ -226,38 +283,57 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=("b200", "reference"))
     ap.add_argument("--size", type=int, default=512)
-    ap.add_argument("--batch", type=int, default=16, help="images per GPU")
+    ap.add_argument("--batch", type=int, default=0, help="images per GPU (default 16; 8 for --model joint)")
+    ap.add_argument("--cpu-batch", type=int, default=1,
+                    help="--impl reference: images per CPU step (a bounded sample of the batch)")
+    ap.add_argument("--fp32-inputs", dest="labels", action="store_false",
+                    help="feed the warp cloth tensors as the fp32 one-hot [B,19,S,S] tensors the reference's DataLoader "
+                         "yields (688 MB of H2D per step at batch 16) instead of uint8 label maps expanded on the device "
+                         "(the default: ops.SegMap, SURVEY 8f rank 4)")
     ap.add_argument("--precision", default="fp32x3", choices=("fp32x3", "bf16"))
     ap.add_argument("--cpu-steps", type=int, default=3,
                     help="timed CPU-oracle steps of the cpu_baseline leg (one step = ~5 s on the usable host cores)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--perceptual", action="store_true",
                     help="--model texture: add the VGG16 content + Gram style terms (lambda 20 / 1e-8)")
-    ap.add_argument("--model", default="warp", choices=("warp", "texture"),
-                    help="warp = the BASELINE.json metric (default); texture = configs[2] (informational)")
+    ap.add_argument("--model", default="warp", choices=("warp", "texture", "joint"),
+                    help="warp = the BASELINE.json metric (default); texture = configs[2]; joint = configs[4] "
+                         "(one warp step + one texture step per iteration)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
-    S, B = args.size, args.batch
+    S = args.size
+    B = args.batch if args.batch else (8 if args.model == "joint" else 16)   # BASELINE configs[1,2]: 16/GPU; [4]: 8/GPU
     cores = host_cores()
-    workload = f"warp_model {S}x{S} synthetic, batch {B}/GPU, full GAN step (G fwd, D step, G step, AdamW x2)"
+    tex_losses = ("L1 + GAN + VGG16 content + Gram style, seeded-random VGG weights" if args.perceptual
+                  else "L1 + GAN; perceptual terms off")
+    workload = {
+        "warp": f"warp_model {S}x{S} synthetic, batch {B}/GPU, full GAN step (G fwd, D step, G step, AdamW x2)",
+        "texture": f"texture_model {S}x{S} synthetic, 12-ROI, batch {B}/GPU, full GAN step ({tex_losses})",
+        "joint": f"joint warp+texture {S}x{S} synthetic, batch {B}/GPU, one full warp GAN step + one full texture GAN step "
+                 f"per iteration ({tex_losses})"}[args.model]
+    config = {"workload": workload, "global_batch": B * world, "parallelism": f"dp{world}",
+              "l2": "inputs+activations per step (>2 GB) exceed the 126 MB L2; no explicit flush",
+              "algorithmic_tflop_per_step": step_gflop_per_img(args) * (S / 512) ** 2 * B * world / 1e3}
 
     if args.impl == "reference":
         if rank != 0:
             return
-        # one CPU step at 512x512, batch 1, takes ~5 s on the 16 usable cores of a GPU box: K and W are clamped so
-        # that the run ends within a few minutes (the line reports the steps actually timed)
-        steps = max(1, min(args.steps, 10))
-        v, med = cpu_reference_run(S, 1, steps, min(args.warmup, 2))
+        # exactly K timed and W warm-up steps of the same workload and config; each CPU step is a BOUNDED SAMPLE of the
+        # batch (`--cpu-batch` images, default 1: the step is per-sample work + batch-mean losses, cost linear in the
+        # batch) so that 25 steps stay within a few minutes on the box's host cores
+        v, med = cpu_reference_run(S, args.cpu_batch, args.steps, args.warmup, args.model, args.perceptual)
         print(json.dumps({
-            "impl": "reference", "metric": "images/sec (G+D fwd+bwd) warp-stage 512x512", "value": v,
-            "unit": "images/s", "n_gpus": args.gpus, "steps": steps, "warmup": min(args.warmup, 2),
+            "impl": "reference", "metric": metric_name(args), "value": v,
+            "unit": "images/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": med * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic",
-            "config": {"workload": workload, "note": "CPU arm runs batch 1 per step (bounded sample of the same workload)",
-                       "steps_requested": args.steps, "warmup_requested": args.warmup},
+            "dtype": "f32", "data": "synthetic", "config": config,
             "cpu_baseline": {"value": v, "unit": "images/s", "cores": cores, "kind": "port",
-                             "sample": f"{steps} timed full training steps at {S}x{S}, batch 1, torch CPU ({cores} threads)"},
+                             "sample": f"{args.steps} timed + {args.warmup} warm-up full training steps at {S}x{S}, each on "
+                                       f"{args.cpu_batch} image(s) of the batch (bounded sample), torch CPU fp32 "
+                                       f"({cores} threads = usable host cores); oracle/nets.py, pinned bit-exactly to the "
+                                       "reference modules (the reference is pure Python: nothing to compile into oracle/_ref, "
+                                       "and /root/reference does not exist on the GPU box)"},
             "e2e": {"value": v, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
         return
 
@@ -273,41 +349,53 @@ def main():
     torch.manual_seed(0)
     import contextlib
 
-    with contextlib.redirect_stdout(sys.stderr):   # stdout carries exactly one JSON line
+    def texture_opt():
         o = warp_opt(B, S, args.precision)
-        if args.model == "texture":
-            o.model, o.name, o.netG, o.lambda_l1, o.lambda_content, o.lambda_style = "texture", "texture", "swapnet", 10, 0, 0
-            if args.perceptual:   # the reference's default texture losses; seeded-random VGG16 (no weight file offline)
-                o.lambda_content, o.lambda_style, o.b200_vgg = 20.0, 1e-8, "random"
-        model = create_model(o)
-        model.setup(model.opt)
-    if args.model == "texture":
-        host = synth_texture_batch(B, S, 1234 + rank)
-        tkeys = ("input_textures", "rois", "cloths", "target_textures")
-    else:
-        host = synth_batch(B, S, 1234 + rank)
-        tkeys = ("bodys", "input_cloths", "target_cloths")
-    for k in tkeys:
-        host[k] = host[k].pin_memory()
-    dev_batch = dict(host)
-    for k in tkeys:
-        dev_batch[k] = host[k].cuda(non_blocking=True)
-    h2d = sum(host[k].numel() * 4 for k in tkeys)
+        o.model, o.name, o.netG, o.lambda_l1, o.lambda_content, o.lambda_style = "texture", "texture", "swapnet", 10, 0, 0
+        if args.perceptual:   # the reference's default texture losses; seeded-random VGG16 (no weight file offline)
+            o.lambda_content, o.lambda_style, o.b200_vgg = 20.0, 1e-8, "random"
+        return o
+
+    # legs = [(model, pinned host batch, device-resident batch)]: one per stage (joint = warp then texture)
+    legs = []
+    with contextlib.redirect_stdout(sys.stderr):   # stdout carries exactly one JSON line
+        for kind in (("warp", "texture") if args.model == "joint" else (args.model,)):
+            o = warp_opt(B, S, args.precision) if kind == "warp" else texture_opt()
+            m = create_model(o)
+            m.setup(m.opt)
+            if kind == "warp":
+                host = synth_batch(B, S, 1234 + rank, labels=args.labels)
+                tkeys = ("bodys", "input_cloths", "target_cloths")
+            else:
+                host = synth_texture_batch(B, S, 1234 + rank)
+                tkeys = ("input_textures", "rois", "cloths", "target_textures")
+            for k in tkeys:
+                host[k] = host[k].pin_memory()
+            devb = dict(host)
+            for k in tkeys:
+                devb[k] = host[k].cuda(non_blocking=True)
+            legs.append((m, host, devb, tkeys))
+    h2d = sum(host[k].numel() * host[k].element_size() for _, host, _, tkeys in legs for k in tkeys)
+    n_losses = sum(len([n for n in m.loss_names if isinstance(n, str)]) for m, *_ in legs)
 
     def barrier():
         if world > 1:
             torch.distributed.barrier()
         torch.cuda.synchronize()
 
-    def timed(n, batch, read_losses):
+    def one_step(on_host, read_losses):
+        for m, host, devb, _ in legs:
+            m.set_input(host if on_host else devb)
+            m.optimize_parameters()
+            if read_losses:
+                m.get_current_losses()
+
+    def timed(n, on_host, read_losses):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(n):
-            model.set_input(batch)
-            model.optimize_parameters()
-            if read_losses:
-                model.get_current_losses()
+            one_step(on_host, read_losses)
         e1.record()
         barrier()
         ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
@@ -316,91 +404,104 @@ def main():
         return ms.item()
 
     for _ in range(max(args.warmup, 3)):
-        model.set_input(dev_batch)
-        model.optimize_parameters()
+        one_step(False, False)
     sampler = ClockSampler(local)
     sampler.start()
     l0 = ops.launch_count()
-    ms = timed(args.steps, dev_batch, False)
+    ms = timed(args.steps, False, False)
     launches = ops.launch_count() - l0
     clocks = sampler.stop()
-    ms_e2e = timed(args.steps, host, True)
+    for _ in range(2):                      # the host-input path has its own staging buffers: warm them
+        one_step(True, True)
+    ms_e2e = timed(args.steps, True, True)
 
-    # ---- roofline pass (untimed): per-launch CUDA events on the tap-GEMM kernel ----
+    # ---- roofline pass (untimed): per-launch CUDA events on the GEMM plans ----
     roof = None
     # every rank runs the traced step (it contains the gradient all-reduces); rank 0 evaluates it
     ops.Plan.trace = []
-    model.set_input(dev_batch)
-    model.optimize_parameters()
+    for m, *_ in legs:
+        m.graph_enabled = False             # per-launch events need eager launches
+    one_step(False, False)
     torch.cuda.synchronize()
     trace, ops.Plan.trace = ops.Plan.trace, None
     if rank == 0:
         info = {}
-        engs = [model._eng_G, model._eng_Dd, model._eng_Dg]
-        pe = getattr(model, "_eng_P", None)
-        if pe is not None and pe.out is not None:
-            engs += [pe.out, pe.tgt]
-        for eng in engs:
-            for st in eng.stages:
-                fl, ly = 2.0 * st.nominal_macs(), st.layer
-                for p in ly.fwd_plans:
-                    info[id(p)] = ("fwd", fl / len(ly.fwd_plans))
-                for p in ly.dgrad_plans:
-                    info[id(p)] = ("dgrad", fl / len(ly.dgrad_plans))
-                if ly.wgrad_plan is not None:
-                    info[id(ly.wgrad_plan)] = ("wgrad", fl)
+        for m, *_ in legs:
+            engs = [m._eng_G, m._eng_Dd, m._eng_Dg]
+            pe = getattr(m, "_eng_P", None)
+            if pe is not None and pe.out is not None:
+                engs += [pe.out, pe.tgt]
+            for eng in engs:
+                for st in eng.stages:
+                    fl, ly = 2.0 * st.nominal_macs(), st.layer
+                    for p in ly.fwd_plans:
+                        info[id(p)] = ("fwd", fl / len(ly.fwd_plans), st.name)
+                    for p in ly.dgrad_plans:
+                        info[id(p)] = ("dgrad", fl / len(ly.dgrad_plans), st.name)
+                    if ly.wgrad_plan is not None:
+                        info[id(ly.wgrad_plan)] = ("wgrad", fl, st.name)
         peak, hbm, how = measured_peaks()
-        tot = {"fwd": [0.0, 0.0, 0], "dgrad": [0.0, 0.0, 0], "wgrad": [0.0, 0.0, 0]}  # flops, ms, launches
+        tot = {k: [0.0, 0.0, 0] for k in ("fwd", "dgrad", "wgrad", "res_fwd", "res_dgrad", "res_wgrad")}  # flops, ms, n
         for plan, a, b_ in trace:
-            kind, fl = info[id(plan)]
-            tot[kind][0] += fl
-            tot[kind][1] += a.elapsed_time(b_)
-            tot[kind][2] += 1
+            kind, fl, name = info[id(plan)]
+            dt = a.elapsed_time(b_)
+            for key in ((kind, "res_" + kind) if name.startswith("resblocks.") else (kind,)):
+                tot[key][0] += fl
+                tot[key][1] += dt
+                tot[key][2] += 1
         gemm_fl = tot["fwd"][0] + tot["dgrad"][0]
         gemm_ms = tot["fwd"][1] + tot["dgrad"][1]
         gemm_n = tot["fwd"][2] + tot["dgrad"][2]
         step_ms = ms / args.steps
+
+        def tf(key):
+            return (tot[key][0] / (tot[key][1] * 1e-3) / 1e12) if tot[key][1] else 0.0
+
         ach = gemm_fl / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
+        res_fl = tot["res_fwd"][0] + tot["res_dgrad"][0]
+        res_ms = tot["res_fwd"][1] + tot["res_dgrad"][1]
+        res = (res_fl / (res_ms * 1e-3) / 1e12) if res_ms else 0.0
+        tr = ncu_traffic()
         roof = {"bound": "tensor", "kernel": "tap_gemm_kernel<3> (tcgen05, fwd+dgrad launches)", "achieved": ach,
                 "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "pipe_frac": 3 * ach / peak, "peak_source": how,
                 "launches_per_step": gemm_n, "avg_launch_ms": gemm_ms / max(gemm_n, 1),
                 "algorithmic_gflop_per_launch": gemm_fl / max(gemm_n, 1) / 1e9,
                 "share_of_step": gemm_ms / step_ms,
-                # DRAM bytes of one launch of the dominant shape from the committed `ncu --set full` capture
-                "traffic": (ncu_traffic() or {}).get("dram_bytes_per_launch"), "traffic_detail": ncu_traffic(),
-                "wgrad_kernel": {"achieved": (tot["wgrad"][0] / (tot["wgrad"][1] * 1e-3) / 1e12) if tot["wgrad"][1] else 0.0,
+                # DRAM bytes of one launch of the dominant shape: a constant from the committed `ncu --set full`
+                # capture (profiles/), NOT measured in this run
+                "traffic": (tr or {}).get("dram_bytes_per_launch"), "traffic_source": "committed ncu capture (profiles/)",
+                "traffic_detail": tr,
+                # the fused U-Net conv blocks the north-star target is read against: the 8 resblock convs
+                # (59 % of generator FLOPs), FLOP-weighted over their fwd + dgrad launches, and their wgrad launches
+                "resblock": {"achieved": res, "frac": res / peak, "pipe_frac": 3 * res / peak,
+                             "launches_per_step": tot["res_fwd"][2] + tot["res_dgrad"][2],
+                             "fwd": tf("res_fwd"), "dgrad": tf("res_dgrad"), "wgrad": tf("res_wgrad")},
+                "wgrad_kernel": {"achieved": tf("wgrad"), "frac": tf("wgrad") / peak,
                                  "share_of_step": tot["wgrad"][1] / step_ms, "launches_per_step": tot["wgrad"][2]}}
 
     if rank != 0:
         torch.distributed.destroy_process_group()
         return
     cpu = None
-    if args.model == "texture":
-        workload = (f"texture_model {S}x{S} synthetic, 12-ROI, batch {B}/GPU, full GAN step "
-                    + ("(L1 + GAN + VGG16 content + Gram style, seeded-random VGG weights)" if args.perceptual
-                       else "(L1 + GAN; perceptual terms off)"))
-    if not args.no_cpu_baseline and args.gpus == 1 and args.model == "warp":
-        v, med = cpu_reference_run(S, 1, args.cpu_steps, 1)
+    if not args.no_cpu_baseline and args.gpus == 1:
+        v, med = cpu_reference_run(S, 1, args.cpu_steps, 1, args.model, args.perceptual)
         cpu = {"value": v, "unit": "images/s", "cores": cores, "kind": "port",
                "sample": f"{args.cpu_steps} timed full training step(s) at {S}x{S}, batch 1, after 1 warm-up step, "
                          f"torch CPU ({cores} threads = usable cores under the cgroup quota)"}
     step_ms = ms / args.steps
     total_imgs = B * world
     out = {
-        "metric": "images/sec (G+D fwd+bwd) warp-stage 512x512" if args.model == "warp"
-        else "images/sec (G+D fwd+bwd) texture-stage 512x512",
+        "metric": metric_name(args),
         "value": total_imgs / (step_ms * 1e-3),
         "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "fp16/bf16-split x3 tensor-core products, fp32 accumulate (fp32-faithful)" if args.precision == "fp32x3"
         else "fp16 single-pass tensor-core products, fp32 accumulate",
-        "data": "synthetic",
-        "config": {"workload": workload, "global_batch": total_imgs, "parallelism": f"dp{world}",
-                   "l2": "inputs+activations per step (>2 GB) exceed the 126 MB L2; no explicit flush",
-                   "algorithmic_tflop_per_step": (FULL_STEP_GFLOP_PER_IMG_512 if args.model == "warp" else (896.0 if args.perceptual else 415.0))
-                   * (S / 512) ** 2 * total_imgs / 1e3},
+        "data": "synthetic", "config": config,
         "e2e": {"value": total_imgs / (ms_e2e / args.steps * 1e-3), "unit": "images/s",
-                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 6 * 8},
+                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": n_losses * 8,
+                "inputs": "uint8 label maps for the cloth tensors, expanded to one-hot planes on the device"
+                if args.labels else "fp32 tensors as the reference's DataLoader yields them"},
         "gpu_launches": launches, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
     }
     print(json.dumps(out))

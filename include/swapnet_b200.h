@@ -38,7 +38,13 @@ extern "C" {
 #define SN_MAX_SRC 3
 
 enum { SN_ACT_NONE = 0, SN_ACT_TANH = 1, SN_ACT_LRELU = 2, SN_ACT_RELU = 3 };
-enum { SN_LAYOUT_NCHW = 0, SN_LAYOUT_NHWC = 1 };
+/* SN_LAYOUT_LABEL_U8 / SN_LAYOUT_MASK_I32: compact encodings of the 0/1-valued cloth segmentation tensors — the wire
+ * format the reference's dataset expands on the host (datasets/data_utils.py:311-343 `to_onehot_tensor`: label L > 0 ->
+ * channel L one-hot, label 0 (background) -> the all-zero vector; after the per-channel augmentation of
+ * data_utils.py:346-361 the channels are independent 0/1 masks).  LABEL_U8: uint8 [n,h,w] label map; MASK_I32: int32
+ * [n,h,w] with bit c = channel c.  The kernels below that take a `layout` expand them on the fly, so the batch travels
+ * over PCIe as 1-4 bytes per pixel instead of 76. */
+enum { SN_LAYOUT_NCHW = 0, SN_LAYOUT_NHWC = 1, SN_LAYOUT_LABEL_U8 = 2, SN_LAYOUT_MASK_I32 = 3 };
 /* 16-bit float format of a split plane pair: bf16 (8+8 mantissa bits, fp32 range: gradients) or
  * fp16 (11+11 bits: activations, pre-scaled weights).  A and B of one GEMM must agree. */
 #define SN_FMT_BF16 0
@@ -126,7 +132,7 @@ void sn_plan_destroy(sn_plan* plan);
 /* ------------------------------------------------------------------------------------------
  * operand packing
  * ---------------------------------------------------------------------------------------- */
-/* fp32 image tensor (NCHW contiguous, or NHWC with src_pitch) -> split planes at channel
+/* fp32 image tensor (NCHW contiguous, or NHWC with src_pitch; or a LABEL_U8 / MASK_I32 map expanded to c channels) -> split planes at channel
  * offset dst_coff of an NHWC plane pair with pitch dst_pitch.  Replaces the torch.cat /
  * .to(device) glue of warp_model.py:99-116 and swapnet_modules.py:258. */
 int sn_pack_planes(const float* src, int src_layout, int src_pitch, int n, int c, int h, int w,
@@ -244,9 +250,10 @@ int sn_dropout_mask(unsigned long long seed, float p, long long count, uint8_t* 
  * losses (value + gradient in one pass)
  * ---------------------------------------------------------------------------------------- */
 /* CrossEntropyLoss(logits, argmax(target,1)) * weight  (warp_model.py:147-150).
- * logits NHWC [n,h,w,c] (pitch), target NCHW [n,c,h,w]; loss accumulated into *loss_acc
- * (double, caller zeroes); grad NHWC fp32 (pitch c). */
-int sn_ce_loss_fwd_bwd(const float* logits, int pitch, const float* target_nchw, int n, int h, int w,
+ * logits NHWC [n,h,w,c] (pitch), target NCHW [n,c,h,w] — or, with target_layout = SN_LAYOUT_LABEL_U8, the uint8
+ * label map [n,h,w] itself (argmax of its one-hot expansion: the label; 0 for background); loss accumulated into
+ * *loss_acc (double, caller zeroes); grad NHWC fp32 (pitch c). */
+int sn_ce_loss_fwd_bwd(const float* logits, int pitch, const void* target, int target_layout, int n, int h, int w,
                        int c, float weight, double* loss_acc, float* grad, int grad_pitch, void* stream);
 /* BCEWithLogitsLoss(pred, t) over two consecutive halves of `count` elements each with its own
  * target (loss.py:58,110-122): loss_acc[half] += mean, dpred = gscale * (sigmoid(x) - t)/count. */

@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(_HERE, "libswapnet_b200.so")
 SN_MAX_TAPS = 32
 SN_MAX_SRC = 3
 ACT_NONE, ACT_TANH, ACT_LRELU, ACT_RELU = 0, 1, 2, 3
-LAYOUT_NCHW, LAYOUT_NHWC = 0, 1
+LAYOUT_NCHW, LAYOUT_NHWC, LAYOUT_LABEL_U8, LAYOUT_MASK_I32 = 0, 1, 2, 3
 FMT_BF16, FMT_F16 = 0, 1
 
 
@@ -121,7 +121,7 @@ SIGNATURES = {
     "sn_upsample_planes": (_I, [_VP, _VP, _I, _I, _I, _I, _I, _I, _I, _VP, _VP, _I, _I, _VP]),
     "sn_adamw_step": (_I, [_VP, _VP, _VP, _VP, _LL, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double, _I, _VP]),
     "sn_dropout_mask": (_I, [_ULL, _F, _LL, _VP, _VP]),
-    "sn_ce_loss_fwd_bwd": (_I, [_VP, _I, _VP, _I, _I, _I, _I, _F, _VP, _VP, _I, _VP]),
+    "sn_ce_loss_fwd_bwd": (_I, [_VP, _I, _VP, _I, _I, _I, _I, _I, _F, _VP, _VP, _I, _VP]),
     "sn_bce_logits_fwd_bwd": (_I, [_VP, _LL, _I, _F, _F, _F, _VP, _VP, _VP]),
     "sn_l1_loss_fwd_bwd": (_I, [_VP, _I, _VP, _I, _I, _I, _I, _F, _VP, _VP, _I, _VP]),
     "sn_tap_sum_fwd": (_I, [_VP, _I, _I, _I, _I, _I, _I, _VP, _VP, _I, _VP]),

@@ -61,7 +61,16 @@ __device__ __forceinline__ void store_split(uint16_t* hi, uint16_t* lo, long lon
 // pack_planes
 // ---------------------------------------------------------------------------------
 // NCHW source: one block per (n, h, 32-pixel run); smem transposes [c][w] -> [w][c].
-__global__ void pack_planes_nchw_kernel(const float* __restrict__ src, int N, int C, int H, int W,
+// value of channel c at a pixel of a compact segmentation map (see SN_LAYOUT_LABEL_U8 / SN_LAYOUT_MASK_I32)
+__device__ __forceinline__ float seg_value(const void* src, int layout, long long pix, int c) {
+  if (layout == SN_LAYOUT_LABEL_U8) {
+    const int lab = reinterpret_cast<const uint8_t*>(src)[pix];
+    return (c > 0 && lab == c) ? 1.f : 0.f;          // label 0 = background = the all-zero vector
+  }
+  return (float)((reinterpret_cast<const uint32_t*>(src)[pix] >> c) & 1u);
+}
+
+__global__ void pack_planes_nchw_kernel(const float* __restrict__ src, int layout, int N, int C, int H, int W,
                                         uint16_t* __restrict__ hi, uint16_t* __restrict__ lo,
                                         int pitch, int coff, int fmt) {
   extern __shared__ float tile[];  // [C][33]
@@ -71,7 +80,10 @@ __global__ void pack_planes_nchw_kernel(const float* __restrict__ src, int N, in
   for (int i = threadIdx.x; i < C * 32; i += blockDim.x) {
     const int c = i / 32, w = i % 32;
     float v = 0.f;
-    if (w0 + w < W) v = src[(((long long)n * C + c) * H + h) * W + w0 + w];
+    if (w0 + w < W) {
+      if (layout == SN_LAYOUT_NCHW) v = src[(((long long)n * C + c) * H + h) * W + w0 + w];
+      else v = seg_value(src, layout, ((long long)n * H + h) * W + w0 + w, c);
+    }
     tile[c * 33 + w] = v;
   }
   __syncthreads();
@@ -119,10 +131,15 @@ __global__ void __launch_bounds__(256) pack_concat_kernel(const PackConcatArgs a
         const int c = i / PW, w = i - c * PW;
         tile[(cbase + c) * TP + w] = (w0 + w < a.W) ? s.p[(((long long)n * s.c + c) * a.H + h) * a.W + w0 + w] : 0.f;
       }
-    } else {
+    } else if (s.layout == SN_LAYOUT_NHWC) {
       for (int i = threadIdx.x; i < s.c * PW; i += blockDim.x) {
         const int w = i / s.c, c = i - w * s.c;
         tile[(cbase + c) * TP + w] = (w0 + w < a.W) ? s.p[(((long long)n * a.H + h) * a.W + w0 + w) * s.pitch + c] : 0.f;
+      }
+    } else {   // compact segmentation map (uint8 labels / int32 bit mask) expanded to s.c 0/1 channels
+      for (int i = threadIdx.x; i < s.c * PW; i += blockDim.x) {
+        const int c = i / PW, w = i - c * PW;
+        tile[(cbase + c) * TP + w] = (w0 + w < a.W) ? seg_value(s.p, s.layout, ((long long)n * a.H + h) * a.W + w0 + w, c) : 0.f;
       }
     }
     cbase += s.c;
@@ -780,8 +797,8 @@ __device__ __forceinline__ void block_add_double(double v, double* dst) {
 
 constexpr int kMaxCE = 32;
 __global__ void ce_loss_kernel(const float* __restrict__ logits, int pitch,
-                               const float* __restrict__ target, int N, int H, int W, int C,
-                               float weight, double* loss_acc, float* __restrict__ grad, int gpitch) {
+                               const float* __restrict__ target, const uint8_t* __restrict__ label, int N, int H, int W,
+                               int C, float weight, double* loss_acc, float* __restrict__ grad, int gpitch) {
   const long long npix = (long long)N * H * W;
   const long long HW = (long long)H * W;
   double local = 0.0;
@@ -795,11 +812,16 @@ __global__ void ce_loss_kernel(const float* __restrict__ logits, int pitch,
     for (int c = 0; c < C; ++c) {
       x[c] = logits[pix * pitch + c];
       mx = fmaxf(mx, x[c]);
+      if (label) continue;
       const float t = target[(n * C + c) * HW + p];
       if (c == 0 || t > best) {  // first maximum wins (torch.argmax tie-break)
         best = t;
         arg = c;
       }
+    }
+    if (label) {   // argmax of the one-hot expansion of a label map: the label (0 = all-zero vector -> index 0)
+      arg = label[pix];
+      if (arg >= C) arg = 0;
     }
     float se = 0.f;
     for (int c = 0; c < C; ++c) se += expf(x[c] - mx);
@@ -1219,11 +1241,13 @@ int sn_pack_planes(const float* src, int src_layout, int src_pitch, int n, int c
   SN_REQUIRE(src && dst_hi, "null pointer");
   SN_REQUIRE(dst_coff + c <= dst_pitch, "channel slice exceeds pitch");
   cudaStream_t st = (cudaStream_t)stream;
-  if (src_layout == SN_LAYOUT_NCHW) {
+  if (src_layout != SN_LAYOUT_NHWC) {
+    SN_REQUIRE(src_layout != SN_LAYOUT_MASK_I32 || c <= 32, "pack_planes: a bit mask holds at most 32 channels");
+    SN_REQUIRE(src_layout != SN_LAYOUT_LABEL_U8 || c <= 256, "pack_planes: a uint8 label map holds at most 256 classes");
     dim3 grid((w + 31) / 32, h, n);
     size_t smem = (size_t)c * 33 * sizeof(float);
     SN_REQUIRE(smem <= 48 * 1024, "pack_planes: too many channels for NCHW path (%d)", c);
-    pack_planes_nchw_kernel<<<grid, 256, smem, st>>>(src, n, c, h, w, (uint16_t*)dst_hi,
+    pack_planes_nchw_kernel<<<grid, 256, smem, st>>>(src, src_layout, n, c, h, w, (uint16_t*)dst_hi,
                                                      (uint16_t*)dst_lo, dst_pitch, dst_coff, fmt);
   } else {
     const long long npix = (long long)n * h * w;
@@ -1528,11 +1552,15 @@ int sn_dropout_mask(unsigned long long seed, float p, long long count, uint8_t* 
   return SN_OK;
 }
 
-int sn_ce_loss_fwd_bwd(const float* logits, int pitch, const float* target_nchw, int n, int h, int w,
+int sn_ce_loss_fwd_bwd(const float* logits, int pitch, const void* target, int target_layout, int n, int h, int w,
                        int c, float weight, double* loss_acc, float* grad, int grad_pitch, void* stream) {
   SN_REQUIRE(c <= kMaxCE, "ce loss supports at most %d classes", kMaxCE);
+  SN_REQUIRE(target_layout == SN_LAYOUT_NCHW || target_layout == SN_LAYOUT_LABEL_U8,
+             "ce loss: target must be NCHW fp32 or a uint8 label map");
+  const bool lab = target_layout == SN_LAYOUT_LABEL_U8;
   ce_loss_kernel<<<grid_for((long long)n * h * w, 128), 128, 0, (cudaStream_t)stream>>>(
-      logits, pitch, target_nchw, n, h, w, c, weight, loss_acc, grad, grad_pitch);
+      logits, pitch, lab ? nullptr : (const float*)target, lab ? (const uint8_t*)target : nullptr, n, h, w, c, weight,
+      loss_acc, grad, grad_pitch);
   LAUNCH_CHECK();
   return SN_OK;
 }

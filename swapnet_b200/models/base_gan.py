@@ -127,11 +127,12 @@ class BaseGAN(BaseModel, ABC):
             self.optimizer_D = define_optimizer(self.net_discriminator, opt, "D")
             self.optimizer_names = ("G", "D")
             self._acc = torch.zeros(8, dtype=torch.float64, device=self.device)  # device-side loss sums
+            self._acc_host = None                       # host copy of _acc for the current step (one D2H per step)
             lam = float(opt.lambda_gan)
-            self.loss_D_fake = LazyLoss(lambda: self._acc[0].item())
-            self.loss_D_real = LazyLoss(lambda: self._acc[1].item())
-            self.loss_D = LazyLoss(lambda: 0.5 * (self._acc[0].item() + self._acc[1].item()))
-            self.loss_G_gan = LazyLoss(lambda: lam * self._acc[2].item())
+            self.loss_D_fake = LazyLoss(lambda: self.loss_values()[0])
+            self.loss_D_real = LazyLoss(lambda: self.loss_values()[1])
+            self.loss_D = LazyLoss(lambda: 0.5 * (self.loss_values()[0] + self.loss_values()[1]))
+            self.loss_G_gan = LazyLoss(lambda: lam * self.loss_values()[2])
             parallel.broadcast_parameters(list(self.net_generator.parameters()) +
                                           list(self.net_discriminator.parameters()))
 
@@ -204,6 +205,13 @@ class BaseGAN(BaseModel, ABC):
             e["dpred_g"] = torch.zeros_like(dg.pred)
         return e
 
+    def loss_values(self):
+        """The device-side loss sums of the last step as Python floats: ONE 64-byte D2H copy (and the step's only host
+        synchronisation) however many terms train.py:74 / get_current_losses() reads."""
+        if self._acc_host is None:
+            self._acc_host = self._acc.tolist()
+        return self._acc_host
+
     def step_seed(self) -> int:
         return (self._seed_base * 1000003 + self._step) & 0xFFFFFFFF
 
@@ -247,6 +255,7 @@ class BaseGAN(BaseModel, ABC):
         return g.dx_in
 
     def optimize_parameters(self):
+        self._acc_host = None
         self._acc.zero_()
         self.forward()
         self._eng_Dd.zero_grad()

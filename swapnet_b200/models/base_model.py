@@ -14,7 +14,8 @@ import torch
 
 class LazyLoss:
     """A loss that lives on the device until somebody asks for a float (train.py:74 does, every
-    iteration — the only host sync of a step)."""
+    iteration — the only host sync of a step: BaseGAN.loss_values() fetches all terms of the step with ONE
+    64-byte device-to-host copy)."""
 
     def __init__(self, fn):
         self._fn = fn
@@ -64,12 +65,23 @@ class BaseModel(ABC):
         self.training = True
 
     # ---- late H2D copies: tensors that the step needs only after its first phase ----
-    def copy_late(self, t: torch.Tensor, key: str = None) -> torch.Tensor:
+    def copy_late(self, t, key: str = None, seg_channels: int = 0):
         """H2D copy on a side stream (pinned host tensors; plain conversion for device tensors).  The step
         waits for it where the tensor is first needed: `wait_copy(key)` or, for everything still pending,
-        `wait_late_copies()`.  Copies run in issue order, so the tensors a step needs first go first."""
+        `wait_late_copies()`.  Copies run in issue order, so the tensors a step needs first go first.
+
+        seg_channels > 0: the entry may also arrive in compact form — a uint8 label map or an int32 bit mask [B,H,W]
+        (ops.SegMap) — which travels as 1-4 bytes per pixel instead of 4*channels and is expanded
+        by the consuming kernels; fp32 [B,C,H,W] tensors are handled as before."""
+        from ..ops import SegMap
+
+        if isinstance(t, SegMap):
+            seg_channels, t = t.channels, t.data
+        compact = seg_channels > 0 and t.dim() == 3 and t.dtype in (torch.uint8, torch.int32)
+        dtype = t.dtype if compact else torch.float32
         if t.is_cuda:
-            return t.to(device=self.device, dtype=torch.float32).contiguous()
+            out = t.to(device=self.device, dtype=dtype).contiguous()
+            return SegMap(out, seg_channels) if compact else out
         if not hasattr(self, "_copy_stream"):
             self._copy_stream = torch.cuda.Stream(device=self.device)
             self._late_events = []
@@ -79,14 +91,19 @@ class BaseModel(ABC):
         # only recycles a block once the streams recorded on it — record_stream below — have passed its last use),
         # so the copy of step N+1's inputs overlaps the compute of step N
         with torch.cuda.stream(self._copy_stream):
-            out = t.to(device=self.device, dtype=torch.float32, non_blocking=True).contiguous()
+            out = t.to(device=self.device, dtype=dtype, non_blocking=True).contiguous()
             ev = torch.cuda.Event()
             ev.record(self._copy_stream)
         out.record_stream(cur)
         self._late_events.append(ev)
         if key is not None:
             self._copy_events[key] = ev
-        return out
+        return SegMap(out, seg_channels) if compact else out
+
+    @staticmethod
+    def dense(t):
+        """fp32 [B,C,H,W] view of an input that may have arrived in compact form (visuals, off the hot path)."""
+        return t.dense() if hasattr(t, "dense") else t
 
     def wait_copy(self, key: str) -> None:
         ev = getattr(self, "_copy_events", {}).pop(key, None)

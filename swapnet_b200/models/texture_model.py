@@ -53,11 +53,11 @@ class TextureModel(BaseGAN):
                 # only needed when the content term is on (the style term uses the raw images)
                 self.net_vgg = M.load_vgg16_features(getattr(opt, "b200_vgg", "pretrained")).to(self.device)
             lam = float(opt.lambda_gan)
-            self.loss_G_l1 = LazyLoss(lambda: self._acc[3].item())
-            self.loss_G_content = LazyLoss(lambda: self._acc[4].item()) if self.lam_content != 0 else 0.0
-            self.loss_G_style = LazyLoss(lambda: self._acc[5].item()) if self.lam_style != 0 else 0.0
-            self.loss_G = LazyLoss(lambda: lam * self._acc[2].item() + self._acc[3].item() + self._acc[4].item()
-                                   + self._acc[5].item())
+            lv = self.loss_values
+            self.loss_G_l1 = LazyLoss(lambda: lv()[3])
+            self.loss_G_content = LazyLoss(lambda: lv()[4]) if self.lam_content != 0 else 0.0
+            self.loss_G_style = LazyLoss(lambda: lv()[5]) if self.lam_style != 0 else 0.0
+            self.loss_G = LazyLoss(lambda: lam * lv()[2] + lv()[3] + lv()[4] + lv()[5])
             for loss in ("l1", "content", "style"):
                 if getattr(opt, "lambda_" + loss, 0) != 0:
                     self.loss_names.append("G_" + loss)
@@ -73,7 +73,7 @@ class TextureModel(BaseGAN):
             draw_rois_on_texture = None
         if draw_rois_on_texture is not None:
             self.textures_unnormalized = draw_rois_on_texture(self.rois, self.textures_unnormalized)
-        self.cloths_decoded = decode_cloth_labels(self.cloths)
+        self.cloths_decoded = decode_cloth_labels(self.dense(self.cloths))
         self.fakes_scaled = scale_tensor(self.fakes, scale_each=True)
         if self.is_train:
             self.targets_unnormalized = unnormalize(self.targets, *self.opt.texture_norm_stats)
@@ -104,7 +104,7 @@ class TextureModel(BaseGAN):
         # side-stream H2D copies in the order the step needs them (see WarpModel.set_input)
         self.textures = self.copy_late(input["input_textures"], "textures")
         self.rois = self.copy_late(input["rois"], "rois")
-        self.cloths = self.copy_late(input["cloths"], "cloths")
+        self.cloths = self.copy_late(input["cloths"], "cloths", seg_channels=self.opt.cloth_channels)
         self.targets = self.copy_late(input["target_textures"], "targets")
         self.image_paths = tuple(zip(input["cloth_paths"], input["texture_paths"]))
 

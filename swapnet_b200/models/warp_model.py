@@ -36,7 +36,7 @@ class WarpModel(BaseGAN):
         self.visual_names = ["inputs_decoded", "bodys_unnormalized", "fakes_decoded"]
         if self.is_train:
             self.visual_names.append("targets_decoded")
-            self.loss_G_ce = LazyLoss(lambda: self._acc[3].item())
+            self.loss_G_ce = LazyLoss(lambda: self.loss_values()[3])
             if opt.warp_mode != "gan":
                 self.model_names = ["generator"]
                 self.loss_names = "G"   # (sic) warp_model.py:71 — a str; get_current_losses iterates its chars
@@ -47,16 +47,16 @@ class WarpModel(BaseGAN):
             else:
                 self.loss_names += ["G_ce"]
                 lam = float(opt.lambda_gan)
-                self.loss_G = LazyLoss(lambda: lam * self._acc[2].item() + self._acc[3].item())
+                self.loss_G = LazyLoss(lambda: lam * self.loss_values()[2] + self.loss_values()[3])
 
     # ---- visuals: off the hot path; reuse the reference's helpers when they are importable ----
     def compute_visuals(self):
         from datasets.data_utils import unnormalize
         from util.decode_labels import decode_cloth_labels
 
-        self.inputs_decoded = decode_cloth_labels(self.inputs)
+        self.inputs_decoded = decode_cloth_labels(self.dense(self.inputs))
         self.bodys_unnormalized = unnormalize(self.bodys, *self.opt.body_norm_stats)
-        self.targets_decoded = decode_cloth_labels(self.targets)
+        self.targets_decoded = decode_cloth_labels(self.dense(self.targets))
         self.fakes_decoded = decode_cloth_labels(self.fakes)
 
     def define_G(self):
@@ -73,8 +73,9 @@ class WarpModel(BaseGAN):
         # body branch and the weight packing run while the 19-channel cloth is still in flight —, the targets
         # last (first needed by the D step, one generator forward later).  No-op for device tensors.
         self.bodys = self.copy_late(input["bodys"], "bodys")
-        self.inputs = self.copy_late(input["input_cloths"], "inputs")
-        self.targets = self.copy_late(input["target_cloths"], "targets")
+        # the cloth tensors may arrive in compact form (uint8 label map / int32 bit mask [B,H,W], ops.SegMap)
+        self.inputs = self.copy_late(input["input_cloths"], "inputs", seg_channels=self.cloth_channels)
+        self.targets = self.copy_late(input["target_cloths"], "targets", seg_channels=self.cloth_channels)
         self.image_paths = tuple(zip(input["cloth_paths"], input["body_paths"]))
 
     def forward(self):
@@ -118,6 +119,7 @@ class WarpModel(BaseGAN):
         if self.opt.warp_mode == "gan":
             super().optimize_parameters()
         else:
+            self._acc_host = None
             self._acc.zero_()
             self.forward()
             self._eng_G.zero_grad()

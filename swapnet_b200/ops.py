@@ -14,8 +14,9 @@ import torch
 from . import _lib
 from . import lowering as L
 
-from ._lib import (ACT_LRELU, ACT_NONE, ACT_RELU, ACT_TANH, FMT_BF16, FMT_F16, LAYOUT_NCHW, LAYOUT_NHWC, SnGradSrc,
-                   SnNormActBwdDesc, SnNormActDesc, SnTap, SnTapGemmDesc, SnWgradDesc, check)
+from ._lib import (ACT_LRELU, ACT_NONE, ACT_RELU, ACT_TANH, FMT_BF16, FMT_F16, LAYOUT_LABEL_U8, LAYOUT_MASK_I32,
+                   LAYOUT_NCHW, LAYOUT_NHWC, SnGradSrc, SnNormActBwdDesc, SnNormActDesc, SnTap, SnTapGemmDesc,
+                   SnWgradDesc, check)
 
 IN_EPS = 1e-5  # nn.InstanceNorm2d default (modules/__init__.py:67-69)
 
@@ -276,8 +277,74 @@ def wgrad_plan(desc: SnWgradDesc, keep: Sequence = ()) -> Plan:
 # ---------------------------------------------------------------------------------------------
 # packing
 # ---------------------------------------------------------------------------------------------
-def pack_planes(src: torch.Tensor, dst: Planes, *, nhwc: bool = False) -> None:
-    """src: fp32 NCHW contiguous [n,c,h,w] (or NHWC [n,h,w,pitch] with nhwc=True, first dst.c channels)."""
+class SegMap:
+    """A 0/1-valued [n, c, h, w] segmentation tensor in compact form: `data` is a uint8 label map
+    [n,h,w] (label L > 0 -> channel L one-hot, 0 -> the all-zero vector: datasets/data_utils.py:330-343) or an int32
+    bit mask [n,h,w] (bit c = channel c: the independently augmented channels of data_utils.py:346-361).  The kernels
+    that consume cloth tensors (pack_concat, pack_planes, ce_loss_fwd_bwd) expand it on the fly."""
+
+    def __init__(self, data: torch.Tensor, channels: int):
+        assert data.dim() == 3 and data.dtype in (torch.uint8, torch.int32), "uint8 label map or int32 bit mask [n,h,w]"
+        assert channels <= (32 if data.dtype == torch.int32 else 256)
+        self.data, self.channels = data.contiguous(), channels
+        self.layout = LAYOUT_LABEL_U8 if data.dtype == torch.uint8 else LAYOUT_MASK_I32
+
+    @property
+    def shape(self):
+        n, h, w = self.data.shape
+        return (n, self.channels, h, w)
+
+    @property
+    def is_cuda(self):
+        return self.data.is_cuda
+
+    def dense(self) -> torch.Tensor:
+        """fp32 [n,c,h,w] expansion with torch ops (visuals / tests; the hot path never calls this)."""
+        ch = torch.arange(self.channels, device=self.data.device).view(1, -1, 1, 1)
+        d = self.data.unsqueeze(1)
+        if self.layout == LAYOUT_LABEL_U8:
+            return ((d.long() == ch) & (ch > 0)).float()
+        return ((d.long() >> ch) & 1).float()
+
+    @staticmethod
+    def from_dense(t: torch.Tensor) -> "SegMap":
+        """Compress an fp32 0/1 tensor [n,c,h,w] (what the reference's dataset yields): a uint8 label map when it is
+        one-hot with an empty channel 0, else an int32 bit mask.  Raises if the tensor is not 0/1-valued."""
+        assert t.dim() == 4 and t.shape[1] <= 32
+        b = t != 0
+        if not torch.equal(b.to(t.dtype), t):
+            raise ValueError("SegMap.from_dense: tensor is not 0/1-valued")
+        c = t.shape[1]
+        if int(b.sum(1).max()) <= 1 and not bool(b[:, 0].any()):
+            return SegMap(b.to(torch.uint8).mul(torch.arange(c, dtype=torch.uint8, device=t.device).view(1, -1, 1, 1))
+                          .sum(1, dtype=torch.uint8), c)
+        w = (1 << torch.arange(c, dtype=torch.int64, device=t.device)).view(1, -1, 1, 1)
+        return SegMap((b.long() * w).sum(1).to(torch.int32), c)
+
+
+def _src_args(t, nhwc: bool):
+    """(pointer, layout, pitch, channels, (n, h, w)) of a pack source: fp32 NCHW / NHWC tensor or SegMap."""
+    if isinstance(t, SegMap):
+        n, h, w = t.data.shape
+        return t.data.data_ptr(), t.layout, 0, t.channels, (n, h, w)
+    assert t.dtype == torch.float32
+    if nhwc:
+        n, h, w, c = t.shape
+        return t.data_ptr(), LAYOUT_NHWC, _pitch(t), c, (n, h, w)
+    assert t.is_contiguous()
+    n, c, h, w = t.shape
+    return t.data_ptr(), LAYOUT_NCHW, 0, c, (n, h, w)
+
+
+def pack_planes(src, dst: Planes, *, nhwc: bool = False) -> None:
+    """src: fp32 NCHW contiguous [n,c,h,w] (or NHWC [n,h,w,pitch] with nhwc=True, first dst.c channels), or a SegMap."""
+    if isinstance(src, SegMap):
+        ptr, layout, _, c, (n, h, w) = _src_args(src, False)
+        assert c <= dst.c and (n, h, w) == (dst.n, dst.h, dst.w)
+        for d_ in ((dst,) if dst.twin is None else (dst, dst.twin)):
+            check(_lib.load().sn_pack_planes(ptr, layout, 0, n, c, h, w, d_.hi_ptr, d_.lo_ptr, d_.pitch, 0, d_.fmt,
+                                             _stream()))
+        return
     assert src.dtype == torch.float32
     if nhwc:
         n, h, w, sp = src.shape
@@ -302,15 +369,9 @@ def pack_concat(srcs, dst: Planes) -> None:
     assert 1 <= len(srcs) <= 2 and dst.c % 8 == 0 and dst.c_off % 8 == 0
     args = []
     for t, nhwc in srcs:
-        assert t.dtype == torch.float32
-        if nhwc:
-            n, h, w, c = t.shape
-            args += [t.data_ptr(), LAYOUT_NHWC, _pitch(t), c]
-        else:
-            assert t.is_contiguous()
-            n, c, h, w = t.shape
-            args += [t.data_ptr(), LAYOUT_NCHW, 0, c]
-        assert (n, h, w) == (dst.n, dst.h, dst.w)
+        ptr, layout, pitch, c, nhw = _src_args(t, nhwc)
+        args += [ptr, layout, pitch, c]
+        assert nhw == (dst.n, dst.h, dst.w)
     if len(srcs) == 1:
         args += [None, 0, 0, 0]
     tw = dst.twin
@@ -508,11 +569,17 @@ def dropout_mask(seed: int, p: float, count: int, device) -> torch.Tensor:
 # ---------------------------------------------------------------------------------------------
 # losses
 # ---------------------------------------------------------------------------------------------
-def ce_loss_fwd_bwd(logits: torch.Tensor, c: int, target_nchw: torch.Tensor, weight: float,
+def ce_loss_fwd_bwd(logits: torch.Tensor, c: int, target, weight: float,
                     loss_acc: torch.Tensor, grad: torch.Tensor) -> None:
+    """target: fp32 NCHW one-hot [n,c,h,w] (argmax taken in the kernel, first maximum wins) or a uint8-label SegMap."""
     n, h, w, pitch = logits.shape
-    assert target_nchw.is_contiguous() and target_nchw.shape == (n, c, h, w)
-    check(_lib.load().sn_ce_loss_fwd_bwd(logits.data_ptr(), pitch, target_nchw.data_ptr(), n, h, w, c, weight,
+    if isinstance(target, SegMap):
+        assert target.layout == LAYOUT_LABEL_U8 and target.shape == (n, c, h, w), "CE target: a uint8 label map"
+        tptr, layout = target.data.data_ptr(), LAYOUT_LABEL_U8
+    else:
+        assert target.is_contiguous() and target.shape == (n, c, h, w)
+        tptr, layout = target.data_ptr(), LAYOUT_NCHW
+    check(_lib.load().sn_ce_loss_fwd_bwd(logits.data_ptr(), pitch, tptr, layout, n, h, w, c, weight,
                                          loss_acc.data_ptr(), grad.data_ptr(), grad.shape[3], _stream()))
 
 

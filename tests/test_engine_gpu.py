@@ -663,3 +663,32 @@ def test_train_loop_protocol():
     m2.set_input(loader[0])
     m2.optimize_parameters()
     assert all(v == v for v in m2.get_current_losses().values())
+
+
+def test_compact_cloth_inputs_equal_dense_inputs():
+    """the cloth tensors fed as a uint8 label map (targets) and an int32 bit mask (independently
+    augmented input channels: not one-hot any more) give the step the dense fp32 tensors give — the planes the
+    kernels expand on the device are identical, so only the atomics' summation order differs."""
+    from swapnet_b200.models import create_model
+    from swapnet_b200.ops import SegMap
+
+    B, S = 2, 128
+    torch.manual_seed(0)
+    model = create_model(_opt(B, S))
+    model.setup(model.opt)
+    model.is_train = True
+    body, inp, tgt = synth_warp_batch(B, S)
+    for c in (3, 7, 11):                       # per-channel augmentation: channels overlap, channel 0 stays empty
+        inp[:, c] = torch.roll(inp[:, c], (c, 2 * c), (1, 2))
+    dense = dict(bodys=body, input_cloths=inp, target_cloths=tgt, cloth_paths=["c"] * B, body_paths=["b"] * B)
+    sm_in, sm_tgt = SegMap.from_dense(inp), SegMap.from_dense(tgt)
+    assert sm_in.data.dtype == torch.int32 and sm_tgt.data.dtype == torch.uint8
+    assert torch.equal(sm_in.dense(), inp) and torch.equal(sm_tgt.dense(), tgt)
+    compact = dict(dense, input_cloths=sm_in.data, target_cloths=sm_tgt.data)    # raw [B,H,W] tensors, as a loader yields
+    l0, gD0, gG0 = _run_phases(model, dense, 5)
+    f0 = model.fakes.clone()
+    l1, gD1, gG1 = _run_phases(model, compact, 5)
+    assert torch.equal(f0, model.fakes), "forward differs between dense and compact inputs"
+    assert relmax(gD1, gD0) < 1e-5 and relmax(gG1, gG0) < 1e-5
+    assert all(abs(l0[k] - l1[k]) <= 1e-6 * abs(l0[k]) for k in l0), (l0, l1)
+    assert torch.equal(model.dense(model.targets).cpu(), tgt)

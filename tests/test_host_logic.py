@@ -59,3 +59,29 @@ def test_host_cores_respects_the_cgroup_quota(monkeypatch):
 
     monkeypatch.setattr(builtins, "open", fake_open_max)
     assert bench.host_cores() == 128
+
+
+def test_segmap_roundtrip_and_format_choice():
+    """ops.SegMap: the compact wire format of the 0/1 cloth tensors (uint8 label map when one-hot with an empty channel
+    0 — datasets/data_utils.py:330-343 —, else an int32 bit mask); dense() restores the tensor exactly."""
+    import torch
+
+    from swapnet_b200.ops import SegMap
+
+    g = torch.Generator().manual_seed(0)
+    lab = torch.randint(0, 19, (2, 8, 8), generator=g)
+    onehot = torch.zeros(2, 19, 8, 8)
+    for c in range(1, 19):
+        onehot[:, c] = (lab == c).float()
+    s = SegMap.from_dense(onehot)
+    assert s.data.dtype == torch.uint8 and torch.equal(s.data, lab.to(torch.uint8)) and s.shape == (2, 19, 8, 8)
+    assert torch.equal(s.dense(), onehot)
+    multi = onehot.clone()
+    multi[:, 5] = torch.roll(multi[:, 5], 1, 1)
+    multi[:, 0, 0, 0] = 1.0                      # something in channel 0: not representable as a label map
+    m = SegMap.from_dense(multi)
+    assert m.data.dtype == torch.int32 and torch.equal(m.dense(), multi)
+    import pytest
+
+    with pytest.raises(ValueError):
+        SegMap.from_dense(onehot * 0.5)
