@@ -54,6 +54,8 @@ const char* sn_version(void);
 const char* sn_last_error(void);
 /* number of kernel launches issued by this library since process start (bench.py: gpu_launches) */
 long long sn_launch_count(void);
+/* a CUDA-graph replay executes launches that were counted once, at capture: the host adds them per replay */
+void sn_count_replayed(long long n);
 
 /* ------------------------------------------------------------------------------------------
  * tensor-core contractions
@@ -182,9 +184,10 @@ typedef struct sn_norm_act_desc {
   unsigned long long drop_offset;        /* added to the NHWC element index of the keep-mask: global sample index *
                                             h*w*c of the first local sample (data-parallel shards draw the masks of
                                             the samples they hold, SURVEY 8e ii) */
-  const unsigned long long* drop_step_seed_dev; unsigned int drop_stage_id; /* non-NULL: the seed is
-                                            mix(*drop_step_seed_dev, drop_stage_id) read on the device (CUDA-graph replay
-                                            with a fresh step seed); drop_seed is ignored */
+  const float* drop_step_seed_dev; unsigned int drop_stage_id; /* non-NULL: the 32-bit step seed is read on the device
+                                            as two exact 16-bit halves (lo, hi) of the float step-parameter buffer
+                                            (sn_set_step_params) and the seed is mix(step_seed, drop_stage_id): a captured
+                                            CUDA graph replays with fresh masks; drop_seed is ignored */
   const float* residual; int res_pitch;  /* optional: out = residual + xhat (ResidualBlock tail) */
   void* out_hi; void* out_lo; int out_pitch, out_coff; /* optional split planes */
   int out_fmt;
@@ -213,7 +216,7 @@ typedef struct sn_norm_act_bwd_desc {
   const double* stats;
   int act; float slope;
   float drop_p; unsigned long long drop_seed;
-  unsigned long long drop_offset; const unsigned long long* drop_step_seed_dev; unsigned int drop_stage_id;
+  unsigned long long drop_offset; const float* drop_step_seed_dev; unsigned int drop_stage_id;
   double* gstats;                        /* scratch [n][c][2] (needed when stats != NULL) */
   void* dy_hi; void* dy_lo; int dy_pitch, dy_coff; /* split planes of dL/dy */
   int dy_fmt;
@@ -241,6 +244,18 @@ int sn_upsample_planes(const void* src_hi, const void* src_lo, int src_pitch, in
  * builds it: decoupled weight decay, bias correction, eps outside the sqrt); step is 1-based. */
 int sn_adamw_step(float* p, const float* g, float* m, float* v, long long n, double lr, double beta1, double beta2,
                   double eps, double weight_decay, int step, void* stream);
+/* the same update with its scalars read from DEVICE memory, so that a captured CUDA graph of the training step replays
+ * with the current step's bias corrections: hyper[8] = { 1 - lr*wd, 1 - beta1, beta2, 1 - beta2, lr / (1 - beta1^t),
+ * 1 / sqrt(1 - beta2^t), eps, gscale } with gscale multiplied into every gradient as it is read (1/world under data
+ * parallelism: the all-reduce leaves the SUM in g).  sn_adamw_hyper fills the 8 floats on the host. */
+int sn_adamw_step_dev(float* p, const float* g, float* m, float* v, long long n, const float* hyper_dev, void* stream);
+void sn_adamw_hyper(double lr, double beta1, double beta2, double eps, double weight_decay, int step, double gscale,
+                    float hyper_out[8]);
+
+/* per-step scalars of the training step (smooth GAN labels, AdamW scalars, the dropout step seed) live in one small
+ * device buffer: dst[0..n) <- vals (n <= 64 floats, passed BY VALUE through the launch, so the host array may be reused
+ * immediately); launched once per step ahead of the (possibly graph-replayed) step kernels. */
+int sn_set_step_params(float* dst, const float* vals, int n, void* stream);
 
 /* deterministic dropout keep-mask shared by forward, backward and the test oracle:
  * keep(seed, idx) with idx the linear NHWC element index; returns 0/1 bytes. */
@@ -259,6 +274,9 @@ int sn_ce_loss_fwd_bwd(const float* logits, int pitch, const void* target, int t
  * target (loss.py:58,110-122): loss_acc[half] += mean, dpred = gscale * (sigmoid(x) - t)/count. */
 int sn_bce_logits_fwd_bwd(const float* pred, long long count_per_half, int halves, float t0, float t1,
                           float gscale, double* loss_acc, float* dpred, void* stream);
+/* targets read from device memory: t_dev[0] (first half) and t_dev[1] (second half) */
+int sn_bce_logits_fwd_bwd_dev(const float* pred, long long count_per_half, int halves, const float* t_dev,
+                              float gscale, double* loss_acc, float* dpred, void* stream);
 /* L1Loss(a, b) * weight (texture_model.py:168-170); a NHWC (pitch), b NCHW; grad wrt a. */
 int sn_l1_loss_fwd_bwd(const float* a, int pitch, const float* b_nchw, int n, int h, int w, int c,
                        float weight, double* loss_acc, float* grad, int grad_pitch, void* stream);

@@ -102,6 +102,7 @@ SIGNATURES = {
     "sn_version": (C.c_char_p, []),
     "sn_last_error": (C.c_char_p, []),
     "sn_launch_count": (_LL, []),
+    "sn_count_replayed": (None, [_LL]),
     "sn_tap_gemm_plan_create": (_I, [C.POINTER(SnTapGemmDesc), C.POINTER(_VP)]),
     "sn_wgrad_plan_create": (_I, [C.POINTER(SnWgradDesc), C.POINTER(_VP)]),
     "sn_plan_run": (_I, [_VP, _VP]),
@@ -120,6 +121,11 @@ SIGNATURES = {
     "sn_tanh_bwd": (_I, [C.POINTER(SnGradSrc), _I, _VP, _I, _I, _I, _I, _I, _VP, _VP, _I, _I, _I, _VP]),
     "sn_upsample_planes": (_I, [_VP, _VP, _I, _I, _I, _I, _I, _I, _I, _VP, _VP, _I, _I, _VP]),
     "sn_adamw_step": (_I, [_VP, _VP, _VP, _VP, _LL, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double, _I, _VP]),
+    "sn_adamw_step_dev": (_I, [_VP, _VP, _VP, _VP, _LL, _VP, _VP]),
+    "sn_adamw_hyper": (None, [C.c_double, C.c_double, C.c_double, C.c_double, C.c_double, _I, C.c_double,
+                              C.POINTER(C.c_float)]),
+    "sn_set_step_params": (_I, [_VP, C.POINTER(C.c_float), _I, _VP]),
+    "sn_bce_logits_fwd_bwd_dev": (_I, [_VP, _LL, _I, _VP, _F, _VP, _VP, _VP]),
     "sn_dropout_mask": (_I, [_ULL, _F, _LL, _VP, _VP]),
     "sn_ce_loss_fwd_bwd": (_I, [_VP, _I, _VP, _I, _I, _I, _I, _I, _F, _VP, _VP, _I, _VP]),
     "sn_bce_logits_fwd_bwd": (_I, [_VP, _LL, _I, _F, _F, _F, _VP, _VP, _VP]),

@@ -37,6 +37,7 @@ extern "C" {
 const char* sn_version(void) { return "swapnet_b200 0.1.0 (sm_100a, tcgen05 split-bf16)"; }
 const char* sn_last_error(void) { return g_err; }
 long long sn_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+void sn_count_replayed(long long n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
 int sn_tap_gemm_plan_create(const sn_tap_gemm_desc* desc, sn_plan** out) {
   SN_REQUIRE(desc && out, "null argument");

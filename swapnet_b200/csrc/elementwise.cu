@@ -47,7 +47,11 @@ __host__ __device__ __forceinline__ unsigned long long sn_mix_seed(unsigned long
 }
 template <class Args>
 __device__ __forceinline__ unsigned long long drop_seed_of(const Args& a) {
-  return a.seed_dev ? sn_mix_seed(*a.seed_dev, a.stage_id) : a.seed;
+  if (!a.seed_dev) return a.seed;
+  // the 32-bit step seed travels in the float step-parameter buffer as two exact 16-bit halves (lo, hi)
+  const unsigned long long step_seed =
+      ((unsigned long long)(unsigned int)a.seed_dev[1] << 16) | (unsigned long long)(unsigned int)a.seed_dev[0];
+  return sn_mix_seed(step_seed, a.stage_id);
 }
 
 __device__ __forceinline__ void store_split(uint16_t* hi, uint16_t* lo, long long off, float v, int fmt) {
@@ -449,7 +453,7 @@ struct NormActFwdArgs {
   const double* stats;
   int act; float slope;
   uint32_t drop_thresh; float drop_scale; unsigned long long seed;
-  unsigned long long drop_off; const unsigned long long* seed_dev; unsigned int stage_id;
+  unsigned long long drop_off; const float* seed_dev; unsigned int stage_id;
   const float* residual; int res_pitch;
   uint16_t* hi; uint16_t* lo; int out_pitch, out_coff, reflect, fmt;
   uint16_t* hi2; uint16_t* lo2; int fmt2;
@@ -581,7 +585,7 @@ struct NormActBwdArgs {
   const double* stats;
   int act; float slope;
   uint32_t drop_thresh; float drop_scale; unsigned long long seed;
-  unsigned long long drop_off; const unsigned long long* seed_dev; unsigned int stage_id;
+  unsigned long long drop_off; const float* seed_dev; unsigned int stage_id;
   double* gstats;
   uint16_t* hi; uint16_t* lo; int dy_pitch, dy_coff, fmt;
 };
@@ -736,20 +740,28 @@ __global__ void upsample_planes_v4_kernel(const uint16_t* __restrict__ shi, cons
 //   p *= 1 - lr*wd;  m += (g - m)(1 - b1);  v = v*b2 + (1 - b2) g*g;
 //   p -= (lr / (1 - b1^t)) * m / (sqrt(v) / sqrt(1 - b2^t) + eps)
 // ---------------------------------------------------------------------------------
+struct AdamHyper { float decay, omb1, b2, omb2, step_size, inv_bc2_sqrt, eps, gscale; };
 __global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ p, const float* __restrict__ g,
                                                     float* __restrict__ m, float* __restrict__ v, long long n,
-                                                    float decay, float omb1, float b2, float omb2, float step_size,
-                                                    float inv_bc2_sqrt, float eps) {
+                                                    const AdamHyper hv, const float* __restrict__ hyper_dev) {
+  AdamHyper h = hv;
+  if (hyper_dev) {
+    h.decay = hyper_dev[0]; h.omb1 = hyper_dev[1]; h.b2 = hyper_dev[2]; h.omb2 = hyper_dev[3];
+    h.step_size = hyper_dev[4]; h.inv_bc2_sqrt = hyper_dev[5]; h.eps = hyper_dev[6]; h.gscale = hyper_dev[7];
+  }
+  const float decay = h.decay, omb1 = h.omb1, b2 = h.b2, omb2 = h.omb2, step_size = h.step_size,
+              inv_bc2_sqrt = h.inv_bc2_sqrt, eps = h.eps, gscale = h.gscale;
   const long long n4 = n >> 2;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4;
        i += (long long)gridDim.x * blockDim.x) {
     float4 P = reinterpret_cast<float4*>(p)[i];
-    const float4 G = reinterpret_cast<const float4*>(g)[i];
+    float4 G = reinterpret_cast<const float4*>(g)[i];
     float4 M = reinterpret_cast<float4*>(m)[i];
     float4 V = reinterpret_cast<float4*>(v)[i];
-    float* pp = &P.x; const float* gg = &G.x; float* mm = &M.x; float* vv = &V.x;
+    float* pp = &P.x; float* gg = &G.x; float* mm = &M.x; float* vv = &V.x;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
+      gg[j] *= gscale;                 // exact for the power-of-two 1/world of 2, 4, 8 ranks
       pp[j] *= decay;
       mm[j] = mm[j] + (gg[j] - mm[j]) * omb1;
       vv[j] = vv[j] * b2 + omb2 * gg[j] * gg[j];
@@ -762,7 +774,7 @@ __global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ p, const
   if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {   // tail
     const long long i = (n4 << 2) + threadIdx.x;
     float P = p[i] * decay;
-    const float G = g[i];
+    const float G = g[i] * gscale;
     const float M = m[i] + (G - m[i]) * omb1;
     const float V = v[i] * b2 + omb2 * G * G;
     P -= step_size * (M / (sqrtf(V) * inv_bc2_sqrt + eps));
@@ -837,9 +849,10 @@ __global__ void ce_loss_kernel(const float* __restrict__ logits, int pitch,
 }
 
 __global__ void bce_logits_kernel(const float* __restrict__ pred, long long count, int halves, float t0,
-                                  float t1, float gscale, double* loss_acc, float* __restrict__ dpred) {
+                                  float t1, const float* __restrict__ t_dev, float gscale, double* loss_acc,
+                                  float* __restrict__ dpred) {
   const int half = blockIdx.y;
-  const float t = half == 0 ? t0 : t1;
+  const float t = t_dev ? t_dev[half] : (half == 0 ? t0 : t1);
   double local = 0.0;
   const float gs = gscale / (float)count;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < count;
@@ -1531,16 +1544,45 @@ int sn_upsample_planes(const void* src_hi, const void* src_lo, int src_pitch, in
   return SN_OK;
 }
 
+void sn_adamw_hyper(double lr, double beta1, double beta2, double eps, double weight_decay, int step, double gscale,
+                    float out[8]) {
+  // scalars are formed in double and rounded once, as torch does with its Python-float hyper-parameters
+  const double bc1 = 1.0 - pow(beta1, (double)step);
+  const double bc2 = 1.0 - pow(beta2, (double)step);
+  out[0] = (float)(1.0 - lr * weight_decay); out[1] = (float)(1.0 - beta1); out[2] = (float)beta2;
+  out[3] = (float)(1.0 - beta2); out[4] = (float)(lr / bc1); out[5] = (float)(1.0 / sqrt(bc2)); out[6] = (float)eps;
+  out[7] = (float)gscale;
+}
+
 int sn_adamw_step(float* p, const float* g, float* m, float* v, long long n, double lr, double beta1, double beta2,
                   double eps, double weight_decay, int step, void* stream) {
   SN_REQUIRE(p && g && m && v && n > 0 && step >= 1, "bad adamw arguments");
   SN_REQUIRE((((uintptr_t)p | (uintptr_t)g | (uintptr_t)m | (uintptr_t)v) & 15) == 0, "adamw buffers must be 16-B aligned");
-  // scalars are formed in double and rounded once, as torch does with its Python-float hyper-parameters
-  const double bc1 = 1.0 - pow(beta1, (double)step);
-  const double bc2 = 1.0 - pow(beta2, (double)step);
-  adamw_kernel<<<grid_for(n / 4 + 1), kEwThreads, 0, (cudaStream_t)stream>>>(
-      p, g, m, v, n, (float)(1.0 - lr * weight_decay), (float)(1.0 - beta1), (float)beta2, (float)(1.0 - beta2),
-      (float)(lr / bc1), (float)(1.0 / sqrt(bc2)), (float)eps);
+  float hp[8];
+  sn_adamw_hyper(lr, beta1, beta2, eps, weight_decay, step, 1.0, hp);
+  const AdamHyper h{hp[0], hp[1], hp[2], hp[3], hp[4], hp[5], hp[6], hp[7]};
+  adamw_kernel<<<grid_for(n / 4 + 1), kEwThreads, 0, (cudaStream_t)stream>>>(p, g, m, v, n, h, nullptr);
+  LAUNCH_CHECK();
+  return SN_OK;
+}
+
+int sn_adamw_step_dev(float* p, const float* g, float* m, float* v, long long n, const float* hyper_dev, void* stream) {
+  SN_REQUIRE(p && g && m && v && n > 0 && hyper_dev, "bad adamw arguments");
+  SN_REQUIRE((((uintptr_t)p | (uintptr_t)g | (uintptr_t)m | (uintptr_t)v) & 15) == 0, "adamw buffers must be 16-B aligned");
+  adamw_kernel<<<grid_for(n / 4 + 1), kEwThreads, 0, (cudaStream_t)stream>>>(p, g, m, v, n, AdamHyper{}, hyper_dev);
+  LAUNCH_CHECK();
+  return SN_OK;
+}
+
+struct StepParams { float v[64]; };
+__global__ void set_step_params_kernel(float* dst, const StepParams sp, int n) {
+  if (threadIdx.x < n) dst[threadIdx.x] = sp.v[threadIdx.x];
+}
+int sn_set_step_params(float* dst, const float* vals, int n, void* stream) {
+  SN_REQUIRE(dst && vals && n >= 1 && n <= 64, "set_step_params: 1..64 floats");
+  StepParams sp;
+  for (int i = 0; i < 64; ++i) sp.v[i] = i < n ? vals[i] : 0.f;
+  set_step_params_kernel<<<1, 64, 0, (cudaStream_t)stream>>>(dst, sp, n);
   LAUNCH_CHECK();
   return SN_OK;
 }
@@ -1569,7 +1611,17 @@ int sn_bce_logits_fwd_bwd(const float* pred, long long count_per_half, int halve
                           float gscale, double* loss_acc, float* dpred, void* stream) {
   SN_REQUIRE(halves == 1 || halves == 2, "halves must be 1 or 2");
   dim3 grid(grid_for(count_per_half), halves);
-  bce_logits_kernel<<<grid, kEwThreads, 0, (cudaStream_t)stream>>>(pred, count_per_half, halves, t0, t1,
+  bce_logits_kernel<<<grid, kEwThreads, 0, (cudaStream_t)stream>>>(pred, count_per_half, halves, t0, t1, nullptr,
+                                                                   gscale, loss_acc, dpred);
+  LAUNCH_CHECK();
+  return SN_OK;
+}
+
+int sn_bce_logits_fwd_bwd_dev(const float* pred, long long count_per_half, int halves, const float* t_dev,
+                              float gscale, double* loss_acc, float* dpred, void* stream) {
+  SN_REQUIRE((halves == 1 || halves == 2) && t_dev, "halves must be 1 or 2, t_dev non-null");
+  dim3 grid(grid_for(count_per_half), halves);
+  bce_logits_kernel<<<grid, kEwThreads, 0, (cudaStream_t)stream>>>(pred, count_per_half, halves, 0.f, 0.f, t_dev,
                                                                    gscale, loss_acc, dpred);
   LAUNCH_CHECK();
   return SN_OK;

@@ -23,6 +23,8 @@ from abc import ABC, abstractmethod
 from argparse import ArgumentParser
 from typing import Optional
 
+import os
+
 import torch
 
 from .. import engine as E
@@ -86,6 +88,9 @@ class BaseGAN(BaseModel, ABC):
             parser.add_argument("--gan_label_mode", default="smooth", choices=("hard", "smooth"),
                                 help="whether to use hard (real 1.0 and fake 0.0) or smooth "
                                      "(real [0.7, 1.1] and fake [0., 0.3]) values for labels")
+        parser.add_argument("--b200_graph", type=int, default=1, choices=(0, 1),
+                            help="1: replay the training step as a captured CUDA graph (single GPU; after two eager "
+                                 "steps per input shape); 0: launch the kernels one by one")
         parser.add_argument("--b200_precision", default="fp32x3", choices=("fp32x3", "bf16"),
                             help="tensor-core arithmetic of the B200 engines: fp32x3 = split-bf16 3-pass "
                                  "(fp32-faithful, parity mode); bf16 = single pass (fast, ~1e-2 relative)")
@@ -127,6 +132,14 @@ class BaseGAN(BaseModel, ABC):
             self.optimizer_D = define_optimizer(self.net_discriminator, opt, "D")
             self.optimizer_names = ("G", "D")
             self._acc = torch.zeros(8, dtype=torch.float64, device=self.device)  # device-side loss sums
+            # per-step scalars read by the kernels from DEVICE memory (one tiny launch per step writes them), so that the
+            # whole step is a fixed launch sequence a CUDA graph can replay: [0:3] smooth labels (D_fake, D_real, G_gan),
+            # [4:12] AdamW scalars of D, [12:20] of G, [20:22] the dropout step seed as two exact 16-bit halves
+            self._sp = torch.zeros(32, dtype=torch.float32, device=self.device)
+            self._sp_ready = False          # True inside optimize_parameters(): labels were drawn by the step prologue
+            self._graphs = {}               # (batch, size, training, input signature) -> captured step
+            self._eager_steps = {}
+            self.graph_enabled = os.environ.get("SN_NO_GRAPH", "0") != "1" and bool(getattr(opt, "b200_graph", 1))
             self._acc_host = None                       # host copy of _acc for the current step (one D2H per step)
             lam = float(opt.lambda_gan)
             self.loss_D_fake = LazyLoss(lambda: self.loss_values()[0])
@@ -220,8 +233,20 @@ class BaseGAN(BaseModel, ABC):
         fp32 `rand(1) * (1.1 - 0.7) + 0.7`, for real AND fake targets."""
         return self._labels.draw()
 
+    def _targets(self, lo: int, hi: int) -> torch.Tensor:
+        """Device view of the smooth-label targets lo..hi-1 of the step-parameter buffer; drawn here (reference order)
+        when the phases are run by hand, by the step prologue inside optimize_parameters()."""
+        if not self._sp_ready:
+            ops.set_step_params(self._sp[lo:hi], [self.draw_label() for _ in range(lo, hi)])
+        return self._sp[lo:hi]
+
     def allreduce_grads(self, eng) -> None:
-        parallel.average_gradients(eng.flat_grad)
+        """Sum over ranks (the 1/world factor is applied by the AdamW kernel as it reads the gradients; code that reads
+        flat_grad directly under DP sees the SUM)."""
+        parallel.sum_gradients(eng.flat_grad)
+
+    def grad_scale(self) -> float:
+        return 1.0 / self._world
 
     # ---- discriminator phases (conditioning supplied by the plugin through pack_D_inputs) ----
     @abstractmethod
@@ -237,8 +262,8 @@ class BaseGAN(BaseModel, ABC):
         d.pack()
         self.pack_D_inputs(d.din.batch_slice(0, B), d.din.batch_slice(B, B))
         pred = d.forward()
-        t_fake, t_real = self.draw_label(), self.draw_label()   # order: D_fake, D_real (loss.py:117,121)
-        ops.bce_logits_fwd_bwd(pred, 2, t_fake, t_real, 0.5, self._acc[0:2], self._dpred_d)
+        t = self._targets(0, 2)                                  # order: D_fake, D_real (loss.py:117,121)
+        ops.bce_logits_fwd_bwd(pred, 2, t, 0.0, 0.5, self._acc[0:2], self._dpred_d)
         d.backward(self._dpred_d)
         self.allreduce_grads(d)
 
@@ -249,19 +274,97 @@ class BaseGAN(BaseModel, ABC):
         g.training = self.training
         g.pack()
         pred = g.forward()
-        t = self.draw_label()
-        ops.bce_logits_fwd_bwd(pred, 1, t, t, float(self.opt.lambda_gan), self._acc[2:3], self._dpred_g)
+        t = self._targets(2, 3)
+        ops.bce_logits_fwd_bwd(pred, 1, t, 0.0, float(self.opt.lambda_gan), self._acc[2:3], self._dpred_g)
         g.backward(self._dpred_g, wgrad=False)
         return g.dx_in
 
-    def optimize_parameters(self):
-        self._acc_host = None
+    # ---- the training step: a prologue on the host, then a fixed launch sequence (eager or graph replay) ----
+    def input_tensors(self) -> dict:
+        """name -> device input of the current step (tensor or ops.SegMap); provided by the plugin."""
+        raise NotImplementedError
+
+    def set_input_tensors(self, d: dict) -> None:
+        for k, v in d.items():
+            setattr(self, k, v)
+
+    def _step_prologue(self, optimizers) -> None:
+        """Everything of a step that is decided on the host, written to the device with ONE tiny launch: the three
+        smooth labels (CPU RNG, reference order), the AdamW scalars of this step, the dropout step seed."""
+        vals = [0.0] * 22
+        for i in range(3 if hasattr(self, "net_discriminator") else 0):
+            vals[i] = self.draw_label()
+        for off, name in ((4, "D"), (12, "G")):
+            if name in optimizers:
+                vals[off:off + 8] = getattr(self, "optimizer_" + name).advance(self.grad_scale())
+        seed = self.step_seed()
+        vals[20], vals[21] = float(seed & 0xFFFF), float(seed >> 16)
+        ops.set_step_params(self._sp, vals)
+
+    def _step_body(self) -> None:
+        """forward -> zero/backward/step D -> zero/backward/step G (base_gan.py:194-203) as device work only."""
         self._acc.zero_()
         self.forward()
         self._eng_Dd.zero_grad()
         self.backward_D()
-        self.optimizer_D.step()
+        self.optimizer_D.launch(self._sp[4:12])
         self._eng_G.zero_grad()
         self.backward_G()
-        self.optimizer_G.step()
+        self.optimizer_G.launch(self._sp[12:20])
+
+    def _run_step(self, optimizers=("D", "G")) -> None:
+        self._acc_host = None
+        ins = self.input_tensors()
+        first = next(iter(ins.values()))
+        B, S = first.shape[0], first.shape[-1]
+        self.ensure_engines(B, S)
+        for eng in (self._eng_G, self._eng_Dd, self._eng_Dg):
+            if eng is not None:
+                eng.seed_dev = self._sp[20:22]
+        self._step_prologue(optimizers)
+        self._sp_ready = True
+        try:
+            sig = tuple((k, str(getattr(v, "data", v).dtype), tuple(v.shape)) for k, v in ins.items())
+            key = (B, S, bool(self.training), sig, optimizers)
+            use_graph = self.graph_enabled and self._world == 1 and ops.Plan.trace is None
+            if not use_graph:
+                self._step_body()
+            else:
+                g = self._graphs.get(key)
+                if g is None and self._eager_steps.get(key, 0) < 2:   # warm-up: lazy allocations, attribute calls
+                    self._eager_steps[key] = self._eager_steps.get(key, 0) + 1
+                    self._step_body()
+                else:
+                    self.wait_late_copies()                          # H2D of this step's inputs (side stream)
+                    if g is None:
+                        g = self._graphs[key] = self._capture(ins)
+                    static = g["static"]
+                    for k, v in ins.items():                          # staging -> the buffers the graph reads
+                        getattr(static[k], "data", static[k]).copy_(getattr(v, "data", v))
+                    self.set_input_tensors(static)
+                    g["graph"].replay()
+                    ops.count_replayed(g["launches"])
+        finally:
+            self._sp_ready = False
+            for eng in (self._eng_G, self._eng_Dd, self._eng_Dg):
+                if eng is not None:
+                    eng.seed_dev = None
         self._step += 1
+
+    def _capture(self, ins: dict) -> dict:
+        """Capture _step_body() on static copies of the inputs.  The kernels of the capture pass are recorded, not
+        executed: the caller replays the graph for the current step right away."""
+        static = {}
+        for k, v in ins.items():
+            d = getattr(v, "data", v).clone()
+            static[k] = ops.SegMap(d, v.channels) if isinstance(v, ops.SegMap) else d
+        self.set_input_tensors(static)
+        torch.cuda.synchronize(self.device)
+        n0 = ops.launch_count()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            self._step_body()
+        return {"graph": graph, "static": static, "launches": ops.launch_count() - n0}
+
+    def optimize_parameters(self):
+        self._run_step()

@@ -108,6 +108,9 @@ class TextureModel(BaseGAN):
         self.targets = self.copy_late(input["target_textures"], "targets")
         self.image_paths = tuple(zip(input["cloth_paths"], input["texture_paths"]))
 
+    def input_tensors(self):
+        return {"textures": self.textures, "rois": self.rois, "cloths": self.cloths, "targets": self.targets}
+
     def forward(self):
         B, _, S, S2 = self.textures.shape
         assert S == S2, "square inputs expected"

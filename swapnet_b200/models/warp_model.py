@@ -109,20 +109,23 @@ class WarpModel(BaseGAN):
             srcs.append(GradSrc(dx, self.body_channels))
         if self._world > 1:
             from .. import parallel
-            avg = parallel.BucketedAverager(g.flat_grad, g.grad_buckets())
+            avg = parallel.BucketedAverager(g.flat_grad, g.grad_buckets(), scale=False)   # 1/world: in the AdamW kernel
             g.backward(srcs, on_bucket=avg.ready)
             avg.finish()
         else:
             g.backward(srcs)
 
-    def optimize_parameters(self):
+    def input_tensors(self):
+        return {"bodys": self.bodys, "inputs": self.inputs, "targets": self.targets}
+
+    def _step_body(self):
         if self.opt.warp_mode == "gan":
-            super().optimize_parameters()
-        else:
-            self._acc_host = None
-            self._acc.zero_()
-            self.forward()
-            self._eng_G.zero_grad()
-            self.backward_G()
-            self.optimizer_G.step()
-            self._step += 1
+            return super()._step_body()
+        self._acc.zero_()                      # --warp_mode ce: generator only (warp_model.py:175-183)
+        self.forward()
+        self._eng_G.zero_grad()
+        self.backward_G()
+        self.optimizer_G.launch(self._sp[12:20])
+
+    def optimize_parameters(self):
+        self._run_step(("D", "G") if self.opt.warp_mode == "gan" else ("G",))

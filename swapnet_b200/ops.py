@@ -560,6 +560,29 @@ def adamw_step(p: torch.Tensor, g: torch.Tensor, m: torch.Tensor, v: torch.Tenso
                                     wd, step, _stream()))
 
 
+def adamw_hyper(lr: float, b1: float, b2: float, eps: float, wd: float, step: int, gscale: float = 1.0):
+    """The 8 fp32 scalars of sn_adamw_step_dev for optimizer step `step` (1-based), as a list of Python floats."""
+    out = (C.c_float * 8)()
+    _lib.load().sn_adamw_hyper(lr, b1, b2, eps, wd, step, gscale, out)
+    return list(out)
+
+
+def adamw_step_dev(p: torch.Tensor, g: torch.Tensor, m: torch.Tensor, v: torch.Tensor, hyper_dev: torch.Tensor) -> None:
+    """AdamW with its scalars read from device memory (hyper_dev: float32[8] view of the step-parameter buffer)."""
+    assert p.is_contiguous() and g.is_contiguous() and p.numel() == g.numel() == m.numel() == v.numel()
+    assert hyper_dev.dtype == torch.float32 and hyper_dev.numel() >= 8
+    check(_lib.load().sn_adamw_step_dev(p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), p.numel(),
+                                        hyper_dev.data_ptr(), _stream()))
+
+
+def set_step_params(dst: torch.Tensor, values) -> None:
+    """dst[:len(values)] <- values (<= 64 floats passed by value through one tiny launch)."""
+    n = len(values)
+    assert dst.dtype == torch.float32 and dst.numel() >= n and n <= 64
+    arr = (C.c_float * n)(*values)
+    check(_lib.load().sn_set_step_params(dst.data_ptr(), arr, n, _stream()))
+
+
 def dropout_mask(seed: int, p: float, count: int, device) -> torch.Tensor:
     out = torch.empty(count, dtype=torch.uint8, device=device)
     check(_lib.load().sn_dropout_mask(seed, p, count, out.data_ptr(), _stream()))
@@ -583,9 +606,15 @@ def ce_loss_fwd_bwd(logits: torch.Tensor, c: int, target, weight: float,
                                          loss_acc.data_ptr(), grad.data_ptr(), grad.shape[3], _stream()))
 
 
-def bce_logits_fwd_bwd(pred: torch.Tensor, halves: int, t0: float, t1: float, gscale: float,
+def bce_logits_fwd_bwd(pred: torch.Tensor, halves: int, t0, t1: float, gscale: float,
                        loss_acc: torch.Tensor, dpred: Optional[torch.Tensor]) -> None:
+    """t0 may be a device float32 tensor holding the target(s) of the half(s) (step-parameter buffer): t1 is ignored."""
     count = pred.numel() // halves
+    if torch.is_tensor(t0):
+        assert t0.dtype == torch.float32 and t0.numel() >= halves and t0.is_cuda
+        check(_lib.load().sn_bce_logits_fwd_bwd_dev(pred.data_ptr(), count, halves, t0.data_ptr(), gscale,
+                                                    loss_acc.data_ptr(), _ptr(dpred), _stream()))
+        return
     check(_lib.load().sn_bce_logits_fwd_bwd(pred.data_ptr(), count, halves, t0, t1, gscale, loss_acc.data_ptr(),
                                             _ptr(dpred), _stream()))
 
@@ -613,6 +642,11 @@ def roi_align_pack(tex_nchw: torch.Tensor, rois: torch.Tensor, pool: int, out_f3
 
 def launch_count() -> int:
     return int(_lib.load().sn_launch_count())
+
+
+def count_replayed(n: int) -> None:
+    """Account for n kernel launches executed by a CUDA-graph replay (they bypass the per-call counter)."""
+    _lib.load().sn_count_replayed(int(n))
 
 
 # ---------------------------------------------------------------------------------------------

@@ -64,6 +64,21 @@ class FusedAdamW(torch.optim.Optimizer):
         for st in self.state.values():
             st["step"].fill_(float(self._step))
 
+    def advance(self, gscale: float = 1.0):
+        """Host half of a step whose kernel reads its scalars from device memory (BaseGAN's step-parameter buffer):
+        bump the step counter and return the 8 scalars of ops.adamw_step_dev for it."""
+        g = self.param_groups[0]
+        self._step += 1
+        for st in self.state.values():
+            st["step"].fill_(float(self._step))
+        return ops.adamw_hyper(g["lr"], g["betas"][0], g["betas"][1], g["eps"], g["weight_decay"], self._step, gscale)
+
+    @torch.no_grad()
+    def launch(self, hyper_dev: torch.Tensor) -> None:
+        """Device half: one fused kernel over the flat buffers (capturable: no host state is touched)."""
+        assert self.flat_grad is not None, "FusedAdamW needs the engine's flat gradient buffer"
+        ops.adamw_step_dev(self.flat_param, self.flat_grad, self.exp_avg, self.exp_avg_sq, hyper_dev)
+
     def load_state_dict(self, state_dict):
         super().load_state_dict(state_dict)
         # torch replaced the per-parameter tensors: copy them back into the flat buffers

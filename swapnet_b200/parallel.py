@@ -41,6 +41,12 @@ def rank() -> int:
     return dist.get_rank() if dist.is_available() and dist.is_initialized() else 0
 
 
+def sum_gradients(flat_grad: torch.Tensor) -> None:
+    """In-place SUM over ranks (the consumer applies 1/world: the fused AdamW kernel's gscale)."""
+    if world_size() > 1:
+        dist.all_reduce(flat_grad, op=dist.ReduceOp.SUM)
+
+
 def average_gradients(flat_grad: torch.Tensor) -> None:
     """In-place mean over ranks of a flat gradient buffer (sum all-reduce + scale)."""
     w = world_size()
@@ -58,8 +64,9 @@ class BucketedAverager:
     NCCL's stream as soon as those kernels finish, while the remaining backward keeps the SMs busy.
     `finish()` waits for all of them and applies the 1/world scale."""
 
-    def __init__(self, flat_grad: torch.Tensor, bounds):
-        self.flat, self.bounds, self.work = flat_grad, list(bounds), []
+    def __init__(self, flat_grad: torch.Tensor, bounds, scale: bool = True):
+        """scale=False: leave the SUM in the buffer (the AdamW kernel multiplies by 1/world as it reads it)."""
+        self.flat, self.bounds, self.work, self.scale = flat_grad, list(bounds), [], scale
 
     def ready(self, i: int) -> None:
         if world_size() > 1:
@@ -72,7 +79,8 @@ class BucketedAverager:
             for wk in self.work:
                 wk.wait()
             self.work.clear()
-            self.flat.mul_(1.0 / w)
+            if self.scale:
+                self.flat.mul_(1.0 / w)
 
 
 def broadcast_parameters(params: Iterable[torch.Tensor], src: int = 0) -> None:

@@ -58,6 +58,10 @@ def main():
     full = dict(bodys=body, input_cloths=inp, target_cloths=tgt, cloth_paths=["c"] * B, body_paths=["b"] * B)
     gD, gG, losses = phases(dp, parallel.shard_batch(full, rank, world))
     assert dp._eng_G.sample_base == rank * per
+    # the all-reduce leaves the SUM over ranks in the flat buffers; the 1/world factor is applied by the fused AdamW
+    # kernel as it reads them (BaseGAN.grad_scale)
+    assert dp.grad_scale() == 1.0 / world
+    gD, gG = gD * dp.grad_scale(), gG * dp.grad_scale()
 
     # single-process reference on the same (broadcast) weights: world forced to 1, no all-reduce
     torch.manual_seed(0)
