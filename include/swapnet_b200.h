@@ -292,6 +292,19 @@ int sn_tap_sum_fwd(const float* p, int p_pitch, int n, int h, int w, int k, int 
 int sn_tap_shift_pack(const void* dy_hi, const void* dy_lo, int dy_pitch, int dy_fmt, int n, int h, int w, int k,
                       int pad, void* dst_hi, void* dst_lo, int dst_pitch, int dst_coff, int fmt, void* stream);
 
+/* the one-output-channel conv on the CUDA cores at stream speed (csrc/patch_logits.cu; k = 4, stride 1):
+ *   sn_to_one_fwd:   p[px][t] = sum_c x[px][c] * weight[c*16 + t]      x: split planes [npix][x_pitch], weight: the torch
+ *                                                                      [1][c][4][4] parameter itself (no packing)
+ *   sn_to_one_wgrad: dw[c*16 + t] += sum_px x[px][c] * dy[px - off_t]  dy: channel 0 of split planes [n][h+2p-3][w+2p-3]
+ *   sn_to_one_dgrad: dx[px][c]  = sum_t dy[px - off_t] * weight[c*16 + t]   (fp32 NHWC, pitch dx_pitch) */
+int sn_to_one_fwd(const void* x_hi, const void* x_lo, int x_pitch, int x_fmt, long long npix, int c, const float* weight,
+                  int k, float* p, int p_pitch, void* stream);
+int sn_to_one_wgrad(const void* x_hi, const void* x_lo, int x_pitch, int x_fmt, int n, int h, int w, int c,
+                    const void* dy_hi, const void* dy_lo, int dy_pitch, int dy_fmt, int k, int pad, float* dw,
+                    void* stream);
+int sn_to_one_dgrad(const void* dy_hi, const void* dy_lo, int dy_pitch, int dy_fmt, int n, int h, int w, int c,
+                    const float* weight, int k, int pad, float* dx, int dx_pitch, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * VGG16 perceptual loss (modules/losses/perceptual.py:6-79, used by texture_model.py:68-69,171-176).
  * The 13 conv3x3(+bias) layers run as tap-GEMM plans; these are the element-wise pieces.

@@ -183,15 +183,16 @@ class ConvLayer:
 
 
 class ToOneConvLayer:
-    """Conv2d(cin, 1, k4, s1, p1) — the PatchGAN logits layer (modules/discriminators.py:131) — as 1-tap GEMMs.
+    """Conv2d(cin, 1, k4, s1, p1) — the PatchGAN logits layer (modules/discriminators.py:131) — on the CUDA cores.
 
-    The generic tap GEMM re-fetches the cin-channel input tile once per tap for ONE output column.  Here
-        P[px, t]   = sum_c x[px, c] W[0, c, t]            one 1-tap GEMM (N = 16): x is read once
+    A conv with one output channel is an HBM-bound op (1 GMAC over a 260 MB input at batch 32); a GEMM with N = 1 —
+    or N = 16 through the tap factorisation below — leaves the tensor core waiting for its operand loads (round 1:
+    forward at 4 TFLOP/s, weight gradient at 2.4).  csrc/patch_logits.cu streams the input once per pass instead:
+        P[px, t]   = sum_c x[px, c] W[0, c, t]            ops.to_one_fwd   (fp32 FMAs on the fp16-split input)
         y[o]       = bias + sum_t P[o + off_t, t]         ops.tap_sum_fwd
-        dP[px, t]  = dy[px - off_t]                       ops.tap_shift_pack
-        dW[0,c,t]  = sum_px x[px, c] dP[px, t]            one 1-tap wgrad GEMM
-        dx[px, c]  = sum_t dP[px, t] W[0, c, t]           one 1-tap GEMM
-    Same interface as ConvLayer (the engines do not care which one they hold)."""
+        dW[0,c,t]  = sum_px x[px, c] dy[px - off_t]       ops.to_one_wgrad
+        dx[px, c]  = sum_t dy[px - off_t] W[0, c, t]      ops.to_one_dgrad
+    No packed weights: the kernels read the torch parameter itself.  Same interface as ConvLayer."""
 
     K, PAD = 4, 1
 
@@ -205,67 +206,41 @@ class ToOneConvLayer:
         self.in_h, self.in_w = x.h, x.w
         self.out_h, self.out_w = L.out_hw(kind, x.h, x.w)
         self.n, self.k_pad, self.t = x.n, x.c, 16
-        assert x.c % 64 == 0 and x.c >= self.cin
-        self.wscale = torch.ones(2, dtype=torch.float32, device=dev)
-        self.wp = PackedWeights(16, self.k_pad, dev, self.wscale)                 # [t][c]
+        assert self.cin % 256 == 0 and x.c >= self.cin
         self.p = torch.zeros(self.n, self.in_h, self.in_w, 16, device=dev)         # per-tap products
-        self._one = L.GemmSpec(False, self.in_h, self.in_w, [L.Tap(0, 0, 0, 0)], a_hw=(self.in_h, self.in_w))
-        self.fwd_plans: List[ops.Plan] = []
+        self.fwd_plans: List[ops.Plan] = []     # no tensor-core plans: nothing for the GEMM roofline trace
         self.dgrad_plans: List[ops.Plan] = []
         self.wgrad_plan: Optional[ops.Plan] = None
-        self.y = self.dy = self.dx = self.dp = self.wd = None
+        self.y = self.dy = self.dx = None
         self.wgrad_out = self.bgrad_out = self._bscratch = None
 
     def bind_forward(self, y: torch.Tensor, y_c_off: int = 0) -> None:
         assert y.shape[:3] == (self.n, self.out_h, self.out_w) and y_c_off == 0
         self.y = y
-        d = ops.tap_gemm_desc(self.x, self._one, self.wp, self.k_pad, self.p, 16, nsplit=self.nsplit, block_n=16)
-        self.fwd_plans = [ops.tap_gemm_plan(d, keep=(self.x.hi, self.x.lo, self.wp.hi, self.wp.lo, self.p))]
-        self.fwd_plans[0].tag = ("fwd", self.name)
 
     def pack(self) -> None:
-        ops.weight_scale(self.weight, self.wscale)
-        ops.pack_weights_raw(self.weight, 1, 16, 16, self.cin, self.k_pad, self.wp)          # rows = tap, k = channel
-        if self.wd is not None:
-            ops.pack_weights_raw(self.weight, 16, 1, self.cin, 16, 64, self.wd)               # rows = channel, k = tap
+        pass
 
     def forward(self) -> None:
-        self.fwd_plans[0].run()
+        ops.to_one_fwd(self.x, self.weight, self.p)
         ops.tap_sum_fwd(self.p, self.K, self.PAD, self.bias, self.y)
 
     def bind_backward(self, dy: Planes, dx: Optional[torch.Tensor], wgrad: Optional[torch.Tensor],
                       bgrad: Optional[torch.Tensor] = None, dx_c_off: int = 0) -> None:
-        dev = self.weight.device
         assert (dy.n, dy.h, dy.w) == (self.n, self.out_h, self.out_w) and dx_c_off == 0
+        assert dx is None or dx.shape[3] == self.cin
         self.dy, self.dx = dy, dx
-        self.dp = Planes(self.n, self.in_h, self.in_w, 64, dev, fmt=dy.fmt)        # 16 real channels, 48 zero
-        self.dgrad_plans = []
-        if dx is not None:
-            self.wd = PackedWeights(self.cin, 64, dev, fmt=dy.fmt)
-            d = ops.tap_gemm_desc(self.dp, self._one, self.wd, 64, dx, self.cin, nsplit=self.nsplit,
-                                  block_n=L.pick_block_n(self.cin))
-            self.dgrad_plans = [ops.tap_gemm_plan(d, keep=(self.dp.hi, self.dp.lo, self.wd.hi, self.wd.lo, dx))]
-            self.dgrad_plans[0].tag = ("dgrad", self.name)
-        self.wgrad_out, self.wgrad_plan = wgrad, None
+        self.wgrad_out = wgrad
         if wgrad is not None:
             assert wgrad.shape == self.weight.shape and wgrad.is_contiguous()
-            xin = self.x if self.x.fmt == dy.fmt else self.x.twin
-            assert xin is not None, f"{self.name}: wgrad needs a twin of the input planes in the gradient format"
-            zero = L.Tap(0, 0, 0, 0)
-            ws = L.WgradSpec(self.in_h, self.in_w, False, False, [zero], [zero], "in", [0])
-            d = ops.wgrad_desc(xin, self.dp, ws, wgrad, 16, 1, [0], self.cin, 16, nsplit=self.nsplit, block_n=64)
-            self.wgrad_plan = ops.wgrad_plan(d, keep=(xin.hi, xin.lo, self.dp.hi, self.dp.lo, wgrad))
-            self.wgrad_plan.tag = ("wgrad", self.name)
         self.bgrad_out = bgrad
         if bgrad is not None:
-            self._bscratch = torch.zeros(1, dtype=torch.float64, device=dev)
+            self._bscratch = torch.zeros(1, dtype=torch.float64, device=self.weight.device)
 
     def backward(self, dgrad: bool = True, wgrad: bool = True) -> None:
-        ops.tap_shift_pack(self.dy, self.K, self.PAD, self.dp.slice(0, 16))
-        if dgrad:
-            for p in self.dgrad_plans:
-                p.run()
-        if wgrad and self.wgrad_plan is not None:
-            self.wgrad_plan.run()
+        if dgrad and self.dx is not None:
+            ops.to_one_dgrad(self.dy, self.weight, self.PAD, self.dx)
+        if wgrad and self.wgrad_out is not None:
+            ops.to_one_wgrad(self.x, self.dy, self.PAD, self.wgrad_out)    # the fp16-split planes: no bf16 twin needed
         if wgrad and self.bgrad_out is not None:
             ops.bias_grad(self.dy, 1, self._bscratch, self.bgrad_out)

@@ -750,3 +750,26 @@ def tap_shift_pack(dy: Planes, k: int, pad: int, dst: Planes) -> None:
     assert (dy.n, dy.h, dy.w) == (dst.n, dst.h + 2 * pad - k + 1, dst.w + 2 * pad - k + 1) and dst.c >= k * k
     check(_lib.load().sn_tap_shift_pack(dy.hi_ptr, dy.lo_ptr, dy.pitch, dy.fmt, dst.n, dst.h, dst.w, k, pad,
                                         dst.hi.data_ptr(), dst.lo.data_ptr(), dst.pitch, dst.c_off, dst.fmt, _stream()))
+
+
+def to_one_fwd(x: Planes, weight: torch.Tensor, p: torch.Tensor) -> None:
+    """p[n,h,w,t] = sum_c x[n,h,w,c] * weight[0,c,t] (t = 4*kh + kw) on the CUDA cores; x is read once."""
+    assert weight.is_contiguous() and weight.shape[0] == 1 and tuple(weight.shape[2:]) == (4, 4)
+    assert p.dtype == torch.float32 and p.shape[:3] == (x.n, x.h, x.w) and x.c_off % 8 == 0
+    check(_lib.load().sn_to_one_fwd(x.hi_ptr, x.lo_ptr, x.pitch, x.fmt, x.n * x.h * x.w, weight.shape[1],
+                                    weight.data_ptr(), 4, p.data_ptr(), _pitch(p), _stream()))
+
+
+def to_one_wgrad(x: Planes, dy: Planes, pad: int, dw: torch.Tensor) -> None:
+    """dw[0,c,kh,kw] += sum_px x[px,c] * dy[px - (kh,kw) + pad] (dy: channel 0 of its planes)."""
+    assert dw.is_contiguous() and dw.dtype == torch.float32 and (dy.h, dy.w) == (x.h + 2 * pad - 3, x.w + 2 * pad - 3)
+    check(_lib.load().sn_to_one_wgrad(x.hi_ptr, x.lo_ptr, x.pitch, x.fmt, x.n, x.h, x.w, dw.shape[1], dy.hi_ptr,
+                                      dy.lo_ptr, dy.pitch, dy.fmt, 4, pad, dw.data_ptr(), _stream()))
+
+
+def to_one_dgrad(dy: Planes, weight: torch.Tensor, pad: int, dx: torch.Tensor) -> None:
+    """dx[n,h,w,c] = sum_t dy[px - off_t] * weight[0,c,t] (fp32 NHWC)."""
+    n, h, w, _ = dx.shape
+    assert (dy.h, dy.w) == (h + 2 * pad - 3, w + 2 * pad - 3)
+    check(_lib.load().sn_to_one_dgrad(dy.hi_ptr, dy.lo_ptr, dy.pitch, dy.fmt, n, h, w, weight.shape[1],
+                                      weight.data_ptr(), 4, pad, dx.data_ptr(), _pitch(dx), _stream()))
