@@ -270,6 +270,12 @@ int sn_dropout_mask(unsigned long long seed, float p, long long count, uint8_t* 
  * *loss_acc (double, caller zeroes); grad NHWC fp32 (pitch c). */
 int sn_ce_loss_fwd_bwd(const float* logits, int pitch, const void* target, int target_layout, int n, int h, int w,
                        int c, float weight, double* loss_acc, float* grad, int grad_pitch, void* stream);
+/* the same cross entropy fused with the backward of the tanh head it is applied to (warp_model.py:147-150: CE on the
+ * tanh OUTPUTS): dy = (weight * dCE/do + sum_i src_i) * (1 - o^2) as split planes, loss value accumulated; the extra
+ * sources carry the other loss terms' gradients w.r.t. o (the GAN term).  Replaces sn_ce_loss_fwd_bwd + sn_tanh_bwd. */
+int sn_ce_tanh_bwd(const float* logits, int pitch, const void* target, int target_layout, const sn_grad_src* src,
+                   int nsrc, int n, int h, int w, int c, float weight, double* loss_acc, void* dy_hi, void* dy_lo,
+                   int dy_pitch, int dy_coff, int dy_fmt, void* stream);
 /* BCEWithLogitsLoss(pred, t) over two consecutive halves of `count` elements each with its own
  * target (loss.py:58,110-122): loss_acc[half] += mean, dpred = gscale * (sigmoid(x) - t)/count. */
 int sn_bce_logits_fwd_bwd(const float* pred, long long count_per_half, int halves, float t0, float t1,

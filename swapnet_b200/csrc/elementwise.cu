@@ -848,6 +848,73 @@ __global__ void ce_loss_kernel(const float* __restrict__ logits, int pitch,
   block_add_double(local * (double)weight / (double)npix, loss_acc);
 }
 
+// CE on the tanh head fused with the head's own backward (warp_model.py:147-150 + swapnet_modules.py:85-90): per pixel
+//   g_c  = weight/npix * (softmax(o)_c - [c == argmax target])  +  sum of the extra gradient sources (the GAN term),
+//   dy_c = g_c * (1 - o_c^2)          written as split planes (channels c..pad8 zero-filled, 16-byte stores)
+// replaces ce_loss + tanh_bwd: the 19-channel logits are read once and the fp32 CE gradient never touches HBM.
+__global__ void __launch_bounds__(128) ce_tanh_bwd_kernel(const float* __restrict__ logits, int pitch,
+                                                          const float* __restrict__ target,
+                                                          const uint8_t* __restrict__ label, const GradSrcs g, int N,
+                                                          int H, int W, int C, float weight, double* loss_acc,
+                                                          uint16_t* __restrict__ hi, uint16_t* __restrict__ lo,
+                                                          int dy_pitch, int dy_coff, int fmt) {
+  const long long npix = (long long)N * H * W;
+  const long long HW = (long long)H * W;
+  double local = 0.0;
+  const float scale = weight / (float)npix;
+  const int C8 = (C + 7) & ~7;
+  for (long long pix = blockIdx.x * (long long)blockDim.x + threadIdx.x; pix < npix;
+       pix += (long long)gridDim.x * blockDim.x) {
+    const long long n = pix / HW, p = pix - n * HW;
+    const int h = (int)(p / W), w = (int)(p - (long long)h * W);
+    float x[kMaxCE];
+    int arg = 0;
+    float best = 0.f, mx = -INFINITY;
+    for (int c = 0; c < C; ++c) {
+      x[c] = logits[pix * pitch + c];
+      mx = fmaxf(mx, x[c]);
+      if (label) continue;
+      const float t = target[(n * C + c) * HW + p];
+      if (c == 0 || t > best) {  // first maximum wins (torch.argmax tie-break)
+        best = t;
+        arg = c;
+      }
+    }
+    if (label) {
+      arg = label[pix];
+      if (arg >= C) arg = 0;
+    }
+    float se = 0.f;
+    for (int c = 0; c < C; ++c) se += expf(x[c] - mx);
+    const float lse = mx + logf(se);
+    local += (double)(lse - x[arg]);
+    const float inv = 1.f / se;
+    for (int c0 = 0; c0 < C8; c0 += 8) {
+      uint16_t hh[8], ll[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int c = c0 + j;
+        float v = 0.f;
+        if (c < C) {
+          float gsum = scale * (expf(x[c] - mx) * inv - (c == arg ? 1.f : 0.f));
+          gsum += gather_grad(g, (int)n, h, w, H, W, c);
+          v = gsum * (1.f - x[c] * x[c]);
+        }
+        split16(v, fmt, hh[j], ll[j]);
+      }
+      const long long off = pix * dy_pitch + dy_coff + c0;
+      uint4 a, b;
+      a.x = hh[0] | ((uint32_t)hh[1] << 16); a.y = hh[2] | ((uint32_t)hh[3] << 16);
+      a.z = hh[4] | ((uint32_t)hh[5] << 16); a.w = hh[6] | ((uint32_t)hh[7] << 16);
+      b.x = ll[0] | ((uint32_t)ll[1] << 16); b.y = ll[2] | ((uint32_t)ll[3] << 16);
+      b.z = ll[4] | ((uint32_t)ll[5] << 16); b.w = ll[6] | ((uint32_t)ll[7] << 16);
+      *reinterpret_cast<uint4*>(hi + off) = a;
+      if (lo) *reinterpret_cast<uint4*>(lo + off) = b;
+    }
+  }
+  block_add_double(local * (double)weight / (double)npix, loss_acc);
+}
+
 __global__ void bce_logits_kernel(const float* __restrict__ pred, long long count, int halves, float t0,
                                   float t1, const float* __restrict__ t_dev, float gscale, double* loss_acc,
                                   float* __restrict__ dpred) {
@@ -1603,6 +1670,29 @@ int sn_ce_loss_fwd_bwd(const float* logits, int pitch, const void* target, int t
   ce_loss_kernel<<<grid_for((long long)n * h * w, 128), 128, 0, (cudaStream_t)stream>>>(
       logits, pitch, lab ? nullptr : (const float*)target, lab ? (const uint8_t*)target : nullptr, n, h, w, c, weight,
       loss_acc, grad, grad_pitch);
+  LAUNCH_CHECK();
+  return SN_OK;
+}
+
+int sn_ce_tanh_bwd(const float* logits, int pitch, const void* target, int target_layout, const sn_grad_src* src,
+                   int nsrc, int n, int h, int w, int c, float weight, double* loss_acc, void* dy_hi, void* dy_lo,
+                   int dy_pitch, int dy_coff, int dy_fmt, void* stream) {
+  SN_REQUIRE(c <= kMaxCE && logits && dy_hi && loss_acc, "ce_tanh_bwd: bad arguments (at most %d classes)", kMaxCE);
+  SN_REQUIRE(target_layout == SN_LAYOUT_NCHW || target_layout == SN_LAYOUT_LABEL_U8,
+             "ce_tanh_bwd: target must be NCHW fp32 or a uint8 label map");
+  SN_REQUIRE(dy_pitch % 8 == 0 && dy_coff % 8 == 0 && ((c + 7) & ~7) + dy_coff <= dy_pitch &&
+                 (((uintptr_t)dy_hi | (uintptr_t)dy_lo) & 15) == 0,
+             "ce_tanh_bwd: dy planes need 8-channel aligned slices and 16-byte aligned bases");
+  GradSrcs g;
+  g.n = 0;
+  if (nsrc > 0) {
+    int rc = fill_srcs(&g, src, nsrc);
+    if (rc) return rc;
+  }
+  const bool lab = target_layout == SN_LAYOUT_LABEL_U8;
+  ce_tanh_bwd_kernel<<<grid_for((long long)n * h * w, 128), 128, 0, (cudaStream_t)stream>>>(
+      logits, pitch, lab ? nullptr : (const float*)target, lab ? (const uint8_t*)target : nullptr, g, n, h, w, c, weight,
+      loss_acc, (uint16_t*)dy_hi, (uint16_t*)dy_lo, dy_pitch, dy_coff, dy_fmt);
   LAUNCH_CHECK();
   return SN_OK;
 }

@@ -123,8 +123,11 @@ class Stage:
         if self.norm:
             self.gstats = torch.zeros(self.n, self.cout, 2, dtype=torch.float64, device=dev)
 
-    def backward(self, srcs: Sequence[GradSrc], wgrad: bool = True) -> None:
-        if self.plain and self.epi_act == ACT_TANH:
+    def backward(self, srcs: Optional[Sequence[GradSrc]], wgrad: bool = True) -> None:
+        """srcs None: `self.dy` already holds dL/d(conv output) (written by a fused loss kernel, ops.ce_tanh_bwd)."""
+        if srcs is None:
+            pass
+        elif self.plain and self.epi_act == ACT_TANH:
             ops.tanh_bwd(srcs, self.y, self.cout, self.dy)
         else:
             p = 0.0 if self.plain else (self.drop_p if self.eng.training else 0.0)
@@ -283,8 +286,9 @@ class WarpEngine(Engine):
 
         return [span(("dual_up", "upsample_and_pad")), span(("resblocks",)), span(("cloth_",)), span(("body_",))]
 
-    def backward(self, srcs: Sequence[GradSrc], on_bucket=None) -> None:
-        """srcs: gradient(s) w.r.t. fakes (NHWC fp32).  Accumulates parameter grads into flat_grad.
+    def backward(self, srcs: Optional[Sequence[GradSrc]], on_bucket=None) -> None:
+        """srcs: gradient(s) w.r.t. fakes (NHWC fp32), or None when the head's dy planes were already written by the
+        fused loss kernel (ops.ce_tanh_bwd).  Accumulates parameter grads into flat_grad.
         on_bucket(i): called when bucket i of grad_buckets() has all its gradient launches enqueued."""
         B, h16 = self.batch, self.size // 16
         done = on_bucket or (lambda i: None)

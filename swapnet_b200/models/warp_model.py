@@ -97,23 +97,22 @@ class WarpModel(BaseGAN):
             ops.pack_concat([(self.bodys, False), (self.targets, False)], din_real)
 
     def backward_G(self):
+        """loss_G = lambda_ce * CE(fakes, argmax(targets)) + lambda_gan * GAN (warp_model.py:141-167).  The GAN term's
+        gradient w.r.t. the fakes comes back from the discriminator first; the cross entropy, the sum of both gradients and
+        the tanh backward of the head are ONE kernel writing the head's dy planes (ops.ce_tanh_bwd)."""
         g = self._eng_G
-        B, S = self._eng_key
-        if not hasattr(self, "_dce") or self._dce.shape[0] != B or self._dce.shape[1] != S:
-            self._dce = torch.zeros(B, S, S, self.cloth_channels, device=self.device)
-        ops.ce_loss_fwd_bwd(g.fakes, self.cloth_channels, self.targets, float(self.opt.lambda_ce), self._acc[3:4],
-                            self._dce)
-        srcs = [GradSrc(self._dce)]
+        extra = []
         if self.opt.warp_mode == "gan":
-            dx = self.gan_backward_through_D()
-            srcs.append(GradSrc(dx, self.body_channels))
+            extra.append(GradSrc(self.gan_backward_through_D(), self.body_channels))
+        ops.ce_tanh_bwd(g.fakes, self.cloth_channels, self.targets, float(self.opt.lambda_ce), self._acc[3:4], extra,
+                        g.head.dy)
         if self._world > 1:
             from .. import parallel
             avg = parallel.BucketedAverager(g.flat_grad, g.grad_buckets(), scale=False)   # 1/world: in the AdamW kernel
-            g.backward(srcs, on_bucket=avg.ready)
+            g.backward(None, on_bucket=avg.ready)
             avg.finish()
         else:
-            g.backward(srcs)
+            g.backward(None)
 
     def input_tensors(self):
         return {"bodys": self.bodys, "inputs": self.inputs, "targets": self.targets}

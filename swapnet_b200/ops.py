@@ -606,6 +606,26 @@ def ce_loss_fwd_bwd(logits: torch.Tensor, c: int, target, weight: float,
                                          loss_acc.data_ptr(), grad.data_ptr(), grad.shape[3], _stream()))
 
 
+def ce_tanh_bwd(out: torch.Tensor, c: int, target, weight: float, loss_acc: torch.Tensor,
+                extra: Sequence[GradSrc], dy: Planes) -> None:
+    """Cross entropy on the tanh head's outputs `out` (NHWC [n,h,w,c]) fused with the head's backward:
+    dy <- (weight * dCE/d(out) + sum(extra)) * (1 - out^2); loss_acc += weight * CE."""
+    n, h, w, pitch = out.shape
+    if isinstance(target, SegMap):
+        assert target.layout == LAYOUT_LABEL_U8 and target.shape == (n, c, h, w), "CE target: a uint8 label map"
+        tptr, layout = target.data.data_ptr(), LAYOUT_LABEL_U8
+    else:
+        assert target.is_contiguous() and target.shape == (n, c, h, w)
+        tptr, layout = target.data_ptr(), LAYOUT_NCHW
+    arr = (SnGradSrc * _lib.SN_MAX_SRC)()
+    if extra:
+        _fill_srcs(arr, extra)
+    assert (dy.n, dy.h, dy.w) == (n, h, w)
+    check(_lib.load().sn_ce_tanh_bwd(out.data_ptr(), pitch, tptr, layout, arr, len(extra), n, h, w, c, weight,
+                                     loss_acc.data_ptr(), dy.hi.data_ptr(), dy.lo.data_ptr(), dy.pitch, dy.c_off,
+                                     dy.fmt, _stream()))
+
+
 def bce_logits_fwd_bwd(pred: torch.Tensor, halves: int, t0, t1: float, gscale: float,
                        loss_acc: torch.Tensor, dpred: Optional[torch.Tensor]) -> None:
     """t0 may be a device float32 tensor holding the target(s) of the half(s) (step-parameter buffer): t1 is ignored."""
