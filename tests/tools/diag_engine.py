@@ -11,7 +11,8 @@ from swapnet_b200 import engine as E, ops
 from test_engine_gpu import make_nets, synth_warp_batch, relmax
 
 dev = torch.device("cuda:0")
-B, S = 2, int(sys.argv[1]) if len(sys.argv) > 1 else 64
+S = int(sys.argv[1]) if len(sys.argv) > 1 else 64
+B = int(sys.argv[2]) if len(sys.argv) > 2 and sys.argv[2].isdigit() else 2
 G, D = make_nets()
 sdG = {k: v.clone().double().requires_grad_() for k, v in G.state_dict().items()}
 sdD = {k: v.clone().double().requires_grad_() for k, v in D.state_dict().items()}
