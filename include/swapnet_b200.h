@@ -157,6 +157,23 @@ int sn_pack_weights(const float* src, long long s_row, long long s_k, int rows, 
                     const int* slot_of_tap /* HOST array [taps] or NULL = identity */, int k_real, int k_pad,
                     void* dst_hi, void* dst_lo, int fmt, const float* scale2, void* stream);
 
+/* multi-tensor variants (one launch per network instead of 3 + 2 per layer).  The item tables live in DEVICE memory and
+ * are built once per engine.  sn_weight_scale_multi: scale2 <- (s, 1/s) of every tensor; scratch: 2 * nitems zeroed
+ * uint32 (left zeroed).  sn_pack_weights_multi: every item is one sn_pack_weights call; block_begin = running sum of
+ * ceil(rows / sn_pack_rows_per_block()) * ceil(k_pad / sn_pack_k_per_block()), total_blocks its end. */
+typedef struct sn_scale_item { const float* w; long long count; float* scale2; } sn_scale_item;
+typedef struct sn_pack_item {
+  const float* src; long long s_row, s_k;
+  int rows, taps, taps_pitch, k_real, k_pad, fmt;
+  void* hi; void* lo; const float* scale2;
+  int slot[16];
+  int block_begin;
+} sn_pack_item;
+int sn_weight_scale_multi(const sn_scale_item* items_dev, int nitems, unsigned int* scratch_dev, void* stream);
+int sn_pack_weights_multi(const sn_pack_item* items_dev, int nitems, int total_blocks, int max_taps, void* stream);
+int sn_pack_rows_per_block(void);
+int sn_pack_k_per_block(void);
+
 /* head conv (swapnet_modules.py:85-90): nearest x2 upsample + ZeroPad2d((1,0,1,0)) + Conv2d(k4,p1)
  * folded into 4 output-parity phases with 2/3 effective taps per dim (25 taps in total).
  *   fwd pack:  dst[phase][row=co (rows_pad)][teff][ci (k_pad)]   (rows >= cout are zero)

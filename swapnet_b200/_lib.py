@@ -60,6 +60,17 @@ class SnWgradDesc(C.Structure):
     ]
 
 
+class SnScaleItem(C.Structure):
+    _fields_ = [("w", C.c_void_p), ("count", C.c_longlong), ("scale2", C.c_void_p)]
+
+
+class SnPackItem(C.Structure):
+    _fields_ = [("src", C.c_void_p), ("s_row", C.c_longlong), ("s_k", C.c_longlong),
+                ("rows", C.c_int), ("taps", C.c_int), ("taps_pitch", C.c_int), ("k_real", C.c_int), ("k_pad", C.c_int),
+                ("fmt", C.c_int), ("hi", C.c_void_p), ("lo", C.c_void_p), ("scale2", C.c_void_p),
+                ("slot", C.c_int * 16), ("block_begin", C.c_int)]
+
+
 class SnNormActDesc(C.Structure):
     _fields_ = [
         ("y", C.c_void_p), ("y_pitch", C.c_int),
@@ -112,6 +123,10 @@ SIGNATURES = {
     "sn_weight_scale": (_I, [_VP, _LL, _VP, _VP]),
     "sn_pack_weights": (_I, [_VP, _LL, _LL, _I, _I, _I, C.POINTER(C.c_int), _I, _I, _VP, _VP, _I, _VP, _VP]),
     "sn_pack_head_weights": (_I, [_VP, _I, _I, _I, _I, _I, _I, _VP, _VP, _I, _VP, _VP]),
+    "sn_weight_scale_multi": (_I, [_VP, _I, _VP, _VP]),
+    "sn_pack_weights_multi": (_I, [_VP, _I, _I, _I, _VP]),
+    "sn_pack_rows_per_block": (_I, []),
+    "sn_pack_k_per_block": (_I, []),
     "sn_fold_head_wgrad": (_I, [_VP, _I, _I, _VP, _VP]),
     "sn_plane_stats": (_I, [_VP, _I, _I, _I, _I, _F, _VP, _VP]),
     "sn_norm_act_fwd": (_I, [C.POINTER(SnNormActDesc), _VP]),

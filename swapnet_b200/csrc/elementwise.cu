@@ -307,6 +307,88 @@ __global__ void weight_scale_finalize_kernel(const unsigned int* amax, float* sc
 }
 
 // ---------------------------------------------------------------------------------
+// multi-tensor variants: ONE launch computes the power-of-two scales of every weight tensor of a network, ONE launch
+// writes every packed copy (forward and input-gradient layouts) — instead of 3 + 2 launches per layer per step.
+// ---------------------------------------------------------------------------------
+// grid (blocks per tensor, tensors).  scratch[2t] = max |w| bits, scratch[2t+1] = blocks done; the last block of a
+// tensor finalises its scale and resets both words (the buffer is zero again when the launch retires).
+__global__ void __launch_bounds__(256) weight_scale_multi_kernel(const sn_scale_item* __restrict__ items,
+                                                                 unsigned int* __restrict__ scratch) {
+  const sn_scale_item it = items[blockIdx.y];
+  float m = 0.f;
+  const long long n4 = it.count >> 2;
+  const float4* w4 = reinterpret_cast<const float4*>(it.w);
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const float4 v = w4[i];
+    m = fmaxf(fmaxf(m, fabsf(v.x)), fmaxf(fabsf(v.y), fmaxf(fabsf(v.z), fabsf(v.w))));
+  }
+  if (blockIdx.x == 0)
+    for (long long i = (n4 << 2) + threadIdx.x; i < it.count; i += blockDim.x) m = fmaxf(m, fabsf(it.w[i]));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  __shared__ float wm[8];
+  if ((threadIdx.x & 31) == 0) wm[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int i = 1; i < (int)(blockDim.x >> 5); ++i) m = fmaxf(m, wm[i]);
+    unsigned int* sc = scratch + 2 * blockIdx.y;
+    atomicMax(sc, __float_as_uint(m));
+    __threadfence();
+    if (atomicAdd(sc + 1, 1u) == gridDim.x - 1) {
+      const float mx = __uint_as_float(atomicExch(sc, 0u));
+      sc[1] = 0u;
+      float sv = 1.f;
+      if (mx > 0.f && isfinite(mx)) {
+        int e;
+        frexpf(mx, &e);
+        sv = ldexpf(1.f, 14 - e);
+      }
+      it.scale2[0] = sv;
+      it.scale2[1] = 1.f / sv;
+    }
+  }
+}
+
+// one block = 8 rows x 64 K x all taps of one pack item; items are found by binary search over block_begin
+constexpr int kPkRows = 8, kPkK = 64;
+__global__ void __launch_bounds__(256) pack_weights_multi_kernel(const sn_pack_item* __restrict__ items, int nitems) {
+  extern __shared__ float tile[];   // [rows][k][taps + 1]
+  int lo = 0, hi = nitems - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (items[mid].block_begin <= (int)blockIdx.x) lo = mid; else hi = mid - 1;
+  }
+  const sn_pack_item it = items[lo];
+  const int local = blockIdx.x - it.block_begin;
+  const int gx = (it.k_pad + kPkK - 1) / kPkK;
+  const int k0 = (local % gx) * kPkK, r0 = (local / gx) * kPkRows;
+  const int taps = it.taps, T1 = taps + 1;
+  const float sc = it.scale2 ? it.scale2[0] : 1.f;
+  const int nr = min(kPkRows, it.rows - r0);
+  // gather: element (r, k, t) at src[r*s_row + k*s_k + t]; walk t fastest, then the dimension with the smaller stride
+  const bool k_minor = it.s_k <= it.s_row;
+  const int total = nr * kPkK * taps;
+  for (int i = threadIdx.x; i < total; i += blockDim.x) {
+    const int t = i % taps, j = i / taps;
+    int r, kk;
+    if (k_minor) { kk = j % kPkK; r = j / kPkK; } else { r = j % nr; kk = j / nr; }
+    float v = 0.f;
+    if (k0 + kk < it.k_real) v = it.src[(long long)(r0 + r) * it.s_row + (long long)(k0 + kk) * it.s_k + t];
+    tile[(r * kPkK + kk) * T1 + t] = v;
+  }
+  __syncthreads();
+  uint16_t* hi16 = (uint16_t*)it.hi;
+  uint16_t* lo16 = (uint16_t*)it.lo;
+  for (int i = threadIdx.x; i < total; i += blockDim.x) {     // scatter: k fastest (128-byte runs per (row, tap))
+    const int kk = i % kPkK, j = i / kPkK, t = j % taps, r = j / taps;
+    if (k0 + kk < it.k_pad) {
+      const long long off = ((long long)(r0 + r) * it.taps_pitch + it.slot[t]) * it.k_pad + k0 + kk;
+      store_split(hi16, lo16, off, tile[(r * kPkK + kk) * T1 + t] * sc, it.fmt);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------
 // plane statistics
 // ---------------------------------------------------------------------------------
 __device__ __forceinline__ double atomic_add_f64(double* a, double v) { return atomicAdd(a, v); }
@@ -1404,6 +1486,30 @@ int sn_weight_scale(const float* w, long long count, float* scale2, void* stream
   LAUNCH_CHECK();
   return SN_OK;
 }
+
+int sn_weight_scale_multi(const sn_scale_item* items_dev, int nitems, unsigned int* scratch_dev, void* stream) {
+  SN_REQUIRE(items_dev && scratch_dev && nitems >= 1, "weight_scale_multi: bad arguments");
+  weight_scale_multi_kernel<<<dim3(32, nitems), 256, 0, (cudaStream_t)stream>>>(items_dev, scratch_dev);
+  LAUNCH_CHECK();
+  return SN_OK;
+}
+
+int sn_pack_weights_multi(const sn_pack_item* items_dev, int nitems, int total_blocks, int max_taps, void* stream) {
+  SN_REQUIRE(items_dev && nitems >= 1 && total_blocks >= 1 && max_taps >= 1 && max_taps <= 16,
+             "pack_weights_multi: bad arguments");
+  const size_t smem = (size_t)kPkRows * kPkK * (max_taps + 1) * sizeof(float);
+  static bool attr = false;
+  if (!attr) {
+    SN_CHECK_CUDA(cudaFuncSetAttribute(pack_weights_multi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    attr = true;
+  }
+  SN_REQUIRE(smem <= 64 * 1024, "pack_weights_multi: tile too large");
+  pack_weights_multi_kernel<<<total_blocks, 256, smem, (cudaStream_t)stream>>>(items_dev, nitems);
+  LAUNCH_CHECK();
+  return SN_OK;
+}
+int sn_pack_rows_per_block(void) { return kPkRows; }
+int sn_pack_k_per_block(void) { return kPkK; }
 
 int sn_fold_head_wgrad(const float* geff, int cout, int cin, float* dw, void* stream) {
   fold_head_wgrad_kernel<<<grid_for((long long)cout * cin * 16), kEwThreads, 0, (cudaStream_t)stream>>>(

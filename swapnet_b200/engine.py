@@ -149,6 +149,8 @@ class Engine:
         self.seed = 0
         self.seed_dev: Optional[torch.Tensor] = None   # device copy of the step seed (CUDA-graph replay), else host seeds
         self.sample_base = 0        # global index of local sample 0 (dropout masks follow the global sample)
+        self._pack_table: Optional[ops.PackTable] = None   # built at the first pack() (after bind_backward)
+        self._pack_extra: list = []
         self.flat_grad: Optional[torch.Tensor] = None
 
     def planes(self, n: int, h: int, w: int, c: int) -> Planes:
@@ -179,12 +181,23 @@ class Engine:
             off += p.numel()
 
     def pack(self) -> None:
-        for s in self.stages:
-            s.layer.pack()
+        """Kernel-layout copies of the (updated) torch weights: one scale launch + one pack launch for the whole
+        network (ops.PackTable), plus the head's effective-tap packs.  SN_PACK_PER_LAYER=1: the per-layer launches."""
+        if os.environ.get("SN_PACK_PER_LAYER", "0") == "1":
+            for s in self.stages:
+                s.layer.pack()
+            return
+        if self._pack_table is None:
+            self._pack_table = ops.PackTable(self.device)
+            self._pack_extra = [s.layer for s in self.stages if s.layer.register_packs(self._pack_table)]
+        self._pack_table.run()
+        for ly in self._pack_extra:
+            ly.pack_extra()
 
     def bind_backward(self, wgrad: bool = True) -> None:
         for s in self.stages:
             s.bind_backward(wgrad=wgrad)
+        self._pack_table = None        # the input-gradient packs exist now: re-register at the next pack()
 
 
 # =============================================================================================

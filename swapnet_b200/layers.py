@@ -90,8 +90,25 @@ class ConvLayer:
             self.fwd_plans.append(ops.tap_gemm_plan(d, keep=(self.x.hi, self.x.lo, self.wp.hi, self.wp.lo, y)))
             self.fwd_plans[-1].tag = ("fwd", self.name)
 
+    def register_packs(self, table: "ops.PackTable") -> bool:
+        """Register this layer's scale and generic packs with the network's PackTable; returns True when a separate
+        `pack_extra()` call is still needed after the table ran (the head's effective-tap packs)."""
+        table.add_scale(self.weight, self.wscale)
+        if self.kind == "head":
+            return True
+        table.add_pack(self.weight, self.kind, False, self.k_pad, self.wp)
+        if self.wd is not None and self.dgrad_plans:
+            table.add_pack(self.weight, self.kind, True, self.dy.c, self.wd)
+        return False
+
+    def pack_extra(self) -> None:
+        assert self.kind == "head"
+        ops.pack_head_weights(self.weight, self.rows_pad, self.k_pad, False, self.wp)
+        if self.wd is not None and self.dgrad_plans:
+            ops.pack_head_weights(self.weight, 0, self.dy.c, True, self.wd)
+
     def pack(self) -> None:
-        """Re-pack the (updated) torch weights into the kernel layouts."""
+        """Re-pack the (updated) torch weights into the kernel layouts (per-layer launches: tests, single layers)."""
         ops.weight_scale(self.weight, self.wscale)
         if self.kind == "head":
             ops.pack_head_weights(self.weight, self.rows_pad, self.k_pad, False, self.wp)
@@ -217,6 +234,9 @@ class ToOneConvLayer:
     def bind_forward(self, y: torch.Tensor, y_c_off: int = 0) -> None:
         assert y.shape[:3] == (self.n, self.out_h, self.out_w) and y_c_off == 0
         self.y = y
+
+    def register_packs(self, table) -> bool:
+        return False            # the kernels read the torch parameter itself
 
     def pack(self) -> None:
         pass

@@ -401,6 +401,70 @@ def pack_weights(weight: torch.Tensor, kind: str, dgrad: bool, k_pad: int, dst: 
                                       _stream()))
 
 
+class PackTable:
+    """All weight-scale and pack launches of one network as TWO launches (sn_weight_scale_multi,
+    sn_pack_weights_multi): layers register their tensors once, the item tables live in device memory."""
+
+    def __init__(self, device):
+        self.device = device
+        self._scales, self._packs, self._keep = [], [], []
+        self._dev = None
+
+    def add_scale(self, weight: torch.Tensor, scale: torch.Tensor) -> None:
+        assert weight.is_contiguous() and weight.dtype == torch.float32 and self._dev is None
+        it = _lib.SnScaleItem()
+        it.w, it.count, it.scale2 = weight.data_ptr(), weight.numel(), scale.data_ptr()
+        self._scales.append(it)
+        self._keep += [weight, scale]
+
+    def add_pack(self, weight: torch.Tensor, kind: str, dgrad: bool, k_pad: int, dst: PackedWeights) -> None:
+        """Same arguments as pack_weights()."""
+        assert weight.is_contiguous() and weight.dtype == torch.float32 and self._dev is None
+        if kind == "convT4s2":
+            cin, cout = weight.shape[0], weight.shape[1]
+        else:
+            cout, cin = weight.shape[0], weight.shape[1]
+        s_row, s_k, rows, k_real = L.pack_strides(kind, cin, cout, dgrad)
+        t = L.ntaps(kind)
+        assert dst.rows >= rows and dst.k_total >= t * k_pad and k_pad >= k_real and dst.k_total % k_pad == 0 and t <= 16
+        it = _lib.SnPackItem()
+        it.src, it.s_row, it.s_k = weight.data_ptr(), s_row, s_k
+        it.rows, it.taps, it.taps_pitch, it.k_real, it.k_pad, it.fmt = rows, t, dst.k_total // k_pad, k_real, k_pad, dst.fmt
+        it.hi, it.lo = dst.hi.data_ptr(), dst.lo.data_ptr()
+        it.scale2 = None if dst.scale is None else dst.scale.data_ptr()
+        for i, sl in enumerate(L.pack_slots(kind, dgrad)):
+            it.slot[i] = sl
+        self._packs.append(it)
+        self._keep += [weight, dst]
+
+    def _upload(self, items, ctype):
+        arr = (ctype * len(items))(*items)
+        return torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).to(self.device)
+
+    def finalize(self) -> None:
+        lib = _lib.load()
+        rpb, kpb = lib.sn_pack_rows_per_block(), lib.sn_pack_k_per_block()
+        begin = 0
+        for it in self._packs:
+            it.block_begin = begin
+            begin += ((it.rows + rpb - 1) // rpb) * ((it.k_pad + kpb - 1) // kpb)
+        self._blocks = begin
+        self._max_taps = max([it.taps for it in self._packs], default=1)
+        self._dev = (self._upload(self._scales, _lib.SnScaleItem) if self._scales else None,
+                     self._upload(self._packs, _lib.SnPackItem) if self._packs else None,
+                     torch.zeros(2 * max(1, len(self._scales)), dtype=torch.int32, device=self.device))
+
+    def run(self) -> None:
+        if self._dev is None:
+            self.finalize()
+        sc, pk, scratch = self._dev
+        lib = _lib.load()
+        if sc is not None:
+            check(lib.sn_weight_scale_multi(sc.data_ptr(), len(self._scales), scratch.data_ptr(), _stream()))
+        if pk is not None:
+            check(lib.sn_pack_weights_multi(pk.data_ptr(), len(self._packs), self._blocks, self._max_taps, _stream()))
+
+
 def pack_head_weights(weight: torch.Tensor, rows_pad: int, k_pad: int, dgrad: bool, dst: PackedWeights) -> None:
     cout, cin = weight.shape[:2]
     assert dst.hi.numel() >= (cin * 25 * k_pad if dgrad else rows_pad * 25 * k_pad)

@@ -731,3 +731,37 @@ def test_graph_replayed_steps_match_eager_steps():
     # AdamW's first steps move every weight by ~lr: the two runs agree far inside that
     assert (wg - we).abs().max().item() < 0.2 * 5e-4, (wg - we).abs().max().item()
     record("graph_vs_eager_5_steps", f"max |dW| {(wg - we).abs().max().item():.2e}; launches/step graph {lg} eager {le}")
+
+
+def test_pack_table_equals_per_layer_packs():
+    """Engine.pack(): one multi-tensor scale launch + one multi-tensor pack launch must write exactly the bytes the
+    per-layer sn_weight_scale / sn_pack_weights launches write (forward and input-gradient layouts, all conv kinds)."""
+    from swapnet_b200 import engine as E
+
+    G, D = make_nets()
+    for net, mk in ((G, lambda n: E.WarpEngine(n, 1, 64, dev())), (D, lambda n: E.PatchGANEngine(n, 2, 64, dev(), input_grad=True))):
+        eng = mk(net.to(dev()))
+        eng.alloc_grads()
+        eng.bind_backward()
+        bufs = []
+        for st in eng.stages:
+            st.layer.pack()                                   # per-layer launches
+            for pw in (getattr(st.layer, "wp", None), getattr(st.layer, "wd", None)):
+                if pw is not None:
+                    bufs.append((st.name, pw, pw.hi.clone(), pw.lo.clone()))
+            if hasattr(st.layer, "wscale"):
+                bufs.append((st.name + ".scale", st.layer.wscale, st.layer.wscale.clone(), None))
+        for _, pw, _, _ in bufs:
+            if hasattr(pw, "hi"):
+                pw.hi.zero_()
+                pw.lo.zero_()
+            else:
+                pw.zero_()
+        eng.pack()                                            # the table
+        eng.pack()                                            # (scratch words self-reset: a second run is identical)
+        torch.cuda.synchronize()
+        for name, pw, hi, lo in bufs:
+            if lo is None:
+                assert torch.equal(pw, hi), name
+            else:
+                assert torch.equal(pw.hi, hi) and torch.equal(pw.lo, lo), name
