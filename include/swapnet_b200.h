@@ -99,6 +99,12 @@ typedef struct sn_tap_gemm_desc {
                                             output parity phase (py, px) = (z >> 1, z & 1) of a stride-2 transposed
                                             structure; phase z writes pixel (h*mul_h + off_h + py, w*mul_w + off_w + px)
                                             — ONE launch (grid.z = 4) instead of four under-filled ones */
+  int stack_slot, stack_c;               /* stack_slot > 0: the N columns are 4 output-parity phases STACKED side by side,
+                                            stack_slot columns apiece of which the first stack_c are real: column
+                                            j = phase*stack_slot + c goes to pixel (h*mul_h + py, w*mul_w + px), channel c
+                                            (bias[c]).  The up-sample+pad head (swapnet_modules.py:85-90) as ONE 9-tap GEMM
+                                            with N = 4 x 24: its 192-channel input is read 9 times instead of 25.
+                                            Needs n_valid = 4*stack_slot, nphase <= 1, out_mul = 2. */
 } sn_tap_gemm_desc;
 
 /* G[i*s_row + j*s_col + tap_off[t]] += sum_{(n,h,w)} X[n, h+dh_t, w+dw_t, xc_t + i] * Y[n, h+dh'_t, w+dw'_t, yc_t + j]
@@ -181,6 +187,11 @@ int sn_pack_k_per_block(void);
  * src is torch OIHW [cout][cin][4][4]. */
 int sn_pack_head_weights(const float* src, int cout, int cin, int rows_pad, int k_pad, int dgrad, int taps_pitch,
                          void* dst_hi, void* dst_lo, int fmt, const float* scale2, void* stream);
+/* the same effective taps laid out for the phase-stacked 9-tap GEMM (sn_tap_gemm_desc.stack_slot):
+ *   dst[row = phase*slot + co][tap = (sy+1)*3 + (sx+1)][ci (k_pad)], zero where the phase has no tap at that shift
+ *   (parity 0 reads shifts -1, 0; parity 1 reads -1, 0, +1) and for co >= cout; rows = 4*slot. */
+int sn_pack_head_stacked(const float* src, int cout, int cin, int slot, int k_pad, void* dst_hi, void* dst_lo, int fmt,
+                         const float* scale2, void* stream);
 /* fold the 25 effective-tap gradients [cout][25][cin] back onto dW [cout][cin][4][4] (+=) */
 int sn_fold_head_wgrad(const float* geff, int cout, int cin, float* dw, void* stream);
 

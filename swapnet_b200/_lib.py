@@ -37,6 +37,7 @@ class SnTapGemmDesc(C.Structure):
         ("out_mul_h", C.c_int), ("out_off_h", C.c_int), ("out_mul_w", C.c_int), ("out_off_w", C.c_int),
         ("n_valid", C.c_int), ("block_n", C.c_int),
         ("bias", C.c_void_p), ("act", C.c_int), ("nsplit", C.c_int), ("nphase", C.c_int),
+        ("stack_slot", C.c_int), ("stack_c", C.c_int),
     ]
 
 
@@ -127,6 +128,7 @@ SIGNATURES = {
     "sn_pack_weights_multi": (_I, [_VP, _I, _I, _I, _VP]),
     "sn_pack_rows_per_block": (_I, []),
     "sn_pack_k_per_block": (_I, []),
+    "sn_pack_head_stacked": (_I, [_VP, _I, _I, _I, _I, _VP, _VP, _I, _VP, _VP]),
     "sn_fold_head_wgrad": (_I, [_VP, _I, _I, _VP, _VP]),
     "sn_plane_stats": (_I, [_VP, _I, _I, _I, _I, _F, _VP, _VP]),
     "sn_norm_act_fwd": (_I, [C.POINTER(SnNormActDesc), _VP]),

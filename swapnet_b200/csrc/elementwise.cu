@@ -262,6 +262,30 @@ __global__ void pack_head_weights_kernel(const float* __restrict__ w, int cout, 
     store_split(hi, lo, off, acc * sc, fmt);
   }
 }
+// stacked-phase layout of the same effective taps: dst[row = phase*slot + co][tap9 = (sy+1)*3 + (sx+1)][ci]
+__global__ void pack_head_stacked_kernel(const float* __restrict__ w, int cout, int cin, int slot, int k_pad,
+                                         uint16_t* __restrict__ hi, uint16_t* __restrict__ lo, int fmt,
+                                         const float* __restrict__ scale2) {
+  const float sc = scale2 ? scale2[0] : 1.f;
+  const long long total = (long long)4 * slot * 9 * k_pad;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int ci = (int)(i % k_pad);
+    const int t9 = (int)((i / k_pad) % 9);
+    const int row = (int)(i / ((long long)k_pad * 9));
+    const int p = row / slot, co = row - p * slot;
+    const int py = p >> 1, px = p & 1;
+    const int ey = t9 / 3, ex = t9 % 3;          // effective tap index = shift + 1
+    float acc = 0.f;
+    if (co < cout && ci < cin && ey < head_neff(py) && ex < head_neff(px)) {
+      int kys[2], kxs[2];
+      const int ny = head_taps_of(py, ey, kys), nx = head_taps_of(px, ex, kxs);
+      for (int a = 0; a < ny; ++a)
+        for (int b = 0; b < nx; ++b) acc += w[(((long long)co * cin + ci) * 4 + kys[a]) * 4 + kxs[b]];
+    }
+    store_split(hi, lo, i, acc * sc, fmt);
+  }
+}
 __global__ void fold_head_wgrad_kernel(const float* __restrict__ geff, int cout, int cin,
                                        float* __restrict__ dw) {
   const long long total = (long long)cout * cin * 16;
@@ -1470,6 +1494,15 @@ int sn_pack_head_weights(const float* src, int cout, int cin, int rows_pad, int 
   SN_REQUIRE(dgrad ? (k_pad >= cout) : (k_pad >= cin && rows_pad >= cout), "bad head pack shape");
   pack_head_weights_kernel<<<grid_for((long long)cout * 25 * cin), kEwThreads, 0, (cudaStream_t)stream>>>(
       src, cout, cin, rows_pad, k_pad, dgrad, taps_pitch, (uint16_t*)dst_hi, (uint16_t*)dst_lo, fmt, scale2);
+  LAUNCH_CHECK();
+  return SN_OK;
+}
+
+int sn_pack_head_stacked(const float* src, int cout, int cin, int slot, int k_pad, void* dst_hi, void* dst_lo, int fmt,
+                         const float* scale2, void* stream) {
+  SN_REQUIRE(src && dst_hi && slot >= cout && k_pad >= cin, "bad stacked head pack shape");
+  pack_head_stacked_kernel<<<grid_for((long long)4 * slot * 9 * k_pad), kEwThreads, 0, (cudaStream_t)stream>>>(
+      src, cout, cin, slot, k_pad, (uint16_t*)dst_hi, (uint16_t*)dst_lo, fmt, scale2);
   LAUNCH_CHECK();
   return SN_OK;
 }

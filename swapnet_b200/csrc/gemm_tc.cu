@@ -243,7 +243,21 @@ tap_gemm_kernel(const __grid_constant__ TapGemmParams p, const int m_tiles, cons
           __syncwarp();
           if (lane == 0) mbar_arrive(&tempty_bar[b]);
         }
-        if (valid) {
+        if (valid && p.stack_slot) {
+          // phase-stacked head: column -> (phase, channel); every phase lands on its own output pixel
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const int col = ncol0 + c0 + j;
+            const int ph = col / p.stack_slot, c = col - ph * p.stack_slot;
+            if (ph < 4 && c < p.stack_c) {
+              float v = __uint_as_float(r[j]) * oscale;
+              if (p.bias) v += p.bias[c];
+              float* o = p.out + (long long)gn * p.out_sn + (long long)(gh * p.omh + (ph >> 1)) * p.out_sh +
+                         (long long)(gw * p.omw + (ph & 1)) * p.out_sw + c;
+              *o = apply_act(v, p.act);
+            }
+          }
+        } else if (valid) {
           if (p.vec4 && ncol0 + c0 + 16 <= p.n_valid) {
 #pragma unroll
             for (int j = 0; j < 16; j += 4) {
@@ -671,6 +685,12 @@ int sn_tap_gemm_plan_init(TapGemmPlan* plan, const sn_tap_gemm_desc* d) {
     SN_REQUIRE(a_chunk == 64 || tpp % (64 / a_chunk) == 0, "4-phase launch: taps per phase must fill whole stages");
   }
   p.bias = d->bias;
+  p.stack_slot = d->stack_slot; p.stack_c = d->stack_c;
+  if (d->stack_slot > 0)
+    SN_REQUIRE(d->nphase <= 1 && d->n_valid == 4 * d->stack_slot && d->stack_c >= 1 && d->stack_c <= d->stack_slot &&
+                   d->out_mul_h == 2 && d->out_mul_w == 2,
+               "phase-stacked output: n_valid = 4*stack_slot, nphase 1, out_mul 2 (slot=%d c=%d n_valid=%d)",
+               d->stack_slot, d->stack_c, d->n_valid);
   p.b_scale = d->b_scale;
   p.a_fmt = d->a_fmt;
   p.b_fmt = d->b_fmt;

@@ -34,6 +34,7 @@ struct alignas(64) TapGemmParams {
   // (an extra outermost box dimension of 2) — the TMA unit is bound by the number of box operations, not bytes
   int a_merged, b_merged;
   int a_lo_off, b_lo_off;   // byte offset of the lo tile behind the hi tile inside a stage
+  int stack_slot, stack_c;  // > 0: N = 4 output-parity phases side by side (sn_tap_gemm_desc.stack_slot)
 };
 
 struct alignas(64) WgradParams {

@@ -16,6 +16,10 @@ from . import lowering as L
 from . import ops
 from .ops import ACT_NONE, PackedWeights, Planes
 
+import os
+
+HEAD_STACKED = os.environ.get("SN_HEAD_STACKED", "1") != "0"   # A/B switch: the head forward as one 9-tap GEMM
+
 
 class ConvLayer:
     def __init__(self, kind: str, weight: torch.Tensor, bias: Optional[torch.Tensor], x: Planes, *,
@@ -39,7 +43,11 @@ class ConvLayer:
         self.block_n = L.pick_block_n(self.cout)
         self.t = L.ntaps(kind)
         self.wscale = torch.ones(2, dtype=torch.float32, device=dev)  # (s, 1/s), shared by fwd and dgrad packs
-        if kind == "head":
+        self.stacked = kind == "head" and HEAD_STACKED and self.cout <= L.HEAD_SLOT and self.k_pad % 64 == 0
+        if self.stacked:
+            self.rows_pad = 4 * L.HEAD_SLOT
+            self.wp = PackedWeights(self.rows_pad, 9 * self.k_pad, dev, self.wscale)
+        elif kind == "head":
             self.rows_pad = (self.cout + self.block_n - 1) // self.block_n * self.block_n
             self.wp = PackedWeights(self.rows_pad, 25 * self.k_pad, dev, self.wscale)
         else:
@@ -70,6 +78,13 @@ class ConvLayer:
         assert y.shape[:3] == (self.n, self.out_h, self.out_w), (self.name, y.shape, self.out_h, self.out_w)
         self.y = y
         self.fwd_plans = []
+        if self.stacked:
+            d = ops.tap_gemm_desc(self.x, L.head_stacked_spec(self.in_h, self.in_w), self.wp, self.k_pad, y,
+                                  4 * L.HEAD_SLOT, bias=self.bias, act=self.act, nsplit=self.nsplit,
+                                  block_n=4 * L.HEAD_SLOT, out_c_off=y_c_off, stack_slot=L.HEAD_SLOT, stack_c=self.cout)
+            self.fwd_plans.append(ops.tap_gemm_plan(d, keep=(self.x.hi, self.x.lo, self.wp.hi, self.wp.lo, y)))
+            self.fwd_plans[-1].tag = ("fwd", self.name)
+            return
         specs = L.forward_specs(self.kind, self.in_h, self.in_w)
         merged = ops.merge_phase_specs(specs)
         if merged is not None and (self.k_pad >= 64 or (len(merged.taps) // 4) % (64 // self.k_pad) == 0):
@@ -103,7 +118,10 @@ class ConvLayer:
 
     def pack_extra(self) -> None:
         assert self.kind == "head"
-        ops.pack_head_weights(self.weight, self.rows_pad, self.k_pad, False, self.wp)
+        if self.stacked:
+            ops.pack_head_stacked(self.weight, L.HEAD_SLOT, self.k_pad, self.wp)
+        else:
+            ops.pack_head_weights(self.weight, self.rows_pad, self.k_pad, False, self.wp)
         if self.wd is not None and self.dgrad_plans:
             ops.pack_head_weights(self.weight, 0, self.dy.c, True, self.wd)
 
@@ -111,7 +129,10 @@ class ConvLayer:
         """Re-pack the (updated) torch weights into the kernel layouts (per-layer launches: tests, single layers)."""
         ops.weight_scale(self.weight, self.wscale)
         if self.kind == "head":
-            ops.pack_head_weights(self.weight, self.rows_pad, self.k_pad, False, self.wp)
+            if self.stacked:
+                ops.pack_head_stacked(self.weight, L.HEAD_SLOT, self.k_pad, self.wp)
+            else:
+                ops.pack_head_weights(self.weight, self.rows_pad, self.k_pad, False, self.wp)
             if self.wd is not None and self.dgrad_plans:
                 ops.pack_head_weights(self.weight, 0, self.dy.c, True, self.wd)
         else:

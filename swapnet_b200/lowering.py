@@ -161,6 +161,18 @@ def forward_specs(kind: str, h: int, w: int) -> List[GemmSpec]:
     raise ValueError(kind)
 
 
+HEAD_SLOT = 24      # columns per output-parity phase in the stacked head GEMM (19 real + 5 zero): N = 4 * 24 = 96
+
+
+def head_stacked_spec(h: int, w: int) -> GemmSpec:
+    """The head forward as ONE 9-tap GEMM whose N columns are the 4 output-parity phases side by side: the union of
+    the phases' effective taps is the 3x3 shift set {-1,0,1}^2 (parity 0 uses shifts -1, 0; parity 1 all three), so the
+    input is read 9 times instead of 4+6+6+9 = 25.  Packed weights: ops.pack_head_stacked (zero where a phase has no
+    tap at a shift)."""
+    taps = [Tap(0, (sy + 1) * 3 + (sx + 1), sx, sy) for sy in (-1, 0, 1) for sx in (-1, 0, 1)]
+    return GemmSpec(False, h, w, taps, (2, 2), (0, 0), a_hw=(h, w))
+
+
 # ------------------------------------------------------------------------------------------
 # dgrad: A = dy planes (spatial = layer OUTPUT size), result = gradient w.r.t. layer input
 # ------------------------------------------------------------------------------------------

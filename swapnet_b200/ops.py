@@ -137,7 +137,7 @@ def tap_gemm_desc(a: Planes, spec: L.GemmSpec, w: PackedWeights, k_per_tap: int,
                   n_valid: int, *, w_row_off: int = 0, w_rows: Optional[int] = None,
                   w_k: Optional[int] = None, w_elem_off: int = 0, bias: Optional[torch.Tensor] = None,
                   act: int = ACT_NONE, nsplit: int = 3, block_n: Optional[int] = None,
-                  out_c_off: int = 0, nphase: int = 1) -> SnTapGemmDesc:
+                  out_c_off: int = 0, nphase: int = 1, stack_slot: int = 0, stack_c: int = 0) -> SnTapGemmDesc:
     """out: fp32 NHWC tensor [n, OH, OW, pitch_out]; rows (h, w) land on pixel
     (h*mul_h + off_h, w*mul_w + off_w)."""
     assert (a.h, a.w) == tuple(spec.a_hw), f"operand is {a.h}x{a.w}, spec wants {spec.a_hw}"
@@ -179,6 +179,7 @@ def tap_gemm_desc(a: Planes, spec: L.GemmSpec, w: PackedWeights, k_per_tap: int,
     d.act = act
     d.nsplit = nsplit
     d.nphase = nphase
+    d.stack_slot, d.stack_c = stack_slot, stack_c
     return d
 
 
@@ -471,6 +472,15 @@ def pack_head_weights(weight: torch.Tensor, rows_pad: int, k_pad: int, dgrad: bo
     taps_pitch = dst.k_total // k_pad if dgrad else 25
     check(_lib.load().sn_pack_head_weights(weight.data_ptr(), cout, cin, rows_pad, k_pad, int(dgrad), taps_pitch,
                                            dst.hi.data_ptr(), dst.lo.data_ptr(), dst.fmt,
+                                           None if dst.scale is None else dst.scale.data_ptr(), _stream()))
+
+
+def pack_head_stacked(weight: torch.Tensor, slot: int, k_pad: int, dst: PackedWeights) -> None:
+    """dst [4*slot rows][9 taps * k_pad]: the head's effective taps, output-parity phases stacked along the rows."""
+    cout, cin = weight.shape[:2]
+    assert dst.rows == 4 * slot and dst.k_total == 9 * k_pad and slot >= cout and k_pad >= cin
+    check(_lib.load().sn_pack_head_stacked(weight.data_ptr(), cout, cin, slot, k_pad, dst.hi.data_ptr(),
+                                           dst.lo.data_ptr(), dst.fmt,
                                            None if dst.scale is None else dst.scale.data_ptr(), _stream()))
 
 

@@ -175,3 +175,38 @@ def test_merged_parity_view_addresses():
         addr = cprime + w2 * s_w2 + h2 * s_h2 + n * s_n
         want = ((n * H + 2 * h2 + hp) * W + 2 * w2 + pw) * pitch + c
         assert addr == want
+
+
+def test_head_stacked_phases_equal_the_reference_head():
+    """The head forward as ONE 9-tap contraction with the 4 output-parity phases stacked along N (lowering.
+    head_stacked_spec + the stacked weight layout of csrc pack_head_stacked_kernel, restated here) reproduces
+    Upsample(2) + ZeroPad2d((1,0,1,0)) + Conv2d(k4, p1) of swapnet_modules.py:85-90."""
+    import torch
+    import torch.nn.functional as F
+
+    from oracle import emulate as EM
+    from swapnet_b200 import lowering as L
+
+    g = torch.Generator().manual_seed(3)
+    n, cin, cout, h, w = 2, 8, 5, 6, 7
+    x = torch.randn(n, cin, h, w, generator=g, dtype=torch.float64)
+    wt = torch.randn(cout, cin, 4, 4, generator=g, dtype=torch.float64)
+    ref = F.conv2d(F.pad(F.interpolate(x, scale_factor=2), (1, 0, 1, 0)), wt, None, 1, 1)
+    eff = EM.head_eff_weights(wt)                     # [cout, 25, cin], phase-major effective taps
+    slot, k_pad = L.HEAD_SLOT, cin
+    Wp = torch.zeros(4 * slot, 9, k_pad, dtype=torch.float64)
+    for p in range(4):
+        py, px = p >> 1, p & 1
+        for ey in range(L.head_neff(py)):
+            for ex in range(L.head_neff(px)):
+                te = L.HEAD_PHASE_OFF[p] + ey * L.head_neff(px) + ex
+                Wp[p * slot:p * slot + cout, ey * 3 + ex] = eff[:, te]
+    spec = L.head_stacked_spec(h, w)
+    A = x.permute(0, 2, 3, 1).contiguous()
+    acc = torch.zeros(n, h, w, 4 * slot, dtype=torch.float64)
+    plain = L.GemmSpec(False, h, w, spec.taps, (1, 1), (0, 0), a_hw=(h, w))
+    EM.emul_tap_gemm(A, plain, Wp.reshape(4 * slot, 9 * k_pad), k_pad, 4 * slot, acc)
+    out = torch.zeros(n, 2 * h, 2 * w, cout, dtype=torch.float64)
+    for p in range(4):
+        out[:, (p >> 1)::2, (p & 1)::2] = acc[..., p * slot:p * slot + cout]
+    assert torch.allclose(out.permute(0, 3, 1, 2), ref, atol=1e-12)
