@@ -277,9 +277,9 @@ static int fill_dy(DyView* d, const void* dy_hi, const void* dy_lo, int dy_pitch
 
 int sn_to_one_fwd(const void* x_hi, const void* x_lo, int x_pitch, int x_fmt, long long npix, int c, const float* weight,
                   int k, float* p, int p_pitch, void* stream) {
-  SN_REQUIRE(x_hi && weight && p && k == 4 && c % 256 == 0 && x_pitch % 8 == 0 && p_pitch >= 16 &&
+  SN_REQUIRE(x_hi && weight && p && k == 4 && c % 8 == 0 && x_pitch % 8 == 0 && p_pitch >= 16 &&
                  ((uintptr_t)x_hi & 15) == 0 && ((uintptr_t)x_lo & 15) == 0,
-             "to_one_fwd: k = 4, channels %% 256 == 0, 16-B aligned planes");
+             "to_one_fwd: k = 4, channels %% 8 == 0, 16-B aligned planes");
   const size_t smem = (size_t)c * 16 * sizeof(float);
   static bool attr = false;
   if (!attr) {

@@ -56,8 +56,8 @@ class Stage:
         eng.stages.append(self)
         dev = eng.device
         # a stride-1 conv with ONE output channel (the PatchGAN logits) runs as 1-tap GEMMs (layers.ToOneConvLayer)
-        to_one = (kind == "conv4s1" and conv.out_channels == 1 and epi_act == ACT_NONE and conv.in_channels % 256 == 0
-                  and x.c_off % 8 == 0 and TO_ONE)
+        to_one = (kind == "conv4s1" and conv.out_channels == 1 and epi_act == ACT_NONE and conv.in_channels % 8 == 0
+                  and conv.in_channels <= 1024 and x.c_off % 8 == 0 and TO_ONE)
         self.layer = (ToOneConvLayer if to_one else ConvLayer)(
             kind, conv.weight.data, None if conv.bias is None else conv.bias.data, x, nsplit=eng.nsplit, act=epi_act,
             name=name)

@@ -244,7 +244,7 @@ class ToOneConvLayer:
         self.in_h, self.in_w = x.h, x.w
         self.out_h, self.out_w = L.out_hw(kind, x.h, x.w)
         self.n, self.k_pad, self.t = x.n, x.c, 16
-        assert self.cin % 256 == 0 and x.c >= self.cin
+        assert self.cin % 8 == 0 and self.cin <= 1024 and x.c >= self.cin and x.c_off % 8 == 0
         self.p = torch.zeros(self.n, self.in_h, self.in_w, 16, device=dev)         # per-tap products
         self.fwd_plans: List[ops.Plan] = []     # no tensor-core plans: nothing for the GEMM roofline trace
         self.dgrad_plans: List[ops.Plan] = []

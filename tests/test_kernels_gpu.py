@@ -578,10 +578,10 @@ def test_upsample_planes(c, f):
     assert torch.all(got[..., c:] == 0)
 
 
-@pytest.mark.parametrize("n,cin,h,w", [(2, 256, 15, 15), (3, 64, 9, 12), (2, 128, 63, 63)])
+@pytest.mark.parametrize("n,cin,h,w", [(2, 256, 15, 15), (3, 64, 9, 12), (2, 128, 63, 63), (2, 512, 63, 63), (3, 512, 5, 5)])
 def test_to_one_conv_layer(n, cin, h, w):
-    """Conv2d(cin, 1, 4, 1, 1) (PatchGAN logits, discriminators.py:131) through layers.ToOneConvLayer:
-    forward, input gradient, weight and bias gradients vs torch (fp64)."""
+    """Conv2d(cin, 1, 4, 1, 1) (PatchGAN logits, discriminators.py:131) through layers.ToOneConvLayer (CUDA-core
+    streaming kernels of csrc/patch_logits.cu): forward, input gradient, weight and bias gradients vs torch (fp64)."""
     from swapnet_b200 import ops
     from swapnet_b200.layers import ToOneConvLayer
 
@@ -607,47 +607,10 @@ def test_to_one_conv_layer(n, cin, h, w):
     layer.pack()
     layer.forward()
     layer.backward()
+    layer.backward()           # weight gradients accumulate (+=); dx and the bias gradient are overwritten
     torch.cuda.synchronize()
     e_y = relmax(y.cpu(), nhwc(yr.detach()))
-    e_dx, e_w, e_b = relmax(dx.cpu(), nhwc(gx)), relmax(wg.cpu(), gw), relmax(bg.cpu(), gb)
-    record(f"to_one_conv[{n},{cin},{h}x{w}]", f"y {e_y:.3e} dx {e_dx:.3e} w {e_w:.3e} b {e_b:.3e}")
-    assert e_y < 1.5e-5 and e_dx < 1e-4 and e_w < 1e-4 and e_b < 1e-4
-
-
-@pytest.mark.parametrize("n,cin,h,w", [(2, 512, 63, 63), (1, 256, 9, 7), (3, 512, 5, 5)])
-def test_to_one_conv_cuda_core_kernels(n, cin, h, w):
-    """The PatchGAN logits conv (discriminators.py:131: Conv2d(cin, 1, 4, 1, 1) + bias) on the CUDA-core kernels of
-    csrc/patch_logits.cu — forward, input gradient, weight and bias gradient vs fp64 torch."""
-    from swapnet_b200 import ops
-    from swapnet_b200.layers import ToOneConvLayer
-
-    g = torch.Generator().manual_seed(n * 100 + cin + h)
-    x = torch.randn(n, cin, h, w, generator=g)
-    wt = torch.randn(1, cin, 4, 4, generator=g) * (1.0 / (cin * 16) ** 0.5)
-    bias = torch.randn(1, generator=g)
-    planes = ops.Planes(n, h, w, cin + 64, dev(), c=cin, c_off=64)
-    ops.pack_planes(x.to(dev()), planes)
-    layer = ToOneConvLayer("conv4s1", wt.to(dev()).contiguous(), bias.to(dev()), planes, name="logits")
-    oh, ow = h - 1, w - 1
-    y = torch.zeros(n, oh, ow, 1, device=dev())
-    layer.bind_forward(y)
-    layer.pack()
-    layer.forward()
-    xr, wr, br = x.double().requires_grad_(), wt.double().requires_grad_(), bias.double().requires_grad_()
-    yr = F.conv2d(xr, wr, br, 1, 1)
-    torch.cuda.synchronize()
-    e_f = relmax(y.cpu(), nhwc(yr.detach()))
-    gy = torch.randn(yr.shape, generator=g)
-    gx, gw, gb = torch.autograd.grad(yr, (xr, wr, br), gy.double())
-    dy = ops.Planes(n, oh, ow, 16, dev(), fmt=ops.FMT_BF16)
-    ops.pack_planes(gy.to(dev()), dy)
-    dx = torch.zeros(n, h, w, cin, device=dev())
-    wg = torch.zeros_like(layer.weight)
-    bg = torch.zeros(1, device=dev())
-    layer.bind_backward(dy, dx, wg, bg)
-    layer.backward()
-    layer.backward()           # weight gradients accumulate (+=); dx is overwritten
-    torch.cuda.synchronize()
     e_dx, e_w, e_b = relmax(dx.cpu(), nhwc(gx)), relmax(wg.cpu(), 2 * gw), relmax(bg.cpu(), gb)
-    record(f"to_one_conv[{n},{cin},{h}x{w}]", f"fwd {e_f:.3e} dx {e_dx:.3e} w {e_w:.3e} b {e_b:.3e}")
-    assert e_f < 1e-5 and e_dx < 1e-4 and e_w < 1e-4 and e_b < 1e-4, (e_f, e_dx, e_w, e_b)
+    record(f"to_one_conv[{n},{cin},{h}x{w}]", f"y {e_y:.3e} dx {e_dx:.3e} w {e_w:.3e} b {e_b:.3e}")
+    # forward: fp32 FMA chain over cin*16 products of 22-bit operands; backward: dy carried as bf16-split planes
+    assert e_y < 3e-5 and e_dx < 1e-4 and e_w < 1e-4 and e_b < 1e-4, (e_y, e_dx, e_w, e_b)

@@ -8,7 +8,7 @@ import torch
 import torch.nn.functional as F
 from oracle import nets as ON
 from swapnet_b200 import engine as E, ops
-from test_engine_gpu import make_nets, synth_warp_batch, relmax
+from test_engine_gpu import make_nets, synth_warp_batch, relmax, stage_gates
 
 dev = torch.device("cuda:0")
 S = int(sys.argv[1]) if len(sys.argv) > 1 else 64
@@ -25,7 +25,12 @@ eng = E.WarpEngine(G, B, S, dev); eng.alloc_grads(); eng.bind_backward(); eng.pa
 fakes = eng.forward(body.to(dev), inp.to(dev), training=False)
 rec = {}
 ON.record_into(rec)
+torch.cuda.synchronize()
+gatesG = stage_gates(eng)          # the oracle evaluates the activations at the gates the device used (see tests)
+ON.gate_with(lambda name, x: gatesG.get(name))
 ref = ON.warp_forward(sdG, body.double(), inp.double())
+print("gate flips G:", {k: v for k, v in ON.GATE_STATS.items() if v and k != "__total__"}, "of", ON.GATE_STATS.get("__total__"))
+ON.gate_with(None)
 ON.record_into(None)
 gout = torch.randn(ref.shape, generator=torch.Generator().manual_seed(5)).double() * 1e-3
 ref.backward(gout)
@@ -55,7 +60,12 @@ pred = Dd.forward()
 rec = {}
 ON.record_into(rec)
 xr = x.double().requires_grad_()
+torch.cuda.synchronize()
+gatesD = stage_gates(Dd)
+ON.gate_with(lambda name, x: gatesD.get(name))
 pr = ON.patchgan_forward(sdD, xr)
+print("gate flips D:", {k: v for k, v in ON.GATE_STATS.items() if v and k != "__total__"}, "of", ON.GATE_STATS.get("__total__"))
+ON.gate_with(None)
 ON.record_into(None)
 gp = torch.randn(pr.shape, generator=torch.Generator().manual_seed(6)).double() * 1e-3
 pr.backward(gp)
