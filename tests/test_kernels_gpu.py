@@ -302,6 +302,38 @@ def test_instance_norm_block_fwd_bwd(c, h, w):
     assert relmax(dy.dense().cpu()[..., :c], nhwc(gy_ref)) < 1e-4
 
 
+@pytest.mark.parametrize("n,c,h,w", [(1, 64, 256, 256), (1, 512, 63, 63), (2, 512, 63, 63), (2, 128, 128, 128), (16, 64, 256, 256),
+                                     (1, 1024, 32, 32)])
+def test_instance_norm_block_fwd_bwd_baseline_planes(n, c, h, w):
+    """The same block at the plane sizes of the 512x512 networks (up to 65536 pixels per plane), two gradient sources,
+    checker = torch fp64 autograd on the GPU."""
+    from swapnet_b200 import ops
+
+    d = dev()
+    g = torch.Generator(device="cpu").manual_seed(n + c + h)
+    y = (torch.randn(n, c, h, w, generator=g) * 2.0 + 0.5).to(d)
+    ga = torch.randn(n, c, h, w, generator=g).to(d)
+    yr = y.double().requires_grad_()
+    a_ref = F.leaky_relu(F.instance_norm(yr, eps=1e-5), 0.2)
+    (gy_ref,) = torch.autograd.grad(a_ref, yr, ga.double())
+    yd = nhwc(y)
+    stats = torch.zeros(n, c, 2, dtype=torch.float64, device=d)
+    ops.plane_stats(yd, c, stats)
+    out = ops.Planes(n, h, w, L.pad64(c), d)
+    ops.norm_act_fwd(yd, c, stats, ops.ACT_LRELU, 0.2, 0.0, 0, out=out)
+    gad = nhwc(ga)
+    half = (gad * 0.25).contiguous()
+    dy = ops.Planes(n, h, w, L.pad64(c), d, fmt=ops.FMT_BF16)
+    gst = torch.zeros(n, c, 2, dtype=torch.float64, device=d)
+    ops.norm_act_bwd([ops.GradSrc(half), ops.GradSrc((gad - half).contiguous())], yd, c, stats, ops.ACT_LRELU, dy, gst, 0.2,
+                     0.0, 0)
+    torch.cuda.synchronize()
+    e_f = relmax(out.dense()[..., :c], nhwc(a_ref.detach()))
+    e_b = relmax(dy.dense()[..., :c], nhwc(gy_ref))
+    record(f"instance_norm_block_baseline[{n},{c},{h}x{w}]", f"fwd {e_f:.3e} bwd {e_b:.3e}")
+    assert e_f < 1e-5 and e_b < 1e-4, (e_f, e_b)
+
+
 def test_residual_tail_and_reflect_pad():
     """ResidualBlock tail: out = x + IN(y2), written as reflect-padded planes + fp32 stream."""
     from swapnet_b200 import ops
@@ -590,7 +622,7 @@ def test_to_one_conv_layer(n, cin, h, w):
     wt = torch.randn(1, cin, 4, 4, generator=g) * (1.0 / (cin * 16) ** 0.5)
     bias = torch.randn(1, generator=g)
     planes = ops.Planes(n, h, w, L.pad64(cin), dev(), dual=True)
-    ops.pack_planes(x.to(dev()), planes)
+    ops.pack_planes(nhwc(x).to(dev()), planes, nhwc=True)
     layer = ToOneConvLayer("conv4s1", wt.to(dev()).contiguous(), bias.to(dev()), planes, nsplit=3, name="logits")
     y = torch.zeros(n, h - 1, w - 1, 1, device=dev())
     layer.bind_forward(y)

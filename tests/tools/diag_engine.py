@@ -52,6 +52,13 @@ for st in eng.stages:
         line += f"  wgrad {relmax(st.conv.weight.grad.cpu(), sdG[wkey[0]].grad):.2e}"
     print(line)
 
+print(f"head.dx[:, :64] (gradient w.r.t. dual_up3's activation) relmax "
+      f"{relmax(eng.head.dx[..., :64].cpu(), nhwc(rec_G['dual_up3.a'].grad)):.2e}")
+print(f"dual_up3.dx[:, :128] (w.r.t. dual_up2's activation) relmax "
+      f"{relmax(eng.d3.dx[..., :128].cpu(), nhwc(rec_G['dual_up2.a'].grad)):.2e}")
+print(f"dual_up3 stats: mean relmax {relmax(eng.d3.stats[..., 0].cpu(), rec_G['dual_up3.y'].detach().mean((2, 3))):.2e} "
+      f"rstd relmax {relmax(eng.d3.stats[..., 1].cpu(), (rec_G['dual_up3.y'].detach().var((2, 3), unbiased=False) + 1e-5).rsqrt()):.2e}")
+
 # ---------------- discriminator ----------------
 x = torch.cat((body, ref.detach().float()), 1)
 Dd = E.PatchGANEngine(D, B, S, dev, input_grad=True); Dd.alloc_grads(); Dd.bind_backward(); Dd.pack()
@@ -84,6 +91,11 @@ for st in Dd.stages:
     if st.dx is not None and not st.plain:
         pass
     print(line)
+
+print(f"last.dx (gradient w.r.t. model.8's activation) relmax {relmax(Dd.last.dx.cpu(), nhwc(rec['model.8.a'].grad)):.2e}")
+st8 = Dd.chain[-1]
+print(f"model.8 stats: mean relmax {relmax(st8.stats[..., 0].cpu(), rec['model.8.y'].detach().mean((2, 3))):.2e} "
+      f"rstd relmax {relmax(st8.stats[..., 1].cpu(), (rec['model.8.y'].detach().var((2, 3), unbiased=False) + 1e-5).rsqrt()):.2e}")
 
 # ---------------- focus: dual_up2 backward ----------------
 if "--focus" in sys.argv:
