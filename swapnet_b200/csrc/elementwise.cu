@@ -177,6 +177,69 @@ __global__ void __launch_bounds__(256) pack_concat_kernel(const PackConcatArgs a
   }
 }
 
+// pack_concat, narrow outputs (c_fill <= 32: the 3/19/22-channel network inputs): one thread = one pixel, no shared
+// memory.  NCHW sources are read one channel at a time (coalesced across the warp's 32 pixels), NHWC sources as the
+// pixel's own run of channels, compact maps as ONE byte / word; the pixel's 16 or 32 channels are written as 16-byte
+// stores (a warp writes 1-2 KB contiguous per plane).  The streams are write-bound: 2 planes (+ 2 twin planes).
+template <int CF>
+__global__ void __launch_bounds__(256) pack_concat_direct_kernel(const PackConcatArgs a) {
+  const long long npix = (long long)a.N * a.H * a.W;
+  const long long HW = (long long)a.H * a.W;
+  for (long long pix = blockIdx.x * (long long)blockDim.x + threadIdx.x; pix < npix;
+       pix += (long long)gridDim.x * blockDim.x) {
+    const long long n = pix / HW, p = pix - n * HW;
+    float v[CF];
+#pragma unroll
+    for (int c = 0; c < CF; ++c) v[c] = 0.f;
+    int cbase = 0;
+    for (int si = 0; si < a.nsrc; ++si) {
+      const PackSrc s = a.s[si];
+      if (s.layout == SN_LAYOUT_NCHW) {
+#pragma unroll
+        for (int c = 0; c < CF; ++c)
+          if (c >= cbase && c < cbase + s.c) v[c] = s.p[(n * s.c + (c - cbase)) * HW + p];
+      } else if (s.layout == SN_LAYOUT_NHWC) {
+#pragma unroll
+        for (int c = 0; c < CF; ++c)
+          if (c >= cbase && c < cbase + s.c) v[c] = s.p[pix * s.pitch + (c - cbase)];
+      } else if (s.layout == SN_LAYOUT_LABEL_U8) {
+        const int lab = reinterpret_cast<const uint8_t*>(s.p)[pix];
+#pragma unroll
+        for (int c = 0; c < CF; ++c)
+          if (c >= cbase && c < cbase + s.c) v[c] = (c - cbase > 0 && lab == c - cbase) ? 1.f : 0.f;
+      } else {
+        const uint32_t m = reinterpret_cast<const uint32_t*>(s.p)[pix];
+#pragma unroll
+        for (int c = 0; c < CF; ++c)
+          if (c >= cbase && c < cbase + s.c) v[c] = (float)((m >> (c - cbase)) & 1u);
+      }
+      cbase += s.c;
+    }
+    const long long off = pix * a.pitch + a.coff;
+#pragma unroll
+    for (int g8 = 0; g8 < CF / 8; ++g8) {
+      uint16_t h1[8], l1[8], h2[8], l2[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        split16(v[g8 * 8 + j], a.fmt, h1[j], l1[j]);
+        if (a.hi2) split16(v[g8 * 8 + j], a.fmt2, h2[j], l2[j]);
+      }
+      auto pk = [](const uint16_t* x) {
+        uint4 r;
+        r.x = x[0] | ((uint32_t)x[1] << 16); r.y = x[2] | ((uint32_t)x[3] << 16);
+        r.z = x[4] | ((uint32_t)x[5] << 16); r.w = x[6] | ((uint32_t)x[7] << 16);
+        return r;
+      };
+      *reinterpret_cast<uint4*>(a.hi + off + g8 * 8) = pk(h1);
+      if (a.lo) *reinterpret_cast<uint4*>(a.lo + off + g8 * 8) = pk(l1);
+      if (a.hi2) {
+        *reinterpret_cast<uint4*>(a.hi2 + off + g8 * 8) = pk(h2);
+        if (a.lo2) *reinterpret_cast<uint4*>(a.lo2 + off + g8 * 8) = pk(l2);
+      }
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------
 // pack_weights: dst[r][t][k] <- src[r*s_row + k*s_k + t]
 // ---------------------------------------------------------------------------------
@@ -403,12 +466,24 @@ __global__ void __launch_bounds__(256) pack_weights_multi_kernel(const sn_pack_i
   __syncthreads();
   uint16_t* hi16 = (uint16_t*)it.hi;
   uint16_t* lo16 = (uint16_t*)it.lo;
-  for (int i = threadIdx.x; i < total; i += blockDim.x) {     // scatter: k fastest (128-byte runs per (row, tap))
-    const int kk = i % kPkK, j = i / kPkK, t = j % taps, r = j / taps;
-    if (k0 + kk < it.k_pad) {
-      const long long off = ((long long)(r0 + r) * it.taps_pitch + it.slot[t]) * it.k_pad + k0 + kk;
-      store_split(hi16, lo16, off, tile[(r * kPkK + kk) * T1 + t] * sc, it.fmt);
-    }
+  // scatter: one thread = 8 consecutive k of one (row, tap): a 16-byte store per plane (k_pad % 8 == 0)
+  constexpr int G = kPkK / 8;
+  const int groups = nr * taps * G;
+  for (int i = threadIdx.x; i < groups; i += blockDim.x) {
+    const int kg = i % G, j = i / G, t = j % taps, r = j / taps;
+    const int kk = kg * 8;
+    if (k0 + kk >= it.k_pad) continue;
+    uint16_t hh[8], ll[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) split16(tile[(r * kPkK + kk + q) * T1 + t] * sc, it.fmt, hh[q], ll[q]);
+    const long long off = ((long long)(r0 + r) * it.taps_pitch + it.slot[t]) * it.k_pad + k0 + kk;
+    uint4 a, b;
+    a.x = hh[0] | ((uint32_t)hh[1] << 16); a.y = hh[2] | ((uint32_t)hh[3] << 16);
+    a.z = hh[4] | ((uint32_t)hh[5] << 16); a.w = hh[6] | ((uint32_t)hh[7] << 16);
+    b.x = ll[0] | ((uint32_t)ll[1] << 16); b.y = ll[2] | ((uint32_t)ll[3] << 16);
+    b.z = ll[4] | ((uint32_t)ll[5] << 16); b.w = ll[6] | ((uint32_t)ll[7] << 16);
+    *reinterpret_cast<uint4*>(hi16 + off) = a;
+    *reinterpret_cast<uint4*>(lo16 + off) = b;
   }
 }
 
@@ -1461,6 +1536,14 @@ int sn_pack_concat(const float* src0, int layout0, int pitch0, int c0, const flo
   a.N = n; a.H = h; a.W = w; a.c_fill = c_fill;
   a.hi = (uint16_t*)dst_hi; a.lo = (uint16_t*)dst_lo; a.hi2 = (uint16_t*)dst2_hi; a.lo2 = (uint16_t*)dst2_lo;
   a.pitch = dst_pitch; a.coff = dst_coff; a.fmt = fmt; a.fmt2 = fmt2;
+  if (c_fill == 16 || c_fill == 32) {   // narrow outputs: thread-per-pixel, no shared memory
+    const long long npix = (long long)n * h * w;
+    const int blocks = grid_for(npix);
+    if (c_fill == 16) pack_concat_direct_kernel<16><<<blocks, 256, 0, (cudaStream_t)stream>>>(a);
+    else pack_concat_direct_kernel<32><<<blocks, 256, 0, (cudaStream_t)stream>>>(a);
+    LAUNCH_CHECK();
+    return SN_OK;
+  }
   const int pw = 32 * (64 / (c_fill < 64 ? c_fill : 64));
   const size_t smem = (size_t)c_fill * (pw + 1) * sizeof(float);
   SN_REQUIRE(smem <= 48 * 1024, "pack_concat: c_fill too large (%d)", c_fill);
@@ -1529,7 +1612,7 @@ int sn_weight_scale_multi(const sn_scale_item* items_dev, int nitems, unsigned i
 
 int sn_pack_weights_multi(const sn_pack_item* items_dev, int nitems, int total_blocks, int max_taps, void* stream) {
   SN_REQUIRE(items_dev && nitems >= 1 && total_blocks >= 1 && max_taps >= 1 && max_taps <= 16,
-             "pack_weights_multi: bad arguments");
+             "pack_weights_multi: bad arguments (k_pad of every item must be a multiple of 8, planes 16-byte aligned)");
   const size_t smem = (size_t)kPkRows * kPkK * (max_taps + 1) * sizeof(float);
   static bool attr = false;
   if (!attr) {
