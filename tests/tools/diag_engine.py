@@ -59,6 +59,21 @@ print(f"dual_up3.dx[:, :128] (w.r.t. dual_up2's activation) relmax "
 print(f"dual_up3 stats: mean relmax {relmax(eng.d3.stats[..., 0].cpu(), rec_G['dual_up3.y'].detach().mean((2, 3))):.2e} "
       f"rstd relmax {relmax(eng.d3.stats[..., 1].cpu(), (rec_G['dual_up3.y'].detach().var((2, 3), unbiased=False) + 1e-5).rsqrt()):.2e}")
 
+# the IN + ReLU backward of dual_up3 recomputed by torch ON THE DEVICE BUFFERS the kernel read (y, upstream gradient)
+st = eng.d3
+yd = st.y.permute(0, 3, 1, 2).double().requires_grad_()
+up = eng.head.dx[..., :64].permute(0, 3, 1, 2).double()
+(gt,) = torch.autograd.grad(F.relu(F.instance_norm(yd, eps=1e-5)), yd, up)
+gt = gt.permute(0, 2, 3, 1)
+print(f"dual_up3: kernel dy vs torch-on-device-buffers {relmax(st.dy.dense()[..., :64], gt):.2e} | torch-on-device-buffers vs oracle "
+      f"{relmax(gt.cpu(), nhwc(rec_G['dual_up3.y'].grad)):.2e}")
+dy2 = ops.Planes(st.n, st.oh, st.ow, 64, dev, fmt=ops.FMT_BF16)
+gs2 = torch.zeros(st.n, st.cout, 2, dtype=torch.float64, device=dev)
+ops.norm_act_bwd([ops.GradSrc(eng.head.dx, 0)], st.y, st.cout, st.stats, st.act, dy2, gs2, st.slope, 0.0, 0)
+torch.cuda.synchronize()
+print(f"dual_up3: a second kernel call on the same buffers vs torch {relmax(dy2.dense()[..., :64], gt):.2e}; vs the engine's dy "
+      f"{relmax(dy2.dense()[..., :64], st.dy.dense()[..., :64]):.2e}")
+
 # ---------------- discriminator ----------------
 x = torch.cat((body, ref.detach().float()), 1)
 Dd = E.PatchGANEngine(D, B, S, dev, input_grad=True); Dd.alloc_grads(); Dd.bind_backward(); Dd.pack()
