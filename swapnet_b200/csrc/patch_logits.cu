@@ -91,7 +91,7 @@ __device__ __forceinline__ void load8(const uint16_t* __restrict__ hi, const uin
 
 // P[px, t] = sum_c x[px, c] W[c*T + t]; one warp = kPx pixels, lane = 8 channels of every 256-channel chunk.
 // smem: W transposed to [t][C] so that a lane's 8 channels are two conflict-free LDS.128.
-constexpr int kPx = 4;
+constexpr int kPx = 2;
 template <int T>
 __global__ void __launch_bounds__(256) to_one_fwd_kernel(const uint16_t* __restrict__ xhi, const uint16_t* __restrict__ xlo,
                                                          int xpitch, int xfmt, long long npix, int C,
@@ -149,14 +149,19 @@ __device__ __forceinline__ float dp_at(const DyView& d, long long n, int h, int 
 }
 
 // dW[c*T + t] += sum over this block's pixels of x[px, c] dP[px, t].  block = (C/4 threads.x, rows threads.y):
-// thread = 4 channels, strided over the block's pixel range; T accumulators per channel.
+// thread = 4 channels, strided over the block's pixel range; T accumulators per channel.  The block first gathers its
+// pixels' dP values (T per pixel) into shared memory, so the main loop is 2 vector loads + T broadcast LDS + 4T FMAs.
+constexpr int kWgPix = 256;     // pixels staged per round
 template <int K>
 __global__ void __launch_bounds__(256) to_one_wgrad_kernel(const uint16_t* __restrict__ xhi, const uint16_t* __restrict__ xlo,
                                                            int xpitch, int xfmt, long long npix, int C, const DyView d,
                                                            float* __restrict__ dW) {
   constexpr int T = K * K;
-  extern __shared__ float red[];   // [rows][C*T] partial sums of the pixel rows > 0
+  extern __shared__ float smem[];
+  float* dps = smem;                       // [kWgPix][T]
+  float* red = smem + kWgPix * T;          // [rows - 1][C*T] partial sums of the pixel rows > 0
   const int c = threadIdx.x * 4;
+  const int tid = threadIdx.y * blockDim.x + threadIdx.x, nthr = blockDim.x * blockDim.y;
   const long long per = (npix + gridDim.x - 1) / gridDim.x;
   const long long p0 = blockIdx.x * per, p1 = p0 + per < npix ? p0 + per : npix;
   float acc[4][T];
@@ -165,27 +170,41 @@ __global__ void __launch_bounds__(256) to_one_wgrad_kernel(const uint16_t* __res
 #pragma unroll
     for (int t = 0; t < T; ++t) acc[j][t] = 0.f;
   const long long HW = (long long)d.H * d.W;
-  for (long long p = p0 + threadIdx.y; p < p1; p += blockDim.y) {
-    const long long n = p / HW;
-    const int r = (int)(p - n * HW), h = r / d.W, w = r - h * d.W;
-    const uint2 a = *reinterpret_cast<const uint2*>(xhi + p * xpitch + c);
-    const uint2 b = xlo ? *reinterpret_cast<const uint2*>(xlo + p * xpitch + c) : make_uint2(0, 0);
-    float xv[4];
-    xv[0] = decode16((uint16_t)(a.x & 0xFFFF), xfmt) + (xlo ? decode16((uint16_t)(b.x & 0xFFFF), xfmt) : 0.f);
-    xv[1] = decode16((uint16_t)(a.x >> 16), xfmt) + (xlo ? decode16((uint16_t)(b.x >> 16), xfmt) : 0.f);
-    xv[2] = decode16((uint16_t)(a.y & 0xFFFF), xfmt) + (xlo ? decode16((uint16_t)(b.y & 0xFFFF), xfmt) : 0.f);
-    xv[3] = decode16((uint16_t)(a.y >> 16), xfmt) + (xlo ? decode16((uint16_t)(b.y >> 16), xfmt) : 0.f);
+  for (long long q0 = p0; q0 < p1; q0 += kWgPix) {
+    const int cnt = (int)(p1 - q0 < kWgPix ? p1 - q0 : kWgPix);
+    __syncthreads();
+    for (int i = tid; i < cnt * T; i += nthr) {
+      const long long p = q0 + i / T;
+      const int t = i % T;
+      const long long n = p / HW;
+      const int r = (int)(p - n * HW), h = r / d.W, w = r - h * d.W;
+      dps[i] = dp_at(d, n, h, w, t / K, t % K);
+    }
+    __syncthreads();
+    for (int pl = threadIdx.y; pl < cnt; pl += blockDim.y) {
+      const long long p = q0 + pl;
+      const uint2 a = *reinterpret_cast<const uint2*>(xhi + p * xpitch + c);
+      const uint2 b = xlo ? *reinterpret_cast<const uint2*>(xlo + p * xpitch + c) : make_uint2(0, 0);
+      float xv[4];
+      xv[0] = decode16((uint16_t)(a.x & 0xFFFF), xfmt) + (xlo ? decode16((uint16_t)(b.x & 0xFFFF), xfmt) : 0.f);
+      xv[1] = decode16((uint16_t)(a.x >> 16), xfmt) + (xlo ? decode16((uint16_t)(b.x >> 16), xfmt) : 0.f);
+      xv[2] = decode16((uint16_t)(a.y & 0xFFFF), xfmt) + (xlo ? decode16((uint16_t)(b.y & 0xFFFF), xfmt) : 0.f);
+      xv[3] = decode16((uint16_t)(a.y >> 16), xfmt) + (xlo ? decode16((uint16_t)(b.y >> 16), xfmt) : 0.f);
+      const float4* g4 = reinterpret_cast<const float4*>(dps + pl * T);
 #pragma unroll
-    for (int kh = 0; kh < K; ++kh)
+      for (int tq = 0; tq < T / 4; ++tq) {
+        const float4 g = g4[tq];             // the same address for the whole pixel row: a broadcast
+        const float gg[4] = {g.x, g.y, g.z, g.w};
 #pragma unroll
-      for (int kw = 0; kw < K; ++kw) {
-        const float g = dp_at(d, n, h, w, kh, kw);     // the same address for the whole pixel row: a broadcast load
+        for (int u = 0; u < 4; ++u)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[j][kh * K + kw] = fmaf(xv[j], g, acc[j][kh * K + kw]);
+          for (int j = 0; j < 4; ++j) acc[j][tq * 4 + u] = fmaf(xv[j], gg[u], acc[j][tq * 4 + u]);
       }
+    }
   }
   // rows 1.. hand their partial sums to row 0 through smem, row 0 adds its own and issues one atomic per (c, t)
   const int CT = C * T;
+  __syncthreads();
   if (threadIdx.y > 0) {
 #pragma unroll
     for (int j = 0; j < 4; ++j)
@@ -309,7 +328,7 @@ int sn_to_one_wgrad(const void* x_hi, const void* x_lo, int x_pitch, int x_fmt, 
   int by = 256 / bx;
   if (by < 1) by = 1;
   const long long npix = (long long)n * h * w;
-  const size_t smem = (size_t)(by - 1) * c * 16 * sizeof(float);
+  const size_t smem = ((size_t)(by - 1) * c * 16 + (size_t)kWgPix * 16) * sizeof(float);
   SN_REQUIRE(smem <= 200 * 1024, "to_one_wgrad: reduction scratch too large");
   if (smem > 48 * 1024) {   // attribute set by the first forward call; set here too for backward-only use
     static bool attr = false;
@@ -318,8 +337,8 @@ int sn_to_one_wgrad(const void* x_hi, const void* x_lo, int x_pitch, int x_fmt, 
       attr = true;
     }
   }
-  long long blocks = npix / (64 * by);
-  if (blocks > 148 * 2) blocks = 148 * 2;
+  long long blocks = npix / kWgPix;
+  if (blocks > 148 * 4) blocks = 148 * 4;
   if (blocks < 1) blocks = 1;
   to_one_wgrad_kernel<4><<<(int)blocks, dim3(bx, by), smem, (cudaStream_t)stream>>>(
       (const uint16_t*)x_hi, (const uint16_t*)x_lo, x_pitch, x_fmt, npix, c, d, dw);
