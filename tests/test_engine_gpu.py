@@ -42,7 +42,7 @@ def stage_gates(eng, n0=0, n1=None):
             m = y > mean
         else:
             m = y > 0
-        out[st.name] = m.permute(0, 3, 1, 2).cpu()
+        out[st.name] = m.permute(0, 3, 1, 2).contiguous().cpu()    # NCHW-contiguous (see oracle/nets.py:_act)
     return out
 
 

@@ -251,3 +251,26 @@ def test_texture_full_step_with_default_losses_matches_golden():
         assert abs(got[k] - v) <= 2e-5 * abs(v), (k, got[k], v)
     close_checksums(checksums({k: v.detach() for k, v in sdG.items()}), g["step_checksums_G"], 5e-6, numel={k: v.numel() for k, v in sdG.items()}, lr=1e-4)
     close_checksums(checksums({k: v.detach() for k, v in sdD.items()}), g["step_checksums_D"], 5e-6, numel={k: v.numel() for k, v in sdD.items()}, lr=4e-4)
+
+
+@pytest.mark.parametrize("B", [1, 2])
+def test_imposed_gates_do_not_change_the_oracle_gradient(B):
+    """Imposing the gates the oracle would choose itself — delivered the way the GPU tests deliver the device's gates,
+    as a permuted NHWC view — must leave every gradient unchanged.  (Regression: with a channels-last-strided mask
+    torch.where returns a channels-last tensor and torch's CPU instance_norm backward returns a wrong gradient for batch
+    size 1; oracle/nets.py:_act makes the mask contiguous.  This cost the 512x512 batch-1 step tests a day.)"""
+    torch.manual_seed(0)
+    G = M.WarpModule(); M.init_weights(G, "kaiming")
+    body, inp, _ = synth_warp_batch(B, 64)
+    grads = {}
+    for mode in ("plain", "gated"):
+        sd = {k: v.detach().double().requires_grad_() for k, v in G.state_dict().items()}
+        if mode == "gated":
+            ON.gate_with(lambda name, x: (x.detach() > 0).permute(0, 2, 3, 1).contiguous().permute(0, 3, 1, 2))
+        out = ON.warp_forward(sd, body.double(), inp.double())
+        ON.gate_with(None)
+        g = torch.randn(out.shape, generator=torch.Generator().manual_seed(5)).double()
+        grads[mode] = torch.autograd.grad(out, list(sd.values()), g, allow_unused=True)
+    for (k, _), a, b in zip(G.state_dict().items(), grads["plain"], grads["gated"]):
+        if a is not None:
+            assert torch.equal(a, b), k
