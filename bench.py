@@ -74,16 +74,20 @@ def synth_batch(B, S, seed, labels=False):
                 body_paths=["synthetic"] * B)
 
 
-def synth_texture_batch(B, S, seed):
+def synth_texture_batch(B, S, seed, labels=False):
     """normalised-RGB-like textures, one-hot cloth, rois = notebook fixture (256 px
-    space, incl. degenerate rows) scaled to S and rotated per sample."""
+    space, incl. degenerate rows) scaled to S and rotated per sample.  labels=True: the cloth tensor as a uint8 label
+    map [B,S,S] (expanded on the device) instead of fp32 one-hot [B,19,S,S]."""
     g = torch.Generator().manual_seed(seed)
     tex = torch.rand(B, 3, S, S, generator=g) * 4.5 - 2.0
     tgt = torch.rand(B, 3, S, S, generator=g) * 4.5 - 2.0
     lab = torch.randint(0, 19, (B, S // 16, S // 16), generator=g).repeat_interleave(16, 1).repeat_interleave(16, 2)
-    cloth = torch.zeros(B, 19, S, S)
-    for c in range(1, 19):
-        cloth[:, c] = (lab == c).float()
+    if labels:
+        cloth = lab.to(torch.uint8).contiguous()
+    else:
+        cloth = torch.zeros(B, 19, S, S)
+        for c in range(1, 19):
+            cloth[:, c] = (lab == c).float()
     base = torch.tensor([[159, 0, 193, 14], [144, 15, 206, 89], [255, 0, 255, 0], [196, 20, 215, 94],
                          [144, 151, 180, 229], [179, 151, 216, 226], [156, 1, 188, 24], [141, 83, 215, 155],
                          [128, 20, 160, 82], [206, 92, 226, 158], [145, 220, 168, 255], [174, 217, 203, 255]],
@@ -367,7 +371,7 @@ def main():
                 host = synth_batch(B, S, 1234 + rank, labels=args.labels)
                 tkeys = ("bodys", "input_cloths", "target_cloths")
             else:
-                host = synth_texture_batch(B, S, 1234 + rank)
+                host = synth_texture_batch(B, S, 1234 + rank, labels=args.labels)
                 tkeys = ("input_textures", "rois", "cloths", "target_textures")
             for k in tkeys:
                 host[k] = host[k].pin_memory()
@@ -500,7 +504,7 @@ def main():
         "data": "synthetic", "config": config,
         "e2e": {"value": total_imgs / (ms_e2e / args.steps * 1e-3), "unit": "images/s",
                 "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": n_losses * 8,
-                "inputs": "uint8 label maps for the cloth tensors, expanded to one-hot planes on the device"
+                "inputs": "uint8 label maps for the cloth tensors (ops.SegMap), expanded to one-hot planes on the device"
                 if args.labels else "fp32 tensors as the reference's DataLoader yields them"},
         "gpu_launches": launches, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
     }

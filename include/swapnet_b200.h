@@ -248,6 +248,8 @@ typedef struct sn_norm_act_bwd_desc {
   double* gstats;                        /* scratch [n][c][2] (needed when stats != NULL) */
   void* dy_hi; void* dy_lo; int dy_pitch, dy_coff; /* split planes of dL/dy */
   int dy_fmt;
+  float* bias_grad;                      /* optional [c], c in {256, 512, 1024}: += sum over pixels of dL/dy (the bias
+                                            gradient of the conv that produced y), fused into the apply pass */
 } sn_norm_act_bwd_desc;
 int sn_norm_act_bwd(const sn_norm_act_bwd_desc* d, void* stream);
 

@@ -104,7 +104,7 @@ class SnNormActBwdDesc(C.Structure):
         ("drop_offset", C.c_ulonglong), ("drop_step_seed_dev", C.c_void_p), ("drop_stage_id", C.c_uint),
         ("gstats", C.c_void_p),
         ("dy_hi", C.c_void_p), ("dy_lo", C.c_void_p), ("dy_pitch", C.c_int), ("dy_coff", C.c_int),
-        ("dy_fmt", C.c_int),
+        ("dy_fmt", C.c_int), ("bias_grad", C.c_void_p),
     ]
 
 

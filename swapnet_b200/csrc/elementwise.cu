@@ -771,6 +771,7 @@ struct NormActBwdArgs {
   unsigned long long drop_off; const float* seed_dev; unsigned int stage_id;
   double* gstats;
   uint16_t* hi; uint16_t* lo; int dy_pitch, dy_coff, fmt;
+  float* bias_grad;   // optional [C]: += per-channel sums of the dy written (the conv's bias gradient)
 };
 
 // gradient w.r.t. xhat (before the InstanceNorm backward), and xhat itself
@@ -1566,6 +1567,7 @@ __global__ void __launch_bounds__(256, 2) norm_act_bwd_apply_v4u_kernel(const No
   const int p0 = blockIdx.x * per, p1 = min(HW, p0 + per);
   const int i1 = (p1 - p0) * Q;   // slab-relative 32-bit index
   const int bd = blockDim.x;
+  float bsum[4] = {0.f, 0.f, 0.f, 0.f};   // bias gradient: this thread's quad is fixed (blockDim % Q == 0)
   for (int ib = threadIdx.x; ib < i1; ib += U * bd) {
     QuadLoad ql[U];
     int pp[U], cc[U];
@@ -1588,6 +1590,24 @@ __global__ void __launch_bounds__(256, 2) norm_act_bwd_apply_v4u_kernel(const No
         for (int j = 0; j < 4; ++j) g[j] = s_rstd[c + j] * (g[j] - s_m1[c + j] - xh[j] * s_m2[c + j]);
       }
       store_split4(a.hi, a.lo, ((long long)n * HW + pp[u]) * a.dy_pitch + a.dy_coff + c, g, a.fmt);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) bsum[j] += g[j];
+    }
+  }
+  if (a.bias_grad) {   // host guarantees blockDim.x % Q == 0: thread t always handled quad t % Q
+    __syncthreads();
+    float4* red = reinterpret_cast<float4*>(sm);     // the statistics are no longer needed: 256 float4 fit in 4*C floats
+    red[threadIdx.x] = make_float4(bsum[0], bsum[1], bsum[2], bsum[3]);
+    __syncthreads();
+    if ((int)threadIdx.x < Q) {
+      float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int r = threadIdx.x; r < (int)blockDim.x; r += Q) {
+        const float4 v = red[r];
+        t.x += v.x; t.y += v.y; t.z += v.z; t.w += v.w;
+      }
+      const int c = threadIdx.x << 2;
+      atomicAdd(a.bias_grad + c, t.x); atomicAdd(a.bias_grad + c + 1, t.y);
+      atomicAdd(a.bias_grad + c + 2, t.z); atomicAdd(a.bias_grad + c + 3, t.w);
     }
   }
 }
@@ -1959,6 +1979,7 @@ int sn_norm_act_bwd(const sn_norm_act_bwd_desc* d, void* stream) {
   a.gstats = d->gstats;
   a.hi = (uint16_t*)d->dy_hi; a.lo = (uint16_t*)d->dy_lo;
   a.dy_pitch = d->dy_pitch; a.dy_coff = d->dy_coff; a.fmt = d->dy_fmt;
+  a.bias_grad = d->bias_grad;
   const int hw = d->h * d->w;
   const bool vec = (d->c % 4 == 0) && al16(d->y) && (d->y_pitch % 4 == 0) && srcs_vec_ok(a.g) &&
                    (d->dy_pitch % 4 == 0) && (d->dy_coff % 4 == 0) && ((uintptr_t)d->dy_hi & 7) == 0 &&
@@ -1988,9 +2009,13 @@ int sn_norm_act_bwd(const sn_norm_act_bwd_desc* d, void* stream) {
   }
   if (vec) {
     dim3 grid(vslabs(hw, d->n), d->n);
+    // the fused bias gradient needs a fixed quad per thread (256 %% (c/4) == 0) and 256 float4 of scratch (4*c >= 1024)
+    SN_REQUIRE(!d->bias_grad || (!ew_use_v4() && 256 % (d->c / 4) == 0 && d->c >= 256),
+               "norm_act_bwd: fused bias gradient needs c in {256, 512, 1024} on the unrolled kernel (c=%d)", d->c);
     if (ew_use_v4()) norm_act_bwd_apply_v4_kernel<<<grid, 256, 4 * d->c * sizeof(float), st>>>(a);
     else norm_act_bwd_apply_v4u_kernel<2><<<grid, 256, 4 * d->c * sizeof(float), st>>>(a);
   } else {
+    SN_REQUIRE(!d->bias_grad, "norm_act_bwd: fused bias gradient is only available on the vectorised path");
     dim3 blk = cblock(d->c);
     dim3 grid(slabs_for(hw, d->n, blk.y), d->n);
     norm_act_bwd_apply_kernel<<<grid, blk, 0, st>>>(a);

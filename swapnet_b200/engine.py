@@ -131,10 +131,18 @@ class Stage:
             ops.tanh_bwd(srcs, self.y, self.cout, self.dy)
         else:
             p = 0.0 if self.plain else (self.drop_p if self.eng.training else 0.0)
+            # the conv's bias gradient (sum of dy over pixels) rides on the pass that writes dy where it can
+            bg = None
+            if wgrad and self.conv.bias is not None and self.conv.bias.grad is not None and ops.fused_bias_grad_ok(self.cout) \
+                    and self.cout % 4 == 0 and getattr(self.layer, "bgrad_out", None) is not None:
+                bg = self.conv.bias.grad
             ops.norm_act_bwd(srcs, self.y, self.cout, None if self.plain else self.stats,
                              ACT_NONE if self.plain else self.act, self.dy, self.gstats, self.slope, p,
                              _mix_seed(self.eng.seed, self.id), drop_offset=self.drop_offset(),
-                             seed_dev=self.eng.seed_dev, stage_id=self.id)
+                             seed_dev=self.eng.seed_dev, stage_id=self.id, bias_grad=bg)
+            if bg is not None:
+                self.layer.backward(dgrad=self.need_dx, wgrad=wgrad, bias=False)
+                return
         self.layer.backward(dgrad=self.need_dx, wgrad=wgrad)
 
 

@@ -206,7 +206,8 @@ class ConvLayer:
         if bgrad is not None:
             self._bscratch = torch.zeros(self.cout, dtype=torch.float64, device=dev)
 
-    def backward(self, dgrad: bool = True, wgrad: bool = True) -> None:
+    def backward(self, dgrad: bool = True, wgrad: bool = True, bias: bool = True) -> None:
+        """bias=False: the caller already accumulated the bias gradient (fused into norm_act_bwd)."""
         if dgrad:
             for p in self.dgrad_plans:
                 p.run()
@@ -216,7 +217,7 @@ class ConvLayer:
             self.wgrad_plan.run()
             if self._geff is not None:
                 ops.fold_head_wgrad(self._geff, self.cout, self.cin, self.wgrad_out)
-        if wgrad and self.bgrad_out is not None:
+        if wgrad and bias and self.bgrad_out is not None:
             ops.bias_grad(self.dy, self.cout, self._bscratch, self.bgrad_out)
 
 
@@ -278,7 +279,7 @@ class ToOneConvLayer:
         if bgrad is not None:
             self._bscratch = torch.zeros(1, dtype=torch.float64, device=self.weight.device)
 
-    def backward(self, dgrad: bool = True, wgrad: bool = True) -> None:
+    def backward(self, dgrad: bool = True, wgrad: bool = True, bias: bool = True) -> None:
         if dgrad and self.dx is not None:
             ops.to_one_dgrad(self.dy, self.weight, self.PAD, self.dx)
         if wgrad and self.wgrad_out is not None:

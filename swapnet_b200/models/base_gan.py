@@ -364,7 +364,9 @@ class BaseGAN(BaseModel, ABC):
         graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(graph):
             self._step_body()
-        return {"graph": graph, "static": static, "launches": ops.launch_count() - n0}
+        n = ops.launch_count() - n0
+        ops.count_replayed(-n)          # the capture pass recorded the launches, it did not execute them
+        return {"graph": graph, "static": static, "launches": n}
 
     def optimize_parameters(self):
         self._run_step()

@@ -575,7 +575,9 @@ def _fill_srcs(arr, srcs: Sequence[GradSrc]) -> None:
 def norm_act_bwd(srcs: Sequence[GradSrc], y: torch.Tensor, c: int, stats: Optional[torch.Tensor], act: int,
                  dy: Planes, gstats: Optional[torch.Tensor] = None, slope: float = 0.2, drop_p: float = 0.0,
                  drop_seed: int = 0, drop_offset: int = 0, seed_dev: Optional[torch.Tensor] = None,
-                 stage_id: int = 0) -> None:
+                 stage_id: int = 0, bias_grad: Optional[torch.Tensor] = None) -> None:
+    """bias_grad (fp32 [c], c in {256, 512, 1024}): += per-channel sums of the dy written — the bias gradient of the
+    conv that produced y — inside the apply pass (see fused_bias_grad_ok)."""
     n, h, w, _ = y.shape
     pitch = _pitch(y)
     d = SnNormActBwdDesc()
@@ -591,7 +593,15 @@ def norm_act_bwd(srcs: Sequence[GradSrc], y: torch.Tensor, c: int, stats: Option
     assert (dy.n, dy.h, dy.w) == (n, h, w) and dy.c >= c
     d.dy_hi, d.dy_lo, d.dy_pitch, d.dy_coff = dy.hi.data_ptr(), dy.lo.data_ptr(), dy.pitch, dy.c_off
     d.dy_fmt = dy.fmt
+    d.bias_grad = _ptr(bias_grad)
     check(_lib.load().sn_norm_act_bwd(C.byref(d), _stream()))
+
+
+def fused_bias_grad_ok(c: int) -> bool:
+    """Channel counts for which norm_act_bwd can accumulate the bias gradient itself."""
+    import os
+
+    return c in (256, 512, 1024) and os.environ.get("SN_EW_V4", "0") != "1"
 
 
 def bias_grad(dy: Planes, c: int, scratch: torch.Tensor, db: torch.Tensor) -> None:

@@ -723,7 +723,7 @@ def test_graph_replayed_steps_match_eager_steps():
                        model.optimizer_G._step)
     (hg, lg, wg, sg), (he, le, we, se) = runs[1], runs[0]
     assert sg == se == 5
-    assert lg[4] == le[4] + 0 or abs(lg[4] - le[4]) <= 2, (lg, le)     # replayed launches are accounted for
+    assert lg == le, (lg, le)     # replayed launches are accounted for; the capture pass itself is not counted
     for a, b in zip(hg, he):
         for k in a:
             assert abs(a[k] - b[k]) <= 2e-3 * abs(b[k]), (k, a[k], b[k])
