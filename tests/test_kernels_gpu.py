@@ -325,13 +325,35 @@ def test_instance_norm_block_fwd_bwd_baseline_planes(n, c, h, w):
     half = (gad * 0.25).contiguous()
     dy = ops.Planes(n, h, w, L.pad64(c), d, fmt=ops.FMT_BF16)
     gst = torch.zeros(n, c, 2, dtype=torch.float64, device=d)
+    bg = torch.full((c,), 3.0, device=d) if ops.fused_bias_grad_ok(c) else None    # += semantics: starts at 3
     ops.norm_act_bwd([ops.GradSrc(half), ops.GradSrc((gad - half).contiguous())], yd, c, stats, ops.ACT_LRELU, dy, gst, 0.2,
-                     0.0, 0)
+                     0.0, 0, bias_grad=bg)
     torch.cuda.synchronize()
     e_f = relmax(out.dense()[..., :c], nhwc(a_ref.detach()))
     e_b = relmax(dy.dense()[..., :c], nhwc(gy_ref))
     record(f"instance_norm_block_baseline[{n},{c},{h}x{w}]", f"fwd {e_f:.3e} bwd {e_b:.3e}")
     assert e_f < 1e-5 and e_b < 1e-4, (e_f, e_b)
+    if bg is not None:   # the fused bias gradient: per-channel sum of the dy written (~0 behind an InstanceNorm)
+        want = dy.dense()[..., :c].double().sum((0, 1, 2))
+        assert (bg.double() - 3.0 - want).abs().max().item() < 1e-3 * gy_ref.abs().max().item() * (n * h * w) ** 0.5
+
+
+@pytest.mark.parametrize("c", [256, 1024])
+def test_fused_bias_grad_without_instance_norm(c):
+    """norm_act_bwd(bias_grad=...) on a block WITHOUT InstanceNorm (a real, non-zero bias gradient): += sum over pixels."""
+    from swapnet_b200 import ops
+
+    d = dev()
+    n, h, w = 2, 8, 8
+    g = torch.Generator().manual_seed(c)
+    y = torch.randn(n, h, w, c, generator=g).to(d)
+    ga = torch.randn(n, h, w, c, generator=g).to(d)
+    dy = ops.Planes(n, h, w, c, d, fmt=ops.FMT_BF16)
+    bg = torch.zeros(c, device=d)
+    ops.norm_act_bwd([ops.GradSrc(ga)], y, c, None, ops.ACT_RELU, dy, None, 0.2, 0.0, 0, bias_grad=bg)
+    torch.cuda.synchronize()
+    ref = (ga.double() * (y > 0)).sum((0, 1, 2))
+    assert relmax(bg, ref) < 1e-5
 
 
 def test_residual_tail_and_reflect_pad():
