@@ -1427,6 +1427,7 @@ __global__ void __launch_bounds__(256, 4) norm_act_bwd_apply_v4_kernel(const Nor
   const int per = (HW + gridDim.x - 1) / gridDim.x;
   const int p0 = blockIdx.x * per, p1 = min(HW, p0 + per);
   const int i1 = (p1 - p0) * Q;   // slab-relative 32-bit index
+  float bsum[4] = {0.f, 0.f, 0.f, 0.f};   // fused bias gradient: the thread's quad is fixed when blockDim % Q == 0
   for (int i = threadIdx.x; i < i1; i += blockDim.x) {
     const int pl = i / Q;
     const int p = p0 + pl;
@@ -1438,15 +1439,32 @@ __global__ void __launch_bounds__(256, 4) norm_act_bwd_apply_v4_kernel(const Nor
       for (int j = 0; j < 4; ++j) g[j] = s_rstd[c + j] * (g[j] - s_m1[c + j] - xh[j] * s_m2[c + j]);
     }
     store_split4(a.hi, a.lo, ((long long)n * HW + p) * a.dy_pitch + a.dy_coff + c, g, a.fmt);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) bsum[j] += g[j];
+  }
+  if (a.bias_grad) {   // host guarantees blockDim.x % Q == 0 and 4*C >= 1024 floats of scratch
+    __syncthreads();
+    float4* red = reinterpret_cast<float4*>(sm);
+    red[threadIdx.x] = make_float4(bsum[0], bsum[1], bsum[2], bsum[3]);
+    __syncthreads();
+    if ((int)threadIdx.x < Q) {
+      float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int r = threadIdx.x; r < (int)blockDim.x; r += Q) {
+        const float4 v = red[r];
+        t.x += v.x; t.y += v.y; t.z += v.z; t.w += v.w;
+      }
+      const int c = threadIdx.x << 2;
+      atomicAdd(a.bias_grad + c, t.x); atomicAdd(a.bias_grad + c + 1, t.y);
+      atomicAdd(a.bias_grad + c + 2, t.z); atomicAdd(a.bias_grad + c + 3, t.w);
+    }
   }
 }
 
 // ---------------------------------------------------------------------------------
-// U-way unrolled variants of the three kernels above: a thread issues the loads of U channel quads (y, residual /
-// every gradient source) BEFORE it computes and stores any of them.  The v4 kernels keep one quad in flight per
-// thread (the stores of an iteration may alias the next iteration's loads as far as the compiler knows), which at
-// ~40 % occupancy leaves ~16-32 KB in flight per SM: ncu shows 45-58 % of the HBM copy rate.  Same arithmetic, same
-// results bit for bit.  (SN_EW_V4=1 selects the v4 kernels for A/B runs.)
+// U-way unrolled variants of the three kernels above (EXPERIMENT, off by default: see ew_use_v4): a thread issues the
+// loads of U channel quads (y, residual / every gradient source) BEFORE it computes and stores any of them.  The v4
+// kernels keep one quad in flight per thread, which at ~40 % occupancy leaves ~16-32 KB in flight per SM (ncu: 45-58 %
+// of the HBM copy rate).  Same arithmetic, same results bit for bit.
 // ---------------------------------------------------------------------------------
 struct QuadLoad {
   float4 y;
@@ -1692,11 +1710,14 @@ __global__ void __launch_bounds__(256, 2) norm_act_fwd_v4u_kernel(const NormActF
   }
 }
 
+// measured (profiles/r02_*): the unrolled variants LOSE — 2 blocks / SM (112-126 registers) hide less latency than the
+// v4 kernels' 4 blocks with one quad in flight: bwd_apply 6.1 vs 4.4 ms per step, reduce 3.2 vs 2.2, forward 3.5 vs
+// 3.3.  They stay selectable (SN_EW_V4U=1) as the A/B evidence; the default is v4.
 inline bool ew_use_v4() {
   static int v = -1;
   if (v < 0) {
-    const char* e = getenv("SN_EW_V4");
-    v = (e && e[0] == '1') ? 1 : 0;
+    const char* e = getenv("SN_EW_V4U");
+    v = (e && e[0] == '1') ? 0 : 1;
   }
   return v == 1;
 }
@@ -2010,8 +2031,8 @@ int sn_norm_act_bwd(const sn_norm_act_bwd_desc* d, void* stream) {
   if (vec) {
     dim3 grid(vslabs(hw, d->n), d->n);
     // the fused bias gradient needs a fixed quad per thread (256 %% (c/4) == 0) and 256 float4 of scratch (4*c >= 1024)
-    SN_REQUIRE(!d->bias_grad || (!ew_use_v4() && 256 % (d->c / 4) == 0 && d->c >= 256),
-               "norm_act_bwd: fused bias gradient needs c in {256, 512, 1024} on the unrolled kernel (c=%d)", d->c);
+    SN_REQUIRE(!d->bias_grad || (256 % (d->c / 4) == 0 && d->c >= 256),
+               "norm_act_bwd: fused bias gradient needs c in {256, 512, 1024} (c=%d)", d->c);
     if (ew_use_v4()) norm_act_bwd_apply_v4_kernel<<<grid, 256, 4 * d->c * sizeof(float), st>>>(a);
     else norm_act_bwd_apply_v4u_kernel<2><<<grid, 256, 4 * d->c * sizeof(float), st>>>(a);
   } else {

@@ -35,6 +35,7 @@ from .ops import ACT_LRELU, ACT_NONE, ACT_RELU, ACT_TANH, FMT_BF16, GradSrc, Pla
 
 
 TO_ONE = os.environ.get("SN_NO_TO_ONE", "0") != "1"    # A/B switch for layers.ToOneConvLayer
+WGRAD_OVERLAP = os.environ.get("SN_NO_WGRAD_OVERLAP", "0") != "1"   # A/B switch: weight gradients on a second stream
 
 
 def _mix_seed(step_seed: int, stage_id: int) -> int:
@@ -141,9 +142,25 @@ class Stage:
                              _mix_seed(self.eng.seed, self.id), drop_offset=self.drop_offset(),
                              seed_dev=self.eng.seed_dev, stage_id=self.id, bias_grad=bg)
             if bg is not None:
-                self.layer.backward(dgrad=self.need_dx, wgrad=wgrad, bias=False)
+                self._layer_backward(wgrad, bias=False)
                 return
-        self.layer.backward(dgrad=self.need_dx, wgrad=wgrad)
+        self._layer_backward(wgrad, bias=True)
+
+    def _layer_backward(self, wgrad: bool, bias: bool) -> None:
+        """Input gradient on the launching stream (it is on the critical path of the backward chain); the weight (and
+        unfused bias) gradient — tensor-core work nothing downstream waits for — on the engine's second stream, where it
+        overlaps the HBM-bound IN/activation backward kernels of the following stages (Engine.join_wgrads() joins)."""
+        side = self.eng.wgrad_stream() if wgrad else None
+        if side is None:
+            self.layer.backward(dgrad=self.need_dx, wgrad=wgrad, bias=bias)
+            return
+        ready = torch.cuda.Event()
+        ready.record()                                   # dy (and everything before it: zero_grad) is complete
+        self.layer.backward(dgrad=self.need_dx, wgrad=False)
+        side.wait_event(ready)
+        with torch.cuda.stream(side):
+            self.layer.backward(dgrad=False, wgrad=True, bias=bias)
+        self.eng._wgrad_pending = True
 
 
 class Engine:
@@ -159,6 +176,25 @@ class Engine:
         self.sample_base = 0        # global index of local sample 0 (dropout masks follow the global sample)
         self._pack_table: Optional[ops.PackTable] = None   # built at the first pack() (after bind_backward)
         self._pack_extra: list = []
+        self._wgrad_stream: Optional[torch.cuda.Stream] = None
+        self._wgrad_pending = False
+
+    def wgrad_stream(self) -> Optional[torch.cuda.Stream]:
+        """Second stream for the weight-gradient GEMMs (None: launch in line — A/B switch, per-launch tracing)."""
+        if not WGRAD_OVERLAP or ops.Plan.trace is not None:
+            return None
+        if self._wgrad_stream is None:
+            self._wgrad_stream = torch.cuda.Stream(device=self.device)
+        return self._wgrad_stream
+
+    def join_wgrads(self) -> None:
+        """The launching stream waits for every weight gradient issued so far (before the optimizer, an all-reduce of
+        the gradients, or the next overwrite of the operand planes)."""
+        if self._wgrad_pending:
+            done = torch.cuda.Event()
+            done.record(self._wgrad_stream)
+            torch.cuda.current_stream(self.device).wait_event(done)
+            self._wgrad_pending = False
         self.flat_grad: Optional[torch.Tensor] = None
 
     def planes(self, n: int, h: int, w: int, c: int) -> Planes:
@@ -312,7 +348,12 @@ class WarpEngine(Engine):
         fused loss kernel (ops.ce_tanh_bwd).  Accumulates parameter grads into flat_grad.
         on_bucket(i): called when bucket i of grad_buckets() has all its gradient launches enqueued."""
         B, h16 = self.batch, self.size // 16
-        done = on_bucket or (lambda i: None)
+
+        def done(i):
+            if on_bucket is not None:
+                self.join_wgrads()          # the bucket's weight gradients run on the second stream
+                on_bucket(i)
+
         self.head.backward(srcs)
         g3 = self.head.dx                                     # d cat3 [.,192]
         self.d3.backward([GradSrc(g3, 0)])
@@ -343,6 +384,7 @@ class WarpEngine(Engine):
         self.b2.backward([GradSrc(self.b3.dx), GradSrc(g2, 128)])
         self.b1.backward([GradSrc(self.b2.dx), GradSrc(g3, 64)])
         done(3)
+        self.join_wgrads()
 
 
 # =============================================================================================
@@ -386,6 +428,7 @@ class PatchGANEngine(Engine):
         for s in reversed(self.chain):
             s.backward([GradSrc(g)], wgrad=wgrad)
             g = s.dx
+        self.join_wgrads()
 
     @property
     def dx_in(self) -> torch.Tensor:
@@ -487,6 +530,7 @@ class TextureEngine(Engine):
             # L_{j+1} feeds D_{j+1} (as leaky_relu) and the skip slot of cu[j] (as relu)
             self.down[j].backward([GradSrc(self.down[j + 1].dx), GradSrc(gcu[j], 0, act=ACT_RELU)])
         self.encode.backward([GradSrc(self.down[0].dx, 0, up=self.up_factor)])
+        self.join_wgrads()
 
 
 # =============================================================================================

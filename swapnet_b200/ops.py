@@ -599,9 +599,7 @@ def norm_act_bwd(srcs: Sequence[GradSrc], y: torch.Tensor, c: int, stats: Option
 
 def fused_bias_grad_ok(c: int) -> bool:
     """Channel counts for which norm_act_bwd can accumulate the bias gradient itself."""
-    import os
-
-    return c in (256, 512, 1024) and os.environ.get("SN_EW_V4", "0") != "1"
+    return c in (256, 512, 1024)
 
 
 def bias_grad(dy: Planes, c: int, scratch: torch.Tensor, db: torch.Tensor) -> None:
