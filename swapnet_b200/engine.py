@@ -178,6 +178,7 @@ class Engine:
         self._pack_extra: list = []
         self._wgrad_stream: Optional[torch.cuda.Stream] = None
         self._wgrad_pending = False
+        self.flat_grad: Optional[torch.Tensor] = None
 
     def wgrad_stream(self) -> Optional[torch.cuda.Stream]:
         """Second stream for the weight-gradient GEMMs (None: launch in line — A/B switch, per-launch tracing)."""
@@ -195,7 +196,6 @@ class Engine:
             done.record(self._wgrad_stream)
             torch.cuda.current_stream(self.device).wait_event(done)
             self._wgrad_pending = False
-        self.flat_grad: Optional[torch.Tensor] = None
 
     def planes(self, n: int, h: int, w: int, c: int) -> Planes:
         """fp16-split activation operand (+ bf16 twin when training)."""
