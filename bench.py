@@ -145,10 +145,11 @@ class ClockSampler(threading.Thread):
 
 def ncu_traffic():
     """dram__bytes_read + dram__bytes_write per launch of the dominant kernel, from the committed
-    `ncu --set full` capture (profiles/r01_ncu_traffic.json); null if absent."""
-    p = os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")
-    if os.path.exists(p):
-        return json.load(open(p))
+    `ncu --set full` capture (profiles/r02_ncu_traffic.json); null if absent."""
+    for name in ("r02_ncu_traffic.json", "r01_ncu_traffic.json"):
+        p = os.path.join(ROOT, "profiles", name)
+        if os.path.exists(p):
+            return json.load(open(p))
     return None
 
 
