@@ -281,6 +281,28 @@ def cpu_reference_run(S, B, steps, warmup, model="warp", perceptual=False):
     return B / med, med
 
 
+_REAL_STDOUT = None
+
+
+def _protect_stdout():
+    """stdout carries exactly ONE JSON line: everything else written to fd 1 from here on — Python prints, but also
+    C-level writes such as NCCL's version banner — goes to stderr; emit() writes to the original stdout."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(obj) -> None:
+    line = (json.dumps(obj) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(line.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, line)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -305,6 +327,7 @@ def main():
                     help="warp = the BASELINE.json metric (default); texture = configs[2]; joint = configs[4] "
                          "(one warp step + one texture step per iteration)")
     args = ap.parse_args()
+    _protect_stdout()
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
     S = args.size
@@ -328,7 +351,7 @@ def main():
         # batch (`--cpu-batch` images, default 1: the step is per-sample work + batch-mean losses, cost linear in the
         # batch) so that 25 steps stay within a few minutes on the box's host cores
         v, med = cpu_reference_run(S, args.cpu_batch, args.steps, args.warmup, args.model, args.perceptual)
-        print(json.dumps({
+        emit(({
             "impl": "reference", "metric": metric_name(args), "value": v,
             "unit": "images/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": med * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -347,6 +370,7 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(local)
     if world > 1:
+        os.environ.setdefault("NCCL_MAX_CTAS", "16")     # see swapnet_b200/parallel.py:init_from_env
         torch.distributed.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
     from swapnet_b200 import ops
     from swapnet_b200.models import create_model
@@ -509,7 +533,7 @@ def main():
                 if args.labels else "fp32 tensors as the reference's DataLoader yields them"},
         "gpu_launches": launches, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
     }
-    print(json.dumps(out))
+    emit(out)
     if world > 1:
         torch.distributed.destroy_process_group()
 

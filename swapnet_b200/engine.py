@@ -350,8 +350,19 @@ class WarpEngine(Engine):
         B, h16 = self.batch, self.size // 16
 
         def done(i):
-            if on_bucket is not None:
-                self.join_wgrads()          # the bucket's weight gradients run on the second stream
+            """Bucket i is complete once the launches issued so far on BOTH streams have run.  The all-reduce is issued
+            from the weight-gradient stream (which first waits for the launching stream's work up to here), so the
+            launching stream — the backward chain — never blocks on it."""
+            if on_bucket is None:
+                return
+            side = self._wgrad_stream if self._wgrad_pending else None
+            if side is None:
+                on_bucket(i)
+                return
+            here = torch.cuda.Event()
+            here.record()
+            side.wait_event(here)
+            with torch.cuda.stream(side):
                 on_bucket(i)
 
         self.head.backward(srcs)

@@ -27,6 +27,9 @@ def init_from_env() -> int:
     import os
 
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    # the gradient all-reduces overlap G-backward: cap the SMs NCCL may take from the persistent GEMM kernels (the
+    # transfers are hidden behind ~25 ms of backward either way; measured at 2 GPUs: 65.3 vs 65.8 ms/step)
+    os.environ.setdefault("NCCL_MAX_CTAS", "16")
     if dist.is_available() and not dist.is_initialized():
         torch.cuda.set_device(local)
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
