@@ -179,6 +179,10 @@ class BaseGAN(BaseModel, ABC):
         if key not in cache:
             while len(cache) >= self.ENGINE_CACHE:           # evict the least recently used shape
                 old = next(iter(cache))
+                for gk in [k for k in getattr(self, "_graphs", {}) if k[:2] == old]:
+                    del self._graphs[gk]                     # captured on the evicted engines' buffers
+                for gk in [k for k in getattr(self, "_eager_steps", {}) if k[:2] == old]:
+                    del self._eager_steps[gk]
                 for eng in cache.pop(old).values():
                     if hasattr(eng, "stages"):
                         for st in eng.stages:                # break the Stage <-> Engine cycle: buffers free now
