@@ -105,6 +105,11 @@ typedef struct sn_tap_gemm_desc {
                                             (bias[c]).  The up-sample+pad head (swapnet_modules.py:85-90) as ONE 9-tap GEMM
                                             with N = 4 x 24: its 192-channel input is read 9 times instead of 25.
                                             Needs n_valid = 4*stack_slot, nphase <= 1, out_mul = 2. */
+  double* stats;                         /* optional [m_n][n_valid][2]: the launch ALSO accumulates (sum, sum of squares) of
+                                            its output per (image, channel) — the InstanceNorm statistics of layers.py:17,
+                                            33,134 — zeroing the buffer first; sn_stats_finalize turns them into (mean,
+                                            rstd).  Only honoured when a tile never spans two images and n_valid % 16 == 0
+                                            (sn_plan_has_stats tells); otherwise call sn_plane_stats. */
 } sn_tap_gemm_desc;
 
 /* G[i*s_row + j*s_col + tap_off[t]] += sum_{(n,h,w)} X[n, h+dh_t, w+dw_t, xc_t + i] * Y[n, h+dh'_t, w+dw'_t, yc_t + j]
@@ -136,6 +141,8 @@ int sn_tap_gemm_plan_create(const sn_tap_gemm_desc* desc, sn_plan** out);
 int sn_wgrad_plan_create(const sn_wgrad_desc* desc, sn_plan** out);
 int sn_plan_run(const sn_plan* plan, void* stream);
 void sn_plan_destroy(sn_plan* plan);
+/* 1 when the plan accumulates the fused InstanceNorm statistics requested through sn_tap_gemm_desc.stats */
+int sn_plan_has_stats(const sn_plan* plan);
 
 /* ------------------------------------------------------------------------------------------
  * operand packing
@@ -202,6 +209,8 @@ int sn_fold_head_wgrad(const float* geff, int cout, int cin, float* dw, void* st
  * as doubles (accumulated in fp64). */
 int sn_plane_stats(const float* y, int pitch, int n, int hw, int c, float eps, double* stats,
                    void* stream);
+/* (sum, sum of squares) over hw pixels -> (mean, 1/sqrt(var_biased + eps)) in place, `count` = n*c pairs */
+int sn_stats_finalize(double* stats, int count, int hw, float eps, void* stream);
 
 typedef struct sn_norm_act_desc {
   const float* y; int y_pitch;           /* conv output, [n, h, w, c] */

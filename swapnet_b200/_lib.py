@@ -37,7 +37,7 @@ class SnTapGemmDesc(C.Structure):
         ("out_mul_h", C.c_int), ("out_off_h", C.c_int), ("out_mul_w", C.c_int), ("out_off_w", C.c_int),
         ("n_valid", C.c_int), ("block_n", C.c_int),
         ("bias", C.c_void_p), ("act", C.c_int), ("nsplit", C.c_int), ("nphase", C.c_int),
-        ("stack_slot", C.c_int), ("stack_c", C.c_int),
+        ("stack_slot", C.c_int), ("stack_c", C.c_int), ("stats", C.c_void_p),
     ]
 
 
@@ -119,6 +119,8 @@ SIGNATURES = {
     "sn_wgrad_plan_create": (_I, [C.POINTER(SnWgradDesc), C.POINTER(_VP)]),
     "sn_plan_run": (_I, [_VP, _VP]),
     "sn_plan_destroy": (None, [_VP]),
+    "sn_plan_has_stats": (_I, [_VP]),
+    "sn_stats_finalize": (_I, [_VP, _I, _I, _F, _VP]),
     "sn_pack_planes": (_I, [_VP, _I, _I, _I, _I, _I, _I, _VP, _VP, _I, _I, _I, _VP]),
     "sn_pack_concat": (_I, [_VP, _I, _I, _I, _VP, _I, _I, _I, _I, _I, _I, _I, _VP, _VP, _VP, _VP, _I, _I, _I, _I, _VP]),
     "sn_weight_scale": (_I, [_VP, _LL, _VP, _VP]),

@@ -72,6 +72,8 @@ int sn_plan_run(const sn_plan* plan, void* stream) {
   return sn_wgrad_plan_launch(&plan->wg, (cudaStream_t)stream);
 }
 
+int sn_plan_has_stats(const sn_plan* plan) { return plan && plan->kind == 0 && plan->tg.p.stats != nullptr; }
+
 void sn_plan_destroy(sn_plan* plan) { delete plan; }
 
 }  // extern "C"

@@ -1934,6 +1934,13 @@ int sn_plane_stats(const float* y, int pitch, int n, int hw, int c, float eps, d
   return SN_OK;
 }
 
+int sn_stats_finalize(double* stats, int count, int hw, float eps, void* stream) {
+  SN_REQUIRE(stats && count >= 1 && hw >= 1, "stats_finalize: bad arguments");
+  stats_finalize_kernel<<<(count + 255) / 256, 256, 0, (cudaStream_t)stream>>>(stats, count, hw, (double)eps);
+  LAUNCH_CHECK();
+  return SN_OK;
+}
+
 int sn_norm_act_fwd(const sn_norm_act_desc* d, void* stream) {
   SN_REQUIRE(d && d->y, "null pointer");
   SN_REQUIRE(!d->out_reflect_pad || (d->h >= 3 && d->w >= 3), "reflect pad needs h, w >= 3");

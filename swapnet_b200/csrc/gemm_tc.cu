@@ -50,6 +50,40 @@ __device__ __forceinline__ float apply_act(float v, int act) {
   return v;
 }
 
+// Column sums over a warp's 32 rows of a 32 x 16 register tile (x[j] = this lane's value of column j): a butterfly that
+// halves the number of live values at every exchange (8 + 4 + 2 + 1 + 1 = 16 shuffles instead of 16 x 5).  On return
+// x[0] holds the total of column (lane >> 1) — both lanes of a pair hold the same total.
+__device__ __forceinline__ void col_sums16(float (&x)[16], int lane) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const bool up = lane & 16;
+    const float send = up ? x[j] : x[j + 8];
+    const float recv = __shfl_xor_sync(0xffffffffu, send, 16);
+    x[j] = (up ? x[j + 8] : x[j]) + recv;
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const bool up = lane & 8;
+    const float send = up ? x[j] : x[j + 4];
+    const float recv = __shfl_xor_sync(0xffffffffu, send, 8);
+    x[j] = (up ? x[j + 4] : x[j]) + recv;
+  }
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+    const bool up = lane & 4;
+    const float send = up ? x[j] : x[j + 2];
+    const float recv = __shfl_xor_sync(0xffffffffu, send, 4);
+    x[j] = (up ? x[j + 2] : x[j]) + recv;
+  }
+  {
+    const bool up = lane & 2;
+    const float send = up ? x[0] : x[1];
+    const float recv = __shfl_xor_sync(0xffffffffu, send, 2);
+    x[0] = (up ? x[1] : x[0]) + recv;
+  }
+  x[0] += __shfl_xor_sync(0xffffffffu, x[0], 1);
+}
+
 // ============================================================================
 // conv mode
 // ============================================================================
@@ -256,6 +290,34 @@ tap_gemm_kernel(const __grid_constant__ TapGemmParams p, const int m_tiles, cons
                          (long long)(gw * p.omw + (ph & 1)) * p.out_sw + c;
               *o = apply_act(v, p.act);
             }
+          }
+        } else if (p.stats && ncol0 + c0 >= p.n_valid) {
+          // a 16-column chunk beyond the last output channel (n_valid % 16 == 0 in this mode): nothing to store or sum
+        } else if (p.stats) {
+          // InstanceNorm statistics fused into the producer (layers.py:17,33,134): every tile row belongs to image gn
+          // (nb == 1, checked by the host), so the warp's 32 rows reduce to per-column sums of y and y^2 — one fp64
+          // atomic pair per column per warp into stats[n][c] = (sum, sum of squares), finalised by stats_finalize.
+          float v[16], sq[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            float t = __uint_as_float(r[j]) * oscale;
+            if (p.bias) t += p.bias[ncol0 + c0 + j];
+            v[j] = valid ? t : 0.f;
+          }
+          if (valid) {
+#pragma unroll
+            for (int j = 0; j < 16; j += 4)
+              *reinterpret_cast<float4*>(optr + c0 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+          }
+#pragma unroll
+          for (int j = 0; j < 16; ++j) sq[j] = v[j] * v[j];
+          col_sums16(v, lane);
+          col_sums16(sq, lane);
+          if ((lane & 1) == 0) {
+            const int tn = (mt / (p.tiles_w * p.tiles_h)) * p.nb;      // the tile's image (uniform over the CTA)
+            double* st = p.stats + ((long long)tn * p.n_valid + ncol0 + c0 + (lane >> 1)) * 2;
+            atomicAdd(st, (double)v[0]);
+            atomicAdd(st + 1, (double)sq[0]);
           }
         } else if (valid) {
           if (p.vec4 && ncol0 + c0 + 16 <= p.n_valid) {
@@ -686,6 +748,7 @@ int sn_tap_gemm_plan_init(TapGemmPlan* plan, const sn_tap_gemm_desc* d) {
   }
   p.bias = d->bias;
   p.stack_slot = d->stack_slot; p.stack_c = d->stack_c;
+  p.stats = nullptr;
   if (d->stack_slot > 0)
     SN_REQUIRE(d->nphase <= 1 && d->n_valid == 4 * d->stack_slot && d->stack_c >= 1 && d->stack_c <= d->stack_slot &&
                    d->out_mul_h == 2 && d->out_mul_w == 2,
@@ -697,6 +760,10 @@ int sn_tap_gemm_plan_init(TapGemmPlan* plan, const sn_tap_gemm_desc* d) {
   p.act = d->act;
   p.vec4 = ((uintptr_t)d->out % 16 == 0) && (d->out_sn % 4 == 0) && (d->out_sh % 4 == 0) &&
            (d->out_sw % 4 == 0) && (!d->bias || (uintptr_t)d->bias % 16 == 0);
+  // fused InstanceNorm statistics: whole tile inside one image, 16-column chunks fully valid, plain vectorised stores
+  if (d->stats && nb == 1 && p.vec4 && d->n_valid % 16 == 0 && d->act == 0 && d->stack_slot == 0 && d->m_n * 1 >= 1)
+    p.stats = d->stats;
+  plan->stats_bytes = p.stats ? sizeof(double) * 2 * (size_t)d->m_n * d->n_valid : 0;
   int rc;
   const void* a_pl[2] = {d->a_hi, d->a_lo};
   const void* b_pl[2] = {d->b_hi, d->b_lo};
@@ -752,6 +819,7 @@ static int launch_tap(const TapGemmPlan* plan, cudaStream_t stream) {
   }
   const int m_tiles = (int)plan->grid.x, n_tiles = (int)plan->grid.y;
   const int total = m_tiles * n_tiles * (int)plan->grid.z;
+  if (plan->p.stats) SN_CHECK_CUDA(cudaMemsetAsync(plan->p.stats, 0, plan->stats_bytes, stream));
   const int ctas = one_tile_per_cta ? total : (total < sms ? total : sms);
   tap_gemm_kernel<NSPLIT, CW><<<ctas, kThreads, Cfg<NSPLIT>::kSmemBytes, stream>>>(plan->p, m_tiles, n_tiles, total);
   SN_CHECK_CUDA(cudaGetLastError());

@@ -35,6 +35,7 @@ struct alignas(64) TapGemmParams {
   int a_merged, b_merged;
   int a_lo_off, b_lo_off;   // byte offset of the lo tile behind the hi tile inside a stage
   int stack_slot, stack_c;  // > 0: N = 4 output-parity phases side by side (sn_tap_gemm_desc.stack_slot)
+  double* stats;            // non-null: accumulate per-(image, channel) sum / sum of squares of the output (fused IN stats)
 };
 
 struct alignas(64) WgradParams {
@@ -62,6 +63,7 @@ struct TapGemmPlan {
   TapGemmParams p;
   dim3 grid;
   int nsplit;
+  size_t stats_bytes;       // bytes of p.stats zeroed ahead of every launch
 };
 struct WgradPlan {
   WgradParams p;

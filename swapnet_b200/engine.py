@@ -66,12 +66,13 @@ class Stage:
         ly = self.layer
         self.n, self.oh, self.ow, self.cout = ly.n, ly.out_h, ly.out_w, ly.cout
         self.y = y if y is not None else torch.zeros(self.n, self.oh, self.ow, self.cout, device=dev)
-        ly.bind_forward(self.y)
+        # InstanceNorm statistics ride on the GEMM epilogue where a tile never spans two images (ConvLayer.fused_stats)
+        self.stats = torch.zeros(self.n, self.cout, 2, dtype=torch.float64, device=dev) if norm else None
+        ly.bind_forward(self.y, stats=self.stats)
         self.norm, self.act, self.slope, self.drop_p = norm, act, slope, drop_p
         self.out, self.reflect_out, self.residual, self.out_f32 = out, reflect_out, residual, out_f32
         self.plain, self.epi_act, self.need_dx = plain, epi_act, need_dx
         self.out_relu = out_relu   # pix2pix skip: a second consumer reads relu() of the same pre-activation
-        self.stats = torch.zeros(self.n, self.cout, 2, dtype=torch.float64, device=dev) if norm else None
         self.dy: Optional[Planes] = None
         self.dx: Optional[torch.Tensor] = None
         self.gstats = None
@@ -98,7 +99,10 @@ class Stage:
         if self.plain:
             return
         if self.norm:
-            ops.plane_stats(self.y, self.cout, self.stats)
+            if getattr(self.layer, "fused_stats", False):
+                ops.stats_finalize(self.stats, self.n * self.cout, self.oh * self.ow)
+            else:
+                ops.plane_stats(self.y, self.cout, self.stats)
         p = self.drop_p if self.eng.training else 0.0
         ops.norm_act_fwd(self.y, self.cout, self.stats, self.act, self.slope, p,
                          _mix_seed(self.eng.seed, self.id), residual=self.residual, out=self.out,

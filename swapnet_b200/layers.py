@@ -72,12 +72,17 @@ class ConvLayer:
         return (t + tps - 1) // tps * tps
 
     # ---- forward --------------------------------------------------------------------------
-    def bind_forward(self, y: torch.Tensor, y_c_off: int = 0) -> None:
+    def bind_forward(self, y: torch.Tensor, y_c_off: int = 0, stats: Optional[torch.Tensor] = None) -> None:
         """y: fp32 NHWC [n, out_h, out_w, pitch]; the conv output (+bias, +act) is written to
-        channels [y_c_off, y_c_off + cout)."""
+        channels [y_c_off, y_c_off + cout).  stats (float64 [n, cout, 2]): ask the launch to accumulate the
+        InstanceNorm statistics of y as it writes it; `self.fused_stats` says whether it will (single-launch layers whose
+        tiles stay inside one image), else the caller runs ops.plane_stats."""
         assert y.shape[:3] == (self.n, self.out_h, self.out_w), (self.name, y.shape, self.out_h, self.out_w)
         self.y = y
         self.fwd_plans = []
+        self.fused_stats = False
+        if os.environ.get("SN_NO_FUSED_STATS", "0") == "1" or y_c_off != 0 or self.act != ACT_NONE:
+            stats = None
         if self.stacked:
             d = ops.tap_gemm_desc(self.x, L.head_stacked_spec(self.in_h, self.in_w), self.wp, self.k_pad, y,
                                   4 * L.HEAD_SLOT, bias=self.bias, act=self.act, nsplit=self.nsplit,
@@ -89,9 +94,10 @@ class ConvLayer:
         merged = ops.merge_phase_specs(specs)
         if merged is not None and (self.k_pad >= 64 or (len(merged.taps) // 4) % (64 // self.k_pad) == 0):
             d = ops.tap_gemm_desc(self.x, merged, self.wp, self.k_pad, y, self.cout, bias=self.bias, act=self.act,
-                                  nsplit=self.nsplit, block_n=self.block_n, out_c_off=y_c_off, nphase=4)
+                                  nsplit=self.nsplit, block_n=self.block_n, out_c_off=y_c_off, nphase=4, stats=stats)
             self.fwd_plans.append(ops.tap_gemm_plan(d, keep=(self.x.hi, self.x.lo, self.wp.hi, self.wp.lo, y)))
             self.fwd_plans[-1].tag = ("fwd", self.name)
+            self.fused_stats = stats is not None and self.fwd_plans[-1].has_stats
             specs = []
         for spec in specs:
             kw = {}
@@ -100,10 +106,14 @@ class ConvLayer:
                 nt = L.head_neff(p >> 1) * L.head_neff(p & 1)
                 kw = dict(w_elem_off=self.rows_pad * self.k_pad * L.HEAD_PHASE_OFF[p], w_rows=self.rows_pad,
                           w_k=nt * self.k_pad)
+            one = len(specs) == 1 and self.kind != "head"
             d = ops.tap_gemm_desc(self.x, spec, self.wp, self.k_pad, y, self.cout, bias=self.bias,
-                                  act=self.act, nsplit=self.nsplit, block_n=self.block_n, out_c_off=y_c_off, **kw)
+                                  act=self.act, nsplit=self.nsplit, block_n=self.block_n, out_c_off=y_c_off,
+                                  stats=stats if one else None, **kw)
             self.fwd_plans.append(ops.tap_gemm_plan(d, keep=(self.x.hi, self.x.lo, self.wp.hi, self.wp.lo, y)))
             self.fwd_plans[-1].tag = ("fwd", self.name)
+            if one:
+                self.fused_stats = stats is not None and self.fwd_plans[-1].has_stats
 
     def register_packs(self, table: "ops.PackTable") -> bool:
         """Register this layer's scale and generic packs with the network's PackTable; returns True when a separate
@@ -253,9 +263,10 @@ class ToOneConvLayer:
         self.y = self.dy = self.dx = None
         self.wgrad_out = self.bgrad_out = self._bscratch = None
 
-    def bind_forward(self, y: torch.Tensor, y_c_off: int = 0) -> None:
+    def bind_forward(self, y: torch.Tensor, y_c_off: int = 0, stats: Optional[torch.Tensor] = None) -> None:
         assert y.shape[:3] == (self.n, self.out_h, self.out_w) and y_c_off == 0
         self.y = y
+        self.fused_stats = False
 
     def register_packs(self, table) -> bool:
         return False            # the kernels read the torch parameter itself

@@ -105,6 +105,11 @@ class Plan:
         self.tag = tag
         self._keep = list(keep)  # tensors whose addresses are baked into the plan
 
+    @property
+    def has_stats(self) -> bool:
+        """True when the launch also accumulates the InstanceNorm statistics requested through its descriptor."""
+        return bool(_lib.load().sn_plan_has_stats(self.handle))
+
     # bench.py's roofline pass: when a list is installed here every plan launch is bracketed by CUDA
     # events on the launching stream and (tag, start, end) is appended
     trace = None
@@ -137,7 +142,8 @@ def tap_gemm_desc(a: Planes, spec: L.GemmSpec, w: PackedWeights, k_per_tap: int,
                   n_valid: int, *, w_row_off: int = 0, w_rows: Optional[int] = None,
                   w_k: Optional[int] = None, w_elem_off: int = 0, bias: Optional[torch.Tensor] = None,
                   act: int = ACT_NONE, nsplit: int = 3, block_n: Optional[int] = None,
-                  out_c_off: int = 0, nphase: int = 1, stack_slot: int = 0, stack_c: int = 0) -> SnTapGemmDesc:
+                  out_c_off: int = 0, nphase: int = 1, stack_slot: int = 0, stack_c: int = 0,
+                  stats: Optional[torch.Tensor] = None) -> SnTapGemmDesc:
     """out: fp32 NHWC tensor [n, OH, OW, pitch_out]; rows (h, w) land on pixel
     (h*mul_h + off_h, w*mul_w + off_w)."""
     assert (a.h, a.w) == tuple(spec.a_hw), f"operand is {a.h}x{a.w}, spec wants {spec.a_hw}"
@@ -180,6 +186,9 @@ def tap_gemm_desc(a: Planes, spec: L.GemmSpec, w: PackedWeights, k_per_tap: int,
     d.nsplit = nsplit
     d.nphase = nphase
     d.stack_slot, d.stack_c = stack_slot, stack_c
+    if stats is not None:      # fused InstanceNorm statistics [n, n_valid, 2] float64 (see Plan.has_stats)
+        assert stats.dtype == torch.float64 and stats.numel() >= a.n * n_valid * 2 and out_c_off == 0
+        d.stats = stats.data_ptr()
     return d
 
 
@@ -514,6 +523,11 @@ def plane_stats(y: torch.Tensor, c: int, stats: torch.Tensor, eps: float = IN_EP
     pitch = _pitch(y)
     assert stats.dtype == torch.float64 and stats.numel() >= n * c * 2
     check(_lib.load().sn_plane_stats(y.data_ptr(), pitch, n, h * w, c, eps, stats.data_ptr(), _stream()))
+
+
+def stats_finalize(stats: torch.Tensor, count: int, hw: int, eps: float = IN_EPS) -> None:
+    """(sum, sum of squares) accumulated by a GEMM launch with fused statistics -> (mean, rstd), in place."""
+    check(_lib.load().sn_stats_finalize(stats.data_ptr(), count, hw, eps, _stream()))
 
 
 def norm_act_fwd(y: torch.Tensor, c: int, stats: Optional[torch.Tensor], act: int, slope: float = 0.2,

@@ -668,3 +668,36 @@ def test_to_one_conv_layer(n, cin, h, w):
     record(f"to_one_conv[{n},{cin},{h}x{w}]", f"y {e_y:.3e} dx {e_dx:.3e} w {e_w:.3e} b {e_b:.3e}")
     # forward: fp32 FMA chain over cin*16 products of 22-bit operands; backward: dy carried as bf16-split planes
     assert e_y < 3e-5 and e_dx < 1e-4 and e_w < 1e-4 and e_b < 1e-4, (e_y, e_dx, e_w, e_b)
+
+
+@pytest.mark.parametrize("kind,n,cin,cout,h,w,fused", [("conv4s2", 2, 64, 128, 32, 64, True), ("convT4s2", 2, 128, 64, 16, 16, True),
+                                                     ("conv3r", 3, 128, 128, 32, 32, True), ("conv4s1", 2, 128, 256, 64, 64, True),
+                                                     ("conv4s2", 3, 128, 192, 16, 16, False)])
+def test_fused_instance_norm_statistics(kind, n, cin, cout, h, w, fused):
+    """InstanceNorm statistics accumulated by the GEMM epilogue (sn_tap_gemm_desc.stats + sn_stats_finalize) equal the
+    per-(image, channel) mean and 1/sqrt(biased variance + eps) of the conv output; planes smaller than a tile (several
+    images per tile) are refused by the plan and fall back to sn_plane_stats."""
+    from swapnet_b200 import ops
+
+    layer, x, wt, bias = make_layer(kind, n, cin, cout, h, w, 3)
+    oh, ow = L.out_hw(kind, h, w)
+    y = torch.zeros(n, oh, ow, cout, device=dev())
+    stats = torch.zeros(n, cout, 2, dtype=torch.float64, device=dev())
+    layer.bind_forward(y, stats=stats)
+    assert layer.fused_stats == fused
+    layer.pack()
+    layer.forward()
+    layer.forward()                       # the launch zeroes the buffer itself: a second run must not double the sums
+    if layer.fused_stats:
+        ops.stats_finalize(stats, n * cout, oh * ow)
+    else:
+        ops.plane_stats(y, cout, stats)
+    torch.cuda.synchronize()
+    ref = ref_forward(kind, x.double(), wt.double(), bias.double())
+    mean = ref.mean((2, 3))
+    rstd = (ref.var((2, 3), unbiased=False) + 1e-5).rsqrt()
+    e_m = ((stats[..., 0].cpu() - mean).abs().max() / ref.abs().max()).item()
+    e_r = relmax(stats[..., 1].cpu(), rstd)
+    record(f"fused_in_stats[{kind},{n},{cin},{cout},{h}x{w}]", f"fused={layer.fused_stats} mean {e_m:.3e} rstd {e_r:.3e}")
+    assert e_m < 1e-5 and e_r < 1e-5, (e_m, e_r)
+    assert relmax(y.cpu(), nhwc(ref)) < 1.5e-5
