@@ -1218,7 +1218,8 @@ __device__ __forceinline__ void store_split4(uint16_t* hi, uint16_t* lo, long lo
   if (lo) *reinterpret_cast<uint2*>(lo + off) = pl;
 }
 
-__global__ void __launch_bounds__(256, 4) norm_act_fwd_v4_kernel(const NormActFwdArgs a) {
+template <int MINB>
+__global__ void __launch_bounds__(256, MINB) norm_act_fwd_v4_kernel(const NormActFwdArgs a) {
   extern __shared__ float sm[];  // mean[C], rstd[C]
   float* s_mean = sm;
   float* s_rstd = sm + a.C;
@@ -1359,7 +1360,8 @@ __device__ __forceinline__ void grad_xhat4(const NormActBwdArgs& a, unsigned lon
 
 // grid (ceil(Q/bx), slabs, N), block (bx, 256/bx) with bx = min(32, pow2 >= Q): thread = channel quad,
 // strided over pixels (C = 64 layers — the largest tensors — use bx = 16, 16 pixel rows)
-__global__ void __launch_bounds__(256, 4) norm_act_bwd_reduce_v4_kernel(const NormActBwdArgs a) {
+template <int MINB>
+__global__ void __launch_bounds__(256, MINB) norm_act_bwd_reduce_v4_kernel(const NormActBwdArgs a) {
   __shared__ float red[256][8];
   const unsigned long long seed = a.drop_thresh ? drop_seed_of(a) : 0ull;
   const int q = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1407,7 +1409,8 @@ __global__ void __launch_bounds__(256, 4) norm_act_bwd_reduce_v4_kernel(const No
   }
 }
 
-__global__ void __launch_bounds__(256, 4) norm_act_bwd_apply_v4_kernel(const NormActBwdArgs a) {
+template <int MINB>
+__global__ void __launch_bounds__(256, MINB) norm_act_bwd_apply_v4_kernel(const NormActBwdArgs a) {
   extern __shared__ float sm[];  // mean, rstd, m1, m2 : 4 x C
   float* s_mean = sm;
   float* s_rstd = sm + a.C;
@@ -1713,6 +1716,16 @@ __global__ void __launch_bounds__(256, 2) norm_act_fwd_v4u_kernel(const NormActF
 // measured (profiles/r02_*): the unrolled variants LOSE — 2 blocks / SM (112-126 registers) hide less latency than the
 // v4 kernels' 4 blocks with one quad in flight: bwd_apply 6.1 vs 4.4 ms per step, reduce 3.2 vs 2.2, forward 3.5 vs
 // 3.3.  They stay selectable (SN_EW_V4U=1) as the A/B evidence; the default is v4.
+// resident blocks per SM the v4 kernels are compiled for (register cap 64 / 51 / 42): SN_EW_MINB=4|5|6, A/B switch
+inline int ew_min_blocks() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("SN_EW_MINB");
+    v = e ? atoi(e) : 4;
+    if (v != 5 && v != 6) v = 4;
+  }
+  return v;
+}
 inline bool ew_use_v4() {
   static int v = -1;
   if (v < 0) {
@@ -1968,8 +1981,14 @@ int sn_norm_act_fwd(const sn_norm_act_desc* d, void* stream) {
                    d->c <= 4096;
   if (vec) {
     dim3 grid(vslabs(d->h * d->w, d->n), d->n);
-    if (ew_use_v4()) norm_act_fwd_v4_kernel<<<grid, 256, 2 * d->c * sizeof(float), (cudaStream_t)stream>>>(a);
-    else norm_act_fwd_v4u_kernel<4><<<grid, 256, 2 * d->c * sizeof(float), (cudaStream_t)stream>>>(a);
+    if (ew_use_v4()) {
+      const int mb = ew_min_blocks();
+      if (mb == 5) norm_act_fwd_v4_kernel<5><<<grid, 256, 2 * d->c * sizeof(float), (cudaStream_t)stream>>>(a);
+      else if (mb == 6) norm_act_fwd_v4_kernel<6><<<grid, 256, 2 * d->c * sizeof(float), (cudaStream_t)stream>>>(a);
+      else norm_act_fwd_v4_kernel<4><<<grid, 256, 2 * d->c * sizeof(float), (cudaStream_t)stream>>>(a);
+    }
+    else
+      norm_act_fwd_v4u_kernel<4><<<grid, 256, 2 * d->c * sizeof(float), (cudaStream_t)stream>>>(a);
   } else {
     dim3 blk = cblock(d->c);
     dim3 grid(slabs_for(d->h * d->w, d->n, blk.y), d->n);
@@ -2022,7 +2041,12 @@ int sn_norm_act_bwd(const sn_norm_act_bwd_desc* d, void* stream) {
       int slabs = (148 * 6 + d->n * qg - 1) / (d->n * qg);
       if (slabs > (hw + 127) / 128) slabs = (hw + 127) / 128;
       if (slabs < 1) slabs = 1;
-      if (ew_use_v4()) norm_act_bwd_reduce_v4_kernel<<<dim3(qg, slabs, d->n), dim3(bx, 256 / bx), 0, st>>>(a);
+      if (ew_use_v4()) {
+        const int mb = ew_min_blocks();
+        if (mb == 5) norm_act_bwd_reduce_v4_kernel<5><<<dim3(qg, slabs, d->n), dim3(bx, 256 / bx), 0, st>>>(a);
+        else if (mb == 6) norm_act_bwd_reduce_v4_kernel<6><<<dim3(qg, slabs, d->n), dim3(bx, 256 / bx), 0, st>>>(a);
+        else norm_act_bwd_reduce_v4_kernel<4><<<dim3(qg, slabs, d->n), dim3(bx, 256 / bx), 0, st>>>(a);
+      }
       else norm_act_bwd_reduce_v4u_kernel<2><<<dim3(qg, slabs, d->n), dim3(bx, 256 / bx), 0, st>>>(a);
     } else {
       const int cg = (d->c + 31) / 32;
@@ -2040,7 +2064,12 @@ int sn_norm_act_bwd(const sn_norm_act_bwd_desc* d, void* stream) {
     // the fused bias gradient needs a fixed quad per thread (256 %% (c/4) == 0) and 256 float4 of scratch (4*c >= 1024)
     SN_REQUIRE(!d->bias_grad || (256 % (d->c / 4) == 0 && d->c >= 256),
                "norm_act_bwd: fused bias gradient needs c in {256, 512, 1024} (c=%d)", d->c);
-    if (ew_use_v4()) norm_act_bwd_apply_v4_kernel<<<grid, 256, 4 * d->c * sizeof(float), st>>>(a);
+    if (ew_use_v4()) {
+      const int mb = ew_min_blocks();
+      if (mb == 5) norm_act_bwd_apply_v4_kernel<5><<<grid, 256, 4 * d->c * sizeof(float), st>>>(a);
+      else if (mb == 6) norm_act_bwd_apply_v4_kernel<6><<<grid, 256, 4 * d->c * sizeof(float), st>>>(a);
+      else norm_act_bwd_apply_v4_kernel<4><<<grid, 256, 4 * d->c * sizeof(float), st>>>(a);
+    }
     else norm_act_bwd_apply_v4u_kernel<2><<<grid, 256, 4 * d->c * sizeof(float), st>>>(a);
   } else {
     SN_REQUIRE(!d->bias_grad, "norm_act_bwd: fused bias gradient is only available on the vectorised path");

@@ -345,7 +345,13 @@ class WarpEngine(Engine):
             assert idx == list(range(idx[0], idx[-1] + 1)), "bucket is not contiguous in the flat buffer"
             return offs[idx[0]], offs[idx[-1] + 1]
 
-        return [span(("dual_up", "upsample_and_pad")), span(("resblocks",)), span(("cloth_",)), span(("body_",))]
+        # in the order backward() retires them: decoder + head; the four resblocks (last first); the four big cloth-branch
+        # layers (cloth_up2, cloth_up1, cloth_down6, cloth_down5: 50 M of the branch's 53 M parameters, finished ~4 ms before
+        # the backward ends); the small down-path layers of both branches.  Finer buckets start their all-reduce earlier:
+        # only the last, 13 MB bucket is issued at the very end of the backward pass.
+        return ([span(("dual_up", "upsample_and_pad"))] + [span((f"resblocks.{k}.",)) for k in (3, 2, 1, 0)] +
+                [span(("cloth_down5", "cloth_down6", "cloth_up")), span(("body_", "cloth_down1", "cloth_down2", "cloth_down3",
+                                                                         "cloth_down4"))])
 
     def backward(self, srcs: Optional[Sequence[GradSrc]], on_bucket=None) -> None:
         """srcs: gradient(s) w.r.t. fakes (NHWC fp32), or None when the head's dy planes were already written by the
@@ -384,21 +390,21 @@ class WarpEngine(Engine):
             r1.backward([GradSrc(r2.dx, 0, True)])
             ops.sum_grads([GradSrc(gx), GradSrc(r1.dx, 0, True)], B, h16, h16, 1024, self._dres[k])
             gx = self._dres[k]
-        done(1)
+            done(1 + (3 - k))                                 # resblock k: buckets 1 (k = 3) .. 4 (k = 0)
         self.u2.backward([GradSrc(gx, 512)])
         self.u1.backward([GradSrc(self.u2.dx)])
         self.c6.backward([GradSrc(self.u1.dx)])
         self.c5.backward([GradSrc(self.c6.dx)])
+        done(5)
         self.c4.backward([GradSrc(self.c5.dx)])
         self.c3.backward([GradSrc(self.c4.dx), GradSrc(g1, 512)])
         self.c2.backward([GradSrc(self.c3.dx), GradSrc(g2, 256)])
         self.c1.backward([GradSrc(self.c2.dx), GradSrc(g3, 128)])
-        done(2)
         self.b4.backward([GradSrc(gx, 0)])
         self.b3.backward([GradSrc(self.b4.dx), GradSrc(g1, 256)])
         self.b2.backward([GradSrc(self.b3.dx), GradSrc(g2, 128)])
         self.b1.backward([GradSrc(self.b2.dx), GradSrc(g3, 64)])
-        done(3)
+        done(6)
         self.join_wgrads()
 
 
