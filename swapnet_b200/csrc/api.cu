@@ -74,6 +74,9 @@ int sn_plan_run(const sn_plan* plan, void* stream) {
 
 int sn_plan_has_stats(const sn_plan* plan) { return plan && plan->kind == 0 && plan->tg.p.stats != nullptr; }
 
-void sn_plan_destroy(sn_plan* plan) { delete plan; }
+void sn_plan_destroy(sn_plan* plan) {
+  if (plan && plan->kind == 0 && plan->tg.p.tile_counter) cudaFree(plan->tg.p.tile_counter);
+  delete plan;
+}
 
 }  // extern "C"

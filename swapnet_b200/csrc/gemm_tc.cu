@@ -34,6 +34,7 @@
 namespace {
 
 constexpr int kBlockM = 128;
+constexpr int kTileRing = 4;
 constexpr int kTileBytes = 16384;  // 128 rows x 128 B (one operand plane of one stage)
 constexpr int kThreads = 192;
 
@@ -102,12 +103,19 @@ tap_gemm_kernel(const __grid_constant__ TapGemmParams p, const int m_tiles, cons
   __shared__ __align__(8) uint64_t empty_bar[C::kStages];
   __shared__ __align__(8) uint64_t tfull_bar[2];    // MMA -> epilogue: accumulator b complete
   __shared__ __align__(8) uint64_t tempty_bar[2];   // epilogue -> MMA: accumulator b drained (4 warps)
+  // dynamic tile schedule (p.tile_counter != null): the producer draws tile numbers from a device counter and hands them
+  // to the MMA and epilogue warps through a 4-deep ring, so a CTA that becomes resident late (SMs held by NCCL or by the
+  // weight-gradient stream's CTAs) finds only the tiles nobody has taken yet instead of a fixed 1/gridDim share
+  __shared__ __align__(8) uint64_t tr_full[kTileRing];
+  __shared__ __align__(8) uint64_t tr_empty[kTileRing];
+  __shared__ int tile_ring[kTileRing];
   __shared__ uint32_t tmem_base_smem;
 
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + (smem_base - smem_u32(smem_raw));
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const bool dyn = p.tile_counter != nullptr;
 
   constexpr int cw = CW;                    // channels per A row: 64, 32 or 16
   constexpr int tps = 64 / cw;              // taps sharing one 64-deep stage (1, 2 or 4)
@@ -123,6 +131,10 @@ tap_gemm_kernel(const __grid_constant__ TapGemmParams p, const int m_tiles, cons
     for (int b = 0; b < 2; ++b) {
       mbar_init(&tfull_bar[b], 1);
       mbar_init(&tempty_bar[b], 4);
+    }
+    for (int r = 0; r < kTileRing; ++r) {
+      mbar_init(&tr_full[r], 1);
+      mbar_init(&tr_empty[r], 5);     // the MMA thread + the four epilogue warps
     }
     mbar_fence_init();
   }
@@ -142,8 +154,19 @@ tap_gemm_kernel(const __grid_constant__ TapGemmParams p, const int m_tiles, cons
     // ===================== TMA producer =====================
     if (lane == 0) {
       const uint32_t stage_tx = C::kPlanes * (p.a_rows * 128 + p.block_n * 128);
-      uint32_t it = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      uint32_t it = 0, tcount = 0;
+      for (int tile = blockIdx.x;; ++tcount) {
+        int next = tile + (int)gridDim.x;
+        if (dyn) {
+          // the first tile is static; every further one a ticket.  The ticket for the NEXT tile is drawn now (its latency
+          // hides behind this tile's loads), the tile number goes to the other warps through the ring
+          if (tile < total_tiles) next = (int)gridDim.x + atomicAdd(p.tile_counter, 1);
+          const uint32_t slot = tcount % kTileRing, rph = (tcount / kTileRing) & 1;
+          mbar_wait(&tr_empty[slot], rph ^ 1);
+          tile_ring[slot] = tile < total_tiles ? tile : -1;
+          mbar_arrive(&tr_full[slot]);
+        }
+        if (tile >= total_tiles) break;
         const int mt = tile % m_tiles;
         const int rest = tile / m_tiles;
         const int ncol0 = (rest % n_tiles) * p.block_n;
@@ -199,6 +222,7 @@ tap_gemm_kernel(const __grid_constant__ TapGemmParams p, const int m_tiles, cons
             }
           }
         }
+        tile = next;
       }
     }
   } else if (warp == 1) {
@@ -206,7 +230,16 @@ tap_gemm_kernel(const __grid_constant__ TapGemmParams p, const int m_tiles, cons
     if (lane == 0) {
       const uint32_t idesc = umma_idesc_16(kBlockM, p.block_n, p.a_fmt, p.b_fmt, 0, 0);
       uint32_t it = 0, tcount = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
+      for (int tile = blockIdx.x;; tile += gridDim.x, ++tcount) {
+        if (dyn) {
+          const uint32_t slot = tcount % kTileRing, rph = (tcount / kTileRing) & 1;
+          mbar_wait(&tr_full[slot], rph);
+          tile = tile_ring[slot];
+          mbar_arrive(&tr_empty[slot]);
+          if (tile < 0) break;
+        } else if (tile >= total_tiles) {
+          break;
+        }
         const uint32_t b = tcount & 1;
         mbar_wait(&tempty_bar[b], ((tcount >> 1) & 1) ^ 1);   // the epilogue has drained accumulator b
         tc_fence_after();
@@ -252,7 +285,17 @@ tap_gemm_kernel(const __grid_constant__ TapGemmParams p, const int m_tiles, cons
     const int n_i = row / (p.tw * p.th);
     const float oscale = p.b_scale ? p.b_scale[1] : 1.f;  // undo the power-of-two weight scale (exact)
     uint32_t tcount = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
+    for (int tile = blockIdx.x;; tile += gridDim.x, ++tcount) {
+      if (dyn) {
+        const uint32_t slot = tcount % kTileRing, rph = (tcount / kTileRing) & 1;
+        mbar_wait(&tr_full[slot], rph);
+        tile = tile_ring[slot];
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tr_empty[slot]);
+        if (tile < 0) break;
+      } else if (tile >= total_tiles) {
+        break;
+      }
       const int mt = tile % m_tiles;
       const int rest = tile / m_tiles;
       const int ncol0 = (rest % n_tiles) * p.block_n;
@@ -357,6 +400,16 @@ tap_gemm_kernel(const __grid_constant__ TapGemmParams p, const int m_tiles, cons
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem_base, 256);
+  if (dyn && threadIdx.x == 0) {
+    // the last CTA to finish re-arms the counters for the next launch of this plan (every CTA's tickets are drawn
+    // before it gets here; launches of one plan never overlap)
+    __threadfence();
+    if (atomicAdd(p.tile_counter + 1, 1) == (int)gridDim.x - 1) {
+      p.tile_counter[0] = 0;
+      p.tile_counter[1] = 0;
+      __threadfence();
+    }
+  }
 }
 
 // ============================================================================
@@ -764,6 +817,18 @@ int sn_tap_gemm_plan_init(TapGemmPlan* plan, const sn_tap_gemm_desc* d) {
   if (d->stats && nb == 1 && p.vec4 && d->n_valid % 16 == 0 && d->act == 0 && d->stack_slot == 0 && d->m_n * 1 >= 1)
     p.stats = d->stats;
   plan->stats_bytes = p.stats ? sizeof(double) * 2 * (size_t)d->m_n * d->n_valid : 0;
+  p.tile_counter = nullptr;
+  {
+    static int dyn_ok = -1;
+    if (dyn_ok < 0) {
+      const char* e = getenv("SN_TAP_STATIC_TILES");   // A/B switch: the static tile striding of round 1
+      dyn_ok = (e && e[0] == '1') ? 0 : 1;
+    }
+    if (dyn_ok) {
+      SN_CHECK_CUDA(cudaMalloc(&p.tile_counter, 2 * sizeof(int)));
+      SN_CHECK_CUDA(cudaMemset(p.tile_counter, 0, 2 * sizeof(int)));
+    }
+  }
   int rc;
   const void* a_pl[2] = {d->a_hi, d->a_lo};
   const void* b_pl[2] = {d->b_hi, d->b_lo};

@@ -36,6 +36,7 @@ struct alignas(64) TapGemmParams {
   int a_lo_off, b_lo_off;   // byte offset of the lo tile behind the hi tile inside a stage
   int stack_slot, stack_c;  // > 0: N = 4 output-parity phases side by side (sn_tap_gemm_desc.stack_slot)
   double* stats;            // non-null: accumulate per-(image, channel) sum / sum of squares of the output (fused IN stats)
+  int* tile_counter;        // non-null: dynamic tile schedule — [0] next ticket, [1] CTAs finished (self-resetting)
 };
 
 struct alignas(64) WgradParams {
