@@ -85,3 +85,69 @@ def test_segmap_roundtrip_and_format_choice():
 
     with pytest.raises(ValueError):
         SegMap.from_dense(onehot * 0.5)
+
+
+def test_grad_buckets_tile_the_flat_gradient_buffer():
+    """WarpEngine.grad_buckets(): the seven all-reduce buckets are disjoint contiguous slices that cover the flat
+    gradient buffer exactly, in the order backward() retires them (decoder + head first, the small down-path layers last)."""
+    from swapnet_b200 import modules as M
+    from swapnet_b200.engine import WarpEngine
+
+    G = M.WarpModule()
+
+    class Stub:          # grad_buckets only reads the parameter names and sizes
+        net = G
+
+    b = WarpEngine.grad_buckets(Stub())
+    total = sum(p.numel() for p in G.parameters())
+    assert len(b) == 7
+    cov = sorted(b)
+    assert cov[0][0] == 0 and cov[-1][1] == total and all(cov[i][1] == cov[i + 1][0] for i in range(len(cov) - 1))
+    names = [n for n, _ in G.named_parameters()]
+    offs, o = {}, 0
+    for n, p in G.named_parameters():
+        offs[n] = o
+        o += p.numel()
+    lo, hi = b[0]
+    assert lo <= offs["upsample_and_pad.2.weight"] < hi and lo <= offs["dual_up1.model.0.weight"] < hi
+    assert b[1][0] <= offs["resblocks.3.conv_block.1.weight"] < b[1][1]          # the last resblock retires first
+    assert b[4][0] <= offs["resblocks.0.conv_block.6.weight"] < b[4][1]
+    assert b[5][0] <= offs["cloth_up2.model.0.weight"] < b[5][1] and b[5][0] <= offs["cloth_down5.model.0.weight"] < b[5][1]
+    assert b[6][0] == 0 and b[6][0] <= offs["cloth_down4.model.0.weight"] < b[6][1]
+    assert names[0].startswith("body_down1")
+
+
+def test_adamw_hyper_matches_torch_formula():
+    """sn_adamw_hyper (host side of the device-parameterised AdamW): the eight fp32 scalars of step t are the ones
+    torch.optim.AdamW forms from its Python-float hyper-parameters (bias corrections in double, rounded once)."""
+    import math
+
+    from swapnet_b200 import ops
+
+    lr, b1, b2, eps, wd = 4e-4, 0.9, 0.999, 1e-8, 0.01
+    for step in (1, 2, 17, 1000):
+        h = ops.adamw_hyper(lr, b1, b2, eps, wd, step, 0.125)
+        bc1, bc2 = 1.0 - b1 ** step, 1.0 - b2 ** step
+        want = [1.0 - lr * wd, 1.0 - b1, b2, 1.0 - b2, lr / bc1, 1.0 / math.sqrt(bc2), eps, 0.125]
+        import numpy as np
+
+        assert np.array_equal(np.float32(want), np.float32(h)), (step, want, h)
+
+
+def test_launcher_path_order(tmp_path, monkeypatch):
+    """swapnet_b200.run puts <repo>/dropin ahead of the script's directory (where the reference's own `models`
+    package lives) and runs the script as __main__ with its argv."""
+    import os
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    ck = tmp_path / "checkout"
+    (ck / "models").mkdir(parents=True)
+    (ck / "models" / "__init__.py").write_text("WHO = 'reference'\n")
+    (ck / "probe.py").write_text("import sys, models\nprint('PROBE', models.__name__, models.__file__, sys.argv[1:], __name__)\n")
+    r = subprocess.run([sys.executable, "-m", "swapnet_b200.run", "probe.py", "--model", "warp"], cwd=str(ck),
+                       env=dict(os.environ, PYTHONPATH=root), capture_output=True, text=True, timeout=300)
+    line = [ln for ln in r.stdout.splitlines() if ln.startswith("PROBE")]
+    assert r.returncode == 0 and line, (r.stdout, r.stderr[-1500:])
+    assert os.path.join(root, "dropin", "models") in line[0] and "['--model', 'warp']" in line[0] and line[0].endswith("__main__")
