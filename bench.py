@@ -97,6 +97,50 @@ def synth_texture_batch(B, S, seed, labels=False):
                 texture_paths=["synthetic"] * B)
 
 
+class device_augment_feed:
+    """SURVEY §8 f4 as a bench leg: what a DataLoader built on swapnet_b200/data.py hands over per step — the body
+    images (fp32, pinned), ONE uint8 label map per sample (in the reference's image mode the input cloth is the target
+    cloth before augmentation, datasets/warp_dataset.py:98-100) and the op table of the per-channel augmentation
+    (drawn here once, before the timed region, with the reference's transform set; the reference draws in its DataLoader
+    workers too).  Calling it does the H2D copies and the augmentation on the device and returns the `set_input` dict."""
+
+    def __init__(self, B, S, seed):
+        import random
+
+        from torchvision import transforms as T
+
+        from swapnet_b200 import data as D
+
+        base = synth_batch(B, S, seed, labels=True)
+        self.body, self.labels = base["bodys"].pin_memory(), base["target_cloths"].pin_memory()
+        tf = T.RandomOrder([T.RandomVerticalFlip(), T.RandomHorizontalFlip(),        # datasets/__init__.py:88-110
+                            T.RandomAffine(degrees=10, translate=(0.1, 0.1), scale=(0.8, 1.2), shear=20),
+                            T.RandomPerspective()])
+        self.aug = D.ClothAugmenter(tf, 19)
+        py_state = random.getstate()
+        with torch.random.fork_rng(devices=[]):          # the plugin's smooth-label draws use the global CPU generator
+            random.seed(seed)
+            torch.manual_seed(seed)
+            t0 = time.perf_counter()
+            self.table = D.OpTable([self.aug.draw(S, S) for _ in range(B)])
+            self.draw_ms_per_sample = (time.perf_counter() - t0) * 1e3 / B
+        random.setstate(py_state)
+        self.B = B
+        self.h2d_bytes = (self.body.numel() * 4 + self.labels.numel() + self.table.nbytes)
+
+    def __call__(self):
+        from swapnet_b200.ops import SegMap
+
+        lab = self.labels.cuda(non_blocking=True)
+        return dict(bodys=self.body, input_cloths=self.aug.apply(lab, self.table), target_cloths=SegMap(lab, 19),
+                    cloth_paths=["synthetic"] * self.B, body_paths=["synthetic"] * self.B)
+
+    def resident(self):
+        d = self()
+        d["bodys"] = self.body.cuda()
+        return d
+
+
 def warp_opt(B, S, precision):
     return argparse.Namespace(
         model="warp", gpu_id=int(os.environ.get("LOCAL_RANK", 0)), is_train=True,
@@ -317,6 +361,10 @@ def main():
                     help="feed the warp cloth tensors as the fp32 one-hot [B,19,S,S] tensors the reference's DataLoader "
                          "yields (688 MB of H2D per step at batch 16) instead of uint8 label maps expanded on the device "
                          "(the default: ops.SegMap, SURVEY 8f rank 4)")
+    ap.add_argument("--device-augment", action="store_true",
+                    help="warp: the e2e leg ships ONE uint8 label map per sample + the drawn op table and runs the reference's "
+                         "per-channel augmentation (datasets/data_utils.py:346-361, --input_transforms hflip vflip affine "
+                         "perspective) on the device (swapnet_b200/data.py) inside the timed region")
     ap.add_argument("--precision", default="fp32x3", choices=("fp32x3", "bf16"))
     ap.add_argument("--cpu-steps", type=int, default=3,
                     help="timed CPU-oracle steps of the cpu_baseline leg (one step = ~5 s on the usable host cores)")
@@ -392,6 +440,11 @@ def main():
             o = warp_opt(B, S, args.precision) if kind == "warp" else texture_opt()
             m = create_model(o)
             m.setup(m.opt)
+            if kind == "warp" and args.device_augment:
+                host, tkeys = device_augment_feed(B, S, 1234 + rank), ("bodys", "input_cloths", "target_cloths")
+                devb = host.resident()
+                legs.append((m, host, devb, tkeys))
+                continue
             if kind == "warp":
                 host = synth_batch(B, S, 1234 + rank, labels=args.labels)
                 tkeys = ("bodys", "input_cloths", "target_cloths")
@@ -404,7 +457,8 @@ def main():
             for k in tkeys:
                 devb[k] = host[k].cuda(non_blocking=True)
             legs.append((m, host, devb, tkeys))
-    h2d = sum(host[k].numel() * host[k].element_size() for _, host, _, tkeys in legs for k in tkeys)
+    h2d = sum(host.h2d_bytes if callable(host) else sum(host[k].numel() * host[k].element_size() for k in tkeys)
+              for _, host, _, tkeys in legs)
     n_losses = sum(len([n for n in m.loss_names if isinstance(n, str)]) for m, *_ in legs)
 
     def barrier():
@@ -414,7 +468,7 @@ def main():
 
     def one_step(on_host, read_losses):
         for m, host, devb, _ in legs:
-            m.set_input(host if on_host else devb)
+            m.set_input((host() if callable(host) else host) if on_host else devb)
             m.optimize_parameters()
             if read_losses:
                 m.get_current_losses()
@@ -529,10 +583,15 @@ def main():
         "data": "synthetic", "config": config,
         "e2e": {"value": total_imgs / (ms_e2e / args.steps * 1e-3), "unit": "images/s",
                 "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": n_losses * 8,
-                "inputs": "uint8 label maps for the cloth tensors (ops.SegMap), expanded to one-hot planes on the device"
+                "inputs": ("ONE uint8 label map per sample + the op table of the reference's per-channel augmentation "
+                           "(hflip, vflip, affine, perspective; draws made beforehand on the host), augmented and expanded "
+                           "on the device inside the timed region (swapnet_b200/data.py)") if args.device_augment else
+                "uint8 label maps for the cloth tensors (ops.SegMap), expanded to one-hot planes on the device"
                 if args.labels else "fp32 tensors as the reference's DataLoader yields them"},
         "gpu_launches": launches, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
     }
+    if args.device_augment:
+        out["e2e"]["host_draw_ms_per_sample"] = legs[0][1].draw_ms_per_sample
     emit(out)
     if world > 1:
         torch.distributed.destroy_process_group()

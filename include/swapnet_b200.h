@@ -392,6 +392,34 @@ int sn_roi_align_pack_fwd(const float* tex_nchw, int b, int ch, int h, int w, co
                           void* out_lo, int plane_pitch, int plane_coff, int plane_fmt, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Per-channel cloth augmentation on the device: replaces datasets/data_utils.py:346-361
+ * `per_channel_transform` — every channel of the one-hot cloth tensor through its own random
+ * RandomOrder([RandomVerticalFlip, RandomHorizontalFlip, RandomAffine, RandomPerspective]) (datasets/__init__.py:88-110,
+ * call site datasets/warp_dataset.py:133-134) — fused with the label map -> one-hot expansion of
+ * data_utils.py:330-343.  The draws are made on the host (torchvision's get_params); an op is one Pillow
+ * resampling, restated bit-exactly (libImaging/Geometry.c): flips, AFFINE+NEAREST in 16.16 fixed point
+ * (p[0..5] = the FIX()ed integer coefficients a0..a5 as doubles), PERSPECTIVE+BILINEAR on mode "F"
+ * (p[0..7] = the 8 coefficients of Image.transform).
+ *   ops_dev[(b*c + ch) * op_stride + j] = j-th op of that plane, `nops` (same in every entry of the plane) of them;
+ *   source = uint8 label map [n,h,w] (label L > 0 -> channel L, 0 -> nothing) or dense fp32 [n,c,h,w];
+ *   out/tmp fp32 [n,c,h,w]; tmp may be null when max_ops < 2.  max_ops = max over planes of nops (passes launched).
+ * ---------------------------------------------------------------------------------------- */
+#define SN_AUG_NONE 0
+#define SN_AUG_HFLIP 1
+#define SN_AUG_VFLIP 2
+#define SN_AUG_AFFINE_NEAREST 3
+#define SN_AUG_PERSPECTIVE_BILINEAR 4
+#define SN_AUG_MAX_OPS 8
+typedef struct sn_aug_op {
+  int kind;     /* SN_AUG_* */
+  int nops;     /* number of ops of this plane */
+  double p[8];
+} sn_aug_op;
+int sn_augment_channels(const void* labels_u8, const float* dense_nchw, int n, int c, int h, int w,
+                        const sn_aug_op* ops_dev, int op_stride, int max_ops, float* out_nchw, float* tmp_nchw,
+                        void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * reference-free fp32 CUDA-core contraction with the tap-GEMM semantics (no tensor cores).
  * Used by the tests as an on-device cross-check of the tcgen05 path, never by the plugin.
  * ---------------------------------------------------------------------------------------- */

@@ -16,6 +16,8 @@ SN_MAX_SRC = 3
 ACT_NONE, ACT_TANH, ACT_LRELU, ACT_RELU = 0, 1, 2, 3
 LAYOUT_NCHW, LAYOUT_NHWC, LAYOUT_LABEL_U8, LAYOUT_MASK_I32 = 0, 1, 2, 3
 FMT_BF16, FMT_F16 = 0, 1
+AUG_NONE, AUG_HFLIP, AUG_VFLIP, AUG_AFFINE_NEAREST, AUG_PERSPECTIVE_BILINEAR = 0, 1, 2, 3, 4
+AUG_MAX_OPS = 8
 
 
 class SnTap(C.Structure):
@@ -164,6 +166,7 @@ SIGNATURES = {
     "sn_gram_bwd": (_I, [_VP, _VP, _LL, _LL, _LL, _I, _I, _LL, _VP, _I, _I, _VP]),
     "sn_roi_align_pack_fwd": (_I, [_VP, _I, _I, _I, _I, _VP, _I, _I, _VP, _I, _VP, _VP, _I, _I, _I, _VP]),
     "sn_tap_gemm_simt": (_I, [C.POINTER(SnTapGemmDesc), _VP]),
+    "sn_augment_channels": (_I, [_VP, _VP, _I, _I, _I, _I, _VP, _I, _I, _VP, _VP, _VP]),
 }
 
 _lib = None

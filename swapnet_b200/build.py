@@ -15,7 +15,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libswapnet_b200.so")
-SOURCES = ["api.cu", "gemm_tc.cu", "elementwise.cu", "roi_align.cu", "perceptual.cu", "patch_logits.cu"]
+SOURCES = ["api.cu", "gemm_tc.cu", "elementwise.cu", "roi_align.cu", "perceptual.cu", "patch_logits.cu", "augment.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-lineinfo", "-O3", "-std=c++17",

@@ -756,6 +756,22 @@ def roi_align_pack(tex_nchw: torch.Tensor, rois: torch.Tensor, pool: int, out_f3
         FMT_F16 if out_planes is None else out_planes.fmt, _stream()))
 
 
+def augment_channels(src, channels: int, ops_dev: torch.Tensor, op_stride: int, max_ops: int, out: torch.Tensor,
+                     tmp: Optional[torch.Tensor]) -> None:
+    """Per-channel geometric augmentation (datasets/data_utils.py:346-361) of a uint8 label map [n,h,w] (expanded to
+    one-hot on the fly, data_utils.py:330-343) or of a dense fp32 [n,c,h,w] tensor -> out fp32 [n,c,h,w].
+    ops_dev: the sn_aug_op table [n*c, op_stride] as bytes on the device (swapnet_b200/data.py builds it)."""
+    labels = src.dtype == torch.uint8
+    assert src.is_cuda and src.is_contiguous() and out.is_contiguous() and out.dtype == torch.float32
+    n, h, w = (src.shape[0], src.shape[-2], src.shape[-1])
+    assert (src.dim() == 3) if labels else (src.dtype == torch.float32 and tuple(src.shape) == (n, channels, h, w))
+    assert tuple(out.shape) == (n, channels, h, w) and (tmp is None or (tmp.shape == out.shape and tmp.dtype == out.dtype))
+    assert ops_dev.is_cuda and ops_dev.dtype == torch.uint8 and ops_dev.numel() == n * channels * op_stride * 72
+    check(_lib.load().sn_augment_channels(src.data_ptr() if labels else None, None if labels else src.data_ptr(),
+                                          n, channels, h, w, ops_dev.data_ptr(), op_stride, max_ops, out.data_ptr(),
+                                          _ptr(tmp), _stream()))
+
+
 def launch_count() -> int:
     return int(_lib.load().sn_launch_count())
 
