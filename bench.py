@@ -1,28 +1,37 @@
 #!/usr/bin/env python
-"""SwapNet warp-stage training throughput on B200 (BASELINE.json metric).
+"""SwapNet GAN-training throughput on B200 (BASELINE.json metric: images/s of the full G+D training step).
 
-    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
-    python bench.py --impl reference ...                     # the reference's CPU path (baseline arm)
-    torchrun --nproc-per-node N bench.py --gpus N ...        # data parallel, one rank per GPU
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path (default: warp stage, configs[1])
+    python bench.py --impl reference --steps K --warmup W    # the reference's CPU path (baseline arm, same config object)
+    torchrun --nproc-per-node N bench.py --gpus N ...        # data parallel, one rank per GPU (NCCL)
+    python bench.py --model texture --perceptual             # BASELINE configs[2] (default texture losses incl. VGG16)
+    python bench.py --model joint --perceptual               # configs[4]: one warp + one texture step, 8 images/GPU
+    python bench.py --device-augment                         # e2e leg with the dataset's augmentation on the device (f4)
 
-One "step" = one WarpModel.optimize_parameters() (G fwd, D step, G step incl. both AdamW updates —
-the full reference training step, models/warp_model.py:169-183) on a synthetic batch of
-`--batch` 512x512 images per GPU (BASELINE.json configs[1]: warp_model 512x512, batch 16, 1xB200).
-Prints ONE JSON line (rank 0).  Field notes:
-  value     images/s, whole job, inputs already resident in HBM, K steps timed with CUDA events;
-  e2e       same metric through the plugin API with HOST (pinned) input tensors: the timed region
-            has, every step, the H2D copy of the batch (set_input) and the D2H read of the six
-            losses (get_current_losses, as train.py:62-74 does);
-  roofline  dominant kernel class = the tcgen05 tap-GEMM (`tap_gemm_kernel<3>`: forward + dgrad
-            launches): algorithmic conv FLOPs of those launches / their summed CUDA-event time,
-            against the measured dense bf16 peak.  The kernel issues 3 MMAs per algorithmic MAC
-            (fp16/bf16-split fp32-faithful product), so frac <= 1/3 by construction; `pipe_frac`
-            is the tensor-pipe view (3x).
-  cpu_baseline  the CPU oracle port (oracle/nets.py, pinned bit-exactly to the reference modules)
-            running the same training step at 512x512, batch 1, on the host cores the cgroup CPU quota
-            allows (host_cores()), a few steps; `--impl reference` times the same port as the reference arm
-            (K <= 10, W <= 2 so that the run stays within a few minutes).
-  --model texture [--perceptual]   informational: the texture stage (BASELINE configs[2]), not the headline.
+One "step" = one `optimize_parameters()` of the plugin (G fwd, D step on fake+real, G step through D, both AdamW updates —
+the full reference training step, models/warp_model.py:169-183 / texture_model.py:127-180) on a synthetic batch of
+`--batch` 512x512 images per GPU (default 16).  stdout carries exactly ONE JSON line (rank 0); everything else that
+libraries print (NCCL banner ...) is routed to stderr.  Field notes:
+  value     images/s, whole job, inputs already resident in HBM, K steps between CUDA events after W >= 3 warm-up steps
+            (the step is replayed as a CUDA graph from the third step of a shape on; multi-GPU steps launch eagerly);
+  e2e       same metric through set_input / optimize_parameters / get_current_losses (train.py:62-74) with PINNED HOST
+            tensors: every step's H2D copy and the one 64-byte D2H of the losses are inside the timed region.  The cloth
+            tensors travel as uint8 label maps (ops.SegMap, expanded on the device) unless --fp32-inputs (the 19-channel
+            fp32 tensors the reference's DataLoader yields: 688 MB per batch-16 step); --device-augment ships one label
+            map per sample + the drawn op table and runs the per-channel augmentation on the device inside the region;
+  roofline  dominant kernel class = the tcgen05 tap-GEMM (`tap_gemm_kernel<3>`: forward + dgrad launches): algorithmic
+            conv FLOPs of those launches / their summed CUDA-event time in one extra eager step, against the measured
+            sustained dense bf16 peak (MEASURED_PEAKS.json).  The kernel issues 3 MMAs per algorithmic MAC (fp16/bf16-split
+            fp32-faithful product), so frac <= 1/3 by construction; `pipe_frac` is the tensor-pipe view (3x);
+            `resblock` = the eight resblock convs alone (fwd / dgrad / wgrad), `wgrad_kernel` = all weight gradients;
+            `traffic` = DRAM bytes per launch from the committed ncu capture (a constant from profiles/, not measured here);
+  cpu_baseline  the CPU oracle port (oracle/nets.py, pinned bit-exactly to the reference modules) running the same
+            training step at 512x512, batch 1, on the host cores the cgroup quota allows (host_cores()), `--cpu-steps`
+            steps (N = 1 only; --no-cpu-baseline skips it);
+  --impl reference   the same port as the reference arm: exactly K timed and W warm-up steps, each on `--cpu-batch`
+            image(s) of the batch (a bounded sample: the step is per-sample work + batch-mean losses), same `config`.
+            The reference is pure Python: there is nothing to compile into oracle/_ref and /root/reference does not exist
+            on the GPU box, so `kind` is "port".
 """
 from __future__ import annotations
 

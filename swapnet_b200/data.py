@@ -34,6 +34,7 @@ import numpy as np
 import torch
 
 from ._lib import AUG_AFFINE_NEAREST, AUG_HFLIP, AUG_MAX_OPS, AUG_PERSPECTIVE_BILINEAR, AUG_VFLIP
+from .ops import SegMap  # noqa: F401  (re-export: the compact form `target_cloths` travels in)
 
 Op = Tuple[int, Sequence[float]]
 # mirrors `sn_aug_op` (include/swapnet_b200.h): int kind, int nops, double p[8] -> 72 bytes
