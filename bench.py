@@ -31,7 +31,8 @@ libraries print (NCCL banner ...) is routed to stderr.  Field notes:
   --impl reference   the same port as the reference arm: exactly K timed and W warm-up steps, each on `--cpu-batch`
             image(s) of the batch (a bounded sample: the step is per-sample work + batch-mean losses), same `config`.
             The reference is pure Python: there is nothing to compile into oracle/_ref and /root/reference does not exist
-            on the GPU box, so `kind` is "port".
+            on the GPU box, so `kind` is "port" there; where /root/reference exists (the build container) the warp arm
+            times the UNMODIFIED reference WarpModel through its own API instead (`kind` "reference").
 """
 from __future__ import annotations
 
@@ -243,6 +244,42 @@ def host_cores() -> int:
     return max(1, n)
 
 
+def cpu_unmodified_reference_run(S, B, steps, warmup):
+    """The UNMODIFIED reference `WarpModel` (models/warp_model.py, imported from /root/reference through
+    oracle/ref_harness.py) timed through its own public API — set_input / optimize_parameters / get_current_losses, the
+    calls of train.py:62-74 — on the host cores.  Only where /root/reference exists (the build container); the GPU
+    box has no reference tree and takes the port (`cpu_reference_run`).  -> (images/s, median s) or None."""
+    from oracle import ref_harness as RH
+
+    if not RH.available() or os.environ.get("SN_BENCH_PORT") == "1":     # SN_BENCH_PORT=1: time the port (A/B)
+        return None
+    import contextlib
+
+    torch.set_num_threads(host_cores())
+    with contextlib.redirect_stdout(sys.stderr):
+        try:
+            RH.import_reference()
+        except RuntimeError:            # this repo's `models` plugin is already imported in this process
+            return None
+        import models as ref_models
+
+        torch.manual_seed(0)
+        model = ref_models.create_model(RH.warp_opt(B, crop_size=S, load_size=S))
+        model.setup(model.opt)
+    batch = synth_batch(B, S, 1234)
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        model.set_input(batch)
+        model.optimize_parameters()
+        model.get_current_losses()
+        if i >= warmup:
+            times.append(time.perf_counter() - t0)
+    times.sort()
+    med = times[len(times) // 2]
+    return B / med, med
+
+
 def cpu_reference_run(S, B, steps, warmup, model="warp", perceptual=False):
     """K timed steps (after W warm-up steps) of the reference training step on the host cores -> (images/s, median s).
     model: warp | texture | joint (one warp step + one texture step per iteration, BASELINE configs[4])."""
@@ -407,6 +444,18 @@ def main():
         # exactly K timed and W warm-up steps of the same workload and config; each CPU step is a BOUNDED SAMPLE of the
         # batch (`--cpu-batch` images, default 1: the step is per-sample work + batch-mean losses, cost linear in the
         # batch) so that 25 steps stay within a few minutes on the box's host cores
+        unmodified = cpu_unmodified_reference_run(S, args.cpu_batch, args.steps, args.warmup) if args.model == "warp" else None
+        if unmodified is not None:
+            v, med = unmodified
+            emit({"impl": "reference", "metric": metric_name(args), "value": v, "unit": "images/s", "n_gpus": args.gpus,
+                  "steps": args.steps, "warmup": args.warmup, "ms_per_step": med * 1e3, "higher_is_better": True,
+                  "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
+                  "cpu_baseline": {"value": v, "unit": "images/s", "cores": cores, "kind": "reference",
+                                   "sample": f"{args.steps} timed + {args.warmup} warm-up steps of the UNMODIFIED reference "
+                                             f"WarpModel (set_input + optimize_parameters + get_current_losses) at {S}x{S}, "
+                                             f"each on {args.cpu_batch} image(s) of the batch, torch CPU fp32, {cores} threads"},
+                  "e2e": {"value": v, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
+            return
         v, med = cpu_reference_run(S, args.cpu_batch, args.steps, args.warmup, args.model, args.perceptual)
         emit(({
             "impl": "reference", "metric": metric_name(args), "value": v,
