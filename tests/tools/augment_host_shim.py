@@ -18,6 +18,7 @@ PRELUDE = r'''
 #define __device__
 #define __forceinline__ inline
 #define __launch_bounds__(x)
+#define __restrict__
 struct D3 { int x, y, z; };
 static D3 blockIdx, threadIdx, blockDim, gridDim;
 using std::min; using std::max;
@@ -34,8 +35,7 @@ extern "C" void run(const uint8_t* labels, const float* dense, int n, int c, int
                     int stride, int max_ops, float* out, float* tmp) {
   AugArgs a; a.labels = labels; a.dense = dense; a.ops = ops; a.out = out; a.tmp = tmp;
   a.n = n; a.c = c; a.h = h; a.w = w; a.stride = stride;
-  const long long hw = (long long)h * w;
-  int gx = (int)((hw + 1023) / 1024); if (gx < 1) gx = 1;
+  const int gx = (h + kAugRows - 1) / kAugRows;
   const int passes = max_ops > 0 ? max_ops : 1;
   blockDim = {256, 1, 1}; gridDim = {gx, n * c, 1};
   for (int j = 0; j < passes; ++j) {
