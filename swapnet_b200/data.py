@@ -144,6 +144,18 @@ def encode_ops(ops_per_plane: Sequence[Sequence[Op]]):
     return table, max_ops
 
 
+def encode_sample(ops_per_channel: Sequence[Sequence[Op]], slots: int) -> torch.Tensor:
+    """One sample's draws as a fixed-size uint8 tensor [channels * slots * 72] (a DataLoader's default collate can
+    stack it); `OpTable.from_collated` turns the stacked batch back into the device table."""
+    table, max_ops = encode_ops(ops_per_channel)
+    if max_ops > slots:
+        raise NotImplementedError(f"{max_ops} ops on one channel, the sample format has {slots} slots")
+    full = np.zeros((len(ops_per_channel), slots), dtype=OP_DTYPE)
+    full[:, :table.shape[1]] = table
+    full["nops"] = table["nops"][:, :1]
+    return torch.from_numpy(full.view(np.uint8).reshape(-1).copy())
+
+
 class OpTable:
     """The encoded draws of a batch: `sn_aug_op[planes][stride]` as pinned host bytes, ready for one async H2D."""
 
@@ -156,6 +168,19 @@ class OpTable:
         self.host = torch.from_numpy(table.view(np.uint8).reshape(-1).copy())
         if pin and torch.cuda.is_available():
             self.host = self.host.pin_memory()
+
+    @classmethod
+    def from_collated(cls, t: torch.Tensor, channels: int) -> "OpTable":
+        """t: uint8 [B, channels * slots * 72], the stacked `encode_sample` tensors of a batch."""
+        assert t.dtype == torch.uint8 and t.dim() == 2 and t.shape[1] % (channels * 72) == 0
+        self = cls.__new__(cls)
+        self.batch, self.channels, self.stride = t.shape[0], channels, t.shape[1] // (channels * 72)
+        self.host = t.contiguous().reshape(-1)
+        nops = self.host.numpy().view(OP_DTYPE)["nops"]
+        self.max_ops = int(nops.max()) if nops.size else 0
+        if self.max_ops > self.stride or (nops.size and int(nops.min()) < 0):
+            raise ValueError("corrupt op table")
+        return self
 
     @property
     def nbytes(self) -> int:

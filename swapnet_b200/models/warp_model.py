@@ -73,9 +73,22 @@ class WarpModel(BaseGAN):
         # body branch and the weight packing run while the 19-channel cloth is still in flight —, the targets
         # last (first needed by the D step, one generator forward later).  No-op for device tensors.
         self.bodys = self.copy_late(input["bodys"], "bodys")
-        # the cloth tensors may arrive in compact form (uint8 label map / int32 bit mask [B,H,W], ops.SegMap)
-        self.inputs = self.copy_late(input["input_cloths"], "inputs", seg_channels=self.cloth_channels)
-        self.targets = self.copy_late(input["target_cloths"], "targets", seg_channels=self.cloth_channels)
+        if "input_labels" in input:
+            # a batch of `--dataset warp_b200` (dropin/datasets/warp_b200_dataset.py): uint8 label maps + the drawn op
+            # table; the one-hot expansion and the per-channel augmentation (datasets/data_utils.py:330-361) run here,
+            # on the device (swapnet_b200/data.py, csrc/augment.cu) — 4 MB + 88 KB of H2D for a 512x512 batch of 16
+            from .. import data as D
+
+            if getattr(self, "_augmenter", None) is None:
+                self._augmenter = D.ClothAugmenter(None, self.cloth_channels)
+            table = D.OpTable.from_collated(input["input_ops"], self.cloth_channels)
+            source = input["input_labels"].to(self.device, non_blocking=True)
+            self.inputs = self._augmenter.apply(source, table)
+            self.targets = self.copy_late(input["target_labels"], "targets", seg_channels=self.cloth_channels)
+        else:
+            # the cloth tensors may arrive in compact form (uint8 label map / int32 bit mask [B,H,W], ops.SegMap)
+            self.inputs = self.copy_late(input["input_cloths"], "inputs", seg_channels=self.cloth_channels)
+            self.targets = self.copy_late(input["target_cloths"], "targets", seg_channels=self.cloth_channels)
         self.image_paths = tuple(zip(input["cloth_paths"], input["body_paths"]))
 
     def forward(self):

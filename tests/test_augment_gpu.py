@@ -133,3 +133,14 @@ def test_plugin_takes_the_device_augmented_batch():
     assert torch.equal(f0, model.fakes)
     assert relmax(gD1, gD0) < 1e-5 and relmax(gG1, gG0) < 1e-5
     assert all(abs(l0[k] - l1[k]) <= 1e-6 * abs(l0[k]) for k in l0), (l0, l1)
+    # ... and the batch format of `--dataset warp_b200` (dropin/datasets/warp_b200_dataset.py after the DataLoader's
+    # default collate): label maps + encoded op tables on the HOST; set_input augments on the device
+    ds_batch = dict(bodys=body, input_labels=torch.from_numpy(labs), target_labels=torch.from_numpy(labs.copy()),
+                    input_ops=torch.stack([D.encode_sample(o, 4) for o in sample_ops]),
+                    cloth_paths=["c"] * B, body_paths=["b"] * B)
+    l2, gD2, gG2 = _run_phases(model, ds_batch, 5)
+    assert torch.equal(model.inputs.cpu(), dense["input_cloths"]), "set_input's device augmentation differs from Pillow"
+    assert torch.equal(model.dense(model.targets).cpu(), tgt)
+    assert torch.equal(f0, model.fakes)
+    assert relmax(gD2, gD0) < 1e-5 and relmax(gG2, gG0) < 1e-5
+    assert all(abs(l0[k] - l2[k]) <= 1e-6 * abs(l0[k]) for k in l0), (l0, l2)

@@ -106,3 +106,63 @@ def test_launcher_option_defaults_match_the_reference_parser(tmp_path):
         assert got.pop("file").startswith(os.path.join(ROOT, "dropin")), got
         for k, v in {**want, **extra[model]}.items():
             assert got[k] == v, (model, k, got[k], v)
+
+
+@needs_ref
+def test_dataset_overlay_and_warp_b200_dataset_match_the_reference_dataset(tmp_path):
+    """SURVEY §8 f4 through the reference's own registry: `--dataset warp_b200` (dropin/datasets, an overlay that leaves
+    every reference module in place) yields, sample by sample and with the generators in the same state afterwards, label
+    maps + op tables that expand to exactly the tensors the reference's WarpDataset yields (image and video mode)."""
+    probe = tmp_path / "probe.py"
+    probe.write_text(
+        "import sys, json, random, hashlib\n"
+        "import numpy as np, torch\n"
+        "import datasets, datasets.warp_dataset, datasets.data_utils\n"
+        "from options.train_options import TrainOptions\n"
+        "from oracle import augment as A\n"
+        "from swapnet_b200 import data as D\n"
+        "opt = TrainOptions().parse()\n"
+        "loader = datasets.create_dataset(opt)\n"
+        "mine = loader.dataset\n"
+        "ref = datasets.warp_dataset.WarpDataset(opt)\n"
+        "def digest():\n"
+        "    h = hashlib.sha256(); h.update(np.asarray(random.getstate()[1], dtype=np.uint64).tobytes())\n"
+        "    h.update(torch.get_rng_state().numpy().tobytes()); return h.hexdigest()\n"
+        "def decode(t, c):\n"
+        "    tab = t.numpy().view(D.OP_DTYPE).reshape(c, -1)\n"
+        "    return [[(int(tab['kind'][i, j]), tab['p'][i, j]) for j in range(int(tab['nops'][i, 0]))] for i in range(c)]\n"
+        "res = dict(datasets_file=datasets.__file__, warp_dataset_file=datasets.warp_dataset.__file__,\n"
+        "           data_utils_file=datasets.data_utils.__file__, cls=type(mine).__name__, n=len(mine), same=[], nops=[])\n"
+        "for mode in ('image', 'video'):\n"
+        "    opt.dataset_mode = mode\n"
+        "    for idx in range(len(mine)):\n"
+        "        random.seed(idx); torch.manual_seed(idx); r = ref[idx]; d_ref = digest()\n"
+        "        random.seed(idx); torch.manual_seed(idx); m = mine[idx]; d_mine = digest()\n"
+        "        ops = decode(m['input_ops'], 19)\n"
+        "        inp = A.per_channel_transform(A.onehot(m['input_labels'].numpy(), 19), ops)\n"
+        "        res['nops'].append(max(len(o) for o in ops))\n"
+        "        res['same'].append(bool(d_ref == d_mine and np.array_equal(inp, r['input_cloths'].numpy())\n"
+        "                           and np.array_equal(A.onehot(m['target_labels'].numpy(), 19), r['target_cloths'].numpy())\n"
+        "                           and torch.equal(m['bodys'], r['bodys']) and m['cloth_paths'] == r['cloth_paths']\n"
+        "                           and m['body_paths'] == r['body_paths']))\n"
+        "opt.dataset_mode = 'image'\n"
+        "batch = next(iter(loader))\n"
+        "res['batch'] = {k: (list(v.shape), str(v.dtype)) if hasattr(v, 'shape') else len(v) for k, v in batch.items()}\n"
+        "t = D.OpTable.from_collated(batch['input_ops'], 19)\n"
+        "res['table'] = [t.batch, t.channels, t.stride]\n"
+        "print('PROBE', json.dumps(res))\n")
+    data = tmp_path / "data"
+    make_dataset(str(data), n=3)
+    r = run([sys.executable, "-m", "swapnet_b200.run", str(probe), "--name", "p", "--model", "warp", "--dataset",
+             "warp_b200", "--dataroot", str(data), "--checkpoints_dir", str(tmp_path / "ck"), "--no_confirm",
+             "--batch_size", "2", "--load_size", "64", "--crop_size", "64", "--num_workers", "0"], cwd=REF, extra_path=[REF])
+    line = [ln for ln in r.stdout.splitlines() if ln.startswith("PROBE ")]
+    assert r.returncode == 0 and line, (r.stdout[-2000:], r.stderr[-3000:])
+    got = json.loads(line[-1][6:])
+    assert got["datasets_file"].startswith(os.path.join(ROOT, "dropin", "datasets"))
+    assert got["warp_dataset_file"].startswith(REF) and got["data_utils_file"].startswith(REF)
+    assert got["cls"] == "WarpB200Dataset" and got["n"] == 3
+    assert got["same"] == [True] * 6, got
+    assert max(got["nops"]) >= 3                      # the default transform set really drew something
+    assert got["batch"]["input_labels"] == [[2, 64, 64], "torch.uint8"] and got["batch"]["bodys"][0] == [2, 3, 64, 64]
+    assert got["batch"]["input_ops"] == [[2, 19 * 4 * 72], "torch.uint8"] and got["table"] == [2, 19, 4]
