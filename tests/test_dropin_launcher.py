@@ -30,9 +30,15 @@ def make_dataset(root, n=2, size=64):
         os.makedirs(os.path.join(root, d), exist_ok=True)
     for i in range(n):
         lab = np.kron(rng.randint(0, 19, (size // 16, size // 16)), np.ones((16, 16), dtype=np.int64))
-        sparse.save_npz(os.path.join(root, "cloth", f"{i}.npz"), sparse.csc_matrix(lab))
+        sparse.save_npz(os.path.join(root, "cloth", f"s{i}.npz"), sparse.csc_matrix(lab))
         for d in ("body", "texture"):
-            Image.fromarray(rng.randint(0, 255, (size, size, 3), dtype=np.uint8)).save(os.path.join(root, d, f"{i}.jpg"))
+            Image.fromarray(rng.randint(0, 255, (size, size, 3), dtype=np.uint8)).save(os.path.join(root, d, f"s{i}.jpg"))
+    with open(os.path.join(root, "rois.csv"), "w") as f:          # 12 ROI rows per file id (texture_dataset.py:73-76,117-119)
+        f.write("id,xmin,ymin,xmax,ymax\n")
+        for i in range(n):
+            for k in range(12):
+                x0, y0 = rng.randint(0, size // 2, 2)
+                f.write(f"s{i},{x0},{y0},{x0 + rng.randint(1, size // 2)},{y0 + rng.randint(1, size // 2)}\n")
     with open(os.path.join(root, "normalization_stats.json"), "w") as f:
         for k in ("body", "texture", "cloth"):
             f.write(json.dumps({"path": k, "means": [0.5, 0.5, 0.5], "stds": [0.25, 0.25, 0.25]}) + "\n")
@@ -166,3 +172,46 @@ def test_dataset_overlay_and_warp_b200_dataset_match_the_reference_dataset(tmp_p
     assert max(got["nops"]) >= 3                      # the default transform set really drew something
     assert got["batch"]["input_labels"] == [[2, 64, 64], "torch.uint8"] and got["batch"]["bodys"][0] == [2, 3, 64, 64]
     assert got["batch"]["input_ops"] == [[2, 19 * 4 * 72], "torch.uint8"] and got["table"] == [2, 19, 4]
+
+
+@needs_ref
+def test_texture_b200_dataset_matches_the_reference_dataset(tmp_path):
+    """`--dataset texture_b200`: same samples as the reference's TextureDataset (textures, ROIs incl. the joint random
+    flips, paths), the cloth as a uint8 label map whose one-hot expansion is the reference's tensor — also when the
+    stored size differs from --load_size (nearest resize of the label plane)."""
+    probe = tmp_path / "probe.py"
+    probe.write_text(
+        "import sys, json, random\n"
+        "import numpy as np, torch\n"
+        "import datasets, datasets.texture_dataset\n"
+        "from options.train_options import TrainOptions\n"
+        "from oracle import augment as A\n"
+        "opt = TrainOptions().parse()\n"
+        "loader = datasets.create_dataset(opt)\n"
+        "mine, ref = loader.dataset, datasets.texture_dataset.TextureDataset(opt)\n"
+        "same = []\n"
+        "for idx in range(len(mine)):\n"
+        "    for seed in (idx, idx + 10):\n"
+        "        random.seed(seed); torch.manual_seed(seed); r = ref[idx]\n"
+        "        random.seed(seed); torch.manual_seed(seed); m = mine[idx]\n"
+        "        same.append(bool(m['cloths'].dtype == torch.uint8 and m['cloths'].dim() == 2\n"
+        "                    and np.array_equal(A.onehot(m['cloths'].numpy(), 19), r['cloths'].numpy())\n"
+        "                    and torch.equal(m['input_textures'], r['input_textures']) and torch.equal(m['rois'], r['rois'])\n"
+        "                    and torch.equal(m['target_textures'], r['target_textures'])\n"
+        "                    and m['cloth_paths'] == r['cloth_paths'] and m['texture_paths'] == r['texture_paths']))\n"
+        "batch = next(iter(loader))\n"
+        "print('PROBE', json.dumps(dict(cls=type(mine).__name__, same=same, cloths=[list(batch['cloths'].shape), str(batch['cloths'].dtype)],\n"
+        "      restored=datasets.texture_dataset.decompress_cloth_segment.__module__)))\n")
+    data = tmp_path / "data"
+    make_dataset(str(data), n=2)
+    for load_size in ("64", "96"):
+        r = run([sys.executable, "-m", "swapnet_b200.run", str(probe), "--name", "p", "--model", "texture", "--dataset",
+                 "texture_b200", "--dataroot", str(data), "--checkpoints_dir", str(tmp_path / "ck"), "--no_confirm",
+                 "--batch_size", "2", "--load_size", load_size, "--crop_size", load_size, "--num_workers", "0"],
+                cwd=REF, extra_path=[REF])
+        line = [ln for ln in r.stdout.splitlines() if ln.startswith("PROBE ")]
+        assert r.returncode == 0 and line, (r.stdout[-2000:], r.stderr[-3000:])
+        got = json.loads(line[-1][6:])
+        assert got["cls"] == "TextureB200Dataset" and got["same"] == [True] * 4, got
+        assert got["cloths"] == [[2, int(load_size), int(load_size)], "torch.uint8"]
+        assert got["restored"] == "datasets.data_utils"           # the substitution does not outlive __getitem__
