@@ -217,3 +217,36 @@ def test_kernel_source_run_on_the_host_equals_oracle(tmp_path):
     sample_ops = [D.draw_channel_ops(tf, 19, 56, 40)]
     sample_ops[0][0] = []                                   # a plane without ops: straight copy
     assert np.array_equal(run(None, dense, sample_ops, 19)[0], A.per_channel_transform(dense[0], sample_ops[0]))
+
+
+def test_sample_format_round_trip_and_guards():
+    """`encode_sample` (what `--dataset warp_b200` puts into a sample) -> default collate -> `OpTable.from_collated`."""
+    tf = reference_transform(("hflip", "vflip", "affine", "perspective"))
+    random.seed(3); torch.manual_seed(3)
+    per_sample = [D.draw_channel_ops(tf, 19, 64, 64) for _ in range(3)]
+    stacked = torch.utils.data.default_collate([{"input_ops": D.encode_sample(o, 4)} for o in per_sample])["input_ops"]
+    t = D.OpTable.from_collated(stacked, 19)
+    want = D.OpTable(per_sample, pin=False)
+    assert (t.batch, t.channels, t.stride) == (3, 19, 4) and t.max_ops == want.max_ops
+    a = t.host.numpy().view(D.OP_DTYPE).reshape(57, 4)
+    b = want.host.numpy().view(D.OP_DTYPE).reshape(57, want.stride)
+    for f in ("kind", "nops", "p"):
+        assert np.array_equal(a[f][:, :want.stride], b[f]), f
+    assert not a["kind"][:, want.stride:].any()
+    with pytest.raises(NotImplementedError):                     # more ops than the sample format has slots for
+        D.encode_sample([[(D.AUG_HFLIP, ())] * 5], 4)
+    bad = stacked.clone()
+    bad.numpy().view(D.OP_DTYPE)["nops"][0] = 9
+    with pytest.raises(ValueError):
+        D.OpTable.from_collated(bad, 19)
+
+
+def test_datasets_overlay_refuses_to_load_without_the_reference_package(tmp_path):
+    """dropin/datasets is an overlay of the reference's package: imported on its own it must say so, not half-work."""
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-c", "import sys; sys.path.insert(0, %r); import datasets" % os.path.join(root, "dropin")],
+                       cwd=str(tmp_path), capture_output=True, text=True, env={**os.environ, "PYTHONPATH": ""})
+    assert r.returncode != 0 and "overlays the reference's `datasets` package" in r.stderr
