@@ -16,7 +16,9 @@ _here = _os.path.dirname(_os.path.abspath(__file__))
 _ref_init = None
 for _p in _sys.path:
     _cand = _os.path.join(_os.path.abspath(_p or _os.getcwd()), "datasets", "__init__.py")
-    if _os.path.isfile(_cand) and _os.path.dirname(_cand) != _here:
+    # the reference's package, not e.g. the HuggingFace `datasets` library in site-packages: it has base_dataset.py
+    if (_os.path.isfile(_cand) and _os.path.dirname(_cand) != _here
+            and _os.path.isfile(_os.path.join(_os.path.dirname(_cand), "base_dataset.py"))):
         _ref_init = _cand
         break
 if _ref_init is None:
