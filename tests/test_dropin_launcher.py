@@ -62,15 +62,19 @@ def test_plain_python_train_py_resolves_the_reference_models_package(tmp_path):
 
 
 @needs_ref
-def test_launcher_runs_unmodified_train_py_through_the_plugin(tmp_path):
+@pytest.mark.parametrize("dataset", [None, "warp_b200"])
+def test_launcher_runs_unmodified_train_py_through_the_plugin(tmp_path, dataset):
+    """dataset=None: the reference's own WarpDataset (through the dropin/datasets overlay, which must be transparent);
+    "warp_b200": the plugin dataset found by the reference's registry (device-side augmentation, f4)."""
     data = tmp_path / "data"
     make_dataset(str(data))
     ck = tmp_path / "ck"
     r = run([sys.executable, "-m", "swapnet_b200.run", "train.py", "--name", "t", "--model", "warp", "--dataroot",
              str(data), "--checkpoints_dir", str(ck), "--display_id", "0", "--batch_size", "1", "--load_size", "64",
-             "--crop_size", "64", "--num_workers", "0", "--no_confirm", "--gpu_id", "0", "--n_epochs", "1"],
-            cwd=REF)
+             "--crop_size", "64", "--num_workers", "0", "--no_confirm", "--gpu_id", "0", "--n_epochs", "1",
+             *(["--dataset", dataset] if dataset else [])], cwd=REF)
     out = r.stdout + r.stderr
+    assert ("dataset [WarpB200Dataset] was created" if dataset else "dataset [WarpDataset] was created") in out, out[-3000:]
     # options parsed through the plugin: our extra flag is in the printed / stored option table (train_options.py)
     assert "b200_precision" in out, out[-3000:]
     assert "The number of training images = 2" in out, out[-3000:]
