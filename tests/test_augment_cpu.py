@@ -183,13 +183,13 @@ def test_load_label_map_equals_the_reference_decompression(tmp_path):
 
 
 def test_kernel_source_run_on_the_host_equals_oracle(tmp_path):
-    """csrc/augment.cu's device code compiled for the host (tests/tools/augment_host_shim.py): same pixels as the
+    """csrc/augment.cu's device code compiled for the host (tests/tools/kernel_host_shim.py): same pixels as the
     oracle for label-map and dense sources, 0-4 ops per plane (the GPU run of the real kernel: test_augment_gpu.py)."""
     import sys
     sys.path.insert(0, os.path.join(os.path.dirname(__file__), "tools"))
-    import augment_host_shim
+    import kernel_host_shim
 
-    lib = augment_host_shim.build(str(tmp_path))
+    lib = kernel_host_shim.build(str(tmp_path))
     if lib is None:
         pytest.skip("no g++")
 

@@ -98,6 +98,27 @@ def test_roi_align_known_answer_notebook_fixture():
     assert np.allclose(out.astype(np.float64).sum((2, 3)), g["sums"].numpy(), rtol=0, atol=1e-9)
 
 
+def test_roi_kernel_source_run_on_the_host_equals_torchvision_fixture(tmp_path):
+    """csrc/roi_align.cu's device code compiled for the host (tests/tools/kernel_host_shim.py, g++ -ffp-contract=off):
+    bit-identical to the torchvision fixture (notebook ROIs incl. zero-area, out-of-bounds and sub-pixel rows) and to the
+    numpy oracle — the operation order of the kernel checked without a GPU (GPU run: test_roi_align_pack_bit_exact)."""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), "tools"))
+    import kernel_host_shim
+
+    lib = kernel_host_shim.build_roi(str(tmp_path))
+    if lib is None:
+        pytest.skip("no g++")
+    g = torch.load(os.path.join(GOLD, "roi_256.pt"))
+    tex = torch.randn(3, 3, 256, 256, generator=torch.Generator().manual_seed(0)).numpy()
+    rois = np.ascontiguousarray(g["rois"].numpy(), dtype=np.float32)
+    out = np.full((3, 128, 128, 36), -5, np.float32)                  # NHWC, channel = 3 * roi + rgb
+    lib.run_roi(tex.ctypes.data, 3, 3, 256, 256, rois.ctypes.data, 12, 128, out.ctypes.data)
+    got = out.transpose(0, 3, 1, 2)
+    assert np.array_equal(got, R.roi_align_pack(tex, rois, 128))
+    assert np.array_equal(got[:, :, ::8, ::8], g["sub"].numpy())
+
+
 def test_dropout_restatement_is_deterministic_and_balanced():
     m = OD.keep_mask(77, 0.5, 1 << 16)
     assert np.array_equal(m, OD.keep_mask(77, 0.5, 1 << 16))

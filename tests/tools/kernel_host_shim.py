@@ -1,5 +1,5 @@
-"""Compile the device code of swapnet_b200/csrc/augment.cu for the HOST (g++, -ffp-contract=off) so that the CPU suite
-can run the kernel's own source — index arithmetic, pass ping-pong, the IEEE double/float sequence — against the oracle
+"""Compile the device code of the bit-exact kernels — swapnet_b200/csrc/augment.cu (`build`) and csrc/roi_align.cu
+(`build_roi`) — for the HOST (g++, -ffp-contract=off) so that the CPU suite can run the kernel's own source — index arithmetic, pass ping-pong, the IEEE double/float sequence — against the oracle
 without a GPU.  Test infrastructure only: the CUDA qualifiers and the round-to-nearest intrinsics are defined away,
 blockIdx/threadIdx are globals that a plain loop nest walks.  Nothing in the product uses this."""
 import ctypes as C
@@ -64,4 +64,47 @@ def build(workdir: str):
     lib.run.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int,
                         C.c_void_p, C.c_void_p]
     lib.run.restype = None
+    return lib
+
+
+ROI_PRELUDE = r'''
+#include <cstdint>
+#include <cmath>
+#include <algorithm>
+#define __global__
+#define __device__
+#define __forceinline__ inline
+struct D3 { long long x, y, z; };
+static D3 blockIdx, threadIdx, blockDim, gridDim;
+static inline float __fadd_rn(float a, float b) { return a + b; }
+static inline float __fsub_rn(float a, float b) { return a - b; }
+static inline float __fmul_rn(float a, float b) { return a * b; }
+static inline float __fdiv_rn(float a, float b) { return a / b; }
+static inline void split16(float, int, uint16_t& h, uint16_t& l) { h = l = 0; }   // the operand-plane output is not exercised
+'''
+
+ROI_DRIVER = r'''
+extern "C" void run_roi(const float* tex, int b, int ch, int h, int w, const float* rois, int nroi, int pool, float* out) {
+  RoiArgs a; a.tex = tex; a.B = b; a.CH = ch; a.H = h; a.W = w; a.rois = rois; a.nroi = nroi; a.pool = pool;
+  a.out = out; a.out_pitch = ch * nroi; a.hi = nullptr; a.lo = nullptr; a.ppitch = 0; a.pcoff = 0; a.fmt = 0;
+  blockDim = {1, 1, 1}; gridDim = {1, 1, 1}; blockIdx = {0, 0, 0}; threadIdx = {0, 0, 0};
+  roi_align_pack_kernel(a);          // one "thread" walks the whole grid-stride loop
+}
+'''
+
+
+def build_roi(workdir: str):
+    """csrc/roi_align.cu's device code for the host -> run_roi(tex, b, ch, h, w, rois, nroi, pool, out[b,pool,pool,ch*nroi])."""
+    gxx = shutil.which("g++")
+    if gxx is None:
+        return None
+    src = open(os.path.join(ROOT, "swapnet_b200", "csrc", "roi_align.cu")).read()
+    body = src[src.index("namespace {"):src.index("}  // namespace") + len("}  // namespace")]
+    cpp, so = os.path.join(workdir, "roi_host.cpp"), os.path.join(workdir, "libroi_host.so")
+    with open(cpp, "w") as f:
+        f.write(ROI_PRELUDE + body + ROI_DRIVER)
+    subprocess.run([gxx, "-O1", "-ffp-contract=off", "-shared", "-fPIC", "-o", so, cpp], check=True)
+    lib = C.CDLL(so)
+    lib.run_roi.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+    lib.run_roi.restype = None
     return lib
