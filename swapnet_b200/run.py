@@ -8,8 +8,10 @@
 over any PYTHONPATH entry.  This launcher reproduces Python's script start-up (sys.argv, sys.path[0] = the script's
 directory, `__main__` namespace) with ONE difference: `<repo>/dropin` — whose `models` package re-exports
 swapnet_b200.models under the top-level name the reference imports (models/__init__.py:5-44, train.py:25,38) — is placed
-AHEAD of the script directory.  Everything else (options/, datasets/, util/, optimizers/, modules/) still resolves to
-the reference checkout.  Under torchrun the process group is created by the plugin itself (BaseModel.__init__), so
+AHEAD of the script directory.  `dropin/datasets` is an overlay of the reference's `datasets` package: it executes the
+reference's own `datasets/__init__.py` and keeps every reference submodule, and only adds the dataset plugins
+`--dataset warp_b200` / `texture_b200` (device-side input pipeline).  Everything else (options/, util/, optimizers/,
+modules/) resolves to the reference checkout.  Under torchrun the process group is created by the plugin itself (BaseModel.__init__), so
 train.py needs no distributed code.
 """
 from __future__ import annotations
