@@ -9,18 +9,22 @@ options are inherited, not restated).  What changes is `__getitem__` (datasets/w
 The pixel work (one-hot expansion + Pillow's resampling, bit-exact) runs on the GPU inside `WarpModel.set_input`, which
 recognises the keys below.  A sample is
   bodys [3,H,W] f32, input_labels / target_labels uint8 [H,W], input_ops uint8 [19 * OP_SLOTS * 72], cloth_paths, body_paths
+(+ resize_iy / resize_ix int64 index vectors when the stored size differs from --load_size or a crop is configured)
 and the DataLoader's default collate stacks them.  With the same seeds the (labels, ops) pair expands to exactly the
 `input_cloths` / `target_cloths` tensors the reference dataset yields (tests/test_dropin_launcher.py).
 
-Not supported (raises): stored label maps whose size differs from --load_size, cropping (--crop_size < --load_size or
---crop_bounds): the reference resizes/crops AFTER the augmentation (warp_dataset.py:150-174), which is not on the device.
+The reference resizes (nearest) and crops AFTER the augmentation (warp_dataset.py:150-174).  Both are gathers: the
+augmentation runs at the stored size and `set_input` applies one index_select per axis with the vectors computed here by
+`data.resize_crop_indices` (torch's own nearest rule on an index ramp).  The body image takes the reference's own host
+path (bilinear resize + crop_tensors).
 """
 import random
 
 import torch
 from torch import nn
 
-from datasets.warp_dataset import WarpDataset      # the reference's (see datasets/__init__.py of this overlay)
+from datasets.data_utils import crop_tensors       # the reference's (see datasets/__init__.py of this overlay)
+from datasets.warp_dataset import WarpDataset
 from swapnet_b200 import data as D
 
 
@@ -29,20 +33,25 @@ class WarpB200Dataset(WarpDataset):
 
     def __init__(self, opt, cloth_dir=None, body_dir=None):
         super().__init__(opt, cloth_dir=cloth_dir, body_dir=body_dir)
-        if self.crop_bounds:
-            raise NotImplementedError("--dataset warp_b200: cropping after the augmentation is not on the device; use "
-                                      "--crop_size == --load_size (or the reference's --dataset warp)")
+        if not isinstance(self.opt.load_size, int):
+            raise NotImplementedError("--dataset warp_b200: square --load_size only (the plugin's engines are square)")
+        self._gather = {}
         n = len(getattr(self.cloth_transform, "transforms", [])) if self.cloth_transform else 0
         if n > self.OP_SLOTS:
             raise NotImplementedError(f"more than {self.OP_SLOTS} transforms per channel")
 
     def _labels(self, fname):
-        lab = D.load_label_map(fname, self.opt.cloth_channels)
-        size = self.opt.load_size if isinstance(self.opt.load_size, (tuple, list)) else (self.opt.load_size,) * 2
-        if tuple(lab.shape) != tuple(size):
-            raise NotImplementedError(f"{fname}: stored size {lab.shape} != --load_size {size}: the resize that follows "
-                                      "the augmentation (warp_dataset.py:150-157) is not on the device")
-        return lab
+        return D.load_label_map(fname, self.opt.cloth_channels)
+
+    def _indices(self, h, w):
+        """(iy, ix) of the nearest resize to --load_size + the crop, or None when both are the identity."""
+        if (h, w) not in self._gather:
+            (x0, y0), (x1, y1) = self.crop_bounds if self.crop_bounds else ((None, None), (None, None))
+            iy = D.resize_crop_indices(h, self.opt.load_size, (y0, y1) if self.crop_bounds else None)
+            ix = D.resize_crop_indices(w, self.opt.load_size, (x0, x1) if self.crop_bounds else None)
+            same = len(iy) == h and len(ix) == w and bool((iy == torch.arange(h)).all()) and bool((ix == torch.arange(w)).all())
+            self._gather[(h, w)] = None if same else (iy, ix)
+        return self._gather[(h, w)]
 
     def __getitem__(self, index):
         cloth_file = self.cloth_files[index]
@@ -61,6 +70,14 @@ class WarpB200Dataset(WarpDataset):
                 ops = D.draw_channel_ops(self.cloth_transform, self.opt.cloth_channels, w, h)
         body_file, body = self._load_body(index)                        # the reference's own loader
         body = nn.functional.interpolate(body.unsqueeze(0), size=self.opt.load_size, mode="bilinear").squeeze()
-        return {"body_paths": body_file, "bodys": body, "cloth_paths": cloth_file,
+        if self.crop_bounds:
+            body = crop_tensors(body, crop_bounds=self.crop_bounds)
+        if source.shape != target.shape:
+            raise NotImplementedError("video mode with frames of different stored sizes")
+        item = {"body_paths": body_file, "bodys": body, "cloth_paths": cloth_file,
                 "input_labels": torch.from_numpy(source), "target_labels": torch.from_numpy(target),
                 "input_ops": D.encode_sample(ops, self.OP_SLOTS)}
+        idx = self._indices(*source.shape)
+        if idx is not None:
+            item["resize_iy"], item["resize_ix"] = idx
+        return item

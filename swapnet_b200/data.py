@@ -22,7 +22,9 @@ uint8 label map itself (`ops.SegMap`).
 Not covered (raises): transforms other than the four above, RandomAffine with an interpolation other than NEAREST or a
 non-zero fill, RandomPerspective with an interpolation other than BILINEAR (torchvision 0.26's default; 0.4 defaulted to
 BICUBIC), affine matrices that Pillow would route to its pure-scale or floating-point code path (rotation and shear both
-exactly zero — probability zero under continuous draws), the dataset's resize/crop (`--load_size` != data size).
+exactly zero — probability zero under continuous draws).  The dataset's nearest resize + crop that FOLLOW the augmentation
+(`--load_size` != stored size, `--crop_size` < `--load_size`) are index gathers: `resize_crop_indices` / `gather_rows_cols`
+(the index rule is torch's own CPU op applied to an index ramp), applied on the device by `WarpModel.set_input`.
 """
 from __future__ import annotations
 
@@ -142,6 +144,23 @@ def encode_ops(ops_per_plane: Sequence[Sequence[Op]]):
             table["kind"][i, j] = kind
             table["p"][i, j, :len(p)] = np.asarray(p, dtype=np.float64)
     return table, max_ops
+
+
+def resize_crop_indices(stored: int, load_size: int, crop=None) -> torch.Tensor:
+    """Source index of every output row (or column) of the reference's post-augmentation glue
+    (datasets/warp_dataset.py:150-174): `F.interpolate(x, size=load_size)` (nearest) followed by the crop
+    `[lo:hi]` (datasets/data_utils.py:186-194).  Both are pure gathers, so they reduce to one index vector per axis.
+    The nearest rule is not restated: torch's own CPU op resizes an index ramp."""
+    ramp = torch.arange(stored, dtype=torch.float32).view(1, 1, stored, 1)
+    idx = torch.nn.functional.interpolate(ramp, size=(int(load_size), 1)).view(-1).long()
+    if crop is not None:
+        idx = idx[crop[0]:crop[1]]
+    return idx.contiguous()
+
+
+def gather_rows_cols(t: torch.Tensor, iy: torch.Tensor, ix: torch.Tensor) -> torch.Tensor:
+    """t[..., iy, :][..., :, ix] — resize (nearest) + crop of [..., H, W] tensors as two index_selects (any device)."""
+    return t.index_select(-2, iy).index_select(-1, ix)
 
 
 def encode_sample(ops_per_channel: Sequence[Sequence[Op]], slots: int) -> torch.Tensor:

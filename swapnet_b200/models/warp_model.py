@@ -84,7 +84,13 @@ class WarpModel(BaseGAN):
             table = D.OpTable.from_collated(input["input_ops"], self.cloth_channels)
             source = input["input_labels"].to(self.device, non_blocking=True)
             self.inputs = self._augmenter.apply(source, table)
-            self.targets = self.copy_late(input["target_labels"], "targets", seg_channels=self.cloth_channels)
+            target = input["target_labels"]
+            if "resize_iy" in input:
+                # the reference's nearest resize + crop AFTER the augmentation (warp_dataset.py:150-174) = one gather per axis
+                iy, ix = input["resize_iy"][0], input["resize_ix"][0]
+                self.inputs = D.gather_rows_cols(self.inputs, iy.to(self.device), ix.to(self.device))
+                target = D.gather_rows_cols(target, iy, ix).contiguous()
+            self.targets = self.copy_late(target, "targets", seg_channels=self.cloth_channels)
         else:
             # the cloth tensors may arrive in compact form (uint8 label map / int32 bit mask [B,H,W], ops.SegMap)
             self.inputs = self.copy_late(input["input_cloths"], "inputs", seg_channels=self.cloth_channels)

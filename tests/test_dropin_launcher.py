@@ -149,10 +149,15 @@ def test_dataset_overlay_and_warp_b200_dataset_match_the_reference_dataset(tmp_p
         "        random.seed(idx); torch.manual_seed(idx); r = ref[idx]; d_ref = digest()\n"
         "        random.seed(idx); torch.manual_seed(idx); m = mine[idx]; d_mine = digest()\n"
         "        ops = decode(m['input_ops'], 19)\n"
-        "        inp = A.per_channel_transform(A.onehot(m['input_labels'].numpy(), 19), ops)\n"
+        "        inp = torch.from_numpy(A.per_channel_transform(A.onehot(m['input_labels'].numpy(), 19), ops))\n"
+        "        tgt = torch.from_numpy(A.onehot(m['target_labels'].numpy(), 19))\n"
+        "        if 'resize_iy' in m:      # what WarpModel.set_input does on the device\n"
+        "            inp = D.gather_rows_cols(inp, m['resize_iy'], m['resize_ix'])\n"
+        "            tgt = D.gather_rows_cols(tgt, m['resize_iy'], m['resize_ix'])\n"
+        "        res['gather'] = 'resize_iy' in m\n"
         "        res['nops'].append(max(len(o) for o in ops))\n"
-        "        res['same'].append(bool(d_ref == d_mine and np.array_equal(inp, r['input_cloths'].numpy())\n"
-        "                           and np.array_equal(A.onehot(m['target_labels'].numpy(), 19), r['target_cloths'].numpy())\n"
+        "        res['same'].append(bool(d_ref == d_mine and torch.equal(inp, r['input_cloths'])\n"
+        "                           and torch.equal(tgt, r['target_cloths'])\n"
         "                           and torch.equal(m['bodys'], r['bodys']) and m['cloth_paths'] == r['cloth_paths']\n"
         "                           and m['body_paths'] == r['body_paths']))\n"
         "opt.dataset_mode = 'image'\n"
@@ -163,19 +168,26 @@ def test_dataset_overlay_and_warp_b200_dataset_match_the_reference_dataset(tmp_p
         "print('PROBE', json.dumps(res))\n")
     data = tmp_path / "data"
     make_dataset(str(data), n=3)
-    r = run([sys.executable, "-m", "swapnet_b200.run", str(probe), "--name", "p", "--model", "warp", "--dataset",
-             "warp_b200", "--dataroot", str(data), "--checkpoints_dir", str(tmp_path / "ck"), "--no_confirm",
-             "--batch_size", "2", "--load_size", "64", "--crop_size", "64", "--num_workers", "0"], cwd=REF, extra_path=[REF])
-    line = [ln for ln in r.stdout.splitlines() if ln.startswith("PROBE ")]
-    assert r.returncode == 0 and line, (r.stdout[-2000:], r.stderr[-3000:])
-    got = json.loads(line[-1][6:])
-    assert got["datasets_file"].startswith(os.path.join(ROOT, "dropin", "datasets"))
-    assert got["warp_dataset_file"].startswith(REF) and got["data_utils_file"].startswith(REF)
-    assert got["cls"] == "WarpB200Dataset" and got["n"] == 3
-    assert got["same"] == [True] * 6, got
-    assert max(got["nops"]) >= 3                      # the default transform set really drew something
-    assert got["batch"]["input_labels"] == [[2, 64, 64], "torch.uint8"] and got["batch"]["bodys"][0] == [2, 3, 64, 64]
-    assert got["batch"]["input_ops"] == [[2, 19 * 4 * 72], "torch.uint8"] and got["table"] == [2, 19, 4]
+    # stored size 64: as is; resized x2 and centre-cropped back to 64 (the reference resizes / crops AFTER the augmentation:
+    # a gather per axis here); resized x2 without a crop
+    for load, crop, out in (("64", "64", 64), ("128", "64", 64), ("128", "128", 128)):
+        r = run([sys.executable, "-m", "swapnet_b200.run", str(probe), "--name", "p", "--model", "warp", "--dataset",
+                 "warp_b200", "--dataroot", str(data), "--checkpoints_dir", str(tmp_path / "ck"), "--no_confirm",
+                 "--batch_size", "2", "--load_size", load, "--crop_size", crop, "--num_workers", "0"], cwd=REF,
+                extra_path=[REF])
+        line = [ln for ln in r.stdout.splitlines() if ln.startswith("PROBE ")]
+        assert r.returncode == 0 and line, (r.stdout[-2000:], r.stderr[-3000:])
+        got = json.loads(line[-1][6:])
+        assert got["datasets_file"].startswith(os.path.join(ROOT, "dropin", "datasets"))
+        assert got["warp_dataset_file"].startswith(REF) and got["data_utils_file"].startswith(REF)
+        assert got["cls"] == "WarpB200Dataset" and got["n"] == 3
+        assert got["same"] == [True] * 6, got
+        assert got["gather"] == (load != "64")
+        assert max(got["nops"]) >= 3                      # the default transform set really drew something
+        assert got["batch"]["input_labels"] == [[2, 64, 64], "torch.uint8"] and got["batch"]["bodys"][0] == [2, 3, out, out]
+        assert got["batch"]["input_ops"] == [[2, 19 * 4 * 72], "torch.uint8"] and got["table"] == [2, 19, 4]
+        if load != "64":
+            assert got["batch"]["resize_iy"] == [[2, out], "torch.int64"]
 
 
 @needs_ref
